@@ -1,0 +1,176 @@
+/* libqkdldpc_cuda -- C ABI of the B200 batched LDPC syndrome decoder for QKD information reconciliation.
+ *
+ * This is the drop-in boundary for the hot path of ColdCloudd/QKD_LDPC_V. The reference has no FFI of its own
+ * (its decoders are plain C++ functions, qkd_ldpc_algorithm.hpp:28-109); each entry point below names the reference
+ * call site(s) it replaces. Conventions:
+ *   - plain C, opaque handles, status-code returns (0 = ok, negative = error) + qkdldpc_last_error();
+ *     no exception crosses the boundary; nothing is read from globals (the reference's `CFG` fields the decoders
+ *     read are explicit fields of qkdldpc_params);
+ *   - the caller owns every host buffer; the library owns device memory and its stream inside the handle;
+ *   - calls on one handle are serialised by the caller; different handles may be used from different threads;
+ *   - there is NO CPU implementation behind this ABI: without a CUDA device every compute entry point fails
+ *     with QKDLDPC_ERR_CUDA.
+ *
+ * Bit packing ("packed frames"): frame f, bit i lives in word  bits[f * words_per_frame + (i >> 5)]  at bit
+ * position (i & 31); words_per_frame = (n + 31) / 32; padding bits are zero. (numpy: packbits(bitorder="little").)
+ */
+#ifndef QKDLDPC_H_
+#define QKDLDPC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QKDLDPC_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define QKDLDPC_API __attribute__((visibility("default")))
+#else
+#define QKDLDPC_API
+#endif
+
+/* Status codes */
+#define QKDLDPC_OK 0
+#define QKDLDPC_ERR_INVALID (-1) /* bad argument / malformed graph */
+#define QKDLDPC_ERR_CUDA (-2)    /* CUDA runtime error or no device */
+#define QKDLDPC_ERR_NOMEM (-3)
+#define QKDLDPC_ERR_STATE (-4)
+
+/* Decoding algorithm selector: same numbering as DEC_* in the reference (config.hpp:201, config.hpp:126-133). */
+#define QKDLDPC_ALG_SPA 0        /* sum_product_decoding,                  qkd_ldpc_algorithm.cpp:3-144    */
+#define QKDLDPC_ALG_SPA_APPROX 1 /* sum_product_linear_approx_decoding,    qkd_ldpc_algorithm.cpp:174-315  */
+#define QKDLDPC_ALG_NMSA 2       /* min_sum_normalized_decoding,           qkd_ldpc_algorithm.cpp:317-482  */
+#define QKDLDPC_ALG_OMSA 3       /* min_sum_offset_decoding,               qkd_ldpc_algorithm.cpp:484-650  */
+#define QKDLDPC_ALG_ANMSA 4      /* adaptive_min_sum_normalized_decoding,  qkd_ldpc_algorithm.cpp:652-839  */
+#define QKDLDPC_ALG_AOMSA 5      /* adaptive_min_sum_offset_decoding,      qkd_ldpc_algorithm.cpp:841-1029 */
+
+/* Output flag bits per frame (decoding_result / LDPC_result, qkd_ldpc_algorithm.hpp:16-26). */
+#define QKDLDPC_FLAG_SYNDROMES_MATCH 1u
+#define QKDLDPC_FLAG_KEYS_MATCH 2u
+
+/* Tally vector layout (uint64 each; what process_trials_results consumes, simulation.cpp:580-624,683-689):
+ *   [0] frames decoded            [1] frames with syndromes_match
+ *   [2] frames with syndromes_match && keys_match        [3] sum of executed decoder iterations over all frames
+ *   [4 + k], k = 0..max_iterations : number of syndrome-matched frames with iterations_num == k
+ * Length = qkdldpc_tally_len(max_iterations) = max_iterations + 5. Integer sums => exact under any sharding
+ * of frames over GPUs; a multi-GPU job all-reduces (sum) this vector once per batch. */
+#define QKDLDPC_TALLY_FRAMES 0
+#define QKDLDPC_TALLY_SYNDROMES_MATCH 1
+#define QKDLDPC_TALLY_KEYS_MATCH 2
+#define QKDLDPC_TALLY_ITERATIONS 3
+#define QKDLDPC_TALLY_HIST 4
+
+typedef struct qkdldpc_code qkdldpc_code; /* one parity-check matrix resident on one GPU + its slot pool */
+
+/* Everything the reference decoders read from the global CFG (qkd_ldpc_algorithm.cpp:73,1056-1085) and from
+ * decoding_scaling_factors (config.hpp:50-54). */
+typedef struct qkdldpc_params {
+    int32_t algorithm;         /* QKDLDPC_ALG_*            = CFG.DECODING_ALGORITHM                         */
+    int32_t max_iterations;    /* >= 1                     = CFG.DECODING_ALG_MAX_ITERATIONS                */
+    double primary;            /* alpha (NMSA/ANMSA) or beta (OMSA/AOMSA)   = scaling_factors.primary        */
+    double secondary;          /* nu (ANMSA) or sigma (AOMSA)               = scaling_factors.secondary      */
+    int32_t enable_threshold;  /* = CFG.ENABLE_DECODING_ALG_MSG_LLR_THRESHOLD                               */
+    double threshold;          /* = CFG.DECODING_ALG_MSG_LLR_THRESHOLD (> 0)                                */
+    int32_t message_precision; /* 32: float32 messages (production); 64: float64 messages (parity mode,
+                                  bit-identical to the reference for the min-sum family)                   */
+} qkdldpc_params;
+
+/* Tuning knobs of a handle (all optional; 0 = library default). */
+typedef struct qkdldpc_options {
+    int64_t pool_bytes;     /* upper bound for the message pool in HBM (default 8 GiB)                      */
+    int32_t pool_slots;     /* resident frame slots (rounded to whole tiles); 0 = derived from pool_bytes    */
+    int32_t steps_per_poll; /* decoder iterations launched between two host checks of the done counter       */
+    int32_t frames_per_lane_f32; /* 1, 2 or 4 (tile = 32 x this many frames); default 4 (128-bit accesses)    */
+    int32_t use_graph;      /* 1 (default): replay one captured CUDA graph per poll interval; -1: plain launches */
+    int32_t reserved[5];
+} qkdldpc_options;
+
+QKDLDPC_API int qkdldpc_version(void);
+/* Message of the last failing call made by the calling thread (thread-local, never NULL). */
+QKDLDPC_API const char *qkdldpc_last_error(void);
+QKDLDPC_API int64_t qkdldpc_tally_len(int32_t max_iterations);
+/* Number of CUDA devices visible (0 if none / no driver). */
+QKDLDPC_API int qkdldpc_device_count(void);
+
+/* Builds the device-resident Tanner graph of one parity-check matrix. Replaces the per-call use of
+ * `H_matrix` (array_and_matrix_operations.hpp:60-77) by the decoders: the host converts
+ * H_matrix.check_nodes to CSR (row_ptr[m+1], col_idx[nnz]); the library derives the column view
+ * (H_matrix.bit_nodes) itself, re-lays both out as edge-indexed CSR/CSC with degree-bucketed rows and
+ * columns, and keeps them on `device`. col_idx must be ascending and duplicate-free inside every row
+ * (true for every matrix the reference ships, quirk Q1); otherwise QKDLDPC_ERR_INVALID.
+ * One handle per matrix, reused for every (QBER, scaling factor, rate adaptation) combination, like
+ * sim_input.matrix (simulation.hpp:29-34). */
+QKDLDPC_API int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, const int32_t *row_ptr,
+                        const int32_t *col_idx, int32_t device, const qkdldpc_options *options /* may be NULL */);
+QKDLDPC_API void qkdldpc_code_destroy(qkdldpc_code *code);
+
+/* Optional: run all work of this handle on a caller-owned CUDA stream (a cudaStream_t passed as void*),
+ * e.g. torch's current stream, so that the caller's CUDA events bracket the decoder's kernels. */
+QKDLDPC_API int qkdldpc_code_set_stream(qkdldpc_code *code, void *cuda_stream);
+
+/* Decodes a batch of independent frames: the drop-in for the trial loop
+ *     pool.detach_loop(0, TRIALS, n -> run_trial(...))              simulation.cpp:740-746
+ * and, per frame, for QKD_LDPC (qkd_ldpc_algorithm.cpp:1031-1119) or QKD_LDPC_RATE_ADAPT (:1121-1258):
+ * a-priori LLRs from Bob's bits and the QBER, Alice's syndrome, the selected decoder, keys compare.
+ *
+ * Inputs (HOST pointers, packed frames, see top of file):
+ *   alice_bits, bob_bits   n_frames x words_per_frame. With rate adaptation these are the EXTENDED frames
+ *                          (alice_bit_array_extended / bob_bit_array_extended, :1136-1174): punctured positions
+ *                          carry each party's random bit, shortened positions carry 0.
+ *   qber                   per-frame QBER used for the LLR magnitude log((1-q)/q) (the "accurate QBER",
+ *                          simulation.cpp:555,565); if qber_is_scalar != 0 only qber[0] is read.
+ *   punct_pos / short_pos  ascending bit positions shared by the whole batch (H_matrix_params.punctured_bits /
+ *                          shortened_bits, array_and_matrix_operations.hpp:44-48); may be NULL with count 0.
+ *                          Punctured LLR = 1e-4 (ALMOST_ZERO, qkd_ldpc_algorithm.hpp:13), shortened LLR = the
+ *                          largest finite value of the message type (DBL_MAX in the reference, :1164).
+ * Outputs (HOST pointers, each may be NULL):
+ *   out_bits   n_frames x words_per_frame, bob_solution = last hard decision (packed)
+ *   out_iters  decoding_result.iterations_num
+ *   out_flags  QKDLDPC_FLAG_* bits
+ *   tally      qkdldpc_tally_len(max_iterations) uint64, overwritten with this batch's tallies
+ */
+QKDLDPC_API int qkdldpc_decode_batch(qkdldpc_code *code, const qkdldpc_params *params, int64_t n_frames,
+                         const uint32_t *alice_bits, const uint32_t *bob_bits, const double *qber,
+                         int32_t qber_is_scalar, const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos,
+                         int32_t n_short, uint32_t *out_bits, int32_t *out_iters, uint8_t *out_flags,
+                         uint64_t *tally);
+
+/* Same call with every frame buffer already resident in device memory (DEVICE pointers for alice_bits, bob_bits,
+ * qber, out_bits, out_iters, out_flags, tally; punct_pos / short_pos stay HOST pointers: they are per-batch
+ * metadata). Work is enqueued on the handle's stream and the call returns after the batch completed. */
+QKDLDPC_API int qkdldpc_decode_batch_device(qkdldpc_code *code, const qkdldpc_params *params, int64_t n_frames,
+                                const uint32_t *d_alice_bits, const uint32_t *d_bob_bits, const double *d_qber,
+                                int32_t qber_is_scalar, const int32_t *punct_pos, int32_t n_punct,
+                                const int32_t *short_pos, int32_t n_short, uint32_t *d_out_bits, int32_t *d_out_iters,
+                                uint8_t *d_out_flags, uint64_t *d_tally);
+
+/* Synthetic keys generated on the device with the distribution of run_trial (simulation.cpp:549-555):
+ * Alice iid uniform bits, Bob = Alice with EXACTLY floor(n * qber) flips at uniformly random distinct positions
+ * (array_and_matrix_operations.cpp:889-933). Device RNG (counter-based), NOT the reference's xoshiro stream:
+ * for throughput runs only. Writes packed frames to DEVICE buffers and returns the accurate QBER. */
+QKDLDPC_API int qkdldpc_generate_keys_device(qkdldpc_code *code, int64_t n_frames, double qber, uint64_t seed,
+                                 uint32_t *d_alice_bits, uint32_t *d_bob_bits, double *accurate_qber_out);
+
+/* Introspection used by benchmarks and tests. */
+typedef struct qkdldpc_info {
+    int32_t n, m;
+    int64_t nnz;
+    int32_t device;
+    int32_t frames_per_tile;   /* of the last batch */
+    int32_t pool_tiles;        /* of the last batch */
+    int64_t pool_bytes;        /* message pool bytes of the last batch */
+    int64_t kernel_launches;   /* kernels launched by this handle so far (counted at launch sites) */
+    int64_t decoder_steps;     /* check-node/variable-node step pairs launched so far */
+    double last_batch_ms;      /* device time of the last batch (CUDA events on the handle's stream) */
+    double last_cn_ms, last_vn_ms, last_sched_ms; /* only filled when profiling is enabled */
+} qkdldpc_info;
+QKDLDPC_API int qkdldpc_code_info(const qkdldpc_code *code, qkdldpc_info *info);
+/* When enabled, every kernel of the step loop is bracketed by CUDA events (slow; for bench roofline numbers). */
+QKDLDPC_API int qkdldpc_code_set_profiling(qkdldpc_code *code, int32_t enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QKDLDPC_H_ */

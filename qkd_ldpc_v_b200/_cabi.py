@@ -1,0 +1,78 @@
+"""ctypes binding of libqkdldpc_cuda.so (include/qkdldpc.h). No fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqkdldpc_cuda.so")
+_LIB = None
+
+
+class Params(C.Structure):
+    _fields_ = [("algorithm", C.c_int32), ("max_iterations", C.c_int32), ("primary", C.c_double),
+                ("secondary", C.c_double), ("enable_threshold", C.c_int32), ("threshold", C.c_double),
+                ("message_precision", C.c_int32)]
+
+
+class Options(C.Structure):
+    _fields_ = [("pool_bytes", C.c_int64), ("pool_slots", C.c_int32), ("steps_per_poll", C.c_int32),
+                ("frames_per_lane_f32", C.c_int32), ("use_graph", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class Info(C.Structure):
+    _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("nnz", C.c_int64), ("device", C.c_int32),
+                ("frames_per_tile", C.c_int32), ("pool_tiles", C.c_int32), ("pool_bytes", C.c_int64),
+                ("kernel_launches", C.c_int64), ("decoder_steps", C.c_int64), ("last_batch_ms", C.c_double),
+                ("last_cn_ms", C.c_double), ("last_vn_ms", C.c_double), ("last_sched_ms", C.c_double)]
+
+
+# every symbol include/qkdldpc.h declares: name -> (restype, argtypes)
+_VP = C.c_void_p
+SYMBOLS = {
+    "qkdldpc_version": (C.c_int, []),
+    "qkdldpc_last_error": (C.c_char_p, []),
+    "qkdldpc_tally_len": (C.c_int64, [C.c_int32]),
+    "qkdldpc_device_count": (C.c_int, []),
+    "qkdldpc_code_create": (C.c_int, [C.POINTER(_VP), C.c_int32, C.c_int32, C.c_int64, _VP, _VP, C.c_int32,
+                                      C.POINTER(Options)]),
+    "qkdldpc_code_destroy": (None, [_VP]),
+    "qkdldpc_code_set_stream": (C.c_int, [_VP, _VP]),
+    "qkdldpc_decode_batch": (C.c_int, [_VP, C.POINTER(Params), C.c_int64, _VP, _VP, _VP, C.c_int32, _VP, C.c_int32,
+                                       _VP, C.c_int32, _VP, _VP, _VP, _VP]),
+    "qkdldpc_decode_batch_device": (C.c_int, [_VP, C.POINTER(Params), C.c_int64, _VP, _VP, _VP, C.c_int32, _VP,
+                                              C.c_int32, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
+    "qkdldpc_generate_keys_device": (C.c_int, [_VP, C.c_int64, C.c_double, C.c_uint64, _VP, _VP,
+                                               C.POINTER(C.c_double)]),
+    "qkdldpc_code_info": (C.c_int, [_VP, C.POINTER(Info)]),
+    "qkdldpc_code_set_profiling": (C.c_int, [_VP, C.c_int32]),
+}
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA library; raises (never falls back) if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C qkd_ldpc_v_b200/csrc` (or __graft_entry__.build()). "
+                "qkd_ldpc_v_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+class QkdLdpcError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = code
+        msg = lib().qkdldpc_last_error().decode(errors="replace")
+        super().__init__(f"{where} failed with status {code}: {msg}")
+
+
+def check(rc: int, where: str) -> None:
+    if rc != 0:
+        raise QkdLdpcError(rc, where)

@@ -1,0 +1,272 @@
+// libqkdldpc_cuda: C ABI (include/qkdldpc.h) over the sm_100a kernels. Host side: graph re-layout (K0), slot-pool
+// management and dispatch to the per-precision step loops (run_batch.cuh).
+#include "handle.hpp"
+#include "common.cuh"
+#include "gen_kernels.cuh"
+
+namespace qkhost {
+template <typename T, int V>
+int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const uint32_t *d_alice,
+              const uint32_t *d_bob, const double *d_qber, int qber_is_scalar, const int32_t *punct, int n_punct,
+              const int32_t *shortd, int n_short, uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags,
+              unsigned long long *d_tally);
+extern template int run_batch<float, 4>(qkdldpc_code *, const qkdldpc_params *, int64_t, const uint32_t *, const uint32_t *, const double *, int, const int32_t *, int, const int32_t *, int, uint32_t *, int32_t *, uint8_t *, unsigned long long *);
+extern template int run_batch<float, 2>(qkdldpc_code *, const qkdldpc_params *, int64_t, const uint32_t *, const uint32_t *, const double *, int, const int32_t *, int, const int32_t *, int, uint32_t *, int32_t *, uint8_t *, unsigned long long *);
+extern template int run_batch<float, 1>(qkdldpc_code *, const qkdldpc_params *, int64_t, const uint32_t *, const uint32_t *, const double *, int, const int32_t *, int, const int32_t *, int, uint32_t *, int32_t *, uint8_t *, unsigned long long *);
+extern template int run_batch<double, 2>(qkdldpc_code *, const qkdldpc_params *, int64_t, const uint32_t *, const uint32_t *, const double *, int, const int32_t *, int, const int32_t *, int, uint32_t *, int32_t *, uint8_t *, unsigned long long *);
+}  // namespace qkhost
+
+namespace {
+
+int check_params(const qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames) {
+    if (!c) return fail(QKDLDPC_ERR_INVALID, "null code handle");
+    if (!P) return fail(QKDLDPC_ERR_INVALID, "null params");
+    if (P->algorithm < 0 || P->algorithm > 5) return fail(QKDLDPC_ERR_INVALID, "algorithm %d not in 0..5", P->algorithm);
+    if (P->max_iterations < 1 || P->max_iterations > (1 << 20))
+        return fail(QKDLDPC_ERR_INVALID, "max_iterations %d out of range", P->max_iterations);
+    if (P->message_precision != 32 && P->message_precision != 64)
+        return fail(QKDLDPC_ERR_INVALID, "message_precision must be 32 or 64");
+    if (P->enable_threshold && !(P->threshold > 0)) return fail(QKDLDPC_ERR_INVALID, "threshold must be > 0");
+    if (n_frames < 0) return fail(QKDLDPC_ERR_INVALID, "negative frame count");
+    return QKDLDPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qkdldpc_version(void) { return QKDLDPC_VERSION; }
+const char *qkdldpc_last_error(void) { return last_error().c_str(); }
+int64_t qkdldpc_tally_len(int32_t max_iterations) { return (int64_t)max_iterations + 5; }
+
+int qkdldpc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, const int32_t *row_ptr,
+                        const int32_t *col_idx, int32_t device, const qkdldpc_options *options) {
+    if (!out) return fail(QKDLDPC_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (n < 1 || m < 1 || nnz < 1 || !row_ptr || !col_idx) return fail(QKDLDPC_ERR_INVALID, "empty graph");
+    if (row_ptr[0] != 0 || row_ptr[m] != nnz) return fail(QKDLDPC_ERR_INVALID, "row_ptr does not span [0, nnz]");
+    // K0: validate (ascending, duplicate-free rows -- quirk Q1) and derive the column view
+    std::vector<int> col_ptr(n + 1, 0);
+    for (int j = 0; j < m; ++j) {
+        if (row_ptr[j + 1] < row_ptr[j]) return fail(QKDLDPC_ERR_INVALID, "row_ptr not monotone at row %d", j);
+        if (row_ptr[j + 1] == row_ptr[j]) return fail(QKDLDPC_ERR_INVALID, "check node %d has no bits", j);
+        for (int e = row_ptr[j]; e < row_ptr[j + 1]; ++e) {
+            const int c = col_idx[e];
+            if (c < 0 || c >= n) return fail(QKDLDPC_ERR_INVALID, "column index %d out of range in row %d", c, j);
+            if (e > row_ptr[j] && col_idx[e - 1] >= c)
+                return fail(QKDLDPC_ERR_INVALID, "row %d is not strictly ascending (reference quirk Q1)", j);
+            col_ptr[c + 1]++;
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        if (col_ptr[i + 1] == 0) return fail(QKDLDPC_ERR_INVALID, "bit node %d has no checks", i);
+        col_ptr[i + 1] += col_ptr[i];
+    }
+    std::vector<int> csc_edge(nnz), csc_row(nnz), cur(col_ptr.begin(), col_ptr.end() - 1);
+    for (int j = 0; j < m; ++j)
+        for (int e = row_ptr[j]; e < row_ptr[j + 1]; ++e) {
+            const int p = cur[col_idx[e]]++;
+            csc_edge[p] = e;
+            csc_row[p] = j;   // rows visited ascending => every column lists its checks ascending
+        }
+    // degree buckets: rows / columns grouped so that every CTA works inside one register-array size
+    auto build_items = [](int count, const std::vector<int> &ptr, int nb, int (*bucket_of)(int), int per_cta,
+                          std::vector<int> &order, std::vector<int2> &items) {
+        order.clear();
+        items.clear();
+        for (int bk = 0; bk < nb; ++bk) {
+            const int first = (int)order.size();
+            for (int i = 0; i < count; ++i)
+                if (bucket_of(ptr[i + 1] - ptr[i]) == bk) order.push_back(i);
+            const int cnt = (int)order.size() - first;
+            for (int o = 0; o < cnt; o += per_cta)
+                items.push_back(make_int2(first + o, (std::min(per_cta, cnt - o) << 8) | bk));
+        }
+    };
+    std::vector<int> row_order, col_order, rp(row_ptr, row_ptr + m + 1);
+    std::vector<int2> cn_items, vn_items;
+    build_items(m, rp, 5, qk::cn_bucket_of, qk::kCnWarps, row_order, cn_items);
+    build_items(n, col_ptr, 5, qk::vn_bucket_of, qk::kVnWarps, col_order, vn_items);
+
+    int ndev = qkdldpc_device_count();
+    if (ndev == 0) return fail(QKDLDPC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(QKDLDPC_ERR_INVALID, "device %d not in [0, %d)", device, ndev);
+    CK(cudaSetDevice(device));
+
+    qkdldpc_code *c = new qkdldpc_code();
+    c->n = n; c->m = m; c->nnz = nnz; c->device = device;
+    if (options) c->opt = *options;
+    auto up = [&](auto &buf, const auto &vec) -> cudaError_t {
+        cudaError_t e = buf.reserve(vec.size());
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
+    };
+    std::vector<int> ci(col_idx, col_idx + nnz);
+    cudaError_t e = cudaSuccess;
+    if ((e = up(c->row_ptr, rp)) || (e = up(c->col_idx, ci)) || (e = up(c->col_ptr, col_ptr)) ||
+        (e = up(c->csc_edge, csc_edge)) || (e = up(c->csc_row, csc_row)) || (e = up(c->row_order, row_order)) ||
+        (e = up(c->col_order, col_order)) || (e = up(c->cn_items, cn_items)) || (e = up(c->vn_items, vn_items)) ||
+        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
+        (e = cudaMallocHost(&c->h_done, sizeof(unsigned long long))) || (e = cudaEventCreate(&c->ev0)) ||
+        (e = cudaEventCreate(&c->ev1)) || (e = cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming))) {
+        qkdldpc_code_destroy(c);
+        return fail(QKDLDPC_ERR_CUDA, "graph upload failed: %s", cudaGetErrorString(e));
+    }
+    c->own_stream = true;
+    c->n_cn_items = (int)cn_items.size();
+    c->n_vn_items = (int)vn_items.size();
+    *out = c;
+    return QKDLDPC_OK;
+}
+
+void qkdldpc_code_destroy(qkdldpc_code *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    c->row_ptr.release(); c->col_idx.release(); c->col_ptr.release(); c->csc_edge.release(); c->csc_row.release();
+    c->row_order.release(); c->col_order.release(); c->cn_items.release(); c->vn_items.release();
+    c->msg.release(); c->bobmask.release(); c->zmask.release(); c->synd.release(); c->par.release();
+    c->tile_active.release(); c->tile_new.release(); c->slot_llr.release(); c->slot_frame.release();
+    c->slot_iter.release(); c->frame_llr.release(); c->synd_all.release(); c->par0_all.release();
+    c->payload.release(); c->pre_done.release(); c->bitclass.release(); c->counters.release();
+    c->st_alice.release(); c->st_bob.release(); c->st_out.release(); c->st_qber.release(); c->st_iters.release();
+    c->st_flags.release(); c->st_tally.release();
+    for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    if (c->h_done) cudaFreeHost(c->h_done);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_poll) cudaEventDestroy(c->ev_poll);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int qkdldpc_code_set_stream(qkdldpc_code *c, void *cuda_stream) {
+    if (!c) return fail(QKDLDPC_ERR_INVALID, "null code handle");
+    CK(cudaSetDevice(c->device));
+    if (c->stream) CK(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
+    c->graph_key.clear();
+    return QKDLDPC_OK;
+}
+
+int qkdldpc_decode_batch_device(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames,
+                                const uint32_t *d_alice_bits, const uint32_t *d_bob_bits, const double *d_qber,
+                                int32_t qber_is_scalar, const int32_t *punct_pos, int32_t n_punct,
+                                const int32_t *short_pos, int32_t n_short, uint32_t *d_out_bits, int32_t *d_out_iters,
+                                uint8_t *d_out_flags, uint64_t *d_tally) {
+    int rc = check_params(c, P, n_frames);
+    if (rc) return rc;
+    if (n_frames == 0) {
+        CK(cudaSetDevice(c->device));
+        if (d_tally)
+            CK(cudaMemsetAsync(d_tally, 0, (size_t)qkdldpc_tally_len(P->max_iterations) * sizeof(uint64_t), c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return QKDLDPC_OK;
+    }
+    if (!d_alice_bits || !d_bob_bits || !d_qber) return fail(QKDLDPC_ERR_INVALID, "null input buffer");
+    if ((n_punct > 0 && !punct_pos) || (n_short > 0 && !short_pos) || n_punct < 0 || n_short < 0)
+        return fail(QKDLDPC_ERR_INVALID, "bad punctured/shortened position list");
+    CK(cudaSetDevice(c->device));
+    auto *tl = reinterpret_cast<unsigned long long *>(d_tally);
+#define RUN(T, V)                                                                                                   \
+    return run_batch<T, V>(c, P, n_frames, d_alice_bits, d_bob_bits, d_qber, qber_is_scalar, punct_pos, n_punct,    \
+                           short_pos, n_short, d_out_bits, d_out_iters, d_out_flags, tl)
+    if (P->message_precision == 64) {
+        RUN(double, 2);
+    } else {
+        switch (c->opt.frames_per_lane_f32) {
+            case 1: RUN(float, 1);
+            case 2: RUN(float, 2);
+            default: RUN(float, 4);
+        }
+    }
+#undef RUN
+}
+
+int qkdldpc_decode_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const uint32_t *alice_bits,
+                         const uint32_t *bob_bits, const double *qber, int32_t qber_is_scalar,
+                         const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos, int32_t n_short,
+                         uint32_t *out_bits, int32_t *out_iters, uint8_t *out_flags, uint64_t *tally) {
+    int rc = check_params(c, P, n_frames);
+    if (rc) return rc;
+    const int64_t tl = qkdldpc_tally_len(P->max_iterations);
+    if (n_frames == 0) {
+        if (tally) memset(tally, 0, tl * sizeof(uint64_t));
+        return QKDLDPC_OK;
+    }
+    if (!alice_bits || !bob_bits || !qber) return fail(QKDLDPC_ERR_INVALID, "null input buffer");
+    CK(cudaSetDevice(c->device));
+    const size_t words = (size_t)(c->n + 31) / 32, tot = (size_t)n_frames * words;
+    const size_t nq = qber_is_scalar ? 1 : (size_t)n_frames;
+    CK(c->st_alice.reserve(tot));
+    CK(c->st_bob.reserve(tot));
+    CK(c->st_qber.reserve(nq));
+    if (out_bits) CK(c->st_out.reserve(tot));
+    CK(c->st_iters.reserve(n_frames));
+    CK(c->st_flags.reserve(n_frames));
+    CK(c->st_tally.reserve(tl));
+    cudaStream_t s = c->stream;
+    CK(cudaMemcpyAsync(c->st_alice.p, alice_bits, tot * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->st_bob.p, bob_bits, tot * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->st_qber.p, qber, nq * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = qkdldpc_decode_batch_device(c, P, n_frames, c->st_alice.p, c->st_bob.p, c->st_qber.p, qber_is_scalar,
+                                     punct_pos, n_punct, short_pos, n_short, out_bits ? c->st_out.p : nullptr,
+                                     c->st_iters.p, c->st_flags.p, reinterpret_cast<uint64_t *>(c->st_tally.p));
+    if (rc) return rc;
+    if (out_bits) CK(cudaMemcpyAsync(out_bits, c->st_out.p, tot * 4, cudaMemcpyDeviceToHost, s));
+    if (out_iters) CK(cudaMemcpyAsync(out_iters, c->st_iters.p, n_frames * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (out_flags) CK(cudaMemcpyAsync(out_flags, c->st_flags.p, n_frames, cudaMemcpyDeviceToHost, s));
+    if (tally) CK(cudaMemcpyAsync(tally, c->st_tally.p, tl * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return QKDLDPC_OK;
+}
+
+int qkdldpc_generate_keys_device(qkdldpc_code *c, int64_t n_frames, double qber, uint64_t seed,
+                                 uint32_t *d_alice_bits, uint32_t *d_bob_bits, double *accurate_qber_out) {
+    if (!c) return fail(QKDLDPC_ERR_INVALID, "null code handle");
+    if (!(qber > 0.) || !(qber < 1.)) return fail(QKDLDPC_ERR_INVALID, "qber must be in (0, 1)");
+    if (n_frames < 0 || (n_frames > 0 && (!d_alice_bits || !d_bob_bits)))
+        return fail(QKDLDPC_ERR_INVALID, "bad frame buffers");
+    // inject_errors: num_errors = size_t(double(N) * QBER) (array_and_matrix_operations.cpp:913-914)
+    const int n_err = (int)(size_t)((double)c->n * qber);
+    if (accurate_qber_out) *accurate_qber_out = (double)n_err / (double)c->n;
+    if (n_frames == 0) return QKDLDPC_OK;
+    CK(cudaSetDevice(c->device));
+    const int words = (c->n + 31) / 32;
+    qk::gen_keys_kernel<<<(unsigned)n_frames, 128, words * sizeof(uint32_t), c->stream>>>(
+        c->n, words, n_err, (unsigned long long)seed, d_alice_bits, d_bob_bits);
+    c->kernel_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    return QKDLDPC_OK;
+}
+
+int qkdldpc_code_info(const qkdldpc_code *c, qkdldpc_info *info) {
+    if (!c || !info) return fail(QKDLDPC_ERR_INVALID, "null argument");
+    info->n = c->n; info->m = c->m; info->nnz = c->nnz; info->device = c->device;
+    info->frames_per_tile = c->frames_per_tile; info->pool_tiles = c->pool_tiles; info->pool_bytes = c->pool_bytes;
+    info->kernel_launches = c->kernel_launches; info->decoder_steps = c->decoder_steps;
+    info->last_batch_ms = c->last_batch_ms;
+    info->last_cn_ms = c->last_cn_ms; info->last_vn_ms = c->last_vn_ms; info->last_sched_ms = c->last_sched_ms;
+    return QKDLDPC_OK;
+}
+
+int qkdldpc_code_set_profiling(qkdldpc_code *c, int32_t enabled) {
+    if (!c) return fail(QKDLDPC_ERR_INVALID, "null code handle");
+    c->profiling = enabled != 0;
+    return QKDLDPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Host-side handle of libqkdldpc_cuda (shared by api.cu and the per-precision instantiation units).
+#pragma once
+#include "../../include/qkdldpc.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+namespace qkhost {
+
+inline std::string &last_error() {
+    static thread_local std::string e;
+    return e;
+}
+
+inline int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? QKDLDPC_ERR_NOMEM : QKDLDPC_ERR_CUDA,          \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+    } while (0)
+
+template <typename U>
+struct DevBuf {
+    U *p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(U));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct EvPair {
+    cudaEvent_t a, b;
+    int kind;   // 0 CN, 1 VN, 2 sched
+};
+
+}  // namespace qkhost
+using namespace qkhost;
+
+struct qkdldpc_code {
+    int n = 0, m = 0, device = 0;
+    int64_t nnz = 0;
+    qkdldpc_options opt{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // graph (device)
+    DevBuf<int> row_ptr, col_idx, col_ptr, csc_edge, csc_row, row_order, col_order;
+    DevBuf<int2> cn_items, vn_items;
+    int n_cn_items = 0, n_vn_items = 0;
+    // pool (device, raw bytes reinterpreted per precision)
+    DevBuf<unsigned char> msg;
+    DevBuf<uint32_t> bobmask, zmask, synd, par, tile_active, tile_new;
+    DevBuf<unsigned char> slot_llr;
+    DevBuf<long long> slot_frame;
+    DevBuf<int32_t> slot_iter;
+    // batch (device)
+    DevBuf<unsigned char> frame_llr;
+    DevBuf<uint32_t> synd_all, par0_all, payload;
+    DevBuf<uint8_t> pre_done, bitclass;
+    DevBuf<unsigned long long> counters;   // [0] next_frame, [1] n_done
+    // staging for the host-pointer entry point
+    DevBuf<uint32_t> st_alice, st_bob, st_out;
+    DevBuf<double> st_qber;
+    DevBuf<int32_t> st_iters;
+    DevBuf<uint8_t> st_flags;
+    DevBuf<unsigned long long> st_tally;
+    unsigned long long *h_done = nullptr;   // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll = nullptr;
+    // captured step graph
+    cudaGraphExec_t graph_exec = nullptr;
+    std::string graph_key;
+    // stats
+    int frames_per_tile = 0, pool_tiles = 0;
+    int64_t pool_bytes = 0, kernel_launches = 0, decoder_steps = 0;
+    double last_batch_ms = 0, last_cn_ms = 0, last_vn_ms = 0, last_sched_ms = 0;
+    bool profiling = false;
+    std::vector<EvPair> ev_pool;
+    size_t ev_used = 0;
+};
+

@@ -1,0 +1,228 @@
+"""Host-side mirror of the reference's decoding interface over the C ABI.
+
+Reference surface mirrored here (names, argument meaning, result fields):
+  * ``H_matrix`` (array_and_matrix_operations.hpp:60-77)                      -> :class:`LdpcCode`
+  * ``CFG.DECODING_ALGORITHM / ..MAX_ITERATIONS / ..MSG_LLR_THRESHOLD``       -> :class:`DecoderConfig`
+  * ``decoding_scaling_factors`` (config.hpp:50-54)                           -> ``scaling_factors=(primary, secondary)``
+  * ``H_matrix_params.punctured_bits / shortened_bits`` (.hpp:44-48)          -> ``punctured_bits= / shortened_bits=``
+  * ``QKD_LDPC`` / ``QKD_LDPC_RATE_ADAPT`` (qkd_ldpc_algorithm.cpp:1031,1121) over the trial loop
+    (simulation.cpp:740-746)                                                  -> :meth:`LdpcCode.QKD_LDPC_batch`
+  * ``LDPC_result{decoding_res{iterations_num, syndromes_match}, keys_match}``-> :class:`BatchResult`
+
+Everything is computed by libqkdldpc_cuda on the GPU; there is no CPU path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import Options, Params
+
+DEC_SPA, DEC_SPA_APPROX, DEC_NMSA, DEC_OMSA, DEC_ANMSA, DEC_AOMSA = range(6)  # config.hpp:201
+ALG_NAMES = ("SPA", "SPA_LIN_APPROX", "NMSA", "OMSA", "ANMSA", "AOMSA")
+
+FLAG_SYNDROMES_MATCH = 1
+FLAG_KEYS_MATCH = 2
+TALLY_FRAMES, TALLY_SYNDROMES_MATCH, TALLY_KEYS_MATCH, TALLY_ITERATIONS, TALLY_HIST = 0, 1, 2, 3, 4
+
+
+def pack_bits(bits) -> np.ndarray:
+    """[F][n] 0/1 -> packed uint32 [F][ceil(n/32)], bit i of a frame at word i>>5, position i&31."""
+    bits = np.ascontiguousarray(bits, np.uint8)
+    if bits.ndim == 1:
+        bits = bits[None, :]
+    f, n = bits.shape
+    w = (n + 31) // 32
+    padded = np.zeros((f, w * 32), np.uint8)
+    padded[:, :n] = bits
+    return np.packbits(padded, axis=1, bitorder="little").view("<u4").reshape(f, w)
+
+
+def unpack_bits(words, n: int) -> np.ndarray:
+    words = np.ascontiguousarray(words, "<u4")
+    f = words.shape[0]
+    return np.unpackbits(words.view(np.uint8).reshape(f, -1), axis=1, bitorder="little")[:, :n]
+
+
+@dataclass
+class DecoderConfig:
+    """The fields of the reference's global ``CFG`` that the hot path reads (config.hpp:103-198)."""
+    decoding_algorithm: int = DEC_NMSA
+    max_iterations: int = 100
+    enable_msg_llr_threshold: bool = True
+    msg_llr_threshold: float = 100.0
+    message_precision: int = 32      # 32 = production; 64 = parity mode (float64 messages)
+
+    def to_params(self, scaling_factors=(0.0, 0.0)) -> Params:
+        pri, sec = (tuple(scaling_factors) + (0.0, 0.0))[:2]
+        return Params(int(self.decoding_algorithm), int(self.max_iterations), float(pri), float(sec),
+                      int(bool(self.enable_msg_llr_threshold)), float(self.msg_llr_threshold),
+                      int(self.message_precision))
+
+
+@dataclass
+class BatchResult:
+    iterations_num: np.ndarray                 # int32 [F]   decoding_result.iterations_num
+    flags: np.ndarray                          # uint8 [F]
+    bob_solution: Optional[np.ndarray]         # packed uint32 [F][W] (last hard decision) or None
+    tally: np.ndarray                          # uint64 [max_iter + 5]
+    n: int = 0
+    device_ms: float = 0.0
+    info: dict = field(default_factory=dict)
+
+    @property
+    def syndromes_match(self) -> np.ndarray:
+        return (self.flags & FLAG_SYNDROMES_MATCH) != 0
+
+    @property
+    def keys_match(self) -> np.ndarray:
+        return (self.flags & FLAG_KEYS_MATCH) != 0
+
+    def bits(self) -> np.ndarray:
+        return unpack_bits(self.bob_solution, self.n)
+
+
+def stats_from_tally(tally: np.ndarray, trials: int) -> dict:
+    """process_trials_results (simulation.cpp:580-624,683-689) from the all-reducible tally vector."""
+    hist = np.asarray(tally[TALLY_HIST:], np.float64)
+    ok = int(tally[TALLY_SYNDROMES_MATCH])
+    its = np.arange(hist.size, dtype=np.float64)
+    out = dict(iter_success_max=0, iter_success_min=0, iter_success_mean=0.0, iter_success_std=0.0)
+    if ok > 0:
+        nz = np.nonzero(hist)[0]
+        mean = float((hist * its).sum() / ok)
+        out.update(iter_success_max=int(nz.max()), iter_success_min=int(nz.min()), iter_success_mean=mean,
+                   iter_success_std=float(np.sqrt((hist * (its - mean) ** 2).sum() / ok)))
+    out["ratio_trials_success_dec_alg"] = ok / trials
+    out["ratio_trials_success_ldpc"] = int(tally[TALLY_KEYS_MATCH]) / trials
+    out["FER"] = round((1.0 - out["ratio_trials_success_ldpc"]) * trials) / trials   # simulation.cpp:117-118
+    return out
+
+
+class LdpcCode:
+    """One parity-check matrix resident on one GPU (handle of ``qkdldpc_code_create``)."""
+
+    def __init__(self, n: int, m: int, row_ptr, col_idx, device: int = 0, pool_bytes: int = 0, pool_slots: int = 0,
+                 steps_per_poll: int = 0, frames_per_lane_f32: int = 0, use_graph: int = 0):
+        L = _cabi.lib()
+        self.n, self.m = int(n), int(m)
+        self.row_ptr = np.ascontiguousarray(row_ptr, np.int32)
+        self.col_idx = np.ascontiguousarray(col_idx, np.int32)
+        self.nnz = int(self.row_ptr[-1]) if self.row_ptr.size else 0
+        self.words = (self.n + 31) // 32
+        self.device = device
+        opt = Options(int(pool_bytes), int(pool_slots), int(steps_per_poll), int(frames_per_lane_f32), int(use_graph))
+        h = C.c_void_p()
+        _cabi.check(L.qkdldpc_code_create(C.byref(h), self.n, self.m, self.nnz, self.row_ptr.ctypes.data,
+                                          self.col_idx.ctypes.data, device, C.byref(opt)), "qkdldpc_code_create")
+        self._h = h
+
+    # -- lifetime -------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            _cabi.lib().qkdldpc_code_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- plumbing -------------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr: int):
+        _cabi.check(_cabi.lib().qkdldpc_code_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    def set_profiling(self, on: bool):
+        _cabi.check(_cabi.lib().qkdldpc_code_set_profiling(self._h, int(on)), "set_profiling")
+
+    def info(self) -> dict:
+        i = _cabi.Info()
+        _cabi.check(_cabi.lib().qkdldpc_code_info(self._h, C.byref(i)), "code_info")
+        return {k: getattr(i, k) for k, _ in _cabi.Info._fields_}
+
+    @staticmethod
+    def _poslist(x):
+        a = np.ascontiguousarray(x if x is not None else [], np.int32)
+        return a, (a.ctypes.data if a.size else None), int(a.size)
+
+    # -- the hot path ---------------------------------------------------------------------------------------
+    def QKD_LDPC_batch(self, alice_bit_array, bob_bit_array, QBER, scaling_factors=(0.0, 0.0),
+                       cfg: Optional[DecoderConfig] = None, punctured_bits: Sequence[int] = (),
+                       shortened_bits: Sequence[int] = (), want_bits: bool = True) -> BatchResult:
+        """Batched ``QKD_LDPC`` / ``QKD_LDPC_RATE_ADAPT`` with HOST buffers (copies inside).
+
+        alice_bit_array / bob_bit_array: packed uint32 [F][W] (or 0/1 arrays [F][n], packed here). With
+        punctured / shortened lists the frames must already be the EXTENDED ones. QBER: scalar or [F].
+        """
+        cfg = cfg or DecoderConfig()
+        L = _cabi.lib()
+        a = self._as_packed(alice_bit_array)
+        b = self._as_packed(bob_bit_array)
+        if a.shape != b.shape:
+            raise ValueError("alice and bob batches differ in shape")
+        F = a.shape[0]
+        q = np.ascontiguousarray(np.atleast_1d(np.asarray(QBER, np.float64)))
+        scalar = int(q.size == 1)
+        if not scalar and q.size != F:
+            raise ValueError("QBER must be a scalar or one value per frame")
+        p = cfg.to_params(scaling_factors)
+        pa, pp, np_ = self._poslist(punctured_bits)
+        sa, sp, ns_ = self._poslist(shortened_bits)
+        out_bits = np.zeros((F, self.words), np.uint32) if want_bits else None
+        iters = np.zeros(F, np.int32)
+        flags = np.zeros(F, np.uint8)
+        tally = np.zeros(int(L.qkdldpc_tally_len(p.max_iterations)), np.uint64)
+        _cabi.check(L.qkdldpc_decode_batch(self._h, C.byref(p), F, a.ctypes.data, b.ctypes.data, q.ctypes.data, scalar,
+                                           pp, np_, sp, ns_, out_bits.ctypes.data if want_bits else None,
+                                           iters.ctypes.data, flags.ctypes.data, tally.ctypes.data),
+                    "qkdldpc_decode_batch")
+        del pa, sa
+        inf = self.info()
+        return BatchResult(iters, flags, out_bits, tally, self.n, inf["last_batch_ms"], inf)
+
+    def decode_batch_device(self, d_alice: int, d_bob: int, d_qber: int, n_frames: int, scaling_factors=(0.0, 0.0),
+                            cfg: Optional[DecoderConfig] = None, qber_is_scalar: bool = True,
+                            punctured_bits: Sequence[int] = (), shortened_bits: Sequence[int] = (),
+                            d_out_bits: int = 0, d_out_iters: int = 0, d_out_flags: int = 0, d_tally: int = 0):
+        """Same with raw DEVICE pointers (ints), e.g. ``tensor.data_ptr()`` of torch tensors on this GPU."""
+        cfg = cfg or DecoderConfig()
+        p = cfg.to_params(scaling_factors)
+        pa, pp, np_ = self._poslist(punctured_bits)
+        sa, sp, ns_ = self._poslist(shortened_bits)
+        vp = lambda x: C.c_void_p(x) if x else None  # noqa: E731
+        _cabi.check(_cabi.lib().qkdldpc_decode_batch_device(
+            self._h, C.byref(p), int(n_frames), vp(d_alice), vp(d_bob), vp(d_qber), int(qber_is_scalar), pp, np_, sp,
+            ns_, vp(d_out_bits), vp(d_out_iters), vp(d_out_flags), vp(d_tally)), "qkdldpc_decode_batch_device")
+        del pa, sa
+
+    def generate_keys_device(self, n_frames: int, qber: float, seed: int, d_alice: int, d_bob: int) -> float:
+        acc = C.c_double()
+        _cabi.check(_cabi.lib().qkdldpc_generate_keys_device(self._h, int(n_frames), float(qber), int(seed),
+                                                             C.c_void_p(d_alice), C.c_void_p(d_bob), C.byref(acc)),
+                    "qkdldpc_generate_keys_device")
+        return acc.value
+
+    def _as_packed(self, x) -> np.ndarray:
+        x = np.asarray(x)
+        if x.dtype == np.uint32 and x.ndim == 2 and x.shape[1] == self.words:
+            return np.ascontiguousarray(x)
+        if x.ndim == 1:
+            x = x[None, :]
+        if x.shape[1] != self.n:
+            raise ValueError(f"expected frames of {self.n} bits (or packed {self.words} words), got {x.shape}")
+        return pack_bits(x)
+
+
+def tally_len(max_iterations: int) -> int:
+    return int(_cabi.lib().qkdldpc_tally_len(int(max_iterations)))

