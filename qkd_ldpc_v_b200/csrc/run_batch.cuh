@@ -155,7 +155,8 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     // steps between two host polls of the done counter: a frame needs at most max_iter steps, and the host
     // only has to look when a whole generation of slots may have drained
     int spp = c->opt.steps_per_poll > 0 ? c->opt.steps_per_poll : std::max(1, std::min(P->max_iterations, 16));
-    const bool use_graph = c->opt.use_graph >= 0 && !c->profiling;
+    // (the legacy default stream cannot be captured: plain launches there)
+    const bool use_graph = c->opt.use_graph >= 0 && !c->profiling && s != nullptr;
 
     if (use_graph) {
         // the captured launches embed every pointer and parameter of this batch: key the cache on all of them
