@@ -78,24 +78,21 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
             csc_edge[p] = e;
             csc_row[p] = j;   // rows visited ascending => every column lists its checks ascending
         }
-    // degree buckets: rows / columns grouped so that every CTA works inside one register-array size
-    auto build_items = [](int count, const std::vector<int> &ptr, int nb, int (*bucket_of)(int), int per_cta,
-                          std::vector<int> &order, std::vector<int2> &items) {
+    // degree buckets: rows / columns grouped so that every kernel instantiation works inside one register-array size
+    auto group = [](int count, const std::vector<int> &ptr, int (*bucket_of)(int), std::vector<int> &order, int *first,
+                    int *cnt) {
         order.clear();
-        items.clear();
-        for (int bk = 0; bk < nb; ++bk) {
-            const int first = (int)order.size();
+        for (int bk = 0; bk < qk::kBuckets; ++bk) {
+            first[bk] = (int)order.size();
             for (int i = 0; i < count; ++i)
                 if (bucket_of(ptr[i + 1] - ptr[i]) == bk) order.push_back(i);
-            const int cnt = (int)order.size() - first;
-            for (int o = 0; o < cnt; o += per_cta)
-                items.push_back(make_int2(first + o, (std::min(per_cta, cnt - o) << 8) | bk));
+            cnt[bk] = (int)order.size() - first[bk];
         }
     };
     std::vector<int> row_order, col_order, rp(row_ptr, row_ptr + m + 1);
-    std::vector<int2> cn_items, vn_items;
-    build_items(m, rp, 5, qk::cn_bucket_of, qk::kCnWarps, row_order, cn_items);
-    build_items(n, col_ptr, 5, qk::vn_bucket_of, qk::kVnWarps, col_order, vn_items);
+    int cn_first[5], cn_count[5], vn_first[5], vn_count[5];
+    group(m, rp, qk::cn_bucket_of, row_order, cn_first, cn_count);
+    group(n, col_ptr, qk::vn_bucket_of, col_order, vn_first, vn_count);
 
     int ndev = qkdldpc_device_count();
     if (ndev == 0) return fail(QKDLDPC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
@@ -114,7 +111,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     cudaError_t e = cudaSuccess;
     if ((e = up(c->row_ptr, rp)) || (e = up(c->col_idx, ci)) || (e = up(c->col_ptr, col_ptr)) ||
         (e = up(c->csc_edge, csc_edge)) || (e = up(c->csc_row, csc_row)) || (e = up(c->row_order, row_order)) ||
-        (e = up(c->col_order, col_order)) || (e = up(c->cn_items, cn_items)) || (e = up(c->vn_items, vn_items)) ||
+        (e = up(c->col_order, col_order)) ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
         (e = cudaMallocHost(&c->h_done, sizeof(unsigned long long))) || (e = cudaEventCreate(&c->ev0)) ||
         (e = cudaEventCreate(&c->ev1)) || (e = cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming))) {
@@ -122,8 +119,10 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         return fail(QKDLDPC_ERR_CUDA, "graph upload failed: %s", cudaGetErrorString(e));
     }
     c->own_stream = true;
-    c->n_cn_items = (int)cn_items.size();
-    c->n_vn_items = (int)vn_items.size();
+    for (int k = 0; k < 5; ++k) {
+        c->cn_first[k] = cn_first[k]; c->cn_count[k] = cn_count[k];
+        c->vn_first[k] = vn_first[k]; c->vn_count[k] = vn_count[k];
+    }
     *out = c;
     return QKDLDPC_OK;
 }
@@ -134,11 +133,11 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     c->row_ptr.release(); c->col_idx.release(); c->col_ptr.release(); c->csc_edge.release(); c->csc_row.release();
-    c->row_order.release(); c->col_order.release(); c->cn_items.release(); c->vn_items.release();
+    c->row_order.release(); c->col_order.release();
     c->msg.release(); c->bobmask.release(); c->zmask.release(); c->synd.release(); c->par.release();
     c->tile_active.release(); c->tile_new.release(); c->slot_llr.release(); c->slot_frame.release();
-    c->slot_iter.release(); c->frame_llr.release(); c->synd_all.release(); c->par0_all.release();
-    c->payload.release(); c->pre_done.release(); c->bitclass.release(); c->counters.release();
+    c->slot_iter.release(); c->frame_llr.release(); c->synd_all.release();
+    c->bitclass.release(); c->counters.release();
     c->st_alice.release(); c->st_bob.release(); c->st_out.release(); c->st_qber.release(); c->st_iters.release();
     c->st_flags.release(); c->st_tally.release();
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }

@@ -18,11 +18,12 @@
 namespace qk {
 
 constexpr int kWarp = 32;
-constexpr int kCnWarps = 8;   // warps (= rows) per CTA in the check-node kernels
-constexpr int kVnWarps = 8;   // warps (= bits) per CTA in the variable-node kernel
+constexpr int kBuckets = 5;   // degree buckets per node type
 constexpr int kSchedThreads = 256;
 
 // Degree buckets: pick the register-array size of the CN (8/16/24/32/re-read) and VN (4/8/16/32/re-read) kernels.
+__host__ __device__ constexpr int cn_bucket_max(int b) { return b == 0 ? 8 : b == 1 ? 16 : b == 2 ? 24 : b == 3 ? 32 : 0; }
+__host__ __device__ constexpr int vn_bucket_max(int b) { return b == 0 ? 4 : b == 1 ? 8 : b == 2 ? 16 : b == 3 ? 32 : 0; }
 __host__ __device__ inline int cn_bucket_of(int dc) { return dc <= 8 ? 0 : dc <= 16 ? 1 : dc <= 24 ? 2 : dc <= 32 ? 3 : 4; }
 __host__ __device__ inline int vn_bucket_of(int dv) { return dv <= 4 ? 0 : dv <= 8 ? 1 : dv <= 16 ? 2 : dv <= 32 ? 3 : 4; }
 
@@ -83,8 +84,6 @@ struct StepArgs {
     const int *csc_row;    // [nnz]  ... -> check id
     const int *row_order;  // [m]    rows grouped by degree bucket
     const int *col_order;  // [n]    bits grouped by degree bucket
-    const int2 *cn_items;  // per CTA of the CN grid: {first index into row_order, (count << 8) | bucket}
-    const int2 *vn_items;  // per CTA of the VN grid: {first index into col_order, (count << 8) | bucket}
     const uint8_t *bitclass;  // [n] 0 payload, 1 punctured, 2 shortened
     // pool (device)
     T *msg;

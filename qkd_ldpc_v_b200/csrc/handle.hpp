@@ -73,8 +73,7 @@ struct qkdldpc_code {
     bool own_stream = false;
     // graph (device)
     DevBuf<int> row_ptr, col_idx, col_ptr, csc_edge, csc_row, row_order, col_order;
-    DevBuf<int2> cn_items, vn_items;
-    int n_cn_items = 0, n_vn_items = 0;
+    int cn_first[5] = {0}, cn_count[5] = {0}, vn_first[5] = {0}, vn_count[5] = {0};   // degree buckets in row/col_order
     // pool (device, raw bytes reinterpreted per precision)
     DevBuf<unsigned char> msg;
     DevBuf<uint32_t> bobmask, zmask, synd, par, tile_active, tile_new;
@@ -83,8 +82,8 @@ struct qkdldpc_code {
     DevBuf<int32_t> slot_iter;
     // batch (device)
     DevBuf<unsigned char> frame_llr;
-    DevBuf<uint32_t> synd_all, par0_all, payload;
-    DevBuf<uint8_t> pre_done, bitclass;
+    DevBuf<uint32_t> synd_all;
+    DevBuf<uint8_t> bitclass;
     DevBuf<unsigned long long> counters;   // [0] next_frame, [1] n_done
     // staging for the host-pointer entry point
     DevBuf<uint32_t> st_alice, st_bob, st_out;

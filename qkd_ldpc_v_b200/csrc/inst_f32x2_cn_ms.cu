@@ -1,0 +1,7 @@
+// Check-node kernels (NMSA and OMSA) for float messages, 2 frame(s) per lane.
+#define QK_DEFINE_CN_LAUNCH
+#include "run_batch.cuh"
+namespace qkhost {
+template int launch_cn_alg<float, 2, 2>(const qkdldpc_code *, bool, int, cudaStream_t, const qk::StepArgs<float> &);
+template int launch_cn_alg<float, 2, 3>(const qkdldpc_code *, bool, int, cudaStream_t, const qk::StepArgs<float> &);
+}

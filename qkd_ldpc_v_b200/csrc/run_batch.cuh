@@ -1,5 +1,6 @@
 // The step loop of one batch: K1 prep -> initial fill -> {CN, VN, scheduler} x steps, replayed as a CUDA graph.
-// Instantiated once per (message type, frames per lane) in inst_*.cu so the units compile in parallel.
+// Instantiated once per (message type, frames per lane) in inst_*.cu so the units compile in parallel; the
+// check-node kernels of each algorithm pair live in their own units (launch_cn_alg<T, V, ALG>).
 #pragma once
 #include "handle.hpp"
 #include "common.cuh"
@@ -10,17 +11,84 @@ namespace qkhost {
 
 using namespace qk;
 
+// FAST check-node / variable-node arithmetic is exact only while no message can become NaN or infinite:
+// a finite clamp guarantees it; without the clamp it holds when no factor can scale a message up (offset
+// variants subtract; normalized variants need factors <= 1). SPA can produce NaN (0/0, quirk Q3) -> never fast.
+inline bool fast_minsum_ok(const qkdldpc_params *P) {
+    if (P->message_precision != 32 || P->algorithm < 2) return false;
+    if (P->enable_threshold) return std::isfinite(P->threshold);
+    if (P->algorithm == 3 || P->algorithm == 5) return P->primary >= 0 && P->secondary >= 0;
+    return P->primary <= 1.0 && (P->algorithm != 4 || P->secondary <= 1.0);
+}
+
+inline unsigned ceil_div(int a, int b) { return (unsigned)((a + b - 1) / b); }
+
+// One launch per non-empty degree bucket. Returns the number of kernels launched.
+template <typename T, int V, int ALG>
+int launch_cn_alg(const qkdldpc_code *c, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a);
 template <typename T, int V>
-inline void launch_cn(int alg, dim3 grid, cudaStream_t s, const StepArgs<T> &a) {
-    const dim3 blk(kCnWarps * kWarp);
+int launch_vn(const qkdldpc_code *c, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a);
+
+template <typename T, int V>
+inline int launch_cn(const qkdldpc_code *c, int alg, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a) {
     switch (alg) {
-        case 0: cn_kernel<T, V, 0><<<grid, blk, 0, s>>>(a); break;
-        case 1: cn_kernel<T, V, 1><<<grid, blk, 0, s>>>(a); break;
-        case 2: cn_kernel<T, V, 2><<<grid, blk, 0, s>>>(a); break;
-        case 3: cn_kernel<T, V, 3><<<grid, blk, 0, s>>>(a); break;
-        case 4: cn_kernel<T, V, 4><<<grid, blk, 0, s>>>(a); break;
-        default: cn_kernel<T, V, 5><<<grid, blk, 0, s>>>(a); break;
+        case 0: return launch_cn_alg<T, V, 0>(c, fast, tiles, s, a);
+        case 1: return launch_cn_alg<T, V, 1>(c, fast, tiles, s, a);
+        case 2: return launch_cn_alg<T, V, 2>(c, fast, tiles, s, a);
+        case 3: return launch_cn_alg<T, V, 3>(c, fast, tiles, s, a);
+        case 4: return launch_cn_alg<T, V, 4>(c, fast, tiles, s, a);
+        default: return launch_cn_alg<T, V, 5>(c, fast, tiles, s, a);
     }
+}
+
+#ifdef QK_DEFINE_CN_LAUNCH
+template <typename T, int V, int ALG, int B>
+inline int launch_cn_bucket(const qkdldpc_code *c, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a) {
+    constexpr int DCMAX = cn_bucket_max(B);
+    const int cnt = c->cn_count[B];
+    if (cnt == 0) return 0;
+    constexpr int threads = cn_threads(sizeof(T), V, DCMAX);
+    const dim3 grid(ceil_div(cnt, threads / 32), (unsigned)tiles);
+    if constexpr (sizeof(T) == 4 && ALG >= 2 && DCMAX > 0) {
+        if (fast) {
+            cn_kernel<T, V, ALG, DCMAX, true><<<grid, threads, 0, s>>>(a, c->cn_first[B], cnt);
+            return 1;
+        }
+    }
+    cn_kernel<T, V, ALG, DCMAX, false><<<grid, threads, 0, s>>>(a, c->cn_first[B], cnt);
+    return 1;
+}
+template <typename T, int V, int ALG>
+int launch_cn_alg(const qkdldpc_code *c, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a) {
+    return launch_cn_bucket<T, V, ALG, 0>(c, fast, tiles, s, a) + launch_cn_bucket<T, V, ALG, 1>(c, fast, tiles, s, a) +
+           launch_cn_bucket<T, V, ALG, 2>(c, fast, tiles, s, a) + launch_cn_bucket<T, V, ALG, 3>(c, fast, tiles, s, a) +
+           launch_cn_bucket<T, V, ALG, 4>(c, fast, tiles, s, a);
+}
+#endif
+
+#ifdef QK_DEFINE_RUN_BATCH
+template <typename T, int V, int B>
+inline int launch_vn_bucket(const qkdldpc_code *c, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a) {
+    constexpr int DVMAX = vn_bucket_max(B);
+    const int cnt = c->vn_count[B];
+    if (cnt == 0) return 0;
+    constexpr int threads = vn_threads(sizeof(T), V, DVMAX);
+    const dim3 grid(ceil_div(cnt, threads / 32), (unsigned)tiles);
+    if constexpr (sizeof(T) == 4) {
+        if (fast) {
+            vn_kernel<T, V, DVMAX, true><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt);
+            return 1;
+        }
+    }
+    vn_kernel<T, V, DVMAX, false><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt);
+    return 1;
+}
+// widest columns first: their warps run longest
+template <typename T, int V>
+int launch_vn(const qkdldpc_code *c, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a) {
+    return launch_vn_bucket<T, V, 4>(c, fast, tiles, s, a) + launch_vn_bucket<T, V, 3>(c, fast, tiles, s, a) +
+           launch_vn_bucket<T, V, 2>(c, fast, tiles, s, a) + launch_vn_bucket<T, V, 1>(c, fast, tiles, s, a) +
+           launch_vn_bucket<T, V, 0>(c, fast, tiles, s, a);
 }
 
 inline EvPair *next_ev(qkdldpc_code *c, int kind) {
@@ -68,11 +136,6 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     CK(c->slot_iter.reserve(slots));
     CK(c->frame_llr.reserve((size_t)n_frames * sizeof(T)));
     CK(c->synd_all.reserve((size_t)n_frames * swords));
-    if (adaptive) {
-        CK(c->par0_all.reserve((size_t)n_frames * swords));
-        CK(c->pre_done.reserve((size_t)n_frames));
-    }
-    CK(c->payload.reserve(words));
     CK(c->bitclass.reserve(n));
     CK(c->counters.reserve(2));
     c->frames_per_tile = FT;
@@ -82,7 +145,6 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     // ---- per-batch metadata: punctured / shortened classes (H_matrix_params, a&m_ops.hpp:44-48) ---------------
     {
         std::vector<uint8_t> cls(n, 0);
-        std::vector<uint32_t> pay(words, 0);
         for (int i = 0; i < n_punct; ++i) {
             if (punct[i] < 0 || punct[i] >= n) return fail(QKDLDPC_ERR_INVALID, "punctured position out of range");
             cls[punct[i]] = 1;
@@ -91,11 +153,8 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
             if (shortd[i] < 0 || shortd[i] >= n) return fail(QKDLDPC_ERR_INVALID, "shortened position out of range");
             if (cls[shortd[i]] == 0) cls[shortd[i]] = 2;   // a position listed twice is punctured (:1150 tested first)
         }
-        for (int i = 0; i < n; ++i)
-            if (cls[i] == 0) pay[i >> 5] |= 1u << (i & 31);
         CK(cudaMemcpyAsync(c->bitclass.p, cls.data(), n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(c->payload.p, pay.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        CK(cudaStreamSynchronize(s));   // the host vectors die at scope end
+        CK(cudaStreamSynchronize(s));   // the host vector dies at scope end
     }
 
     CK(cudaMemsetAsync(c->tile_active.p, 0, (size_t)tiles * V * sizeof(uint32_t), s));
@@ -110,7 +169,6 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     a.row_ptr = c->row_ptr.p; a.col_idx = c->col_idx.p; a.col_ptr = c->col_ptr.p;
     a.csc_edge = c->csc_edge.p; a.csc_row = c->csc_row.p;
     a.row_order = c->row_order.p; a.col_order = c->col_order.p;
-    a.cn_items = c->cn_items.p; a.vn_items = c->vn_items.p;
     a.bitclass = c->bitclass.p;
     a.msg = reinterpret_cast<T *>(c->msg.p);
     a.bobmask = c->bobmask.p; a.zmask = c->zmask.p; a.synd = c->synd.p; a.par = c->par.p;
@@ -123,9 +181,8 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     BatchArgs<T> b{};
     b.n_frames = n_frames; b.words = words; b.swords = swords;
     b.alice_bits = d_alice; b.bob_bits = d_bob; b.qber = d_qber; b.qber_is_scalar = qber_is_scalar;
-    b.payload = c->payload.p;
     b.frame_llr = reinterpret_cast<T *>(c->frame_llr.p);
-    b.synd_all = c->synd_all.p; b.par0_all = c->par0_all.p; b.pre_done = c->pre_done.p;
+    b.synd_all = c->synd_all.p;
     b.out_bits = d_out_bits; b.out_iters = d_out_iters; b.out_flags = d_out_flags;
     b.tally = d_tally;
     b.next_frame = c->counters.p; b.n_done = c->counters.p + 1;
@@ -139,17 +196,19 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     c->kernel_launches += 2;
     CK(cudaGetLastError());
 
-    const dim3 cn_grid(c->n_cn_items, (unsigned)tiles), vn_grid(c->n_vn_items, (unsigned)tiles);
     const int alg = P->algorithm;
+    const bool fast = fast_minsum_ok(P);
+    int launches_per_step = 0;
     auto one_step = [&](cudaStream_t st, bool prof) {
         EvPair *e = nullptr;
         if (prof) { e = next_ev(c, 0); cudaEventRecord(e->a, st); }
-        launch_cn<T, V>(alg, cn_grid, st, a);
+        int nl = launch_cn<T, V>(c, alg, fast, (int)tiles, st, a);
         if (prof) { cudaEventRecord(e->b, st); e = next_ev(c, 1); cudaEventRecord(e->a, st); }
-        vn_kernel<T, V><<<vn_grid, kVnWarps * kWarp, 0, st>>>(a);
+        nl += launch_vn<T, V>(c, fast, (int)tiles, st, a);
         if (prof) { cudaEventRecord(e->b, st); e = next_ev(c, 2); cudaEventRecord(e->a, st); }
         sched_kernel<T, V><<<(unsigned)tiles, kSchedThreads, 0, st>>>(a, b);
         if (prof) cudaEventRecord(e->b, st);
+        launches_per_step = nl + 1;
     };
 
     // steps between two host polls of the done counter: a frame needs at most max_iter steps, and the host
@@ -167,7 +226,7 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
         };
         mixin(&a, sizeof a);
         mixin(&b, sizeof b);
-        const int geo[6] = {(int)sizeof(T), V, alg, (int)tiles, spp, c->n_cn_items};
+        const int geo[6] = {(int)sizeof(T), V, alg, (int)tiles, spp, fast ? 1 : 0};
         mixin(geo, sizeof geo);
         char key[64];
         snprintf(key, sizeof key, "%016llx", h);
@@ -198,7 +257,11 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
             CK(cudaMemcpyAsync(c->h_done, c->counters.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         }
         steps += spp;
-        c->kernel_launches += 3 * (int64_t)spp;
+        if (use_graph && launches_per_step == 0) {   // graph came from the cache: count its kernels once
+            for (int k = 0; k < kBuckets; ++k) launches_per_step += (c->cn_count[k] > 0) + (c->vn_count[k] > 0);
+            launches_per_step += 1;
+        }
+        c->kernel_launches += (int64_t)launches_per_step * spp;
         c->decoder_steps += spp;
         CK(cudaEventRecord(c->ev_poll, s));
         CK(cudaEventSynchronize(c->ev_poll));
@@ -221,5 +284,7 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     CK(cudaGetLastError());
     return QKDLDPC_OK;
 }
+
+#endif  // QK_DEFINE_RUN_BATCH
 
 }  // namespace qkhost

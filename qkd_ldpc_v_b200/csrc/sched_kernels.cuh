@@ -16,11 +16,8 @@ struct BatchArgs {
     const uint32_t *alice_bits, *bob_bits;
     const double *qber;
     int qber_is_scalar;
-    const uint32_t *payload;   // [words] bits that are neither punctured nor shortened
     T *frame_llr;              // [n_frames]
     uint32_t *synd_all;        // [n_frames][swords]  Alice's syndrome, packed
-    uint32_t *par0_all;        // [n_frames][swords]  adaptive only: syndrome XOR H*z0, z0 = (llr <= 0)
-    uint8_t *pre_done;         // [n_frames]          adaptive only: frame finished by the prep kernel
     uint32_t *out_bits;
     int32_t *out_iters;
     uint8_t *out_flags;
@@ -28,7 +25,7 @@ struct BatchArgs {
     u64 *next_frame;           // work queue head
     u64 *n_done;               // frames finished so far
     long long *slot_frame;     // [tiles*FT] frame in the slot, -1 = idle
-    int32_t *slot_iter;        // [tiles*FT] completed iterations of that frame
+    int32_t *slot_iter;        // [tiles*FT] completed iterations of that frame; -1 = refilled, VN-side init pending
     int max_iter;
     int adaptive;
 };
@@ -44,66 +41,36 @@ __device__ __forceinline__ void tally_frame(u64 *tally, bool syn_ok, bool keys_o
     atomicAdd(tally + 3, (u64)iters_run);
 }
 
-// K1: per frame -- LLR magnitude log((1-q)/q) (qkd_ldpc_algorithm.cpp:1043), Alice's syndrome
-// (calculate_syndrome, array_and_matrix_operations.cpp:936-950) and, for ANMSA/AOMSA, the check values of the
-// initial decision z0 = (llr <= 0) (:683-691). An adaptive frame whose z0 already satisfies every check returns
-// iterations_num = 1 without any message update (:770-776, quirk Q10); it is finished right here.
+// K1: per frame -- LLR magnitude log((1-q)/q) (qkd_ldpc_algorithm.cpp:1043) and Alice's syndrome
+// (calculate_syndrome, array_and_matrix_operations.cpp:936-950), packed 32 checks per word.
 template <typename T>
 __global__ void __launch_bounds__(256) prep_kernel(int n, int m, const int *row_ptr, const int *col_idx, BatchArgs<T> b) {
     const long long f = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const uint32_t *al = b.alice_bits + f * b.words;
-    const uint32_t *bo = b.bob_bits + f * b.words;
     if (threadIdx.x == 0) {
         const double q = b.qber_is_scalar ? b.qber[0] : b.qber[f];
         b.frame_llr[f] = (T)log((1. - q) / q);
     }
-    uint32_t mism = 0;
     for (int jb = warp; jb * 32 < m; jb += nwarps) {
         const int j = jb * 32 + lane;
-        uint32_t s = 0, p = 0;
+        uint32_t s = 0;
         if (j < m) {
             const int e1 = row_ptr[j + 1];
             for (int e = row_ptr[j]; e < e1; ++e) {
                 const int c = col_idx[e];
                 s ^= (al[c >> 5] >> (c & 31)) & 1u;
-                if (b.adaptive) p ^= ((bo[c >> 5] & b.payload[c >> 5]) >> (c & 31)) & 1u;
             }
         }
         const uint32_t sw = __ballot_sync(0xffffffffu, s);
         if (lane == 0) b.synd_all[f * b.swords + jb] = sw;
-        if (b.adaptive) {
-            const uint32_t pw = __ballot_sync(0xffffffffu, s ^ p);
-            if (lane == 0) b.par0_all[f * b.swords + jb] = pw;
-            mism |= pw;
-        }
-    }
-    if (!b.adaptive) return;
-    const int any_mismatch = __syncthreads_or(mism != 0);
-    if (any_mismatch) {
-        if (threadIdx.x == 0) b.pre_done[f] = 0;
-        return;
-    }
-    uint32_t diff = 0;
-    for (int w = threadIdx.x; w < b.words; w += blockDim.x) {
-        const uint32_t z0 = bo[w] & b.payload[w];
-        if (b.out_bits) b.out_bits[f * b.words + w] = z0;
-        diff |= z0 ^ al[w];
-    }
-    const int keys_differ = __syncthreads_or(diff != 0);
-    if (threadIdx.x == 0) {
-        b.pre_done[f] = 1;
-        if (b.out_iters) b.out_iters[f] = 1;
-        if (b.out_flags) b.out_flags[f] = (uint8_t)(1u | (keys_differ ? 0u : 2u));
-        tally_frame(b.tally, true, !keys_differ, 1, 0);
-        atomicAdd(b.n_done, 1ull);
     }
 }
 
 // K4: one CTA per tile, after every CN+VN step.
 //  1. all-checks-satisfied test per slot: OR over rows of par (quirk Q9: non-adaptive variants test the decision
-//     of iteration t and return t; quirk Q10: adaptive variants find it one iteration later, return t+1, and never
-//     test the decision of the last allowed iteration);
+//     of iteration t and return t; quirk Q10: adaptive variants test the INITIAL decision too, find success one
+//     iteration later (return t+1) and never test the decision of the last allowed iteration);
 //  2. retire finished frames: unpack the hard decision into out_bits, compare with Alice's key (arrays_equal,
 //     qkd_ldpc_algorithm.cpp:1087), write iterations / flags, update the tallies;
 //  3. refill free slots from the frame queue (continuous batching): transpose the new frame's key bits, syndrome
@@ -151,11 +118,12 @@ __global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, Bat
     if (tid < FT) {
         frame = b.slot_frame[(size_t)tile * FT + tid];
         if (frame >= 0) {
-            const int it = b.slot_iter[(size_t)tile * FT + tid] + 1;   // iterations completed, this step included
+            // iterations completed, this step included; 0 = this step only initialised the slot (VN-side init)
+            const int it = b.slot_iter[(size_t)tile * FT + tid] + 1;
             const bool ok = !((s_unsat[sv] >> sl) & 1u);
             int succ = 0, iters = 0;
             if (!b.adaptive) {
-                if (ok) { done = true; succ = 1; iters = it; }
+                if (it >= 1 && ok) { done = true; succ = 1; iters = it; }
                 else if (it >= b.max_iter) { done = true; iters = b.max_iter; }
             } else {
                 if (ok && it < b.max_iter) { done = true; succ = 1; iters = it + 1; }
@@ -215,10 +183,9 @@ __global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, Bat
         if (is_free) {
             const u64 cand = s_base + (u64)(s_wfree[tid >> 5] + __popc(fm & ((1u << lane) - 1u)));
             nf = (cand < (u64)b.n_frames) ? (long long)cand : -1;
-            if (nf >= 0 && b.adaptive && b.pre_done[nf]) nf = -1;   // finished by prep; slot claims again next step
             b.slot_frame[(size_t)tile * FT + tid] = nf;
             if (nf >= 0) {
-                b.slot_iter[(size_t)tile * FT + tid] = 0;
+                b.slot_iter[(size_t)tile * FT + tid] = -1;
                 a.slot_llr[(size_t)tile * FT + tid] = b.frame_llr[nf];
                 const int idx = atomicAdd(&s_nnew, 1);
                 s_newslot[idx] = tid;
@@ -262,7 +229,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, Bat
             const int s = s_newslot[q];
             const size_t off = s_newframe[q] * b.swords + (j >> 5);
             const uint32_t sbit = (b.synd_all[off] >> (j & 31)) & 1u;
-            const uint32_t pbit = b.adaptive ? (b.par0_all[off] >> (j & 31)) & 1u : sbit;
+            const uint32_t pbit = sbit;   // the VN-side init XORs the parity of the initial decision on top
             const int l = s / V;
 #pragma unroll
             for (int v = 0; v < V; ++v)

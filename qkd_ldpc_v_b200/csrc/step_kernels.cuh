@@ -1,13 +1,21 @@
 // Check-node (K2a-f) and fused variable-node / hard-decision / syndrome-accumulate (K3) kernels.
 //
 // One warp = one Tanner-graph node x one tile of FT = 32*V frame slots; lane l handles slots l*V..l*V+V-1 with one
-// 128-bit access per edge. Because all 32 lanes work on the same node, node degree is warp-uniform: irregular
-// graphs cause no divergence, and rows / columns are only bucketed by degree to pick the register-array size.
+// 128-bit access per edge. All 32 lanes work on the same node, so node degree is warp-uniform: irregular graphs
+// cause no divergence. Rows / columns are bucketed by degree and every bucket is its OWN kernel instantiation
+// (register array sized for the bucket, own launch bounds), so a few wide nodes do not dictate the occupancy of
+// the many narrow ones.
 //
-// Arithmetic follows the reference operation by operation (same order, same comparisons, no FMA contraction:
-// the library is compiled with -fmad=false), so float64 messages reproduce the reference bit for bit for the
-// min-sum family and the linear-approximation SPA, and float32 messages reproduce "the reference with every
-// double replaced by float" (oracle/ldpc_oracle_body.inc, f32 flavour) bit for bit.
+// Two arithmetic flavours, both operation-for-operation equal to the reference on their domain:
+//  * EXACT  (any message type, any algorithm): the reference's comparison chains literally (NaN / inf / -0 behave
+//    as in the C++ code). Used for float64 parity mode, for SPA / SPA-lin-approx, and whenever the fast flavour's
+//    precondition does not hold.
+//  * FAST   (float32 min-sum family): branch-free bit arithmetic -- sign parity by XOR of raw bits, min1/min2 by
+//    FMNMX, the two possible output magnitudes computed once per row. Identical results to EXACT whenever no
+//    message is NaN, which the host guarantees before selecting it (clamp enabled, or all factors <= 1; see
+//    fast_minsum_ok in run_batch.cuh). Exact zeros (quirk Q4) are handled: a zero message is "positive" for the
+//    row parity and "negative" for its own exclusion.
+// The library is compiled with -fmad=false: no FMA contraction anywhere.
 #pragma once
 #include "common.cuh"
 
@@ -21,12 +29,9 @@ __device__ __forceinline__ Vec<T, V> lane_llr(const StepArgs<T> &a, int tile, in
     Vec<T, V> r;
     const uint8_t cls = __ldg(a.bitclass + col);
     if (cls == 0) {
-        const uint32_t *bm = a.bobmask + ((size_t)tile * a.n + col) * V;
+        const Vec<uint32_t, V> bm = *reinterpret_cast<const Vec<uint32_t, V> *>(a.bobmask + ((size_t)tile * a.n + col) * V);
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const uint32_t w = __ldg(bm + v);
-            r.v[v] = ((w >> lane) & 1u) ? -lp.v[v] : lp.v[v];
-        }
+        for (int v = 0; v < V; ++v) r.v[v] = ((bm.v[v] >> lane) & 1u) ? -lp.v[v] : lp.v[v];
     } else {
 #pragma unroll
         for (int v = 0; v < V; ++v) r.v[v] = (cls == 1) ? (T)1e-4 : Lim<T>::max();
@@ -70,7 +75,7 @@ __device__ __forceinline__ T cn_two_atanh(T y) {
     }
 }
 
-// Running state of one check node for one slot.
+// EXACT flavour: running state of one check node for one slot.
 template <typename T, int ALG>
 struct RowState {
     T a, b;   // min-sum: min1, min2 ; SPA: row product, unused
@@ -89,8 +94,9 @@ struct RowState {
         } else {
             if (msg < (T)0) ++neg;
             const T ab = fabs(msg);
-            if (ab < a) { b = a; a = ab; }
-            else if (ab < b) { b = ab; }
+            const bool lt1 = ab < a, lt2 = ab < b;
+            b = lt1 ? a : (lt2 ? ab : b);
+            a = lt1 ? ab : a;
             return msg;
         }
     }
@@ -113,18 +119,41 @@ struct RowState {
     }
 };
 
-// One check node (row) for this lane's V slots. DCMAX > 0: the row lives in registers between the two passes
-// (one read + one write of every message); DCMAX == 0: rows wider than 32 edges are re-read in the second pass.
-template <typename T, int V, int ALG, int DCMAX>
-__device__ __forceinline__ void cn_row(const StepArgs<T> &a, int tile, int row, int lane, bool lane_act, bool any_new,
-                                       const uint32_t (&newm)[V], const Vec<T, V> &lp) {
+__host__ __device__ constexpr int cn_threads(int elem_bytes, int V, int DCMAX) {
+    return (DCMAX == 0 || DCMAX * V * elem_bytes <= 256) ? 256 : 128;
+}
+__host__ __device__ constexpr int vn_threads(int elem_bytes, int V, int DVMAX) {
+    return (DVMAX == 0 || DVMAX * V * elem_bytes <= 128) ? 256 : 128;
+}
+
+// K2: flooding check-node update. One kernel instantiation per (algorithm variant, degree bucket, flavour).
+// grid = (ceil(count / warps per CTA), tiles); one row per warp; rows [first, first+count) of row_order.
+// DCMAX > 0: the row lives in registers between the two passes (one read + one write of every message);
+// DCMAX == 0: rows wider than 32 edges are re-read in the second pass.
+template <typename T, int V, int ALG, int DCMAX, bool FAST>
+__global__ void __launch_bounds__(cn_threads(sizeof(T), V, DCMAX))
+cn_kernel(const StepArgs<T> a, const int first, const int count) {
     constexpr int FT = kWarp * V;
     constexpr bool kAdaptive = (ALG >= 4);
+    static_assert(!FAST || (sizeof(T) == 4 && ALG >= 2), "fast flavour: float32 min-sum family only");
+    const int tile = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // slots that take part in this check-node pass: active and not waiting for their VN-side initialisation
+    bool any_act = false, lane_act = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const uint32_t act = a.tile_active[tile * V + v] & ~a.tile_new[tile * V + v];
+        any_act |= act != 0;
+        lane_act |= (act >> lane) & 1u;
+    }
+    if (!any_act || idx >= count) return;
+    const int row = __ldg(a.row_order + first + idx);
     const int e0 = __ldg(a.row_ptr + row);
     const int dc = __ldg(a.row_ptr + row + 1) - e0;
     T *base = a.msg + (size_t)tile * a.e_stride + (size_t)e0 * FT + lane * V;
 
-    // syndrome bit, row-satisfied bit of the previous hard decision, and reset of the parity accumulator
+    // syndrome bit, check value of the previous hard decision, and reset of the parity accumulator
     const size_t rb = ((size_t)tile * a.m + row) * V;
     bool syn[V];
     T factor[V];
@@ -146,205 +175,224 @@ __device__ __forceinline__ void cn_row(const StepArgs<T> &a, int tile, int row, 
     }
     if (!lane_act) return;
 
-    auto fetch = [&](int k) -> Vec<T, V> {
-        Vec<T, V> x = ld_msg<T, V>(base + (size_t)k * FT);
-        if (any_new) {   // slots refilled by the scheduler: first iteration reads the a-priori LLR (:21-29)
-            const int col = __ldg(a.col_idx + e0 + k);
-            const Vec<T, V> l = lane_llr<T, V>(a, tile, col, lane, lp);
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                if ((newm[v] >> lane) & 1u) x.v[v] = l.v[v];
-        }
-        return x;
-    };
-
-    RowState<T, ALG> st[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) st[v].init(syn[v]);
-
-    if constexpr (DCMAX > 0) {
-        Vec<T, V> x[DCMAX];
+    if constexpr (FAST) {
+        // ---- float32 min-sum, branch-free ---------------------------------------------------------------------
+        static_assert(DCMAX > 0, "fast flavour keeps the row in registers");
+        Vec<float, V> x[DCMAX];
 #pragma unroll
         for (int k = 0; k < DCMAX; ++k)
-            if (k < dc) x[k] = fetch(k);
+            if (k < dc) x[k] = ld_msg<float, V>(base + (size_t)k * FT);
+        float m1[V], m2[V];
+        uint32_t sx[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { m1[v] = FLT_MAX; m2[v] = FLT_MAX; sx[v] = syn[v] ? 0x80000000u : 0u; }
 #pragma unroll
         for (int k = 0; k < DCMAX; ++k)
             if (k < dc) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) x[k].v[v] = st[v].absorb(x[k].v[v]);
+                for (int v = 0; v < V; ++v) {
+                    const float xv = x[k].v[v];
+                    sx[v] ^= __float_as_uint(xv);                 // sign parity lives in bit 31 (:383,398)
+                    const float ax = fabsf(xv);
+                    m2[v] = fminf(m2[v], fmaxf(ax, m1[v]));       // == the reference's if / else-if chain (:386-396)
+                    m1[v] = fminf(m1[v], ax);
+                }
             }
+        uint32_t o1[V], o2[V];   // signed outputs for "own |msg| != min1" / "== min1", row sign already applied
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            float c1, c2;
+            if constexpr (ALG == 2 || ALG == 4) {
+                c1 = factor[v] * m1[v];
+                c2 = factor[v] * m2[v];
+            } else {
+                const float d1 = m1[v] - factor[v], d2 = m2[v] - factor[v];
+                c1 = (d1 < 0.f) ? 0.f : d1;
+                c2 = (d2 < 0.f) ? 0.f : d2;
+            }
+            if (a.enable_thr) { c1 = fminf(c1, a.thr); c2 = fminf(c2, a.thr); }   // magnitudes: clamp is symmetric
+            const uint32_t rs = sx[v] & 0x80000000u;
+            o1[v] = __float_as_uint(c1) ^ rs;
+            // a message that is exactly 0 has min1 == 0, takes the "== min1" output and counts as negative for its
+            // own exclusion ((m > 0) ? 1 : -1, :402) although its sign bit is clear (quirk Q4)
+            o2[v] = __float_as_uint(c2) ^ rs ^ ((m1[v] == 0.f) ? 0x80000000u : 0u);
+        }
 #pragma unroll
         for (int k = 0; k < DCMAX; ++k)
             if (k < dc) {
+                Vec<float, V> o;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float xv = x[k].v[v];
+                    const uint32_t sel = (fabsf(xv) == m1[v]) ? o2[v] : o1[v];
+                    o.v[v] = __uint_as_float(sel ^ (__float_as_uint(xv) & 0x80000000u));
+                }
+                st_msg<float, V>(base + (size_t)k * FT, o);
+            }
+    } else {
+        // ---- exact flavour ------------------------------------------------------------------------------------
+        RowState<T, ALG> st[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) st[v].init(syn[v]);
+        if constexpr (DCMAX > 0) {
+            Vec<T, V> x[DCMAX];
+#pragma unroll
+            for (int k = 0; k < DCMAX; ++k)
+                if (k < dc) x[k] = ld_msg<T, V>(base + (size_t)k * FT);
+#pragma unroll
+            for (int k = 0; k < DCMAX; ++k)
+                if (k < dc) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) x[k].v[v] = st[v].absorb(x[k].v[v]);
+                }
+#pragma unroll
+            for (int k = 0; k < DCMAX; ++k)
+                if (k < dc) {
+                    Vec<T, V> o;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        T c = st[v].emit(x[k].v[v], syn[v], factor[v]);
+                        o.v[v] = a.enable_thr ? clamp_msg(c, a.thr) : c;   // threshold_matrix(check_to_bit_msg), :73-74
+                    }
+                    st_msg<T, V>(base + (size_t)k * FT, o);
+                }
+        } else {
+            for (int k = 0; k < dc; ++k) {
+                Vec<T, V> x = ld_msg<T, V>(base + (size_t)k * FT);
+#pragma unroll
+                for (int v = 0; v < V; ++v) st[v].absorb(x.v[v]);
+            }
+            for (int k = 0; k < dc; ++k) {
+                Vec<T, V> x = ld_msg<T, V>(base + (size_t)k * FT);
                 Vec<T, V> o;
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    T c = st[v].emit(x[k].v[v], syn[v], factor[v]);
-                    o.v[v] = a.enable_thr ? clamp_msg(c, a.thr) : c;   // threshold_matrix(check_to_bit_msg), :73-74
+                    T kept = x.v[v];
+                    if constexpr (ALG <= 1) kept = cn_tanh_half<T, ALG>(kept);
+                    T c = st[v].emit(kept, syn[v], factor[v]);
+                    o.v[v] = a.enable_thr ? clamp_msg(c, a.thr) : c;
                 }
                 st_msg<T, V>(base + (size_t)k * FT, o);
             }
-    } else {
-        for (int k = 0; k < dc; ++k) {
-            Vec<T, V> x = fetch(k);
-#pragma unroll
-            for (int v = 0; v < V; ++v) st[v].absorb(x.v[v]);
         }
-        for (int k = 0; k < dc; ++k) {
-            Vec<T, V> x = fetch(k);
-            Vec<T, V> o;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                T kept = x.v[v];
-                if constexpr (ALG <= 1) kept = cn_tanh_half<T, ALG>(kept);
-                T c = st[v].emit(kept, syn[v], factor[v]);
-                o.v[v] = a.enable_thr ? clamp_msg(c, a.thr) : c;
-            }
-            st_msg<T, V>(base + (size_t)k * FT, o);
-        }
-    }
-}
-
-// K2: flooding check-node update, one kernel instantiation per algorithm variant.
-// grid = (CTAs over degree-bucketed rows, tiles); block = kCnWarps warps, one row per warp.
-template <typename T, int V, int ALG>
-__global__ void __launch_bounds__(kCnWarps * kWarp) cn_kernel(const StepArgs<T> a) {
-    constexpr int FT = kWarp * V;
-    const int tile = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t newm[V];
-    bool any_act = false, any_new = false, lane_act = false;
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        const uint32_t act = a.tile_active[tile * V + v];
-        newm[v] = a.tile_new[tile * V + v];
-        any_act |= act != 0;
-        any_new |= newm[v] != 0;
-        lane_act |= (act >> lane) & 1u;
-    }
-    if (!any_act) return;
-    const int2 item = a.cn_items[blockIdx.x];
-    if (warp >= (item.y >> 8)) return;
-    const int row = __ldg(a.row_order + item.x + warp);
-    const Vec<T, V> lp = *reinterpret_cast<const Vec<T, V> *>(a.slot_llr + (size_t)tile * FT + lane * V);
-    switch (item.y & 255) {
-        case 0: cn_row<T, V, ALG, 8>(a, tile, row, lane, lane_act, any_new, newm, lp); break;
-        case 1: cn_row<T, V, ALG, 16>(a, tile, row, lane, lane_act, any_new, newm, lp); break;
-        case 2: cn_row<T, V, ALG, 24>(a, tile, row, lane, lane_act, any_new, newm, lp); break;
-        case 3: cn_row<T, V, ALG, 32>(a, tile, row, lane, lane_act, any_new, newm, lp); break;
-        default: cn_row<T, V, ALG, 0>(a, tile, row, lane, lane_act, any_new, newm, lp); break;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K3: variable-node update + hard decision + syndrome accumulation for one bit and this lane's V slots.
+// K3: variable-node update + hard decision + syndrome accumulation; one bit per warp, this lane's V slots.
 //   L = llr + sum_k c2b_k in ascending check order (std::accumulate from the LLR, :78), z = (L <= 0) (:80-83),
 //   b2c_k = clamp(L - c2b_k) (:109-123). The parity of z is XOR-ed into par[] of every check of the bit, so that
 //   par == 0 over all rows <=> calculate_syndrome(z) == syndrome (:86,101).
-template <typename T, int V, int DVMAX>
-__device__ __forceinline__ void vn_col(const StepArgs<T> &a, int tile, int bit, int lane, bool lane_act,
-                                       const uint32_t (&act)[V], const Vec<T, V> &lp) {
+// Slots the scheduler has just refilled ("new") are initialised here instead: b2c_k = llr (not clamped, :21-29),
+// z = (llr <= 0) (the adaptive variants' initial decision, :683-691).
+// FAST: clamp by FMNMX (valid when no message can be NaN); otherwise the reference's compare chain.
+template <typename T, int V, bool FAST, bool HASNEW>
+__device__ __forceinline__ Vec<T, V> vn_out(const StepArgs<T> &a, const Vec<T, V> &L, const Vec<T, V> &c,
+                                            const Vec<T, V> &llr, const bool (&isnew)[V]) {
+    Vec<T, V> o;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        T s = L.v[v] - c.v[v];
+        if (a.enable_thr) {
+            if constexpr (FAST) s = fminf(fmaxf(s, -a.thr), a.thr);
+            else s = clamp_msg(s, a.thr);
+        }
+        if constexpr (HASNEW) s = isnew[v] ? llr.v[v] : s;
+        o.v[v] = s;
+    }
+    return o;
+}
+
+template <typename T, int V, int DVMAX, bool FAST, bool HASNEW>
+__device__ __forceinline__ void vn_body(const StepArgs<T> &a, int tile, int bit, int lane, bool lane_act,
+                                        const uint32_t (&act)[V], const uint32_t (&newm)[V]) {
     constexpr int FT = kWarp * V;
     const int c0 = __ldg(a.col_ptr + bit);
     const int dv = __ldg(a.col_ptr + bit + 1) - c0;
     T *tbase = a.msg + (size_t)tile * a.e_stride + lane * V;
-    Vec<T, V> L = lane_llr<T, V>(a, tile, bit, lane, lp);
-    bool z[V];
+    const Vec<T, V> lp = *reinterpret_cast<const Vec<T, V> *>(a.slot_llr + (size_t)tile * FT + lane * V);
+    const Vec<T, V> llr = lane_llr<T, V>(a, tile, bit, lane, lp);
+    Vec<T, V> L = llr;
+    bool isnew[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) isnew[v] = HASNEW && ((newm[v] >> lane) & 1u);
 
-    if constexpr (DVMAX > 0) {
-        Vec<T, V> c[DVMAX];
-        int e[DVMAX];
-#pragma unroll
-        for (int k = 0; k < DVMAX; ++k)
-            if (k < dv) e[k] = __ldg(a.csc_edge + c0 + k);
-        if (lane_act) {
+    if (lane_act) {
+        if constexpr (DVMAX > 0) {
+            Vec<T, V> c[DVMAX];
 #pragma unroll
             for (int k = 0; k < DVMAX; ++k)
-                if (k < dv) c[k] = ld_msg<T, V>(tbase + (size_t)e[k] * FT);
+                if (k < dv) c[k] = ld_msg<T, V>(tbase + (size_t)__ldg(a.csc_edge + c0 + k) * FT);
 #pragma unroll
             for (int k = 0; k < DVMAX; ++k)
                 if (k < dv) {
-#pragma unroll
-                    for (int v = 0; v < V; ++v) L.v[v] = L.v[v] + c[k].v[v];
-                }
-#pragma unroll
-            for (int k = 0; k < DVMAX; ++k)
-                if (k < dv) {
-                    Vec<T, V> o;
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
-                        T s = L.v[v] - c[k].v[v];
-                        o.v[v] = a.enable_thr ? clamp_msg(s, a.thr) : s;
+                        if constexpr (HASNEW) c[k].v[v] = isnew[v] ? (T)0 : c[k].v[v];
+                        L.v[v] = L.v[v] + c[k].v[v];
                     }
-                    st_msg<T, V>(tbase + (size_t)e[k] * FT, o);
                 }
-        }
-    } else {
-        if (lane_act) {
-            for (int k = 0; k < dv; ++k) {
-                const Vec<T, V> c = ld_msg<T, V>(tbase + (size_t)__ldg(a.csc_edge + c0 + k) * FT);
 #pragma unroll
-                for (int v = 0; v < V; ++v) L.v[v] = L.v[v] + c.v[v];
+            for (int k = 0; k < DVMAX; ++k)
+                if (k < dv)
+                    st_msg<T, V>(tbase + (size_t)__ldg(a.csc_edge + c0 + k) * FT,
+                                 vn_out<T, V, FAST, HASNEW>(a, L, c[k], llr, isnew));
+        } else {
+            for (int k = 0; k < dv; ++k) {
+                Vec<T, V> c = ld_msg<T, V>(tbase + (size_t)__ldg(a.csc_edge + c0 + k) * FT);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    if constexpr (HASNEW) c.v[v] = isnew[v] ? (T)0 : c.v[v];
+                    L.v[v] = L.v[v] + c.v[v];
+                }
             }
             for (int k = 0; k < dv; ++k) {
                 T *p = tbase + (size_t)__ldg(a.csc_edge + c0 + k) * FT;
-                const Vec<T, V> c = ld_msg<T, V>(p);
-                Vec<T, V> o;
+                Vec<T, V> c = ld_msg<T, V>(p);
+                if constexpr (HASNEW) {
 #pragma unroll
-                for (int v = 0; v < V; ++v) {
-                    T s = L.v[v] - c.v[v];
-                    o.v[v] = a.enable_thr ? clamp_msg(s, a.thr) : s;
+                    for (int v = 0; v < V; ++v) c.v[v] = isnew[v] ? (T)0 : c.v[v];
                 }
-                st_msg<T, V>(p, o);
+                st_msg<T, V>(p, vn_out<T, V, FAST, HASNEW>(a, L, c, llr, isnew));
             }
         }
     }
-#pragma unroll
-    for (int v = 0; v < V; ++v) z[v] = lane_act && (L.v[v] <= (T)0);   // NaN decides 0 (quirk Q2)
-
-    // pack the decisions of the tile: word v, bit lane; only active slots contribute
+    // pack the decisions of the tile: word v, bit lane; only active slots contribute. NaN decides 0 (quirk Q2).
     uint32_t zw = 0;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        const uint32_t w = __ballot_sync(0xffffffffu, z[v]) & act[v];
+        const uint32_t w = __ballot_sync(0xffffffffu, lane_act && (L.v[v] <= (T)0)) & act[v];
         if (lane == v) zw = w;
     }
     if (lane < V) {
         a.zmask[((size_t)tile * a.n + bit) * V + lane] = zw;
         if (zw != 0) {
-            for (int k = 0; k < dv; ++k) {
-                const int row = __ldg(a.csc_row + c0 + k);
-                atomicXor(a.par + ((size_t)tile * a.m + row) * V + lane, zw);
-            }
+            for (int k = 0; k < dv; ++k)
+                atomicXor(a.par + ((size_t)tile * a.m + __ldg(a.csc_row + c0 + k)) * V + lane, zw);
         }
     }
 }
 
-template <typename T, int V>
-__global__ void __launch_bounds__(kVnWarps * kWarp) vn_kernel(const StepArgs<T> a) {
-    constexpr int FT = kWarp * V;
+template <typename T, int V, int DVMAX, bool FAST>
+__global__ void __launch_bounds__(vn_threads(sizeof(T), V, DVMAX))
+vn_kernel(const StepArgs<T> a, const int first, const int count) {
     const int tile = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t act[V];
-    bool any_act = false, lane_act = false;
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t act[V], newm[V];
+    bool any_act = false, any_new = false, lane_act = false;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         act[v] = a.tile_active[tile * V + v];
+        newm[v] = a.tile_new[tile * V + v];
         any_act |= act[v] != 0;
+        any_new |= newm[v] != 0;
         lane_act |= (act[v] >> lane) & 1u;
     }
-    if (!any_act) return;
-    const int2 item = a.vn_items[blockIdx.x];
-    if (warp >= (item.y >> 8)) return;
-    const int bit = __ldg(a.col_order + item.x + warp);
-    const Vec<T, V> lp = *reinterpret_cast<const Vec<T, V> *>(a.slot_llr + (size_t)tile * FT + lane * V);
-    switch (item.y & 255) {
-        case 0: vn_col<T, V, 4>(a, tile, bit, lane, lane_act, act, lp); break;
-        case 1: vn_col<T, V, 8>(a, tile, bit, lane, lane_act, act, lp); break;
-        case 2: vn_col<T, V, 16>(a, tile, bit, lane, lane_act, act, lp); break;
-        case 3: vn_col<T, V, 32>(a, tile, bit, lane, lane_act, act, lp); break;
-        default: vn_col<T, V, 0>(a, tile, bit, lane, lane_act, act, lp); break;
-    }
+    if (!any_act || idx >= count) return;
+    const int bit = __ldg(a.col_order + first + idx);
+    if (any_new) vn_body<T, V, DVMAX, FAST, true>(a, tile, bit, lane, lane_act, act, newm);
+    else vn_body<T, V, DVMAX, FAST, false>(a, tile, bit, lane, lane_act, act, newm);
 }
 
 }  // namespace qk
