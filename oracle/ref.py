@@ -62,6 +62,18 @@ def lib() -> C.CDLL:
                                           C.c_double, _i32p, C.POINTER(C.c_int64), _i32p, C.POINTER(C.c_int64),
                                           _i32p, C.POINTER(C.c_int64), _f64p]
         L.ref_adapt_code_rate.restype = C.c_int
+        L.ref_describe_config.restype = C.c_int64
+        L.ref_describe_config.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+        L.ref_describe_inputs.restype = C.c_int64
+        L.ref_describe_inputs.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64]
+        L.ref_csv_from_trials.restype = C.c_int64
+        L.ref_csv_from_trials.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int64, C.c_int,
+                                          C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_char_p, C.c_char_p,
+                                          C.c_int64]
+        L.ref_bits_to_remove_rate_adapt.restype = C.c_int64
+        L.ref_bits_to_remove_rate_adapt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        L.ref_untainted.restype = C.c_int64
+        L.ref_untainted.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -166,3 +178,56 @@ def trial_seeds(simulation_seed, count):
     s = np.zeros(count, np.uint64)
     lib().ref_trial_seeds(int(simulation_seed), count, s)
     return s
+
+
+def _text(fn, *args, cap=1 << 22) -> str:
+    buf = C.create_string_buffer(cap)
+    k = fn(*args, buf, cap)
+    if k < 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    if k >= cap:
+        return _text(fn, *args, cap=k + 1)
+    return buf.value.decode()
+
+
+def describe_config(path: str) -> str:
+    """The reference's parse_config_data (config.cpp:89-403) as canonical text."""
+    return _text(lib().ref_describe_config, os.fsencode(path))
+
+
+def describe_inputs(config_path: str, matrix_dir: str) -> str:
+    """The reference's prepare_sim_inputs (simulation.cpp:371-537): one line per (matrix, combination)."""
+    return _text(lib().ref_describe_inputs, os.fsencode(config_path), os.fsencode(matrix_dir))
+
+
+def csv_from_trials(config_path, iters, flags, name, n, m, is_regular, config_qber, accurate_qber, primary=0.0, secondary=0.0,
+                    adapt5=None, tmp_dir="/tmp") -> str:
+    """process_trials_results + write_file (simulation.cpp:580-690, 4-176) on given per-trial results -> CSV text."""
+    iters = np.ascontiguousarray(iters, np.int32)
+    flags = np.ascontiguousarray(flags, np.uint8)
+    a5 = np.ascontiguousarray(adapt5, np.float64) if adapt5 is not None else None
+    return _text(lib().ref_csv_from_trials, os.fsencode(config_path), iters.ctypes.data, flags.ctypes.data, iters.size, name.encode(),
+                 n, m, int(is_regular), config_qber, accurate_qber, primary, secondary,
+                 a5.ctypes.data if a5 is not None else None, os.fsencode(tmp_dir))
+
+
+def untainted(matrix: "RefMatrix", seed: int) -> np.ndarray:
+    out = np.zeros(matrix.n, np.int32)
+    k = lib().ref_untainted(matrix._h, int(seed), out.ctypes.data)
+    if k < 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    return out[:k].copy()
+
+
+def bits_to_remove_rate_adapt(matrix: "RefMatrix", punct, short, pad: int = 1) -> np.ndarray:
+    """get_bits_positions_to_remove_rate_adapt (array_and_matrix_operations.cpp:189-256). The reference reads
+    shortened_bits[s] / punctured_bits[p] one past the end (:215,:220, undefined behaviour); pad=1 makes that read
+    hit a -1 sentinel instead of heap garbage."""
+    punct = np.ascontiguousarray(punct, np.int32)
+    short = np.ascontiguousarray(short, np.int32)
+    out = np.zeros(matrix.n, np.int32)
+    k = lib().ref_bits_to_remove_rate_adapt(matrix._h, punct.ctypes.data, punct.size, short.ctypes.data, short.size, pad,
+                                            out.ctypes.data)
+    if k < 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    return out[:k].copy()

@@ -11,6 +11,9 @@
 // sum_product_decoding / ... / QKD_LDPC / run_trial of the reference itself.
 #include <cstdint>
 #include <cstring>
+#include <fstream>
+#include <sstream>
+#include <algorithm>
 #include <memory>
 #include <string>
 #include <thread>
@@ -238,6 +241,172 @@ int ref_adapt_code_rate(void *mv, uint64_t seed, int untainted, const int32_t *u
         fractions[1] = mp.shortened_fraction;
         fractions[2] = mp.adapted_code_rate;
         return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// ---- host-surface views (config parser, combination builder, statistics, CSV writer) of the reference ----------
+// Same canonical text as qkdhost_describe_config / qkdhost_describe_inputs / qkdhost_csv_from_trials, produced by the
+// reference's own parse_config_data, prepare_sim_inputs, process_trials_results and write_file.
+static int64_t emit_text(const std::string &s, char *out, int64_t cap) {
+    if (out && cap > 0) {
+        const size_t k = std::min<size_t>(s.size(), static_cast<size_t>(cap - 1));
+        std::memcpy(out, s.data(), k);
+        out[k] = 0;
+    }
+    return static_cast<int64_t>(s.size());
+}
+
+static uint64_t fnv_ints(const std::vector<int> &v) {
+    uint64_t h = 1469598103934665603ull;
+    for (int x : v) h = (h ^ static_cast<uint32_t>(x)) * 1099511628211ull;
+    return h;
+}
+
+int64_t ref_describe_config(const char *config_path, char *out, int64_t cap) {
+    try {
+        const config_data c = parse_config_data(config_path);
+        std::ostringstream o;
+        o.precision(17);
+        o << "threads=" << c.THREADS_NUMBER << " trials=" << c.TRIALS_NUMBER << " seed=" << c.SIMULATION_SEED
+          << " privacy=" << c.ENABLE_PRIVACY_MAINTENANCE << " throughput=" << c.ENABLE_THROUGHPUT_MEASUREMENT << " rtt_on=" << c.CONSIDER_RTT
+          << " rtt=" << c.RTT << " alg=" << c.DECODING_ALGORITHM << " max_iter=" << c.DECODING_ALG_MAX_ITERATIONS
+          << " format=" << c.MATRIX_FORMAT << " thr_on=" << c.ENABLE_DECODING_ALG_MSG_LLR_THRESHOLD << " thr=" << c.DECODING_ALG_MSG_LLR_THRESHOLD
+          << " adapt=" << c.ENABLE_CODE_RATE_ADAPTATION << " untainted=" << c.ENABLE_UNTAINTED_PUNCTURING
+          << " adapt_ranges=" << c.USE_ADAPTATION_PARAMETERS_RANGES << "\n";
+        auto src = [&](const char *name, const auto &sf) {
+            o << name << ": use_range=" << sf.use_range << " range=" << sf.range.begin << ":" << sf.range.end << ":" << sf.range.step << " maps=";
+            for (const auto &m : sf.maps) o << m.code_rate << ">" << m.scaling_factor << ",";
+            o << "\n";
+        };
+        src("primary", c.DECODING_ALG_PARAMS.primary);
+        src("secondary", c.DECODING_ALG_PARAMS.secondary);
+        o << "qber_ranges=";
+        for (const auto &r : c.R_QBER_RANGES) o << r.code_rate << ">" << r.QBER_begin << ":" << r.QBER_end << ":" << r.QBER_step << ",";
+        o << "\nadapt_param_ranges=";
+        for (const auto &r : c.R_ADAPT_PARAMS_RANGES)
+            o << r.code_rate << ">" << r.delta_begin << ":" << r.delta_end << ":" << r.delta_step << "/" << r.efficiency_begin << ":"
+              << r.efficiency_end << ":" << r.efficiency_step << ",";
+        o << "\nadapt_param_maps=";
+        for (const auto &r : c.R_QBER_ADAPT_PARAMS_MAPS)
+            o << r.code_rate << ">" << r.QBER_adapt_params.QBER << "/" << r.QBER_adapt_params.delta << "/" << r.QBER_adapt_params.efficiency << ",";
+        o << "\n";
+        return emit_text(o.str(), out, cap);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+int64_t ref_describe_inputs(const char *config_path, const char *matrix_dir, char *out, int64_t cap) {
+    try {
+        CFG = parse_config_data(config_path);
+        std::vector<fs::path> paths = get_file_paths_in_directory(matrix_dir, ".mtrx");
+        const std::vector<sim_input> inputs = prepare_sim_inputs(paths);
+        std::ostringstream o;
+        o.precision(17);
+        size_t k = 0;
+        for (const auto &in : inputs)
+            for (const auto &c : in.combinations) {
+                const auto &mp = c.matrix_params;
+                o << k++ << " " << in.matrix_path.filename().string() << " n=" << in.matrix.bit_nodes.size() << " m=" << in.matrix.check_nodes.size()
+                  << " regular=" << in.matrix.is_regular << " qber=" << c.config_QBER << " delta=" << mp.delta << " eff=" << mp.efficiency
+                  << " pf=" << mp.punctured_fraction << " sf=" << mp.shortened_fraction << " ra=" << mp.adapted_code_rate
+                  << " p=" << mp.punctured_bits.size() << ":" << fnv_ints(mp.punctured_bits) << " s=" << mp.shortened_bits.size() << ":"
+                  << fnv_ints(mp.shortened_bits) << " rm=" << mp.bits_to_remove.size() << ":" << fnv_ints(mp.bits_to_remove)
+                  << " f1=" << c.scaling_factors.primary << " f2=" << c.scaling_factors.secondary << "\n";
+            }
+        return emit_text(o.str(), out, cap);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// process_trials_results + write_file on caller-provided per-trial results; returns the CSV text.
+int64_t ref_csv_from_trials(const char *config_path, const int32_t *iters, const uint8_t *flags, int64_t count, const char *matrix_name,
+                            int64_t n, int64_t m, int is_regular, double config_qber, double accurate_qber, double primary, double secondary,
+                            const double *adapt5, const char *tmp_dir, char *out, int64_t cap) {
+    try {
+        CFG = parse_config_data(config_path);
+        CFG.TRIALS_NUMBER = static_cast<size_t>(count);
+        CFG.ENABLE_THROUGHPUT_MEASUREMENT = false;
+        std::vector<trial_result> tr(static_cast<size_t>(count));
+        for (int64_t i = 0; i < count; ++i) {
+            tr[i].ldpc_res.decoding_res.iterations_num = static_cast<size_t>(iters[i]);
+            tr[i].ldpc_res.decoding_res.syndromes_match = (flags[i] & 1u) != 0;
+            tr[i].ldpc_res.keys_match = (flags[i] & 2u) != 0;
+            tr[i].accurate_QBER = accurate_qber;
+        }
+        H_matrix h;
+        h.bit_nodes.resize(static_cast<size_t>(n));
+        h.check_nodes.resize(static_cast<size_t>(m));
+        h.is_regular = is_regular != 0;
+        H_matrix_params mp{};
+        std::vector<sim_result> res(1);
+        res[0].sim_number = 0;
+        res[0].matrix_filename = matrix_name;
+        res[0].is_regular = h.is_regular;
+        res[0].num_bit_nodes = static_cast<size_t>(n);
+        res[0].num_check_nodes = static_cast<size_t>(m);
+        res[0].config_QBER = config_qber;
+        res[0].accurate_QBER = accurate_qber;
+        res[0].scaling_factors.primary = primary;
+        res[0].scaling_factors.secondary = secondary;
+        if (adapt5) {
+            res[0].delta = adapt5[0]; res[0].efficiency = adapt5[1]; res[0].punctured_fraction = adapt5[2];
+            res[0].shortened_fraction = adapt5[3]; res[0].adapted_code_rate = adapt5[4];
+        }
+        process_trials_results(tr, h, mp, res[0]);
+        const fs::path file = write_file(res, "00h-00m-00s", tmp_dir);
+        std::ifstream in(file);
+        std::stringstream ss;
+        ss << in.rdbuf();
+        in.close();
+        fs::remove(file);
+        return emit_text(ss.str(), out, cap);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// select_punctured_bits_untainted (array_and_matrix_operations.cpp:1002-1068) with a fresh generator.
+int64_t ref_untainted(void *mv, uint64_t seed, int32_t *out) {
+    try {
+        XoshiroCpp::Xoshiro256PlusPlus prng(seed);
+        const std::vector<int> v = select_punctured_bits_untainted(prng, static_cast<RefMatrix *>(mv)->h);
+        std::copy(v.begin(), v.end(), out);
+        return static_cast<int64_t>(v.size());
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+// get_bits_positions_to_remove_rate_adapt (array_and_matrix_operations.cpp:189-256) on given position lists.
+// pad > 0 appends `pad` sentinel entries (-1) beyond the logical end of both lists' STORAGE (capacity, not size) so
+// that the reference's unchecked reads of shortened_bits[s] / punctured_bits[p] past the end (:215,:220) hit a
+// defined value instead of heap garbage.
+int64_t ref_bits_to_remove_rate_adapt(void *mv, const int32_t *punct, int64_t n_p, const int32_t *shortd, int64_t n_s, int pad,
+                                      int32_t *out) {
+    try {
+        H_matrix_params mp{};
+        mp.punctured_bits.reserve(static_cast<size_t>(n_p + pad));
+        mp.shortened_bits.reserve(static_cast<size_t>(n_s + pad));
+        mp.punctured_bits.assign(punct, punct + n_p);
+        mp.shortened_bits.assign(shortd, shortd + n_s);
+        for (int k = 0; k < pad; ++k) {   // write sentinels into the spare capacity, then shrink the size back
+            mp.punctured_bits.push_back(-1);
+            mp.shortened_bits.push_back(-1);
+        }
+        mp.punctured_bits.resize(static_cast<size_t>(n_p));
+        mp.shortened_bits.resize(static_cast<size_t>(n_s));
+        const std::vector<int> v = get_bits_positions_to_remove_rate_adapt(static_cast<RefMatrix *>(mv)->h, mp);
+        std::copy(v.begin(), v.end(), out);
+        return static_cast<int64_t>(v.size());
     } catch (const std::exception &e) {
         g_err = e.what();
         return -1;

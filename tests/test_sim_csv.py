@@ -1,0 +1,138 @@
+"""CSV-level parity: the reference's whole QKD_LDPC executable (oracle/_ref/qkd_ldpc_ref = its unmodified main.cpp and
+sources, built by oracle/Makefile with -DUSE_CURRENT_DIR) and our qkdldpc_sim (C++ host + libqkdldpc_cuda) are run on the
+same config and matrix directory; the results files must agree. With float64 messages the min-sum family is
+bit-identical, so every CSV field must match; float32 runs are compared on FER."""
+import json
+import os
+import subprocess
+
+import pytest
+
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "qkd_ldpc_ref")
+SIM_BIN = os.path.join(ROOT, "qkd_ldpc_v_b200", "qkdldpc_sim")
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/qkd_ldpc_ref not built")]
+
+BASE = dict(threads_number=4, use_config_simulation_seed=True, simulation_seed=20251018, enable_privacy_maintenance=False,
+            enable_throughput_measurement=False, throughput_measurement_parameters=dict(consider_RTT=False, RTT=0.0),
+            min_sum_normalized_parameters=dict(use_alpha_range=False, alpha_range=dict(begin=0.6, end=0.8, step=0.1),
+                                               code_rate_alpha_maps=[dict(code_rate=0.95, alpha=0.75)]),
+            min_sum_offset_parameters=dict(use_beta_range=False, beta_range=dict(begin=0.1, end=0.3, step=0.1),
+                                           code_rate_beta_maps=[dict(code_rate=0.95, beta=0.2)]),
+            adaptive_min_sum_normalized_parameters=dict(use_alpha_range=False, alpha_range=dict(begin=0.6, end=0.8, step=0.1),
+                                                        code_rate_alpha_maps=[dict(code_rate=0.95, alpha=0.8)], use_nu_range=False,
+                                                        nu_range=dict(begin=0.5, end=0.7, step=0.1),
+                                                        code_rate_nu_maps=[dict(code_rate=0.95, nu=0.6)]),
+            adaptive_min_sum_offset_parameters=dict(use_beta_range=False, beta_range=dict(begin=0.6, end=0.8, step=0.1),
+                                                    code_rate_beta_maps=[dict(code_rate=0.95, beta=0.7)], use_sigma_range=False,
+                                                    sigma_range=dict(begin=0.5, end=0.7, step=0.1),
+                                                    code_rate_sigma_maps=[dict(code_rate=0.95, sigma=0.99)]),
+            decoding_algorithm_max_iterations=100, trace_qkd_ldpc=False, trace_decoding_algorithm=False,
+            trace_decoding_algorithm_llr=False, enable_decoding_algorithm_msg_llr_threshold=True,
+            decoding_algorithm_msg_llr_threshold=100.0, enable_code_rate_adaptation=False,
+            code_rate_adaptation_parameters=dict(enable_untainted_puncturing=False, use_adaptation_parameters_ranges=True,
+                                                 code_rate_adaptation_parameters_ranges=[
+                                                     dict(code_rate=0.95, delta=dict(begin=0.05, end=0.1, step=0.05),
+                                                          efficiency=dict(begin=1.3, end=1.3, step=0.1))],
+                                                 code_rate_QBER_adaptation_parameters_maps=[]))
+
+
+def _setup(tmp_path, cfg, matrices):
+    """matrices: list of (golden code name, format). Builds <tmp>/configs, <tmp>/sparse_matrices/<dir>."""
+    (tmp_path / "configs").mkdir()
+    (tmp_path / "configs" / "run.json").write_text(json.dumps(cfg))
+    sub = {1: "matrices_alist", 3: "matrices_2"}[cfg["matrix_format"]]
+    mdir = tmp_path / "sparse_matrices" / sub
+    mdir.mkdir(parents=True)
+    for name in matrices:
+        fname = util.code_arrays(name)["file"]
+        (util.write_alist if cfg["matrix_format"] == 1 else util.write_sparse2)(str(mdir / fname), name)
+    return mdir
+
+
+def _run_reference(tmp_path):
+    with open(os.devnull) as nul:
+        subprocess.run([REF_BIN], cwd=tmp_path, stdin=nul, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, check=True, timeout=900)
+    files = [f for f in os.listdir(tmp_path / "results") if f.endswith(".csv")]
+    assert len(files) == 1
+    return files[0], (tmp_path / "results" / files[0]).read_text().splitlines()
+
+
+def _run_ours(tmp_path, precision, extra=()):
+    out = tmp_path / "results_gpu"
+    r = subprocess.run([SIM_BIN, "--root", str(tmp_path), "--results-dir", str(out), "--precision", str(precision), "--quiet", *extra],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    files = [f for f in os.listdir(out) if f.endswith(".csv")]
+    assert len(files) == 1
+    assert os.path.exists(out / files[0].replace(".csv", ".gpu.json"))
+    return files[0], (out / files[0]).read_text().splitlines()
+
+
+def _strip_duration(name):
+    return name.split(",sim_duration=")[0]
+
+
+@pytest.mark.parametrize("alg", [2, 3, 4, 5])
+def test_csv_identical_minsum_fp64(built, tmp_path, alg):
+    cfg = dict(BASE, trials_number=400, decoding_algorithm=alg, matrix_format=1,
+               code_rate_QBER_ranges=[dict(code_rate=0.7, QBER=dict(begin=0.03, end=0.05, step=0.01)),
+                                      dict(code_rate=0.95, QBER=dict(begin=0.015, end=0.025, step=0.01))])
+    _setup(tmp_path, cfg, ["K1_4", "K1_5"])
+    rname, ref_lines = _run_reference(tmp_path)
+    oname, our_lines = _run_ours(tmp_path, 64)
+    assert _strip_duration(rname) == _strip_duration(oname)
+    assert len(ref_lines) == 1 + 3 + 2
+    # the reference enumerates matrices in directory order; so do we (same directory) -> rows line up
+    assert our_lines == ref_lines
+
+
+def test_csv_rate_adaptation_untainted_fp64(built, tmp_path):
+    cra = dict(enable_untainted_puncturing=True, use_adaptation_parameters_ranges=False, code_rate_adaptation_parameters_ranges=[],
+               code_rate_QBER_adaptation_parameters_maps=[dict(code_rate=0.805, QBER=0.0116, delta=0.09, efficiency=1.5),
+                                                          dict(code_rate=0.805, QBER=0.0196, delta=0.03, efficiency=1.28),
+                                                          dict(code_rate=0.805, QBER=0.0276, delta=0.11, efficiency=1.2)])
+    cfg = dict(BASE, trials_number=48, decoding_algorithm=5, matrix_format=3, enable_code_rate_adaptation=True,
+               code_rate_adaptation_parameters=cra, code_rate_QBER_ranges=[dict(code_rate=0.95, QBER=dict(begin=0.01, end=0.01, step=0.01))])
+    _setup(tmp_path, cfg, ["I80"])
+    rname, ref_lines = _run_reference(tmp_path)
+    oname, our_lines = _run_ours(tmp_path, 64, ["--gpus", "1", "--chunk-frames", "20"])   # several chunks per combination
+    assert _strip_duration(rname) == _strip_duration(oname)
+    assert len(ref_lines) == 4 and "DELTA;EFFICIENCY;PUNCT_FRACTION" in ref_lines[0]
+    assert our_lines == ref_lines
+
+
+def test_csv_random_puncturing_and_spa(built, tmp_path):
+    # SPA in float64: CUDA's tanh/atanh vs glibc's differ in the last ulp, so allow a small iteration-mean difference
+    cra = dict(BASE["code_rate_adaptation_parameters"],
+               code_rate_adaptation_parameters_ranges=[dict(code_rate=0.95, delta=dict(begin=0.05, end=0.1, step=0.05),
+                                                            efficiency=dict(begin=1.8, end=2.0, step=0.2))])
+    cfg = dict(BASE, trials_number=300, decoding_algorithm=0, matrix_format=1, enable_code_rate_adaptation=True,
+               code_rate_adaptation_parameters=cra,
+               code_rate_QBER_ranges=[dict(code_rate=0.95, QBER=dict(begin=0.01, end=0.015, step=0.005))])
+    _setup(tmp_path, cfg, ["K1_5"])
+    _, ref_lines = _run_reference(tmp_path)
+    _, our_lines = _run_ours(tmp_path, 64)
+    assert our_lines[0] == ref_lines[0] and len(our_lines) == len(ref_lines) >= 3
+    for a, b in zip(our_lines[1:], ref_lines[1:]):
+        fa, fb = a.split(";"), b.split(";")
+        assert fa[:8] == fb[:8] and fa[15:] == fb[15:]          # identity columns and rate-adaptation columns
+        assert abs(float(fa[8].replace(",", ".")) - float(fb[8].replace(",", "."))) <= 0.05   # ITER_SUCCESS_MEAN
+        assert abs(float(fa[14].replace(",", ".")) - float(fb[14].replace(",", "."))) <= 0.01  # FER
+
+
+def test_csv_fp32_fer(built, tmp_path):
+    cfg = dict(BASE, trials_number=2000, decoding_algorithm=2, matrix_format=1,
+               code_rate_QBER_ranges=[dict(code_rate=0.95, QBER=dict(begin=0.02, end=0.03, step=0.01))])
+    _setup(tmp_path, cfg, ["K1_5"])
+    _, ref_lines = _run_reference(tmp_path)
+    _, our_lines = _run_ours(tmp_path, 32)
+    assert our_lines[0] == ref_lines[0]
+    for a, b in zip(our_lines[1:], ref_lines[1:]):
+        fa, fb = a.split(";"), b.split(";")
+        assert fa[:8] == fb[:8]
+        assert abs(float(fa[14].replace(",", ".")) - float(fb[14].replace(",", "."))) <= 0.005
+        assert abs(float(fa[8].replace(",", ".")) - float(fb[8].replace(",", "."))) <= 0.1

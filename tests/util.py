@@ -39,3 +39,33 @@ def load_case(case):
 def unpack(words_u8, n):
     """golden words are np.packbits(..., bitorder='little') over uint8."""
     return np.unpackbits(words_u8, axis=-1, bitorder="little")[..., :n]
+
+
+def write_alist(path, name):
+    """Writes golden code `name` as an alist file (format 1 of the reference)."""
+    a = code_arrays(name)
+    n, m = a["n"], a["m"]
+    cw = np.diff(a["col_ptr"])
+    rw = np.diff(a["row_ptr"])
+    with open(path, "w") as f:
+        f.write(f"{n} {m}\n{cw.max()} {rw.max()}\n")
+        f.write(" ".join(map(str, cw)) + "\n" + " ".join(map(str, rw)) + "\n")
+        for i in range(n):
+            f.write(" ".join(str(x + 1) for x in a["row_idx"][a["col_ptr"][i]:a["col_ptr"][i + 1]]) + "\n")
+        for j in range(m):
+            f.write(" ".join(str(x + 1) for x in a["col_idx"][a["row_ptr"][j]:a["row_ptr"][j + 1]]) + "\n")
+
+
+def write_sparse2(path, name, with_untp=True):
+    """Writes golden code `name` in the "sparse_2" format (format 3) plus its .untp side-car when the code has one."""
+    a = code_arrays(name)
+    n, m = a["n"], a["m"]
+    with open(path, "w") as f:
+        f.write(f"{n} {m}\n")
+        for j in range(m):
+            f.write(" ".join(map(str, a["col_idx"][a["row_ptr"][j]:a["row_ptr"][j + 1]])) + "\n")
+        for i in range(n):
+            f.write(" ".join(map(str, a["row_idx"][a["col_ptr"][i]:a["col_ptr"][i + 1]])) + "\n")
+    if with_untp and a["untp"] is not None and a["untp"].size:
+        with open(os.path.splitext(path)[0] + ".untp", "w") as f:
+            f.write(" ".join(map(str, a["untp"])) + "\n")
