@@ -191,6 +191,14 @@ class LdpcCode:
         inf = self.info()
         return BatchResult(iters, flags, out_bits, tally, self.n, inf["last_batch_ms"], inf)
 
+    def QKD_LDPC_RATE_ADAPT_batch(self, alice_bit_array_extended, bob_bit_array_extended, QBER, scaling_factors=(0.0, 0.0),
+                                  cfg: Optional[DecoderConfig] = None, punctured_bits: Sequence[int] = (),
+                                  shortened_bits: Sequence[int] = (), want_bits: bool = True) -> BatchResult:
+        """Batched ``QKD_LDPC_RATE_ADAPT`` (qkd_ldpc_algorithm.cpp:1121-1258) on EXTENDED frames: the same C-ABI call
+        as :meth:`QKD_LDPC_batch` with the position lists of ``H_matrix_params`` (sorted ascending)."""
+        return self.QKD_LDPC_batch(alice_bit_array_extended, bob_bit_array_extended, QBER, scaling_factors, cfg,
+                                   punctured_bits, shortened_bits, want_bits)
+
     def decode_batch_device(self, d_alice: int, d_bob: int, d_qber: int, n_frames: int, scaling_factors=(0.0, 0.0),
                             cfg: Optional[DecoderConfig] = None, qber_is_scalar: bool = True,
                             punctured_bits: Sequence[int] = (), shortened_bits: Sequence[int] = (),

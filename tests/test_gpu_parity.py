@@ -160,3 +160,44 @@ def test_adaptive_bob_already_correct(q):
                                               precision=prec)
             assert (r.iterations_num == it).all() and (r.flags == fl).all() and (r.bits() == bits).all()
             assert (r.iterations_num[:20] == 1).all()
+
+
+@pytest.mark.parametrize("alg,pri,sec,point,untainted", [
+    (2, 0.7, 0.0, (0.0116, 0.09, 1.5), True),
+    (5, 0.7, 0.99, (0.0196, 0.03, 1.28), True),
+    (4, 0.8, 0.71, (0.0276, 0.11, 1.2), False),
+    (0, 0.0, 0.0, (0.0156, 0.06, 1.39), False),
+])
+def test_rate_adaptation_against_reference(q, tmp_path, alg, pri, sec, point, untainted):
+    """QKD_LDPC_RATE_ADAPT (qkd_ldpc_algorithm.cpp:1121-1258): punctured bits (LLR 1e-4, a random bit per party) and
+    shortened bits (LLR DBL_MAX, value 0) on the irregular R=0.8 code, frames built by the C++ host from the per-trial
+    generator -- against run_trial of the compiled reference on the same seeds and position lists."""
+    from oracle import ref
+    from qkd_ldpc_v_b200 import hostlib
+    if not ref.available():
+        pytest.skip("oracle/_ref/libqkdref.so not built")
+    path = str(tmp_path / "I80.mtrx")
+    util.write_sparse2(path, "I80")
+    arr = util.code_arrays("I80")
+    rm, hm = ref.RefMatrix(path, 3), hostlib.HostMatrix(path, 3)
+    qber, delta, eff = point
+    p, s, rmv, fr = hm.adapt_code_rate(5555, qber, delta, eff, untainted=untainted, untp=arr["untp"])
+    assert p.size > 0 and s.size > 0
+    seeds = hostlib.trial_seeds(424242, 96)
+    ref.set_cfg(alg, 100, True, 100.0, False, True)
+    it, fl, acc = rm.run_trials(qber, seeds, pri, sec, punct=p, shortd=s, remove=rmv)
+    a, b, acc2 = hostlib.gen_keys_rate_adapt(seeds, arr["n"], qber, p, s)
+    assert acc2 == acc[0]
+    h = handle(q, "I80")
+    r64 = h.QKD_LDPC_batch(a, b, acc2, (pri, sec), q.DecoderConfig(decoding_algorithm=alg, message_precision=64),
+                           punctured_bits=p, shortened_bits=s)
+    if alg in EXACT_ALGS:
+        assert (r64.iterations_num == it).all() and (r64.flags == fl).all()
+    else:
+        assert (r64.iterations_num == it).mean() >= 0.97 and ((r64.flags & 1) == (fl & 1)).mean() >= 0.97
+    r32 = h.QKD_LDPC_batch(a, b, acc2, (pri, sec), q.DecoderConfig(decoding_algorithm=alg, message_precision=32),
+                           punctured_bits=p, shortened_bits=s)
+    assert ((r32.flags & 1) == (fl & 1)).mean() >= 0.95
+    assert (r32.iterations_num == it).mean() >= 0.9
+    both = r32.syndromes_match & ((fl & 1) != 0)
+    assert (r32.keys_match[both] == ((fl[both] & 2) != 0)).all()
