@@ -14,6 +14,10 @@ extern template int run_batch<float, 4>(qkdldpc_code *, const qkdldpc_params *, 
 extern template int run_batch<float, 2>(qkdldpc_code *, const qkdldpc_params *, int64_t, const uint32_t *, const uint32_t *, const double *, int, const int32_t *, int, const int32_t *, int, uint32_t *, int32_t *, uint8_t *, unsigned long long *);
 extern template int run_batch<float, 1>(qkdldpc_code *, const qkdldpc_params *, int64_t, const uint32_t *, const uint32_t *, const double *, int, const int32_t *, int, const int32_t *, int, uint32_t *, int32_t *, uint8_t *, unsigned long long *);
 extern template int run_batch<double, 2>(qkdldpc_code *, const qkdldpc_params *, int64_t, const uint32_t *, const uint32_t *, const double *, int, const int32_t *, int, const int32_t *, int, uint32_t *, int32_t *, uint8_t *, unsigned long long *);
+int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const uint32_t *d_alice, const uint32_t *d_bob,
+               const double *d_qber, int qber_is_scalar, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short,
+               uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally);
+bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P);
 }  // namespace qkhost
 
 namespace {
@@ -94,6 +98,60 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     group(m, rp, qk::cn_bucket_of, row_order, cn_first, cn_count);
     group(n, col_ptr, qk::vn_bucket_of, col_order, vn_first, vn_count);
 
+    // On-chip path layout (onchip_minsum.cuh): rows and bits sorted by degree (widest first), cut into groups of 32 that
+    // never mix degrees (the last group of a degree class is padded with a scratch node), ELL index arrays per group.
+    int max_dc = 0;
+    for (int j = 0; j < m; ++j) max_dc = std::max(max_dc, row_ptr[j + 1] - row_ptr[j]);
+    const bool oc_ok = n < 65535 && m < 65535 && max_dc <= 32;
+    std::vector<int2> oc_cn_ginfo, oc_vn_ginfo;
+    std::vector<uint16_t> oc_cnT, oc_cn_row, oc_vn_bit;
+    std::vector<uint32_t> oc_vT;
+    if (oc_ok) {
+        auto sorted_by_degree = [](int count, const std::vector<int> &ptr) {
+            std::vector<int> order(count);
+            for (int i = 0; i < count; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ptr[x + 1] - ptr[x] > ptr[y + 1] - ptr[y]; });
+            return order;
+        };
+        // groups: [begin, end) ranges of `order` with one degree and at most 32 members
+        auto cut = [](const std::vector<int> &order, const std::vector<int> &ptr, std::vector<std::pair<int, int>> &groups) {
+            size_t i = 0;
+            while (i < order.size()) {
+                const int d = ptr[order[i] + 1] - ptr[order[i]];
+                size_t j = i;
+                while (j < order.size() && j - i < 32 && ptr[order[j] + 1] - ptr[order[j]] == d) ++j;
+                groups.emplace_back((int)i, (int)j);
+                i = j;
+            }
+        };
+        const std::vector<int> rows = sorted_by_degree(m, rp), bits = sorted_by_degree(n, col_ptr);
+        std::vector<std::pair<int, int>> rg, bg;
+        cut(rows, rp, rg);
+        cut(bits, col_ptr, bg);
+        for (auto [b0, b1] : rg) {
+            const int dc = rp[rows[b0] + 1] - rp[rows[b0]];
+            oc_cn_ginfo.push_back(make_int2((int)oc_cnT.size(), dc));
+            for (int l = 0; l < 32; ++l) oc_cn_row.push_back(b0 + l < b1 ? (uint16_t)rows[b0 + l] : (uint16_t)m);
+            for (int k = 0; k < dc; ++k)
+                for (int l = 0; l < 32; ++l) oc_cnT.push_back(b0 + l < b1 ? (uint16_t)col_idx[rp[rows[b0 + l]] + k] : (uint16_t)0);
+        }
+        for (auto [b0, b1] : bg) {
+            const int dv = col_ptr[bits[b0] + 1] - col_ptr[bits[b0]];
+            oc_vn_ginfo.push_back(make_int2((int)oc_vT.size(), dv));
+            for (int l = 0; l < 32; ++l) oc_vn_bit.push_back(b0 + l < b1 ? (uint16_t)bits[b0 + l] : (uint16_t)n);
+            for (int k = 0; k < dv; ++k)
+                for (int l = 0; l < 32; ++l) {
+                    uint32_t ent = (uint32_t)m;   // padding lanes read the scratch record
+                    if (b0 + l < b1) {
+                        const int p = col_ptr[bits[b0 + l]] + k, r = csc_row[p];
+                        const int pos = csc_edge[p] - rp[r], dcr = rp[r + 1] - rp[r];
+                        ent = (uint32_t)r | ((uint32_t)(32 - dcr + pos) << 16);
+                    }
+                    oc_vT.push_back(ent);
+                }
+        }
+    }
+
     int ndev = qkdldpc_device_count();
     if (ndev == 0) return fail(QKDLDPC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(QKDLDPC_ERR_INVALID, "device %d not in [0, %d)", device, ndev);
@@ -112,6 +170,8 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     if ((e = up(c->row_ptr, rp)) || (e = up(c->col_idx, ci)) || (e = up(c->col_ptr, col_ptr)) ||
         (e = up(c->csc_edge, csc_edge)) || (e = up(c->csc_row, csc_row)) || (e = up(c->row_order, row_order)) ||
         (e = up(c->col_order, col_order)) ||
+        (oc_ok && ((e = up(c->oc_cn_ginfo, oc_cn_ginfo)) || (e = up(c->oc_cnT, oc_cnT)) || (e = up(c->oc_cn_row, oc_cn_row)) || (e = up(c->oc_vn_ginfo, oc_vn_ginfo)) ||
+                   (e = up(c->oc_vn_bit, oc_vn_bit)) || (e = up(c->oc_vT, oc_vT)))) ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
         (e = cudaMallocHost(&c->h_done, sizeof(unsigned long long))) || (e = cudaEventCreate(&c->ev0)) ||
         (e = cudaEventCreate(&c->ev1)) || (e = cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming))) {
@@ -119,6 +179,10 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         return fail(QKDLDPC_ERR_CUDA, "graph upload failed: %s", cudaGetErrorString(e));
     }
     c->own_stream = true;
+    c->oc_max_dc = max_dc;
+    c->oc_groups_cn = (int)oc_cn_ginfo.size();
+    c->oc_groups_vn = (int)oc_vn_ginfo.size();
+    c->oc_eligible = oc_ok;
     for (int k = 0; k < 5; ++k) {
         c->cn_first[k] = cn_first[k]; c->cn_count[k] = cn_count[k];
         c->vn_first[k] = vn_first[k]; c->vn_count[k] = vn_count[k];
@@ -134,6 +198,8 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     c->row_ptr.release(); c->col_idx.release(); c->col_ptr.release(); c->csc_edge.release(); c->csc_row.release();
     c->row_order.release(); c->col_order.release();
+    c->oc_cn_ginfo.release(); c->oc_vn_ginfo.release(); c->oc_cnT.release(); c->oc_cn_row.release(); c->oc_vn_bit.release(); c->oc_vT.release();
+    c->oc_cls.release();
     c->msg.release(); c->bobmask.release(); c->zmask.release(); c->synd.release(); c->par.release();
     c->tile_active.release(); c->tile_new.release(); c->slot_llr.release(); c->slot_frame.release();
     c->slot_iter.release(); c->frame_llr.release(); c->synd_all.release();
@@ -179,6 +245,14 @@ int qkdldpc_decode_batch_device(qkdldpc_code *c, const qkdldpc_params *P, int64_
         return fail(QKDLDPC_ERR_INVALID, "bad punctured/shortened position list");
     CK(cudaSetDevice(c->device));
     auto *tl = reinterpret_cast<unsigned long long *>(d_tally);
+    // decoder_path: 0 auto (on-chip min-sum when the graph and the parameters allow it), 1 streaming, 2 on-chip or fail
+    const bool oc = onchip_usable(c, P);
+    if (c->opt.decoder_path == 2 && !oc)
+        return fail(QKDLDPC_ERR_INVALID, "on-chip path requested but not usable for this code / these parameters");
+    if (oc && c->opt.decoder_path != 1)
+        return run_onchip(c, P, n_frames, d_alice_bits, d_bob_bits, d_qber, qber_is_scalar, punct_pos, n_punct, short_pos,
+                          n_short, d_out_bits, d_out_iters, d_out_flags, tl);
+    c->last_path = 1;
 #define RUN(T, V)                                                                                                   \
     return run_batch<T, V>(c, P, n_frames, d_alice_bits, d_bob_bits, d_qber, qber_is_scalar, punct_pos, n_punct,    \
                            short_pos, n_short, d_out_bits, d_out_iters, d_out_flags, tl)
@@ -258,6 +332,7 @@ int qkdldpc_code_info(const qkdldpc_code *c, qkdldpc_info *info) {
     info->frames_per_tile = c->frames_per_tile; info->pool_tiles = c->pool_tiles; info->pool_bytes = c->pool_bytes;
     info->kernel_launches = c->kernel_launches; info->decoder_steps = c->decoder_steps;
     info->last_batch_ms = c->last_batch_ms;
+    info->last_path = c->last_path;
     info->last_cn_ms = c->last_cn_ms; info->last_vn_ms = c->last_vn_ms; info->last_sched_ms = c->last_sched_ms;
     return QKDLDPC_OK;
 }

@@ -74,6 +74,14 @@ struct qkdldpc_code {
     // graph (device)
     DevBuf<int> row_ptr, col_idx, col_ptr, csc_edge, csc_row, row_order, col_order;
     int cn_first[5] = {0}, cn_count[5] = {0}, vn_first[5] = {0}, vn_count[5] = {0};   // degree buckets in row/col_order
+    // on-chip min-sum path (onchip_minsum.cuh): ELL index arrays per 32-node group; eligible == the graph fits
+    bool oc_eligible = false;
+    int oc_groups_cn = 0, oc_groups_vn = 0, oc_max_dc = 0;
+    size_t oc_smem = 0;
+    DevBuf<int2> oc_cn_ginfo, oc_vn_ginfo;
+    DevBuf<uint16_t> oc_cnT, oc_cn_row, oc_vn_bit;
+    DevBuf<uint32_t> oc_vT, oc_cls;   // oc_cls: [2][words] punctured / shortened bit masks of the current batch
+    int last_path = 0;                // 1 streaming, 2 on-chip (of the last batch)
     // pool (device, raw bytes reinterpreted per precision)
     DevBuf<unsigned char> msg;
     DevBuf<uint32_t> bobmask, zmask, synd, par, tile_active, tile_new;

@@ -1,0 +1,108 @@
+// On-chip min-sum path: host-side launcher (one persistent kernel per batch) and the four kernel instantiations.
+#include "handle.hpp"
+#include "onchip_minsum.cuh"
+
+namespace qkhost {
+
+using namespace qk;
+
+bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
+    if (!c->oc_eligible || P->message_precision != 32 || P->algorithm < 2) return false;
+    // same precondition as the FAST streaming kernels (fast_minsum_ok, run_batch.cuh): no message can become NaN / inf
+    if (P->enable_threshold) {
+        if (!std::isfinite(P->threshold)) return false;
+    } else if (P->algorithm == 3 || P->algorithm == 5) {
+        if (!(P->primary >= 0 && P->secondary >= 0)) return false;
+    } else if (!(P->primary <= 1.0 && (P->algorithm != 4 || P->secondary <= 1.0))) {
+        return false;
+    }
+    int dev_smem = 0;
+    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return false;
+    return onchip_smem_bytes(c->n, c->m, c->oc_groups_cn) <= (size_t)dev_smem;
+}
+
+template <int ALG>
+static cudaError_t launch(const OnchipArgs &a, int sms, int threads, size_t smem, cudaStream_t s, long long n_frames, int *grid_out) {
+    cudaError_t e = cudaFuncSetAttribute(onchip_minsum_kernel<ALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onchip_minsum_kernel<ALG>, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const long long grid = std::min<long long>(n_frames, (long long)per_sm * sms);   // persistent CTAs pull frames from a queue
+    *grid_out = (int)grid;
+    onchip_minsum_kernel<ALG><<<(unsigned)grid, threads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const uint32_t *d_alice, const uint32_t *d_bob,
+               const double *d_qber, int qber_is_scalar, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short,
+               uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally) {
+    const int n = c->n, m = c->m, words = (n + 31) / 32;
+    cudaStream_t s = c->stream;
+    CK(c->oc_cls.reserve((size_t)2 * words));
+    CK(c->counters.reserve(2));
+    // punctured / shortened position masks (H_matrix_params, array_and_matrix_operations.hpp:44-48)
+    const bool has_cls = n_punct > 0 || n_short > 0;
+    if (has_cls) {
+        std::vector<uint32_t> cls((size_t)2 * words, 0u);
+        for (int i = 0; i < n_punct; ++i) {
+            if (punct[i] < 0 || punct[i] >= n) return fail(QKDLDPC_ERR_INVALID, "punctured position out of range");
+            cls[punct[i] >> 5] |= 1u << (punct[i] & 31);
+        }
+        for (int i = 0; i < n_short; ++i) {
+            if (shortd[i] < 0 || shortd[i] >= n) return fail(QKDLDPC_ERR_INVALID, "shortened position out of range");
+            cls[(size_t)words + (shortd[i] >> 5)] |= 1u << (shortd[i] & 31);   // in both lists: punctured wins (:1150 tested first)
+        }
+        CK(cudaMemcpyAsync(c->oc_cls.p, cls.data(), cls.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));   // the host vector dies at scope end
+    }
+    CK(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), s));
+    if (d_tally) CK(cudaMemsetAsync(d_tally, 0, (size_t)qkdldpc_tally_len(P->max_iterations) * sizeof(uint64_t), s));
+
+    OnchipArgs a{};
+    a.n = n; a.m = m; a.words = words;
+    a.n_groups_cn = c->oc_groups_cn; a.n_groups_vn = c->oc_groups_vn;
+    a.cn_ginfo = c->oc_cn_ginfo.p; a.cn_row = c->oc_cn_row.p; a.cnT = c->oc_cnT.p;
+    a.vn_ginfo = c->oc_vn_ginfo.p; a.vn_bit = c->oc_vn_bit.p; a.vT = c->oc_vT.p;
+    a.cls_punct = c->oc_cls.p; a.cls_short = c->oc_cls.p + words; a.has_cls = has_cls ? 1 : 0;
+    a.n_frames = n_frames; a.alice_bits = d_alice; a.bob_bits = d_bob; a.qber = d_qber; a.qber_is_scalar = qber_is_scalar;
+    a.out_bits = d_out_bits; a.out_iters = d_out_iters; a.out_flags = d_out_flags; a.tally = d_tally;
+    a.next_frame = c->counters.p;
+    a.max_iter = P->max_iterations;
+    a.primary = (float)P->primary; a.secondary = (float)P->secondary;
+    a.thr = P->enable_threshold ? (float)P->threshold : INFINITY;
+
+    // CTA size: one lane per row in the check phase; small codes get small CTAs (more frames per SM)
+    int threads = c->opt.onchip_threads > 0 ? c->opt.onchip_threads : std::max(128, std::min(512, (m + 31) / 32 * 32));
+    threads = std::max(32, std::min(512, threads / 32 * 32));
+    const size_t smem = onchip_smem_bytes(n, m, c->oc_groups_cn);
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+
+    CK(cudaEventRecord(c->ev0, s));
+    int grid = 0;
+    cudaError_t e;
+    switch (P->algorithm) {
+        case 2: e = launch<2>(a, sms, threads, smem, s, n_frames, &grid); break;
+        case 3: e = launch<3>(a, sms, threads, smem, s, n_frames, &grid); break;
+        case 4: e = launch<4>(a, sms, threads, smem, s, n_frames, &grid); break;
+        default: e = launch<5>(a, sms, threads, smem, s, n_frames, &grid); break;
+    }
+    if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel launch failed: %s", cudaGetErrorString(e));
+    c->kernel_launches += 1;
+    CK(cudaEventRecord(c->ev1, s));
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_batch_ms = ms;
+    c->last_cn_ms = c->last_vn_ms = c->last_sched_ms = 0;
+    c->last_path = 2;
+    c->frames_per_tile = 1;
+    c->pool_tiles = grid;
+    c->pool_bytes = (int64_t)grid * (int64_t)smem;   // bytes of on-chip decoder state in flight
+    CK(cudaGetLastError());
+    return QKDLDPC_OK;
+}
+
+}  // namespace qkhost

@@ -1,0 +1,259 @@
+// On-chip min-sum decoder: one frame per CTA, the whole belief-propagation state of the frame lives in shared memory
+// for all iterations; HBM is touched only for the packed key bits going in and the packed decision coming out.
+//
+// Why this is possible. For the min-sum family a check node's dc outgoing messages take only two magnitudes
+// (qkd_ldpc_algorithm.cpp:400-408): factor*min1 for every edge except the one holding the minimum, which gets
+// factor*min2 (ties: min2 == min1, so "first minimum" and the reference's by-value test `|m| == min1` select the
+// same number). A row is therefore fully described by a 16-byte RECORD {c1, c2, sign bits, argmin}, and the
+// bit-to-check message need not be stored at all: b2c = clamp(L - c2b) (:447-461) is recomputed from the bit's
+// total L and the row's previous record when the check node needs it. State per frame:
+//     L[n]   float   total LLR after the last variable-node phase (llr before the first iteration)
+//     rec[m] uint4   {bits(c1), bits(c2), sign bit per edge of the row, position of the first minimum}
+// = 4n + 16m bytes (72 KB for n=10240, m=2048 instead of 242 KB of float messages), so two frames fit one SM.
+// Every float operation of the reference is performed on the same operands in the same order (the sum over a
+// bit's checks runs in ascending check order starting from the LLR, :414-422), so the results are bit-identical
+// to the streaming float32 kernels (step_kernels.cuh) and to the f32 oracle.
+//
+// Phases per iteration (two __syncthreads):
+//   CN  thread per row: gather L of the row's bits, rebuild b2c with the OLD record, min1/min2/signs -> NEW record.
+//       The parity of the current hard decision z = (L <= 0) falls out of the same gather, which gives the syndrome
+//       test of the previous iteration (:424-445) and the adaptive variants' per-row factor (:745-757) for free.
+//   VN  thread per bit: L = llr + sum over the bit's checks of the message rebuilt from the row record.
+// Graph indices are stored per 32-node group in ELL form ([k][lane], coalesced) and shared by all CTAs through L1/L2;
+// rows and bits are sorted by degree and a group never mixes degrees, so the inner loops carry no validity tests.
+//
+// Eligibility (host): float32 messages, min-sum family with the FAST precondition of run_batch.cuh (no NaN possible),
+// every check degree <= 32, n and m < 65535, state fits the 227 KB of shared memory. Everything else (SPA, float64,
+// n = 100k codes, very wide rows) takes the streaming path.
+#pragma once
+#include "common.cuh"
+
+namespace qk {
+
+typedef unsigned long long u64;
+
+struct OnchipArgs {
+    int n, m, words;
+    int n_groups_cn, n_groups_vn;
+    const int2 *cn_ginfo;       // [groups] {offset into cnT, degree of the group's rows}; rows sorted by degree, a group
+                                //          never mixes degrees (last group of a degree class is padded)
+    const uint16_t *cn_row;     // [groups*32] row handled by (group, lane); padding lanes hold m (a scratch record slot)
+    const uint16_t *cnT;        // [off + k*32 + lane] bit index of the k-th edge of that row (padding lanes: 0)
+    const int2 *vn_ginfo;       // [groups] {offset into vT, degree of the group's bits}; bits sorted by degree
+    const uint16_t *vn_bit;     // [groups*32] bit handled by (group, lane); padding lanes hold n (a scratch L slot)
+    const uint32_t *vT;         // [off + k*32 + lane] row | sh << 16 of the k-th check of that bit, sh = 32 - dc(row) + position
+    const uint32_t *cls_punct;  // [words] packed: punctured positions (all zero without rate adaptation)
+    const uint32_t *cls_short;  // [words] packed: shortened positions
+    int has_cls;
+    long long n_frames;
+    const uint32_t *alice_bits, *bob_bits;
+    const double *qber;
+    int qber_is_scalar;
+    uint32_t *out_bits;
+    int32_t *out_iters;
+    uint8_t *out_flags;
+    u64 *tally;
+    u64 *next_frame;
+    int max_iter;
+    float primary, secondary, thr;   // thr = +inf when the clamp is disabled
+};
+
+// Shared-memory layout: rec[m+1] uint4 | L[n+1] float (padded to 16 B) | bob[words] | alice[words] | syn[groups_cn] | misc
+__host__ __device__ inline size_t onchip_l_slots(int n) { return ((size_t)n + 1 + 3) / 4 * 4; }
+__host__ __device__ inline size_t onchip_smem_bytes(int n, int m, int groups_cn) {
+    const size_t words = (size_t)(n + 31) / 32;
+    return ((size_t)m + 1) * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn) * 4 + 64;
+}
+
+// Record of a row: x = bits(c1), y = bits(c2) (non-negative magnitudes), z = final sign of the message on edge k in bit
+// (dc-1-k), w = 32 - dc + position of the first minimum. A reader that knows sh = 32 - dc + k gets the sign with
+// (z << sh) & 0x80000000 and the magnitude with (sh == w) ? c2 : c1.
+__device__ __forceinline__ float rec_message(const uint4 &r, uint32_t sh) {
+    const uint32_t mag = (sh == r.w) ? r.y : r.x;
+    return __uint_as_float(mag ^ ((r.z << sh) & 0x80000000u));
+}
+
+template <int ALG>
+__device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float *L, uint4 *rec, const uint32_t *synw,
+                                                float thr_b, int warp, int lane, int nwarps) {
+    bool unsat = false;
+    for (int g = warp; g < a.n_groups_cn; g += nwarps) {
+        const int2 gi = __ldg(a.cn_ginfo + g);
+        const int dc = gi.y;
+        const uint32_t row = __ldg(a.cn_row + g * 32 + lane);
+        const uint4 ro = rec[row];
+        const uint16_t *cp = a.cnT + gi.x + lane;
+        float m1 = FLT_MAX, m2 = FLT_MAX;
+        uint32_t zs = ro.z << (32 - dc);          // sign of the old message on the current edge in bit 31
+        const int arg_old = (int)ro.w - (32 - dc);
+        uint32_t own = 0, pacc = 0, zacc = 0;
+        int arg = 0;
+#pragma unroll 4
+        for (int k = 0; k < dc; ++k) {
+            const float Lv = L[__ldg(cp + k * 32)];
+            // bit-to-check message of the previous variable-node update: clamp(L - c2b) (:447-461); in the first
+            // iteration the record is zero and thr_b = +inf, which leaves the unclamped LLR (:336-350)
+            const uint32_t mag = (k == arg_old) ? ro.y : ro.x;
+            float b = Lv - __uint_as_float(mag ^ (zs & 0x80000000u));
+            zs <<= 1;
+            b = fminf(fmaxf(b, -thr_b), thr_b);
+            // For a float x that is neither NaN nor -0: (x <= 0) == sign bit of (bits(x) - 1). L and b are never -0.
+            zacc ^= __float_as_uint(Lv) - 1u;                                  // parity of the hard decision L <= 0 (:414-422)
+            pacc ^= __float_as_uint(b);                                        // parity of m < 0 (:383)
+            own = __funnelshift_l(__float_as_uint(b) - 1u, own, 1);            // (m > 0) ? +1 : -1 (:402): zero is negative (Q4)
+            const float ab = fabsf(b);
+            arg = (ab < m1) ? k : arg;                                         // first minimum
+            m2 = fminf(m2, fmaxf(ab, m1));                                     // == the if / else-if chain (:386-396)
+            m1 = fminf(m1, ab);
+        }
+        const uint32_t syn = (synw[g] >> lane) & 1u;
+        const bool viol = (((zacc >> 31) ^ syn) & 1u) != 0;    // check not satisfied by the current hard decision
+        unsat |= viol && row < (uint32_t)a.m;
+        const float factor = (ALG >= 4 && viol) ? a.secondary : a.primary;   // (:749-757, :939-947)
+        float c1, c2;
+        if constexpr (ALG == 2 || ALG == 4) {
+            c1 = factor * m1;
+            c2 = factor * m2;
+        } else {
+            const float d1 = m1 - factor, d2 = m2 - factor;    // max(min - beta, 0) (:573-574)
+            c1 = (d1 < 0.f) ? 0.f : d1;
+            c2 = (d2 < 0.f) ? 0.f : d2;
+        }
+        c1 = fminf(c1, a.thr);                                 // threshold_matrix(check_to_bit), magnitudes (:411-412)
+        c2 = fminf(c2, a.thr);
+        const uint32_t rowneg = ((pacc >> 31) ^ syn) & 1u;     // (syndrome ? -1 : 1) * (-1)^negatives (:398-399)
+        uint4 rn;
+        rn.x = __float_as_uint(c1);
+        rn.y = __float_as_uint(c2);
+        rn.z = own ^ (0u - rowneg);
+        rn.w = (uint32_t)(arg + 32 - dc);
+        rec[row] = rn;
+    }
+    return unsat;
+}
+
+__device__ __forceinline__ float onchip_llr(const OnchipArgs &a, const uint32_t *bobw, uint32_t bit, float lp) {
+    const uint32_t w = bit >> 5, s = bit & 31u;
+    float v = ((bobw[w] >> s) & 1u) ? -lp : lp;                // qkd_ldpc_algorithm.cpp:1043-1049
+    if (a.has_cls) {
+        if ((__ldg(a.cls_punct + w) >> s) & 1u) v = 1e-4f;     // punctured: ALMOST_ZERO (:1155)
+        else if ((__ldg(a.cls_short + w) >> s) & 1u) v = FLT_MAX;   // shortened: largest finite value (:1164)
+    }
+    return v;
+}
+
+__device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, float *L, const uint4 *rec, const uint32_t *bobw, float lp, int warp,
+                                                int lane, int nwarps) {
+    for (int g = warp; g < a.n_groups_vn; g += nwarps) {
+        const int2 gi = __ldg(a.vn_ginfo + g);
+        const uint32_t bit = __ldg(a.vn_bit + g * 32 + lane);
+        float acc = onchip_llr(a, bobw, bit < (uint32_t)a.n ? bit : 0u, lp);
+        const uint32_t *ep = a.vT + gi.x + lane;
+#pragma unroll 4
+        for (int k = 0; k < gi.y; ++k) {
+            const uint32_t ent = __ldg(ep + k * 32);
+            const uint4 r = rec[ent & 0xFFFFu];
+            acc = acc + rec_message(r, ent >> 16);             // ascending check order, starting from the LLR (:414-417)
+        }
+        L[bit] = acc;                                          // padding lanes write the scratch slot L[n]
+    }
+}
+
+template <int ALG>
+__global__ void __launch_bounds__(512, 2) onchip_minsum_kernel(const OnchipArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *rec = reinterpret_cast<uint4 *>(smem_raw);
+    float *L = reinterpret_cast<float *>(rec + a.m + 1);
+    uint32_t *bobw = reinterpret_cast<uint32_t *>(L + onchip_l_slots(a.n));
+    uint32_t *alw = bobw + a.words;
+    uint32_t *synw = alw + a.words;
+    uint32_t *tail = synw + a.n_groups_cn;
+    long long *s_frame = reinterpret_cast<long long *>(tail + ((2 * a.words + a.n_groups_cn) & 1));
+    float *s_lp = reinterpret_cast<float *>(s_frame + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    constexpr bool kAdaptive = (ALG >= 4);
+    const float inf = __int_as_float(0x7f800000);
+
+    for (;;) {
+        __syncthreads();   // previous frame fully written out before the state is reused
+        if (tid == 0) {
+            const long long f = (long long)atomicAdd(a.next_frame, 1ull);
+            *s_frame = f;
+            if (f < a.n_frames) {
+                const double q = a.qber_is_scalar ? a.qber[0] : a.qber[f];
+                *s_lp = (float)log((1. - q) / q);
+            }
+        }
+        __syncthreads();
+        const long long f = *s_frame;
+        if (f >= a.n_frames) break;
+        const float lp = *s_lp;
+        for (int w = tid; w < a.words; w += blockDim.x) {
+            bobw[w] = a.bob_bits[f * a.words + w];
+            alw[w] = a.alice_bits[f * a.words + w];
+        }
+        __syncthreads();
+        // L = a-priori LLR; Alice's syndrome (calculate_syndrome, array_and_matrix_operations.cpp:936-950); records = 0
+        for (int i = tid; i <= a.n; i += blockDim.x) L[i] = (i < a.n) ? onchip_llr(a, bobw, (uint32_t)i, lp) : 1.f;
+        for (int g = warp; g < a.n_groups_cn; g += nwarps) {
+            const int2 gi = __ldg(a.cn_ginfo + g);
+            const uint32_t row = __ldg(a.cn_row + g * 32 + lane);
+            const uint16_t *cp = a.cnT + gi.x + lane;
+            uint32_t s = 0;
+            for (int k = 0; k < gi.y; ++k) {
+                const uint32_t col = __ldg(cp + k * 32);
+                s ^= alw[col >> 5] >> (col & 31u);
+            }
+            const uint32_t sw = __ballot_sync(0xffffffffu, (s & 1u) != 0 && row < (uint32_t)a.m);
+            if (lane == 0) synw[g] = sw;
+            rec[row] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+
+        int iters = a.max_iter, run = a.max_iter;
+        bool success = false;
+        for (int it = 1;; ++it) {
+            // the check-node pass of iteration `it`; at it = max_iter + 1 it only serves as the syndrome test of the
+            // last hard decision (non-adaptive variants, :424-445)
+            const bool unsat = onchip_cn_phase<ALG>(a, L, rec, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
+            const bool any_unsat = __syncthreads_or(unsat) != 0;
+            if (!kAdaptive) {
+                if (it > 1 && !any_unsat) { success = true; iters = run = it - 1; break; }   // z of iteration it-1 (:439-445)
+                if (it > a.max_iter) break;
+            } else {
+                if (!any_unsat) { success = true; iters = it; run = it - 1; break; }         // exit test before the VN step (:770-776)
+            }
+            onchip_vn_phase(a, L, rec, bobw, lp, warp, lane, nwarps);
+            __syncthreads();
+            if (kAdaptive && it == a.max_iter) break;          // the decision of the last iteration is never tested (Q10)
+        }
+
+        // bob_solution = last hard decision (L <= 0), packed; keys compare (arrays_equal, :1087)
+        uint32_t diff = 0;
+        for (int w = warp; w < a.words; w += nwarps) {
+            const int i = w * 32 + lane;
+            const uint32_t word = __ballot_sync(0xffffffffu, i < a.n && L[i < a.n ? i : 0] <= 0.f);
+            if (lane == 0) {
+                if (a.out_bits) a.out_bits[f * a.words + w] = word;
+                diff |= word ^ alw[w];
+            }
+        }
+        const bool keys_differ = __syncthreads_or(diff != 0) != 0;
+        if (tid == 0) {
+            if (a.out_iters) a.out_iters[f] = iters;
+            if (a.out_flags) a.out_flags[f] = (uint8_t)((success ? 1u : 0u) | (keys_differ ? 0u : 2u));
+            if (a.tally) {
+                atomicAdd(a.tally + 0, 1ull);
+                if (success) {
+                    atomicAdd(a.tally + 1, 1ull);
+                    if (!keys_differ) atomicAdd(a.tally + 2, 1ull);
+                    atomicAdd(a.tally + 4 + iters, 1ull);
+                }
+                atomicAdd(a.tally + 3, (u64)run);
+            }
+        }
+    }
+}
+
+}  // namespace qk

@@ -1,0 +1,157 @@
+"""GPU: the on-chip min-sum path (frame state in shared memory, onchip_minsum.cuh) against the f32 oracle and the
+streaming float32 kernels: all three perform the same float operations in the same order, so per-frame iteration
+counts, flags, decoded words and tallies must be IDENTICAL -- including the edge cases of the iteration accounting
+(quirks Q9/Q10), tiny iteration limits, clamp off, rate adaptation, and ragged batches."""
+import numpy as np
+import pytest
+
+import util
+from oracle import cpu
+
+pytestmark = pytest.mark.gpu
+
+FACT = {2: (0.75, 0.0), 3: (0.3, 0.0), 4: (0.8, 0.6), 5: (0.3, 0.9)}
+
+
+@pytest.fixture(scope="module")
+def q(built):
+    import qkd_ldpc_v_b200 as q
+    return q
+
+
+_handles = {}
+
+
+def handle(q, name, **kw):
+    key = (name, tuple(sorted(kw.items())))
+    if key not in _handles:
+        a = util.code_arrays(name)
+        _handles[key] = q.LdpcCode(a["n"], a["m"], a["row_ptr"], a["col_idx"], device=0, **kw)
+    return _handles[key]
+
+
+def keys(name, seed, frames, qber):
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays(name)
+    return hostlib.gen_keys(hostlib.trial_seeds(seed, frames), arr["n"], qber)
+
+
+def same(r1, r2):
+    assert (r1.iterations_num == r2.iterations_num).all()
+    assert (r1.flags == r2.flags).all()
+    assert (r1.bob_solution == r2.bob_solution).all()
+    assert (r1.tally == r2.tally).all()
+
+
+@pytest.mark.parametrize("alg", [2, 3, 4, 5])
+@pytest.mark.parametrize("name,qber,frames", [("K1_5", 0.02, 700), ("K1_4", 0.035, 500), ("K1_3", 0.06, 300), ("A79", 0.021, 400),
+                                              ("I80", 0.017, 300), ("I65", 0.03, 200), ("N100", 0.03, 257), ("N6", 0.2, 33)])
+def test_onchip_equals_streaming_and_oracle(q, alg, name, qber, frames):
+    arr = util.code_arrays(name)
+    a, b, acc = keys(name, 99 + alg, frames, qber)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32)
+    ro = handle(q, name, decoder_path=2).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    rs = handle(q, name, decoder_path=1).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    assert ro.info["last_path"] == 2 and rs.info["last_path"] == 1
+    same(ro, rs)
+    if arr["n"] <= 1024 or alg == 2:   # the oracle is a scalar CPU loop: keep the big codes to one algorithm
+        ab, bb = q.unpack_bits(a, arr["n"]), q.unpack_bits(b, arr["n"])
+        it, fl, bits = cpu.qkd_ldpc_batch(util.oracle_code(name), alg, ab, bb, acc, primary=FACT[alg][0], secondary=FACT[alg][1],
+                                          precision=32)
+        assert (ro.iterations_num == it).all() and (ro.flags == fl).all() and (ro.bits() == bits).all()
+    if name not in ("N6", "I65"):
+        assert ro.syndromes_match.any(), "operating point should converge at least sometimes"
+
+
+@pytest.mark.parametrize("alg", [2, 3, 4, 5])
+@pytest.mark.parametrize("max_iter", [1, 2, 3, 7])
+def test_iteration_limits(q, alg, max_iter):
+    """Q9/Q10: a frame that needs exactly max_iter iterations; the adaptive variants never test the last decision."""
+    a, b, acc = keys("K1_5", 5, 600, 0.022)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32, max_iterations=max_iter)
+    ro = handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    rs = handle(q, "K1_5", decoder_path=1).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    same(ro, rs)
+    arr = util.code_arrays("K1_5")
+    it, fl, bits = cpu.qkd_ldpc_batch(util.oracle_code("K1_5"), alg, q.unpack_bits(a, arr["n"]), q.unpack_bits(b, arr["n"]), acc,
+                                      max_iter=max_iter, primary=FACT[alg][0], secondary=FACT[alg][1], precision=32)
+    assert (ro.iterations_num == it).all() and (ro.flags == fl).all() and (ro.bits() == bits).all()
+    assert ro.iterations_num.max() <= max_iter
+
+
+@pytest.mark.parametrize("alg,fac", [(2, (0.9, 0.0)), (4, (1.0, 0.5)), (3, (0.2, 0.0))])
+def test_clamp_disabled(q, alg, fac):
+    a, b, acc = keys("K1_4", 17, 300, 0.03)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32, enable_msg_llr_threshold=False)
+    ro = handle(q, "K1_4", decoder_path=2).QKD_LDPC_batch(a, b, acc, fac, cfg)
+    rs = handle(q, "K1_4", decoder_path=1).QKD_LDPC_batch(a, b, acc, fac, cfg)
+    same(ro, rs)
+    arr = util.code_arrays("K1_4")
+    it, fl, bits = cpu.qkd_ldpc_batch(util.oracle_code("K1_4"), alg, q.unpack_bits(a, arr["n"]), q.unpack_bits(b, arr["n"]), acc,
+                                      primary=fac[0], secondary=fac[1], precision=32, enable_thr=False)
+    assert (ro.iterations_num == it).all() and (ro.flags == fl).all() and (ro.bits() == bits).all()
+
+
+def test_small_threshold_and_per_frame_qber(q):
+    """A clamp that actually bites (threshold 3) and one QBER per frame."""
+    a, b, acc = keys("K1_5", 23, 400, 0.02)
+    qb = np.full(400, acc)
+    qb[::3] *= 1.5
+    cfg = q.DecoderConfig(decoding_algorithm=2, message_precision=32, msg_llr_threshold=3.0)
+    ro = handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(a, b, qb, (0.8, 0), cfg)
+    rs = handle(q, "K1_5", decoder_path=1).QKD_LDPC_batch(a, b, qb, (0.8, 0), cfg)
+    same(ro, rs)
+
+
+@pytest.mark.parametrize("alg", [2, 5])
+def test_rate_adaptation_paths_agree(q, tmp_path, alg):
+    from qkd_ldpc_v_b200 import hostlib
+    path = str(tmp_path / "I80.mtrx")
+    util.write_sparse2(path, "I80")
+    arr = util.code_arrays("I80")
+    hm = hostlib.HostMatrix(path, 3)
+    p, s, _, _ = hm.adapt_code_rate(5555, 0.0196, 0.05, 1.3, untainted=True, untp=arr["untp"])
+    assert p.size and s.size
+    seeds = hostlib.trial_seeds(31337, 200)
+    a, b, acc = hostlib.gen_keys_rate_adapt(seeds, arr["n"], 0.0196, p, s)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32)
+    ro = handle(q, "I80", decoder_path=2).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg, punctured_bits=p, shortened_bits=s)
+    rs = handle(q, "I80", decoder_path=1).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg, punctured_bits=p, shortened_bits=s)
+    same(ro, rs)
+    assert ro.syndromes_match.mean() > 0.5
+    # and a second batch WITHOUT positions on the same handle must not see stale masks
+    a2, b2, acc2 = hostlib.gen_keys(seeds[:64], arr["n"], 0.015)
+    same(handle(q, "I80", decoder_path=2).QKD_LDPC_batch(a2, b2, acc2, FACT[alg], cfg),
+         handle(q, "I80", decoder_path=1).QKD_LDPC_batch(a2, b2, acc2, FACT[alg], cfg))
+
+
+def test_ineligible_requests(q):
+    """Wide rows (dc > 32), SPA, float64 and n = 100k codes cannot run on chip: explicit request fails, auto streams."""
+    from qkd_ldpc_v_b200._cabi import QkdLdpcError
+    a, b, acc = keys("K1_hi", 3, 40, 0.004)
+    cfg = q.DecoderConfig(decoding_algorithm=2, message_precision=32)
+    with pytest.raises(QkdLdpcError):
+        handle(q, "K1_hi", decoder_path=2).QKD_LDPC_batch(a, b, acc, (0.8, 0), cfg)
+    r = handle(q, "K1_hi").QKD_LDPC_batch(a, b, acc, (0.8, 0), cfg)
+    assert r.info["last_path"] == 1
+    a, b, acc = keys("K1_5", 3, 40, 0.02)
+    for c in (q.DecoderConfig(decoding_algorithm=0, message_precision=32), q.DecoderConfig(decoding_algorithm=2, message_precision=64)):
+        with pytest.raises(QkdLdpcError):
+            handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(a, b, acc, (0.8, 0), c)
+        assert handle(q, "K1_5").QKD_LDPC_batch(a, b, acc, (0.8, 0), c).info["last_path"] == 1
+
+
+@pytest.mark.parametrize("threads", [32, 64, 256, 512])
+def test_cta_sizes_agree(q, threads):
+    a, b, acc = keys("K1_5", 8, 300, 0.02)
+    cfg = q.DecoderConfig(decoding_algorithm=4, message_precision=32)
+    same(handle(q, "K1_5", decoder_path=2, onchip_threads=threads).QKD_LDPC_batch(a, b, acc, FACT[4], cfg),
+         handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(a, b, acc, FACT[4], cfg))
+
+
+def test_out_bits_optional_and_single_frame(q):
+    a, b, acc = keys("A79", 77, 1, 0.02)
+    cfg = q.DecoderConfig(decoding_algorithm=2, message_precision=32)
+    r1 = handle(q, "A79", decoder_path=2).QKD_LDPC_batch(a, b, acc, (0.71, 0), cfg, want_bits=False)
+    r2 = handle(q, "A79", decoder_path=1).QKD_LDPC_batch(a, b, acc, (0.71, 0), cfg)
+    assert r1.iterations_num[0] == r2.iterations_num[0] and r1.flags[0] == r2.flags[0] == 3

@@ -67,16 +67,26 @@ def test_fp64_messages_against_reference_golden(q, case):
     assert (t[4:] == hist).all()
 
 
+def onchip_eligible(name, alg):
+    """float32 min-sum family, every check degree <= 32, n < 65535 (onchip_minsum.cuh)."""
+    arr = util.code_arrays(name)
+    return alg >= 2 and int(np.diff(arr["row_ptr"]).max()) <= 32 and arr["n"] < 65535
+
+
+@pytest.mark.parametrize("path", [1, 2], ids=["streaming", "onchip"])
 @pytest.mark.parametrize("case", util.decode_cases())
-def test_fp32_messages(q, case):
+def test_fp32_messages(q, case, path):
     g = util.load_case(case)
     name, alg = str(g["code"]), int(g["alg"])
+    if path == 2 and not onchip_eligible(name, alg):
+        pytest.skip("code / algorithm not eligible for the on-chip path")
     arr = util.code_arrays(name)
     oc = util.oracle_code(name)
     a, b, acc = inputs(q, g, arr["n"])
     pri, sec, mi = float(g["primary"]), float(g["secondary"]), int(g["max_iter"])
     cfg = q.DecoderConfig(decoding_algorithm=alg, max_iterations=mi, message_precision=32)
-    r = handle(q, name).QKD_LDPC_batch(a, b, acc, (pri, sec), cfg)
+    r = handle(q, name, decoder_path=path).QKD_LDPC_batch(a, b, acc, (pri, sec), cfg)
+    assert r.info["last_path"] == path
     ab, bb = q.unpack_bits(a, arr["n"]), q.unpack_bits(b, arr["n"])
     it32, fl32, bits32 = cpu.qkd_ldpc_batch(oc, alg, ab, bb, acc, max_iter=mi, primary=pri, secondary=sec,
                                             precision=32)
@@ -102,8 +112,8 @@ def test_tile_widths_agree(q, fpl):
     arr = util.code_arrays("K1_5")
     a, b, acc = inputs(q, g, arr["n"])
     cfg = q.DecoderConfig(decoding_algorithm=2, message_precision=32)
-    r0 = handle(q, "K1_5").QKD_LDPC_batch(a, b, acc, (0.75, 0.0), cfg)
-    r1 = handle(q, "K1_5", frames_per_lane_f32=fpl).QKD_LDPC_batch(a, b, acc, (0.75, 0.0), cfg)
+    r0 = handle(q, "K1_5", decoder_path=1).QKD_LDPC_batch(a, b, acc, (0.75, 0.0), cfg)
+    r1 = handle(q, "K1_5", frames_per_lane_f32=fpl, decoder_path=1).QKD_LDPC_batch(a, b, acc, (0.75, 0.0), cfg)
     assert (r0.iterations_num == r1.iterations_num).all() and (r0.bob_solution == r1.bob_solution).all()
 
 
