@@ -98,57 +98,117 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     group(m, rp, qk::cn_bucket_of, row_order, cn_first, cn_count);
     group(n, col_ptr, qk::vn_bucket_of, col_order, vn_first, vn_count);
 
-    // On-chip path layout (onchip_minsum.cuh): rows and bits sorted by degree (widest first), cut into groups of 32 that
-    // never mix degrees (the last group of a degree class is padded with a scratch node), ELL index arrays per group.
+    // On-chip path layout (onchip_minsum.cuh): rows and bits are split into degree classes; inside a class the nodes are
+    // packed into groups of 32 lanes by a greedy conflict-aware heuristic (below); index tables are stored per group in
+    // blocks of 4 edges per lane.
     int max_dc = 0;
     for (int j = 0; j < m; ++j) max_dc = std::max(max_dc, row_ptr[j + 1] - row_ptr[j]);
     const bool oc_ok = n < 65535 && m < 65535 && max_dc <= 32;
     std::vector<int2> oc_cn_ginfo, oc_vn_ginfo;
-    std::vector<uint16_t> oc_cnT, oc_cn_row, oc_vn_bit;
-    std::vector<uint32_t> oc_vT;
+    std::vector<uint16_t> oc_cn_row, oc_vn_bit;
+    std::vector<uint2> oc_cnT;
+    std::vector<uint4> oc_vT;
     if (oc_ok) {
-        auto sorted_by_degree = [](int count, const std::vector<int> &ptr) {
+        // Shared-memory bank model: a warp-wide 4-byte gather (L[bit], check phase) is conflict-free when the 32 lanes hit
+        // 32 different banks, i.e. bit index mod 32 all different; a 16-byte gather (row record, variable phase) is
+        // served per quarter-warp, conflict-free when its 8 lanes hit 8 different 16-byte bank groups, i.e. row index
+        // mod 8 all different. `pack` builds sets of `width` nodes of one degree so that, step by step (k-th neighbour of
+        // every member), as few members as possible share a bank: greedy -- start from the first free node, add the
+        // node whose neighbours collide least with the banks already used at each step. Measured effect on n=10240
+        // codes: 9.9 -> 6.9 wavefronts per 32 record gathers (irregular R=0.8), 9.8 -> 4.5 (alist R=0.79).
+        auto pack = [](const std::vector<int> &members, const std::vector<int> &ptr, const int *nbr, int ncol, int width,
+                       std::vector<std::vector<int>> &out) {
+            const int d = ptr[members[0] + 1] - ptr[members[0]];
+            std::vector<unsigned char> col((size_t)members.size() * d);
+            for (size_t i = 0; i < members.size(); ++i)
+                for (int k = 0; k < d; ++k) col[i * d + k] = (unsigned char)(nbr[ptr[members[i]] + k] % ncol);
+            std::vector<char> used(members.size(), 0);
+            std::vector<int> cnt((size_t)d * ncol);
+            size_t next_free = 0, left = members.size();
+            while (left > 0) {
+                while (used[next_free]) ++next_free;
+                std::vector<int> cur{members[next_free]};
+                used[next_free] = 1;
+                --left;
+                std::fill(cnt.begin(), cnt.end(), 0);
+                for (int k = 0; k < d; ++k) cnt[(size_t)k * ncol + col[next_free * d + k]]++;
+                while ((int)cur.size() < width && left > 0) {
+                    size_t best = members.size();
+                    int best_cost = 1 << 30;
+                    for (size_t i = next_free + 1; i < members.size(); ++i) {
+                        if (used[i]) continue;
+                        int cost = 0;
+                        for (int k = 0; k < d; ++k) cost += cnt[(size_t)k * ncol + col[i * d + k]];
+                        if (cost < best_cost) {
+                            best_cost = cost;
+                            best = i;
+                            if (cost == 0) break;
+                        }
+                    }
+                    used[best] = 1;
+                    --left;
+                    cur.push_back(members[best]);
+                    for (int k = 0; k < d; ++k) cnt[(size_t)k * ncol + col[best * d + k]]++;
+                }
+                out.push_back(std::move(cur));
+            }
+        };
+        auto degree_classes = [](int count, const std::vector<int> &ptr) {   // widest first
+            std::vector<std::vector<int>> cls;
             std::vector<int> order(count);
             for (int i = 0; i < count; ++i) order[i] = i;
             std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ptr[x + 1] - ptr[x] > ptr[y + 1] - ptr[y]; });
-            return order;
-        };
-        // groups: [begin, end) ranges of `order` with one degree and at most 32 members
-        auto cut = [](const std::vector<int> &order, const std::vector<int> &ptr, std::vector<std::pair<int, int>> &groups) {
-            size_t i = 0;
-            while (i < order.size()) {
-                const int d = ptr[order[i] + 1] - ptr[order[i]];
-                size_t j = i;
-                while (j < order.size() && j - i < 32 && ptr[order[j] + 1] - ptr[order[j]] == d) ++j;
-                groups.emplace_back((int)i, (int)j);
-                i = j;
+            for (int i = 0; i < count; ++i) {
+                if (i == 0 || ptr[order[i] + 1] - ptr[order[i]] != ptr[order[i - 1] + 1] - ptr[order[i - 1]]) cls.emplace_back();
+                cls.back().push_back(order[i]);
             }
+            return cls;
         };
-        const std::vector<int> rows = sorted_by_degree(m, rp), bits = sorted_by_degree(n, col_ptr);
-        std::vector<std::pair<int, int>> rg, bg;
-        cut(rows, rp, rg);
-        cut(bits, col_ptr, bg);
-        for (auto [b0, b1] : rg) {
-            const int dc = rp[rows[b0] + 1] - rp[rows[b0]];
-            oc_cn_ginfo.push_back(make_int2((int)oc_cnT.size(), dc));
-            for (int l = 0; l < 32; ++l) oc_cn_row.push_back(b0 + l < b1 ? (uint16_t)rows[b0 + l] : (uint16_t)m);
-            for (int k = 0; k < dc; ++k)
-                for (int l = 0; l < 32; ++l) oc_cnT.push_back(b0 + l < b1 ? (uint16_t)col_idx[rp[rows[b0 + l]] + k] : (uint16_t)0);
-        }
-        for (auto [b0, b1] : bg) {
-            const int dv = col_ptr[bits[b0] + 1] - col_ptr[bits[b0]];
-            oc_vn_ginfo.push_back(make_int2((int)oc_vT.size(), dv));
-            for (int l = 0; l < 32; ++l) oc_vn_bit.push_back(b0 + l < b1 ? (uint16_t)bits[b0 + l] : (uint16_t)n);
-            for (int k = 0; k < dv; ++k)
-                for (int l = 0; l < 32; ++l) {
-                    uint32_t ent = (uint32_t)m;   // padding lanes read the scratch record
-                    if (b0 + l < b1) {
-                        const int p = col_ptr[bits[b0 + l]] + k, r = csc_row[p];
-                        const int pos = csc_edge[p] - rp[r], dcr = rp[r + 1] - rp[r];
-                        ent = (uint32_t)r | ((uint32_t)(32 - dcr + pos) << 16);
+        // check phase: groups of 32 rows
+        for (const auto &cls : degree_classes(m, rp)) {
+            std::vector<std::vector<int>> groups;
+            pack(cls, rp, col_idx, 32, 32, groups);
+            const int dc = rp[cls[0] + 1] - rp[cls[0]], blocks = (dc + 3) / 4;
+            for (const auto &gr : groups) {
+                oc_cn_ginfo.push_back(make_int2((int)oc_cnT.size(), dc));
+                for (int l = 0; l < 32; ++l) oc_cn_row.push_back(l < (int)gr.size() ? (uint16_t)gr[l] : (uint16_t)m);
+                for (int kb = 0; kb < blocks; ++kb)
+                    for (int l = 0; l < 32; ++l) {
+                        uint32_t c[4] = {0, 0, 0, 0};
+                        if (l < (int)gr.size())
+                            for (int j = 0; j < 4 && kb * 4 + j < dc; ++j) c[j] = (uint32_t)col_idx[rp[gr[l]] + kb * 4 + j];
+                        oc_cnT.push_back(make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16)));
                     }
-                    oc_vT.push_back(ent);
+            }
+        }
+        // variable phase: octets (one quarter-warp each), four octets per group
+        for (const auto &cls : degree_classes(n, col_ptr)) {
+            std::vector<std::vector<int>> octets;
+            pack(cls, col_ptr, csc_row.data(), 8, 8, octets);
+            const int dv = col_ptr[cls[0] + 1] - col_ptr[cls[0]], blocks = (dv + 3) / 4;
+            for (size_t o = 0; o < octets.size(); o += 4) {
+                int lane_bit[32];
+                for (int l = 0; l < 32; ++l) {
+                    const size_t oi = o + (size_t)l / 8;
+                    lane_bit[l] = (oi < octets.size() && (size_t)(l % 8) < octets[oi].size()) ? octets[oi][l % 8] : -1;
                 }
+                oc_vn_ginfo.push_back(make_int2((int)oc_vT.size(), dv));
+                for (int l = 0; l < 32; ++l) oc_vn_bit.push_back(lane_bit[l] >= 0 ? (uint16_t)lane_bit[l] : (uint16_t)n);
+                for (int kb = 0; kb < blocks; ++kb)
+                    for (int l = 0; l < 32; ++l) {
+                        uint32_t e[4];
+                        for (int j = 0; j < 4; ++j) {
+                            e[j] = (uint32_t)m << 9;   // padding: the scratch record
+                            const int k = kb * 4 + j;
+                            if (lane_bit[l] >= 0 && k < dv) {
+                                const int p = col_ptr[lane_bit[l]] + k, r = csc_row[p];
+                                const int pos = csc_edge[p] - rp[r], dcr = rp[r + 1] - rp[r];
+                                e[j] = ((uint32_t)r << 9) | (uint32_t)(32 - dcr + pos);
+                            }
+                        }
+                        oc_vT.push_back(make_uint4(e[0], e[1], e[2], e[3]));
+                    }
+            }
         }
     }
 

@@ -79,8 +79,10 @@ struct qkdldpc_code {
     int oc_groups_cn = 0, oc_groups_vn = 0, oc_max_dc = 0;
     size_t oc_smem = 0;
     DevBuf<int2> oc_cn_ginfo, oc_vn_ginfo;
-    DevBuf<uint16_t> oc_cnT, oc_cn_row, oc_vn_bit;
-    DevBuf<uint32_t> oc_vT, oc_cls;   // oc_cls: [2][words] punctured / shortened bit masks of the current batch
+    DevBuf<uint16_t> oc_cn_row, oc_vn_bit;
+    DevBuf<uint2> oc_cnT;
+    DevBuf<uint4> oc_vT;
+    DevBuf<uint32_t> oc_cls;   // oc_cls: [2][words] punctured / shortened bit masks of the current batch
     int last_path = 0;                // 1 streaming, 2 on-chip (of the last batch)
     // pool (device, raw bytes reinterpreted per precision)
     DevBuf<unsigned char> msg;

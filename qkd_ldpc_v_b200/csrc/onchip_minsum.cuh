@@ -35,13 +35,16 @@ typedef unsigned long long u64;
 struct OnchipArgs {
     int n, m, words;
     int n_groups_cn, n_groups_vn;
-    const int2 *cn_ginfo;       // [groups] {offset into cnT, degree of the group's rows}; rows sorted by degree, a group
-                                //          never mixes degrees (last group of a degree class is padded)
+    // Index tables: one entry per (group, block of 4 edges, lane), so a lane fetches the indices of 4 edges with ONE
+    // 8- or 16-byte load. A group holds 32 rows (bits) of ONE degree; which nodes share a group is chosen on the host
+    // so that the lanes' shared-memory gathers fall into different banks (conflict-aware grouping, api.cu).
+    const int2 *cn_ginfo;       // [groups] {offset into cnT (in uint2), degree of the group's rows}
     const uint16_t *cn_row;     // [groups*32] row handled by (group, lane); padding lanes hold m (a scratch record slot)
-    const uint16_t *cnT;        // [off + k*32 + lane] bit index of the k-th edge of that row (padding lanes: 0)
-    const int2 *vn_ginfo;       // [groups] {offset into vT, degree of the group's bits}; bits sorted by degree
+    const uint2 *cnT;           // [off + kb*32 + lane] 4 x uint16: bit index of edges 4kb..4kb+3 of that row (padding: 0)
+    const int2 *vn_ginfo;       // [groups] {offset into vT (in uint4), degree of the group's bits}
     const uint16_t *vn_bit;     // [groups*32] bit handled by (group, lane); padding lanes hold n (a scratch L slot)
-    const uint32_t *vT;         // [off + k*32 + lane] row | sh << 16 of the k-th check of that bit, sh = 32 - dc(row) + position
+    const uint4 *vT;            // [off + kb*32 + lane] 4 x uint32: row << 9 | sh of checks 4kb..4kb+3 of that bit,
+                                //                      sh = 32 - dc(row) + position in the row (padding: scratch row m)
     const uint32_t *cls_punct;  // [words] packed: punctured positions (all zero without rate adaptation)
     const uint32_t *cls_short;  // [words] packed: shortened positions
     int has_cls;
@@ -68,10 +71,25 @@ __host__ __device__ inline size_t onchip_smem_bytes(int n, int m, int groups_cn)
 // Record of a row: x = bits(c1), y = bits(c2) (non-negative magnitudes), z = final sign of the message on edge k in bit
 // (dc-1-k), w = 32 - dc + position of the first minimum. A reader that knows sh = 32 - dc + k gets the sign with
 // (z << sh) & 0x80000000 and the magnitude with (sh == w) ? c2 : c1.
-__device__ __forceinline__ float rec_message(const uint4 &r, uint32_t sh) {
-    const uint32_t mag = (sh == r.w) ? r.y : r.x;
-    return __uint_as_float(mag ^ ((r.z << sh) & 0x80000000u));
-}
+
+// One edge of a check node: gather L of the bit, rebuild the bit-to-check message with the OLD record, update the
+// running min1 / min2 / argmin / sign state.  `rel` = old argmin - index of the first edge of the current block.
+#define QK_CN_EDGE(J, COL)                                                                                              \
+    {                                                                                                                   \
+        const float Lv = L[(COL)];                                                                                      \
+        const uint32_t mag = (rel == (J)) ? ro.y : ro.x;                                                                \
+        /* clamp(L - c2b) (:447-461); first iteration: zero record and thr_b = +inf leave the unclamped LLR (:336-350) */ \
+        const float braw = Lv - __uint_as_float(mag ^ (zs & 0x80000000u));                                              \
+        zs <<= 1;                                                                                                       \
+        /* for x neither NaN nor -0: (x <= 0) == sign bit of (bits(x) - 1); L and b are never -0 */                     \
+        zacc ^= __float_as_uint(Lv) - 1u;                 /* parity of the hard decision L <= 0 (:414-422) */            \
+        pacc ^= __float_as_uint(braw);                    /* parity of m < 0 (:383); the clamp keeps the sign */         \
+        own = __funnelshift_l(__float_as_uint(braw) - 1u, own, 1);   /* (m > 0) ? +1 : -1 (:402): zero is negative (Q4) */ \
+        const float ab = fminf(fabsf(braw), thr_b);       /* |clamp(x)| == min(|x|, thr) */                              \
+        arg = (ab < m1) ? (kb + (J)) : arg;               /* first minimum */                                            \
+        m2 = fminf(m2, fmaxf(ab, m1));                    /* == the if / else-if chain (:386-396) */                     \
+        m1 = fminf(m1, ab);                                                                                             \
+    }
 
 template <int ALG>
 __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float *L, uint4 *rec, const uint32_t *synw,
@@ -82,29 +100,27 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float
         const int dc = gi.y;
         const uint32_t row = __ldg(a.cn_row + g * 32 + lane);
         const uint4 ro = rec[row];
-        const uint16_t *cp = a.cnT + gi.x + lane;
+        const uint2 *cp = a.cnT + gi.x + lane;
         float m1 = FLT_MAX, m2 = FLT_MAX;
         uint32_t zs = ro.z << (32 - dc);          // sign of the old message on the current edge in bit 31
         const int arg_old = (int)ro.w - (32 - dc);
         uint32_t own = 0, pacc = 0, zacc = 0;
-        int arg = 0;
-#pragma unroll 4
-        for (int k = 0; k < dc; ++k) {
-            const float Lv = L[__ldg(cp + k * 32)];
-            // bit-to-check message of the previous variable-node update: clamp(L - c2b) (:447-461); in the first
-            // iteration the record is zero and thr_b = +inf, which leaves the unclamped LLR (:336-350)
-            const uint32_t mag = (k == arg_old) ? ro.y : ro.x;
-            float b = Lv - __uint_as_float(mag ^ (zs & 0x80000000u));
-            zs <<= 1;
-            b = fminf(fmaxf(b, -thr_b), thr_b);
-            // For a float x that is neither NaN nor -0: (x <= 0) == sign bit of (bits(x) - 1). L and b are never -0.
-            zacc ^= __float_as_uint(Lv) - 1u;                                  // parity of the hard decision L <= 0 (:414-422)
-            pacc ^= __float_as_uint(b);                                        // parity of m < 0 (:383)
-            own = __funnelshift_l(__float_as_uint(b) - 1u, own, 1);            // (m > 0) ? +1 : -1 (:402): zero is negative (Q4)
-            const float ab = fabsf(b);
-            arg = (ab < m1) ? k : arg;                                         // first minimum
-            m2 = fminf(m2, fmaxf(ab, m1));                                     // == the if / else-if chain (:386-396)
-            m1 = fminf(m1, ab);
+        int arg = 0, kb = 0;
+#pragma unroll 2
+        for (; kb + 4 <= dc; kb += 4) {
+            const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+            const int rel = arg_old - kb;
+            QK_CN_EDGE(0, cw.x & 0xFFFFu)
+            QK_CN_EDGE(1, cw.x >> 16)
+            QK_CN_EDGE(2, cw.y & 0xFFFFu)
+            QK_CN_EDGE(3, cw.y >> 16)
+        }
+        if (kb < dc) {                            // warp-uniform tail of 1..3 edges
+            const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+            const int rel = arg_old - kb, left = dc - kb;
+            QK_CN_EDGE(0, cw.x & 0xFFFFu)
+            if (left > 1) QK_CN_EDGE(1, cw.x >> 16)
+            if (left > 2) QK_CN_EDGE(2, cw.y & 0xFFFFu)
         }
         const uint32_t syn = (synw[g] >> lane) & 1u;
         const bool viol = (((zacc >> 31) ^ syn) & 1u) != 0;    // check not satisfied by the current hard decision
@@ -131,6 +147,7 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float
     }
     return unsat;
 }
+#undef QK_CN_EDGE
 
 __device__ __forceinline__ float onchip_llr(const OnchipArgs &a, const uint32_t *bobw, uint32_t bit, float lp) {
     const uint32_t w = bit >> 5, s = bit & 31u;
@@ -142,25 +159,47 @@ __device__ __forceinline__ float onchip_llr(const OnchipArgs &a, const uint32_t 
     return v;
 }
 
+// The check-to-bit message addressed by table entry `ent` = row << 9 | sh, added to the running sum.
+#define QK_VN_EDGE(ENT)                                                                                                 \
+    {                                                                                                                   \
+        const uint4 r = *reinterpret_cast<const uint4 *>(recb + ((ENT) >> 5));                                          \
+        const uint32_t mag = (((ENT) ^ r.w) & 31u) ? r.x : r.y;                                                         \
+        acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.z, (ENT)) & 0x80000000u));   /* r.z << sh */           \
+    }
+
 __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, float *L, const uint4 *rec, const uint32_t *bobw, float lp, int warp,
                                                 int lane, int nwarps) {
+    const unsigned char *recb = reinterpret_cast<const unsigned char *>(rec);
     for (int g = warp; g < a.n_groups_vn; g += nwarps) {
         const int2 gi = __ldg(a.vn_ginfo + g);
+        const int dv = gi.y;
         const uint32_t bit = __ldg(a.vn_bit + g * 32 + lane);
         float acc = onchip_llr(a, bobw, bit < (uint32_t)a.n ? bit : 0u, lp);
-        const uint32_t *ep = a.vT + gi.x + lane;
-#pragma unroll 4
-        for (int k = 0; k < gi.y; ++k) {
-            const uint32_t ent = __ldg(ep + k * 32);
-            const uint4 r = rec[ent & 0xFFFFu];
-            acc = acc + rec_message(r, ent >> 16);             // ascending check order, starting from the LLR (:414-417)
+        const uint4 *ep = a.vT + gi.x + lane;
+        int kb = 0;
+        // ascending check order, starting from the LLR (std::accumulate, :414-417)
+#pragma unroll 2
+        for (; kb + 4 <= dv; kb += 4) {
+            const uint4 ew = __ldg(ep + (kb >> 2) * 32);
+            QK_VN_EDGE(ew.x)
+            QK_VN_EDGE(ew.y)
+            QK_VN_EDGE(ew.z)
+            QK_VN_EDGE(ew.w)
         }
-        L[bit] = acc;                                          // padding lanes write the scratch slot L[n]
+        if (kb < dv) {                            // warp-uniform tail of 1..3 checks
+            const uint4 ew = __ldg(ep + (kb >> 2) * 32);
+            const int left = dv - kb;
+            QK_VN_EDGE(ew.x)
+            if (left > 1) QK_VN_EDGE(ew.y)
+            if (left > 2) QK_VN_EDGE(ew.z)
+        }
+        L[bit] = acc;                             // padding lanes write the scratch slot L[n]
     }
 }
+#undef QK_VN_EDGE
 
 template <int ALG>
-__global__ void __launch_bounds__(512, 2) onchip_minsum_kernel(const OnchipArgs a) {
+__global__ void __launch_bounds__(512, 3) onchip_minsum_kernel(const OnchipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *rec = reinterpret_cast<uint4 *>(smem_raw);
     float *L = reinterpret_cast<float *>(rec + a.m + 1);
@@ -199,11 +238,16 @@ __global__ void __launch_bounds__(512, 2) onchip_minsum_kernel(const OnchipArgs 
         for (int g = warp; g < a.n_groups_cn; g += nwarps) {
             const int2 gi = __ldg(a.cn_ginfo + g);
             const uint32_t row = __ldg(a.cn_row + g * 32 + lane);
-            const uint16_t *cp = a.cnT + gi.x + lane;
+            const uint2 *cp = a.cnT + gi.x + lane;
             uint32_t s = 0;
-            for (int k = 0; k < gi.y; ++k) {
-                const uint32_t col = __ldg(cp + k * 32);
-                s ^= alw[col >> 5] >> (col & 31u);
+            for (int kb = 0; kb < gi.y; kb += 4) {
+                const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+                const int left = gi.y - kb;
+                const uint32_t c0 = cw.x & 0xFFFFu, c1 = cw.x >> 16, c2 = cw.y & 0xFFFFu, c3 = cw.y >> 16;
+                s ^= alw[c0 >> 5] >> (c0 & 31u);
+                if (left > 1) s ^= alw[c1 >> 5] >> (c1 & 31u);
+                if (left > 2) s ^= alw[c2 >> 5] >> (c2 & 31u);
+                if (left > 3) s ^= alw[c3 >> 5] >> (c3 & 31u);
             }
             const uint32_t sw = __ballot_sync(0xffffffffu, (s & 1u) != 0 && row < (uint32_t)a.m);
             if (lane == 0) synw[g] = sw;

@@ -110,10 +110,10 @@ def test_rate_adaptation_paths_agree(q, tmp_path, alg):
     util.write_sparse2(path, "I80")
     arr = util.code_arrays("I80")
     hm = hostlib.HostMatrix(path, 3)
-    p, s, _, _ = hm.adapt_code_rate(5555, 0.0196, 0.05, 1.3, untainted=True, untp=arr["untp"])
+    p, s, _, _ = hm.adapt_code_rate(5555, 0.0116, 0.09, 1.5, untainted=True, untp=arr["untp"])
     assert p.size and s.size
     seeds = hostlib.trial_seeds(31337, 200)
-    a, b, acc = hostlib.gen_keys_rate_adapt(seeds, arr["n"], 0.0196, p, s)
+    a, b, acc = hostlib.gen_keys_rate_adapt(seeds, arr["n"], 0.0116, p, s)
     cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32)
     ro = handle(q, "I80", decoder_path=2).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg, punctured_bits=p, shortened_bits=s)
     rs = handle(q, "I80", decoder_path=1).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg, punctured_bits=p, shortened_bits=s)
