@@ -86,7 +86,7 @@ typedef struct qkdldpc_options {
     int32_t use_graph;      /* 1 (default): replay one captured CUDA graph per poll interval; -1: plain launches */
     int32_t decoder_path;   /* 0 auto; 1 streaming kernels (messages in HBM); 2 on-chip min-sum (frame state in shared
                                memory; float32 min-sum family, check degrees <= 32, n < 65535) or QKDLDPC_ERR_INVALID */
-    int32_t onchip_threads; /* CTA size of the on-chip kernel (multiple of 32, <= 512); 0 = derived from the code size */
+    int32_t onchip_threads; /* CTA size of the on-chip kernel (multiple of 32, <= 768); 0 = derived from the code size */
     int32_t reserved[3];
 } qkdldpc_options;
 
@@ -169,6 +169,7 @@ typedef struct qkdldpc_info {
     double last_batch_ms;      /* device time of the last batch (CUDA events on the handle's stream) */
     double last_cn_ms, last_vn_ms, last_sched_ms; /* only filled when profiling is enabled */
     int32_t last_path;         /* decoder path of the last batch: 1 streaming, 2 on-chip */
+    int32_t onchip_threads;    /* CTA size of the last on-chip launch */
 } qkdldpc_info;
 QKDLDPC_API int qkdldpc_code_info(const qkdldpc_code *code, qkdldpc_info *info);
 /* When enabled, every kernel of the step loop is bracketed by CUDA events (slow; for bench roofline numbers). */

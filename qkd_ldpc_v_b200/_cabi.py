@@ -26,7 +26,7 @@ class Info(C.Structure):
                 ("frames_per_tile", C.c_int32), ("pool_tiles", C.c_int32), ("pool_bytes", C.c_int64),
                 ("kernel_launches", C.c_int64), ("decoder_steps", C.c_int64), ("last_batch_ms", C.c_double),
                 ("last_cn_ms", C.c_double), ("last_vn_ms", C.c_double), ("last_sched_ms", C.c_double),
-                ("last_path", C.c_int32)]
+                ("last_path", C.c_int32), ("onchip_threads", C.c_int32)]
 
 
 # every symbol include/qkdldpc.h declares: name -> (restype, argtypes)

@@ -393,6 +393,7 @@ int qkdldpc_code_info(const qkdldpc_code *c, qkdldpc_info *info) {
     info->kernel_launches = c->kernel_launches; info->decoder_steps = c->decoder_steps;
     info->last_batch_ms = c->last_batch_ms;
     info->last_path = c->last_path;
+    info->onchip_threads = c->oc_threads;
     info->last_cn_ms = c->last_cn_ms; info->last_vn_ms = c->last_vn_ms; info->last_sched_ms = c->last_sched_ms;
     return QKDLDPC_OK;
 }

@@ -83,6 +83,7 @@ struct qkdldpc_code {
     DevBuf<uint2> oc_cnT;
     DevBuf<uint4> oc_vT;
     DevBuf<uint32_t> oc_cls;   // oc_cls: [2][words] punctured / shortened bit masks of the current batch
+    int oc_threads = 0;               // CTA size of the last on-chip launch
     int last_path = 0;                // 1 streaming, 2 on-chip (of the last batch)
     // pool (device, raw bytes reinterpreted per precision)
     DevBuf<unsigned char> msg;

@@ -199,7 +199,7 @@ __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, float *L, c
 #undef QK_VN_EDGE
 
 template <int ALG>
-__global__ void __launch_bounds__(512, 3) onchip_minsum_kernel(const OnchipArgs a) {
+__global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *rec = reinterpret_cast<uint4 *>(smem_raw);
     float *L = reinterpret_cast<float *>(rec + a.m + 1);
