@@ -79,7 +79,7 @@ typedef struct qkdldpc_params {
 
 /* Tuning knobs of a handle (all optional; 0 = library default). */
 typedef struct qkdldpc_options {
-    int64_t pool_bytes;     /* upper bound for the message pool in HBM (default 8 GiB)                      */
+    int64_t pool_bytes;     /* upper bound for the message pool in HBM (default 2 GiB)                      */
     int32_t pool_slots;     /* resident frame slots (rounded to whole tiles); 0 = derived from pool_bytes    */
     int32_t steps_per_poll; /* decoder iterations launched between two host checks of the done counter       */
     int32_t frames_per_lane_f32; /* 1, 2 or 4 (tile = 32 x this many frames); default 4 (128-bit accesses)    */

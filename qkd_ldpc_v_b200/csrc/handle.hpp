@@ -82,7 +82,13 @@ struct qkdldpc_code {
     DevBuf<uint16_t> oc_cn_row, oc_vn_bit;
     DevBuf<uint2> oc_cnT;
     DevBuf<uint4> oc_vT;
-    DevBuf<uint32_t> oc_cls;   // oc_cls: [2][words] punctured / shortened bit masks of the current batch
+    DevBuf<uint32_t> oc_cls;
+    // variable-phase groups as built by code_create; the device copies (oc_vn_ginfo / oc_vn_bit) are re-laid out in
+    // schedule order for the number of warps per CTA of the launch (inst_onchip.cu)
+    std::vector<int> oc_vn_degree;
+    std::vector<int2> oc_vn_ginfo_host;
+    std::vector<uint16_t> oc_vn_bit_host;
+    int oc_sched_warps = 0;   // oc_cls: [2][words] punctured / shortened bit masks of the current batch
     int oc_threads = 0;               // CTA size of the last on-chip launch
     int last_path = 0;                // 1 streaming, 2 on-chip (of the last batch)
     // pool (device, raw bytes reinterpreted per precision)

@@ -25,13 +25,11 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
 // to the smaller CTA -- measured: 3 x 512 beats 2 x 768 on n=10240 m=2048, 2 x 768 beats 2 x 512 on m=2201). A CTA
 // never has more lanes than the check phase has rows.
 template <int ALG>
-static cudaError_t launch(const OnchipArgs &a, int sms, int threads, size_t smem, cudaStream_t s, long long n_frames, int *grid_out,
-                          int *threads_out) {
+static cudaError_t pick_geometry(int m, int sms, size_t smem, long long n_frames, int *threads, int *grid) {
     cudaError_t e = cudaFuncSetAttribute(onchip_minsum_kernel<ALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    if (threads == 0) {
-        const int cap = std::max(128, std::min(768, (a.m + 31) / 32 * 32));
+    if (*threads == 0) {
+        const int cap = std::max(128, std::min(768, (m + 31) / 32 * 32));
         int best = 0;
         for (int t = 128; t <= cap; t += 128) {
             int k = 0;
@@ -39,19 +37,45 @@ static cudaError_t launch(const OnchipArgs &a, int sms, int threads, size_t smem
             if (e != cudaSuccess) return e;
             if (k * t > best) {
                 best = k * t;
-                threads = t;
+                *threads = t;
             }
         }
-        if (threads == 0) return cudaErrorLaunchOutOfResources;
+        if (*threads == 0) return cudaErrorLaunchOutOfResources;
     }
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onchip_minsum_kernel<ALG>, threads, smem);
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onchip_minsum_kernel<ALG>, *threads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    *threads_out = threads;
-    const long long grid = std::min<long long>(n_frames, (long long)per_sm * sms);   // persistent CTAs pull frames from a queue
-    *grid_out = (int)grid;
+    *grid = (int)std::min<long long>(n_frames, (long long)per_sm * sms);   // persistent CTAs pull frames from a queue
+    return cudaSuccess;
+}
+
+template <int ALG>
+static cudaError_t launch(const OnchipArgs &a, int grid, int threads, size_t smem, cudaStream_t s) {
     onchip_minsum_kernel<ALG><<<(unsigned)grid, threads, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+// Variable-phase schedule for `nwarps` warps per CTA: warp w handles entries w, w + nwarps, ... of the returned list.
+// Groups differ in cost (degree 2 ... 73), so they are dealt longest-processing-time-first to the least loaded warp
+// (round-robin over the degree-sorted list leaves the busiest warp ~10 % above the mean on the irregular codes).
+static std::vector<int> vn_schedule(const std::vector<int> &group_degree, int nwarps) {
+    std::vector<std::vector<int>> per_warp(nwarps);
+    std::vector<long long> load(nwarps, 0);
+    std::vector<int> order(group_degree.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return group_degree[x] > group_degree[y]; });
+    for (int g : order) {
+        const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        per_warp[w].push_back(g);
+        load[w] += group_degree[g] + 3;   // + per-group overhead (header, LLR, store)
+    }
+    size_t rounds = 0;
+    for (auto &v : per_warp) rounds = std::max(rounds, v.size());
+    std::vector<int> sched(rounds * nwarps, -1);
+    for (int w = 0; w < nwarps; ++w)
+        for (size_t i = 0; i < per_warp[w].size(); ++i) sched[i * nwarps + w] = per_warp[w][i];
+    return sched;
 }
 
 int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const uint32_t *d_alice, const uint32_t *d_bob,
@@ -97,14 +121,43 @@ int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 
-    CK(cudaEventRecord(c->ev0, s));
     int grid = 0;
     cudaError_t e;
     switch (P->algorithm) {
-        case 2: e = launch<2>(a, sms, threads, smem, s, n_frames, &grid, &threads); break;
-        case 3: e = launch<3>(a, sms, threads, smem, s, n_frames, &grid, &threads); break;
-        case 4: e = launch<4>(a, sms, threads, smem, s, n_frames, &grid, &threads); break;
-        default: e = launch<5>(a, sms, threads, smem, s, n_frames, &grid, &threads); break;
+        case 2: e = pick_geometry<2>(m, sms, smem, n_frames, &threads, &grid); break;
+        case 3: e = pick_geometry<3>(m, sms, smem, n_frames, &threads, &grid); break;
+        case 4: e = pick_geometry<4>(m, sms, smem, n_frames, &threads, &grid); break;
+        default: e = pick_geometry<5>(m, sms, smem, n_frames, &threads, &grid); break;
+    }
+    if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel geometry failed: %s", cudaGetErrorString(e));
+    if (c->oc_sched_warps != threads / 32) {   // the variable-phase schedule depends on the number of warps per CTA
+        const std::vector<int> sched = vn_schedule(c->oc_vn_degree, threads / 32);
+        std::vector<int2> ginfo(sched.size(), make_int2(0, 0));
+        std::vector<uint16_t> bits(sched.size() * 32, (uint16_t)n);
+        for (size_t i = 0; i < sched.size(); ++i)
+            if (sched[i] >= 0) {
+                ginfo[i] = c->oc_vn_ginfo_host[sched[i]];
+                std::copy(c->oc_vn_bit_host.begin() + (size_t)sched[i] * 32, c->oc_vn_bit_host.begin() + (size_t)sched[i] * 32 + 32,
+                          bits.begin() + i * 32);
+            }
+        CK(c->oc_vn_ginfo.reserve(ginfo.size()));
+        CK(c->oc_vn_bit.reserve(bits.size()));
+        CK(cudaMemcpyAsync(c->oc_vn_ginfo.p, ginfo.data(), ginfo.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(c->oc_vn_bit.p, bits.data(), bits.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        c->oc_sched_warps = threads / 32;
+        c->oc_groups_vn = (int)sched.size();
+    }
+    a.n_groups_vn = c->oc_groups_vn;
+    a.vn_ginfo = c->oc_vn_ginfo.p;
+    a.vn_bit = c->oc_vn_bit.p;
+
+    CK(cudaEventRecord(c->ev0, s));
+    switch (P->algorithm) {
+        case 2: e = launch<2>(a, grid, threads, smem, s); break;
+        case 3: e = launch<3>(a, grid, threads, smem, s); break;
+        case 4: e = launch<4>(a, grid, threads, smem, s); break;
+        default: e = launch<5>(a, grid, threads, smem, s); break;
     }
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel launch failed: %s", cudaGetErrorString(e));
     c->kernel_launches += 1;

@@ -41,7 +41,8 @@ struct OnchipArgs {
     const int2 *cn_ginfo;       // [groups] {offset into cnT (in uint2), degree of the group's rows}
     const uint16_t *cn_row;     // [groups*32] row handled by (group, lane); padding lanes hold m (a scratch record slot)
     const uint2 *cnT;           // [off + kb*32 + lane] 4 x uint16: bit index of edges 4kb..4kb+3 of that row (padding: 0)
-    const int2 *vn_ginfo;       // [groups] {offset into vT (in uint4), degree of the group's bits}
+    const int2 *vn_ginfo;       // [groups] {offset into vT (in uint4), degree of the group's bits}, in schedule order
+                                //          (degree 0 = an empty slot of the schedule)
     const uint16_t *vn_bit;     // [groups*32] bit handled by (group, lane); padding lanes hold n (a scratch L slot)
     const uint4 *vT;            // [off + kb*32 + lane] 4 x uint32: row << 9 | sh of checks 4kb..4kb+3 of that bit,
                                 //                      sh = 32 - dc(row) + position in the row (padding: scratch row m)
@@ -170,6 +171,8 @@ __device__ __forceinline__ float onchip_llr(const OnchipArgs &a, const uint32_t 
 __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, float *L, const uint4 *rec, const uint32_t *bobw, float lp, int warp,
                                                 int lane, int nwarps) {
     const unsigned char *recb = reinterpret_cast<const unsigned char *>(rec);
+    // groups come in SCHEDULE order: entry g is handled by warp g % nwarps, and the host dealt the groups to the warps
+    // longest-first so that all warps of the CTA finish the phase together (inst_onchip.cu)
     for (int g = warp; g < a.n_groups_vn; g += nwarps) {
         const int2 gi = __ldg(a.vn_ginfo + g);
         const int dv = gi.y;

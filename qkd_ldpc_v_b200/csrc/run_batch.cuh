@@ -117,7 +117,10 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     // ---- pool geometry -------------------------------------------------------------------------------------
     const int64_t tiles_needed = (n_frames + FT - 1) / FT;
     const int64_t per_tile = (int64_t)c->nnz * FT * (int64_t)sizeof(T);
-    int64_t budget = c->opt.pool_bytes > 0 ? c->opt.pool_bytes : (int64_t)8 << 30;
+    // default 2 GiB: enough frames in flight to saturate HBM (>= 8k frames of a 10k code), small enough that a batch
+    // refills every slot several times -- at converging operating points a pool as large as the batch leaves most lanes
+    // idle while each tile waits for its slowest frame
+    int64_t budget = c->opt.pool_bytes > 0 ? c->opt.pool_bytes : (int64_t)2 << 30;
     int64_t tiles = std::max<int64_t>(1, budget / std::max<int64_t>(per_tile, 1));
     if (c->opt.pool_slots > 0) tiles = std::max<int64_t>(1, (c->opt.pool_slots + FT - 1) / FT);
     tiles = std::min<int64_t>(tiles, tiles_needed);

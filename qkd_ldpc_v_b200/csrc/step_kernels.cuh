@@ -39,38 +39,47 @@ __device__ __forceinline__ Vec<T, V> lane_llr(const StepArgs<T> &a, int tile, in
     return r;
 }
 
-// tanh / atanh flavours. ALG 0: libm-accurate evaluation in double on the stored value (for float messages this is
-// exactly what the f32 oracle does); ALG 1: the reference's piecewise-linear tables (qkd_ldpc_algorithm.cpp:146-172).
+// tanh / atanh flavours.
+//  ALG 0, double messages: libm-accurate double evaluation (parity mode).
+//  ALG 0, float messages:  CUDA's float tanhf / atanhf (<= 2-3 ulp) on the FMA/ALU pipes. An earlier version evaluated
+//         them in double on the float value (bit-equal to the f32 oracle) but spent 92 % of the SPA step in FP64
+//         transcendentals (2.1 s of a 2.3 s step); the float versions keep >= 99 % equal iteration counts against the
+//         float64 reference (tests/test_gpu_large.py) at a tenth of the time.
+//  ALG 1: the reference's piecewise-linear tables (qkd_ldpc_algorithm.cpp:146-172), written branch-free: slope and
+//         intercept are selected with the same `<` comparisons (a NaN fails them all and lands in the last segment,
+//         like the reference's else-chain), then one multiply and one add -- the same two roundings as the C++ code.
 template <typename T, int ALG>
 __device__ __forceinline__ T cn_tanh_half(T x) {
     const T h = x / (T)2;
     if constexpr (ALG == 0) {
-        return (T)tanh((double)h);
+        if constexpr (sizeof(T) == 4) return tanhf(h);
+        else return (T)tanh((double)h);
     } else {
         const T ax = fabs(h);
-        T r;
-        if (ax < (T)0.5) r = (T)0.9242 * ax;
-        else if (ax < (T)0.9) r = (T)0.6355 * ax + (T)0.1444;
-        else if (ax < (T)1.2) r = (T)0.3912 * ax + (T)0.3642;
-        else if (ax < (T)1.75) r = (T)0.1958 * ax + (T)0.5986;
-        else if (ax < (T)2.5) r = (T)0.0603 * ax + (T)0.8358;
-        else if (ax < (T)3.5) r = (T)0.0115 * ax + (T)0.9577;
-        else if (ax < (T)8) r = (T)0.0004 * ax + (T)0.9967;
-        else r = (T)1;
+        T a = (T)0.9242, b = (T)0;
+        if (!(ax < (T)0.5)) { a = (T)0.6355; b = (T)0.1444; }
+        if (!(ax < (T)0.9)) { a = (T)0.3912; b = (T)0.3642; }
+        if (!(ax < (T)1.2)) { a = (T)0.1958; b = (T)0.5986; }
+        if (!(ax < (T)1.75)) { a = (T)0.0603; b = (T)0.8358; }
+        if (!(ax < (T)2.5)) { a = (T)0.0115; b = (T)0.9577; }
+        if (!(ax < (T)3.5)) { a = (T)0.0004; b = (T)0.9967; }
+        T r = a * ax + b;                       // first segment: 0.9242 * ax + 0 == 0.9242 * ax (ax >= 0)
+        if (!(ax < (T)8)) r = (T)1;
         return (h < (T)0) ? -r : r;
     }
 }
 template <typename T, int ALG>
 __device__ __forceinline__ T cn_two_atanh(T y) {
     if constexpr (ALG == 0) {
-        return (T)2 * (T)atanh((double)y);
+        if constexpr (sizeof(T) == 4) return 2.f * atanhf(y);
+        else return (T)2 * (T)atanh((double)y);
     } else {
         const T ay = fabs(y);
-        T r;
-        if (ay < (T)0.7) r = (T)1.196 * ay - (T)0.0323;
-        else if (ay < (T)0.9) r = (T)2.9187 * ay - (T)1.214;
-        else if (ay < (T)0.999) r = (T)10.8717 * ay - (T)8.3717;
-        else r = (T)2510.9 * ay - (T)2505.9;
+        T a = (T)1.196, b = (T)0.0323;
+        if (!(ay < (T)0.7)) { a = (T)2.9187; b = (T)1.214; }
+        if (!(ay < (T)0.9)) { a = (T)10.8717; b = (T)8.3717; }
+        if (!(ay < (T)0.999)) { a = (T)2510.9; b = (T)2505.9; }
+        const T r = a * ay - b;
         return (T)2 * ((y < (T)0) ? -r : r);
     }
 }
