@@ -35,6 +35,8 @@ const char *kHelp =
     "  --precision 32|64   float32 messages (default) or float64 parity mode (bit-identical to the CPU reference\n"
     "                      for the min-sum family)\n"
     "  --chunk-frames K    frames per decode call and device (default 65536)\n"
+    "  --concurrent K      combinations decoded concurrently per device (own handle and stream each); default: automatic\n"
+    "                      (1 for large trial counts, up to 8 for rate-adaptation sweeps of ~100 trials)\n"
     "  --trials T          override trials_number of the config\n"
     "  --quiet             no per-combination progress lines\n"
     "  --wait              wait for Enter before exiting, like the reference\n"
@@ -146,6 +148,7 @@ int main(int argc, char *argv[]) {
                 }
             } else if (arg == "--precision") dev.message_precision = std::stoi(value());
             else if (arg == "--chunk-frames") dev.chunk_frames = std::stoll(value());
+            else if (arg == "--concurrent") dev.concurrent_combinations = std::stoi(value());
             else if (arg == "--trials") trials_override = std::stol(value());
             else if (arg == "--quiet") dev.verbose = false;
             else if (arg == "--wait") wait = true;

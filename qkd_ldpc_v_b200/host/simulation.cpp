@@ -253,6 +253,54 @@ void generate_chunk(const config_data &cfg, const H_matrix &matrix, const sim_co
 
 }  // namespace
 
+namespace {
+
+// Decodes trials [lo, hi) of one combination on one handle, chunk by chunk: the next chunk's inputs are generated on
+// host threads while the GPU decodes the current one. Adds the chunk tallies to `tally`.
+struct range_outcome {
+    double accurate_qber = 0., ms = 0.;
+};
+range_outcome decode_trial_range(const config_data &cfg, const decoder_api &api, qkdldpc_code *code, const qkdldpc_params &P,
+                                 const H_matrix &matrix, const sim_combination &comb, const std::vector<uint64_t> &seeds, size_t curr_sim,
+                                 size_t lo, size_t hi, size_t chunk, size_t gen_threads, std::vector<uint64_t> &tally) {
+    range_outcome out;
+    chunk_buffers cur, nxt;
+    std::vector<uint64_t> t(tally.size());
+    size_t pos = lo;
+    if (pos < hi) generate_chunk(cfg, matrix, comb, seeds, curr_sim, pos, std::min(chunk, hi - pos), gen_threads, cur);
+    while (pos < hi) {
+        const size_t cnt = std::min(chunk, hi - pos), npos = pos + cnt;
+        std::future<void> prefetch;
+        if (npos < hi)
+            prefetch = std::async(std::launch::async, [&, npos] {
+                generate_chunk(cfg, matrix, comb, seeds, curr_sim, npos, std::min(chunk, hi - npos), gen_threads, nxt);
+            });
+        const double q = cur.accurate_qber;
+        const auto &mp = comb.matrix_params;
+        const auto t0 = std::chrono::steady_clock::now();
+        const int rc = api.decode_batch(code, &P, static_cast<int64_t>(cnt), cur.alice.data(), cur.bob.data(), &q, 1, mp.punctured_bits.data(),
+                                        static_cast<int32_t>(mp.punctured_bits.size()), mp.shortened_bits.data(),
+                                        static_cast<int32_t>(mp.shortened_bits.size()), nullptr, nullptr, nullptr, t.data());
+        out.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (prefetch.valid()) prefetch.get();
+        if (rc != 0) throw std::runtime_error(std::string("qkdldpc_decode_batch: ") + api.last_error());
+        for (size_t k = 0; k < tally.size(); ++k) tally[k] += t[k];
+        if (pos == lo) out.accurate_qber = q;
+        pos = npos;
+        std::swap(cur, nxt);
+    }
+    return out;
+}
+
+}  // namespace
+
+// Two ways to keep the GPUs busy, chosen per config:
+//  * many trials per combination (the FER configs: 10^5 .. 10^6): combinations run one after the other, the trials of
+//    each are split into contiguous ranges over the devices (the reference's detach_loop over threads);
+//  * few trials per combination (the rate-adaptation sweeps: thousands of combinations x 100 trials): a batch of 100
+//    frames cannot fill a B200, so several combinations are decoded CONCURRENTLY -- every device gets a few handles
+//    (each with its own stream) and worker threads pull combinations from a queue. Results are stored by combination
+//    index, so the CSV is the same either way (quirk Q16: a trial's inputs depend only on seeds[n] + combination index).
 std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const std::vector<sim_input> &sim_in,
                                                   const decoder_api &api, const device_options &dev) {
     size_t sim_total = 0;
@@ -262,92 +310,105 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
     const size_t trials = cfg.TRIALS_NUMBER;
     const size_t n_dev = std::max<size_t>(1, dev.devices.size());
     const size_t tally_len = cfg.DECODING_ALG_MAX_ITERATIONS + 5;
-    const size_t gen_threads = std::max<size_t>(1, cfg.THREADS_NUMBER / n_dev);
+    const size_t chunk = static_cast<size_t>(std::max<int64_t>(1, dev.chunk_frames));
+    // concurrent combinations per device: enough small batches in flight to cover ~2 frames per SM-resident CTA slot
+    size_t per_dev = 1;
+    if (dev.concurrent_combinations > 0) per_dev = static_cast<size_t>(dev.concurrent_combinations);
+    else if (trials < 2048) per_dev = std::min<size_t>(8, (2048 + trials - 1) / trials);
+    const bool sweep_mode = per_dev > 1 || (n_dev > 1 && trials < 2048);
+    const size_t lanes = sweep_mode ? n_dev * per_dev : n_dev;
+    const size_t gen_threads = std::max<size_t>(1, cfg.THREADS_NUMBER / lanes);
 
-    size_t curr_sim = 0;
+    qkdldpc_params P0{};
+    P0.algorithm = static_cast<int32_t>(cfg.DECODING_ALGORITHM);
+    P0.max_iterations = static_cast<int32_t>(cfg.DECODING_ALG_MAX_ITERATIONS);
+    P0.enable_threshold = cfg.ENABLE_DECODING_ALG_MSG_LLR_THRESHOLD ? 1 : 0;
+    P0.threshold = cfg.DECODING_ALG_MSG_LLR_THRESHOLD;
+    P0.message_precision = dev.message_precision;
+
+    size_t first_sim = 0;
     for (const auto &in : sim_in) {
         const H_matrix &matrix = in.matrix;
         const std::string name = in.matrix_path.filename().string();
         const CsrGraph g = to_csr_checked(matrix, name);
-        const size_t n = matrix.n(), words = (n + 31) / 32;
+        const size_t n_comb = in.combinations.size();
 
-        std::vector<qkdldpc_code *> codes(n_dev, nullptr);
+        std::vector<qkdldpc_code *> codes(lanes, nullptr);   // lane l runs on device l % n_dev
         auto destroy_all = [&] { for (auto *c : codes) if (c) api.code_destroy(c); };
         qkdldpc_options opt{};
         opt.pool_bytes = dev.pool_bytes;
-        for (size_t d = 0; d < n_dev; ++d) {
-            const int device = dev.devices.empty() ? 0 : dev.devices[d];
-            if (api.code_create(&codes[d], g.n, g.m, static_cast<int64_t>(g.col_idx.size()), g.row_ptr.data(), g.col_idx.data(), device, &opt) != 0) {
+        for (size_t l = 0; l < lanes; ++l) {
+            const int device = dev.devices.empty() ? 0 : dev.devices[l % n_dev];
+            if (api.code_create(&codes[l], g.n, g.m, static_cast<int64_t>(g.col_idx.size()), g.row_ptr.data(), g.col_idx.data(), device, &opt) != 0) {
                 const std::string msg = api.last_error();
                 destroy_all();
                 throw std::runtime_error("qkdldpc_code_create failed for " + name + ": " + msg);
             }
         }
 
-        for (const auto &comb : in.combinations) {
-            qkdldpc_params P{};
-            P.algorithm = static_cast<int32_t>(cfg.DECODING_ALGORITHM);
-            P.max_iterations = static_cast<int32_t>(cfg.DECODING_ALG_MAX_ITERATIONS);
+        std::vector<std::vector<uint64_t>> totals(n_comb, std::vector<uint64_t>(tally_len, 0));
+        std::vector<double> acc_qber(n_comb, 0.), comb_ms(n_comb, 0.);
+        std::vector<std::string> errors(lanes);
+        auto params_of = [&](const sim_combination &comb) {
+            qkdldpc_params P = P0;
             P.primary = comb.scaling_factors.primary;
             P.secondary = comb.scaling_factors.secondary;
-            P.enable_threshold = cfg.ENABLE_DECODING_ALG_MSG_LLR_THRESHOLD ? 1 : 0;
-            P.threshold = cfg.DECODING_ALG_MSG_LLR_THRESHOLD;
-            P.message_precision = dev.message_precision;
+            return P;
+        };
 
-            std::vector<std::vector<uint64_t>> tallies(n_dev, std::vector<uint64_t>(tally_len, 0));
-            std::vector<double> acc_qber(n_dev, 0.), dev_ms(n_dev, 0.);
-            std::vector<std::string> errors(n_dev);
+        if (sweep_mode) {
+            std::atomic<size_t> next{0};
             std::vector<std::thread> workers;
-            for (size_t d = 0; d < n_dev; ++d) {
-                workers.emplace_back([&, d] {
+            for (size_t l = 0; l < lanes; ++l)
+                workers.emplace_back([&, l] {
                     try {
-                        const size_t lo = trials * d / n_dev, hi = trials * (d + 1) / n_dev;   // contiguous trial range
-                        const size_t chunk = static_cast<size_t>(std::max<int64_t>(1, dev.chunk_frames));
-                        chunk_buffers cur, nxt;
-                        std::vector<uint64_t> t(tally_len);
-                        size_t pos = lo;
-                        if (pos < hi) generate_chunk(cfg, matrix, comb, seeds, curr_sim, pos, std::min(chunk, hi - pos), gen_threads, cur);
-                        while (pos < hi) {
-                            const size_t cnt = std::min(chunk, hi - pos);
-                            const size_t npos = pos + cnt;
-                            std::future<void> prefetch;   // generate the next chunk while the GPU decodes this one
-                            if (npos < hi)
-                                prefetch = std::async(std::launch::async, [&, npos] {
-                                    generate_chunk(cfg, matrix, comb, seeds, curr_sim, npos, std::min(chunk, hi - npos), gen_threads, nxt);
-                                });
-                            const double q = cur.accurate_qber;
-                            const auto &mp = comb.matrix_params;
-                            const auto t0 = std::chrono::steady_clock::now();
-                            const int rc = api.decode_batch(codes[d], &P, static_cast<int64_t>(cnt), cur.alice.data(), cur.bob.data(), &q, 1,
-                                                            mp.punctured_bits.data(), static_cast<int32_t>(mp.punctured_bits.size()),
-                                                            mp.shortened_bits.data(), static_cast<int32_t>(mp.shortened_bits.size()),
-                                                            nullptr, nullptr, nullptr, t.data());
-                            dev_ms[d] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-                            if (prefetch.valid()) prefetch.get();
-                            if (rc != 0) throw std::runtime_error(std::string("qkdldpc_decode_batch: ") + api.last_error());
-                            for (size_t k = 0; k < tally_len; ++k) tallies[d][k] += t[k];
-                            if (pos == lo) acc_qber[d] = q;
-                            pos = npos;
-                            std::swap(cur, nxt);
+                        for (size_t ci = next.fetch_add(1); ci < n_comb; ci = next.fetch_add(1)) {
+                            const sim_combination &comb = in.combinations[ci];
+                            const range_outcome o = decode_trial_range(cfg, api, codes[l], params_of(comb), matrix, comb, seeds, first_sim + ci,
+                                                                       0, trials, chunk, gen_threads, totals[ci]);
+                            acc_qber[ci] = o.accurate_qber;
+                            comb_ms[ci] = o.ms;
                         }
-                        (void)words;
                     } catch (const std::exception &e) {
-                        errors[d] = e.what();
+                        errors[l] = e.what();
+                        next.store(n_comb);   // stop the other workers
                     }
                 });
-            }
             for (auto &w : workers) w.join();
-            for (const auto &e : errors)
-                if (!e.empty()) {
-                    destroy_all();
-                    throw std::runtime_error(e);
+        } else {
+            for (size_t ci = 0; ci < n_comb && errors[0].empty(); ++ci) {
+                const sim_combination &comb = in.combinations[ci];
+                std::vector<std::vector<uint64_t>> part(n_dev, std::vector<uint64_t>(tally_len, 0));
+                std::vector<range_outcome> outc(n_dev);
+                std::vector<std::thread> workers;
+                for (size_t d = 0; d < n_dev; ++d)
+                    workers.emplace_back([&, d] {
+                        try {
+                            const size_t lo = trials * d / n_dev, hi = trials * (d + 1) / n_dev;   // contiguous trial range
+                            outc[d] = decode_trial_range(cfg, api, codes[d], params_of(comb), matrix, comb, seeds, first_sim + ci, lo, hi, chunk,
+                                                         gen_threads, part[d]);
+                        } catch (const std::exception &e) {
+                            errors[d] = e.what();
+                        }
+                    });
+                for (auto &w : workers) w.join();
+                // the multi-GPU "all-reduce" of this in-process driver: integer sums of the per-device tallies
+                for (size_t d = 0; d < n_dev; ++d) {
+                    for (size_t k = 0; k < tally_len; ++k) totals[ci][k] += part[d][k];
+                    comb_ms[ci] = std::max(comb_ms[ci], outc[d].ms);
                 }
+                acc_qber[ci] = outc[0].accurate_qber;
+                for (size_t d = 1; d < n_dev; ++d)
+                    if (!errors[d].empty()) errors[0] = errors[d];
+            }
+        }
+        destroy_all();
+        for (const auto &e : errors)
+            if (!e.empty()) throw std::runtime_error(e);
 
-            // the multi-GPU "all-reduce" of this in-process driver: integer sums of the per-device tallies
-            std::vector<uint64_t> total(tally_len, 0);
-            for (size_t d = 0; d < n_dev; ++d)
-                for (size_t k = 0; k < tally_len; ++k) total[k] += tallies[d][k];
-
+        for (size_t ci = 0; ci < n_comb; ++ci) {
+            const sim_combination &comb = in.combinations[ci];
+            const size_t curr_sim = first_sim + ci;
             sim_result &r = results[curr_sim];
             r.sim_number = curr_sim;
             r.matrix_filename = name;
@@ -360,13 +421,13 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
             r.shortened_fraction = comb.matrix_params.shortened_fraction;
             r.adapted_code_rate = comb.matrix_params.adapted_code_rate;
             r.config_QBER = comb.config_QBER;
-            r.accurate_QBER = acc_qber[0];
+            r.accurate_QBER = acc_qber[ci];
             r.scaling_factors = comb.scaling_factors;
-            process_tally(total.data(), cfg.DECODING_ALG_MAX_ITERATIONS, trials, r);
+            process_tally(totals[ci].data(), cfg.DECODING_ALG_MAX_ITERATIONS, trials, r);
 
             // Throughput columns: the reference times every single-frame CPU call (simulation.cpp:559-568); a batched
             // GPU call has no per-trial time, so every trial is attributed the batch's mean time per frame.
-            r.gpu_ms = *std::max_element(dev_ms.begin(), dev_ms.end());
+            r.gpu_ms = comb_ms[ci];
             const double out_key_length = (cfg.ENABLE_CODE_RATE_ADAPTATION || cfg.ENABLE_PRIVACY_MAINTENANCE)
                                               ? static_cast<double>(matrix.n() - comb.matrix_params.bits_to_remove.size())
                                               : static_cast<double>(matrix.n());
@@ -382,9 +443,8 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
                 std::fprintf(stderr, "[%zu/%zu] %s QBER=%.4f: FER=%.6f, mean it %.2f, %.1f ms, %.3f Gbit/s\n", curr_sim + 1, sim_total,
                              name.c_str(), comb.config_QBER, 1. - r.ratio_trials_success_ldpc, r.iter_success_dec_alg_mean, r.gpu_ms,
                              r.gpu_gbit_s);
-            ++curr_sim;
         }
-        destroy_all();
+        first_sim += n_comb;
     }
     return results;
 }

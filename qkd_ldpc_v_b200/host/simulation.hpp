@@ -69,6 +69,8 @@ struct device_options {
     int message_precision = 32;      // 32: float32 messages; 64: float64 parity mode
     int64_t chunk_frames = 65536;    // frames generated / uploaded per qkdldpc_decode_batch call and device
     int64_t pool_bytes = 0;          // 0 = library default
+    int concurrent_combinations = 0; // combinations decoded at the same time per device (own handle + stream each);
+                                     // 0 = automatic: 1 for large trial counts, up to 8 for sweeps of small batches
     bool verbose = true;
 };
 

@@ -83,7 +83,9 @@ def test_csv_identical_minsum_fp64(built, tmp_path, alg):
                                       dict(code_rate=0.95, QBER=dict(begin=0.015, end=0.025, step=0.01))])
     _setup(tmp_path, cfg, ["K1_4", "K1_5"])
     rname, ref_lines = _run_reference(tmp_path)
-    oname, our_lines = _run_ours(tmp_path, 64)
+    # 400 trials per combination: qkdldpc_sim decodes several combinations concurrently (own handle + stream each);
+    # alg 2 is also run strictly one combination at a time -- the CSV must not depend on it
+    oname, our_lines = _run_ours(tmp_path, 64, ["--concurrent", "1"] if alg == 2 else [])
     assert _strip_duration(rname) == _strip_duration(oname)
     assert len(ref_lines) == 1 + 3 + 2
     # the reference enumerates matrices in directory order; so do we (same directory) -> rows line up
