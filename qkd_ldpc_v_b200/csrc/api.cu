@@ -212,6 +212,49 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         }
     }
 
+    if (oc_ok) {
+        // Self-check of the tables the on-chip kernel indexes shared memory with (the kernel itself does no bounds tests):
+        // every bit index < n, every record slot <= m (m = scratch), every shift in [0, 31], every edge present once.
+        size_t edges_cn = 0, edges_vn = 0;
+        for (size_t g = 0; g < oc_cn_ginfo.size(); ++g) {
+            const int dc = oc_cn_ginfo[g].y, blocks = (dc + 3) / 4;
+            if (dc < 1 || dc > 32 || (size_t)oc_cn_ginfo[g].x + (size_t)blocks * 32 > oc_cnT.size())
+                return fail(QKDLDPC_ERR_STATE, "on-chip check table: bad group header %zu", g);
+            for (int l = 0; l < 32; ++l) {
+                const int row = oc_cn_row[g * 32 + l];
+                if (row > m) return fail(QKDLDPC_ERR_STATE, "on-chip check table: row %d out of range", row);
+                for (int k = 0; k < dc; ++k) {
+                    const uint2 w = oc_cnT[oc_cn_ginfo[g].x + (k / 4) * 32 + l];
+                    const uint32_t c = (k % 4 == 0) ? (w.x & 0xFFFFu) : (k % 4 == 1) ? (w.x >> 16) : (k % 4 == 2) ? (w.y & 0xFFFFu) : (w.y >> 16);
+                    if ((int)c >= n || (row < m && (int)c != col_idx[rp[row] + k]))
+                        return fail(QKDLDPC_ERR_STATE, "on-chip check table: wrong bit index in row %d", row);
+                    edges_cn += row < m;
+                }
+            }
+        }
+        for (size_t g = 0; g < oc_vn_ginfo.size(); ++g) {
+            const int dv = oc_vn_ginfo[g].y, blocks = (dv + 3) / 4;
+            if (dv < 1 || (size_t)oc_vn_ginfo[g].x + (size_t)blocks * 32 > oc_vT.size())
+                return fail(QKDLDPC_ERR_STATE, "on-chip variable table: bad group header %zu", g);
+            for (int l = 0; l < 32; ++l) {
+                const int bit = oc_vn_bit[g * 32 + l];
+                if (bit > n) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: bit %d out of range", bit);
+                for (int k = 0; k < blocks * 4; ++k) {
+                    const uint4 w = oc_vT[oc_vn_ginfo[g].x + (k / 4) * 32 + l];
+                    const uint32_t e = (k % 4 == 0) ? w.x : (k % 4 == 1) ? w.y : (k % 4 == 2) ? w.z : w.w;
+                    const int r = (int)(e >> 9), sh = (int)(e & 511u);
+                    if (r > m || sh > 31) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: bad entry for bit %d", bit);
+                    if (bit < n && k < dv) {
+                        if (r != csc_row[col_ptr[bit] + k]) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: wrong check for bit %d", bit);
+                        ++edges_vn;
+                    }
+                }
+            }
+        }
+        if (edges_cn != (size_t)nnz || edges_vn != (size_t)nnz)
+            return fail(QKDLDPC_ERR_STATE, "on-chip tables cover %zu / %zu of %lld edges", edges_cn, edges_vn, (long long)nnz);
+    }
+
     int ndev = qkdldpc_device_count();
     if (ndev == 0) return fail(QKDLDPC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(QKDLDPC_ERR_INVALID, "device %d not in [0, %d)", device, ndev);

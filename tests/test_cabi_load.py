@@ -59,3 +59,19 @@ def test_invalid_graphs_are_rejected(built):
     oob = np.array([0, 5, 0, 1], np.int32)
     rc = L.qkdldpc_code_create(C.byref(h), 2, 2, 4, rp.ctypes.data, oob.ctypes.data, 0, None)
     assert rc == -1 and b"out of range" in L.qkdldpc_last_error()
+
+
+def test_onchip_tables_build_for_every_golden_code(built):
+    """qkdldpc_code_create builds (and self-checks: every edge once, every index in range) the index tables of the
+    on-chip kernel BEFORE it touches the device, so the table builder -- including the conflict-aware grouping -- is
+    exercised here without a GPU: on this box the call must get as far as "no CUDA device" (-2), never -4 (table
+    self-check) or -1."""
+    import ctypes as C
+    L = _cabi.lib()
+    if L.qkdldpc_device_count() > 0:
+        pytest.skip("a GPU is present")
+    for name in ("N6", "N7", "N100", "N10s1", "K1_3", "K1_4", "K1_5", "K1_hi", "A79", "A82", "I80", "I65", "I50"):
+        a = util.code_arrays(name)
+        h = C.c_void_p()
+        rc = L.qkdldpc_code_create(C.byref(h), a["n"], a["m"], a["nnz"], a["row_ptr"].ctypes.data, a["col_idx"].ctypes.data, 0, None)
+        assert rc == -2, (name, rc, L.qkdldpc_last_error())
