@@ -156,6 +156,26 @@ QKDLDPC_API int qkdldpc_decode_batch_device(qkdldpc_code *code, const qkdldpc_pa
 QKDLDPC_API int qkdldpc_generate_keys_device(qkdldpc_code *code, int64_t n_frames, double qber, uint64_t seed,
                                  uint32_t *d_alice_bits, uint32_t *d_bob_bits, double *accurate_qber_out);
 
+/* Trial inputs generated ON THE DEVICE, bit-identical to what the reference's run_trial builds on the CPU for the
+ * same per-trial seed (simulation.cpp:549-555): prng = Xoshiro256++(trial_seeds[f] + seed_offset) -- seed_offset is the
+ * running combination index the reference adds (simulation.cpp:743) --, fill_random_bits, inject_errors (libstdc++'s
+ * std::shuffle reproduced draw for draw), and, when position lists are given, the extended frames of
+ * QKD_LDPC_RATE_ADAPT (qkd_ldpc_algorithm.cpp:1148-1174: one more draw per party and punctured bit).
+ * trial_seeds is a HOST array (simulation.cpp:713-719); the frames go to DEVICE buffers of n_frames x words_per_frame. */
+QKDLDPC_API int qkdldpc_generate_trial_inputs_device(qkdldpc_code *code, int64_t n_frames, const uint64_t *trial_seeds,
+                                         uint64_t seed_offset, double qber, const int32_t *punct_pos, int32_t n_punct,
+                                         const int32_t *short_pos, int32_t n_short, uint32_t *d_alice_bits,
+                                         uint32_t *d_bob_bits, double *accurate_qber_out);
+
+/* The batched run_trial (simulation.cpp:540-577): generate the inputs of n_trials trials on the device as above and decode
+ * them; nothing but the seeds goes in and the per-trial results / tallies come out (HOST pointers, each may be NULL).
+ * This is the call that replaces  pool.detach_loop(0, TRIALS, n -> run_trial(matrix, QBER, seeds[n] + curr_sim, ...)).
+ * Fails with QKDLDPC_ERR_INVALID ("Key size ... is too small for QBER.") where run_trial throws (floor(n*QBER) == 0). */
+QKDLDPC_API int qkdldpc_run_trials(qkdldpc_code *code, const qkdldpc_params *params, int64_t n_trials, const uint64_t *trial_seeds,
+                       uint64_t seed_offset, double qber, const int32_t *punct_pos, int32_t n_punct,
+                       const int32_t *short_pos, int32_t n_short, uint32_t *out_bits, int32_t *out_iters,
+                       uint8_t *out_flags, uint64_t *tally, double *accurate_qber_out);
+
 /* Introspection used by benchmarks and tests. */
 typedef struct qkdldpc_info {
     int32_t n, m;

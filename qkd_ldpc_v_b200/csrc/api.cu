@@ -312,6 +312,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->bitclass.release(); c->counters.release();
     c->st_alice.release(); c->st_bob.release(); c->st_out.release(); c->st_qber.release(); c->st_iters.release();
     c->st_flags.release(); c->st_tally.release();
+    c->gen_seeds.release(); c->gen_masks.release(); c->gen_scratch.release();
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (c->h_done) cudaFreeHost(c->h_done);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -434,6 +435,101 @@ int qkdldpc_generate_keys_device(qkdldpc_code *c, int64_t n_frames, double qber,
     c->kernel_launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
+    return QKDLDPC_OK;
+}
+
+int qkdldpc_generate_trial_inputs_device(qkdldpc_code *c, int64_t n_frames, const uint64_t *trial_seeds, uint64_t seed_offset,
+                                         double qber, const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos,
+                                         int32_t n_short, uint32_t *d_alice_bits, uint32_t *d_bob_bits, double *accurate_qber_out) {
+    if (!c) return fail(QKDLDPC_ERR_INVALID, "null code handle");
+    if (!(qber >= 0.) || !(qber < 1.)) return fail(QKDLDPC_ERR_INVALID, "qber must be in [0, 1)");
+    if (n_frames < 0 || (n_frames > 0 && (!trial_seeds || !d_alice_bits || !d_bob_bits))) return fail(QKDLDPC_ERR_INVALID, "bad frame buffers");
+    if ((n_punct > 0 && !punct_pos) || (n_short > 0 && !short_pos) || n_punct < 0 || n_short < 0)
+        return fail(QKDLDPC_ERR_INVALID, "bad punctured/shortened position list");
+    const int n = c->n, words = (n + 31) / 32;
+    // inject_errors: num_errors = size_t(double(N) * QBER) (array_and_matrix_operations.cpp:913-914)
+    const int n_err = (int)(size_t)((double)n * qber);
+    if (accurate_qber_out) *accurate_qber_out = (double)n_err / (double)n;
+    if (n_frames == 0) return QKDLDPC_OK;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const bool ra = n_punct > 0 || n_short > 0;
+    CK(c->gen_seeds.reserve((size_t)n_frames));
+    CK(cudaMemcpyAsync(c->gen_seeds.p, trial_seeds, (size_t)n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    if (ra) {
+        std::vector<uint32_t> masks((size_t)2 * words, 0u);
+        for (int i = 0; i < n_punct; ++i) {
+            if (punct_pos[i] < 0 || punct_pos[i] >= n) return fail(QKDLDPC_ERR_INVALID, "punctured position out of range");
+            masks[punct_pos[i] >> 5] |= 1u << (punct_pos[i] & 31);
+        }
+        for (int i = 0; i < n_short; ++i) {
+            if (short_pos[i] < 0 || short_pos[i] >= n) return fail(QKDLDPC_ERR_INVALID, "shortened position out of range");
+            if (!((masks[short_pos[i] >> 5] >> (short_pos[i] & 31)) & 1u))   // punctured is tested first (:1150)
+                masks[(size_t)words + (short_pos[i] >> 5)] |= 1u << (short_pos[i] & 31);
+        }
+        CK(c->gen_masks.reserve(masks.size()));
+        CK(cudaMemcpyAsync(c->gen_masks.p, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));   // the host vector dies at scope end
+    }
+    // one thread per frame; sub-batches bound the per-thread scratch (raw keys for rate adaptation + shuffle prefix)
+    const long long per_thread = (ra ? 2ll * words : 0ll) + std::max(n_err, 1);
+    const long long sub = std::max<long long>(128, std::min<long long>(n_frames, ((long long)256 << 20) / (per_thread * 4)) / 128 * 128);
+    CK(c->gen_scratch.reserve((size_t)(per_thread * sub)));
+    for (long long f0 = 0; f0 < n_frames; f0 += sub) {
+        qk::RefKeygenArgs a{};
+        a.n = n; a.words = words; a.n_err = n_err;
+        a.n_frames = std::min<long long>(sub, n_frames - f0);
+        a.seeds = reinterpret_cast<const qk::u64 *>(c->gen_seeds.p) + f0;
+        a.seed_offset = seed_offset;
+        a.alice = d_alice_bits + f0 * words; a.bob = d_bob_bits + f0 * words;
+        a.rate_adapt = ra ? 1 : 0;
+        a.punct_mask = c->gen_masks.p; a.short_mask = ra ? c->gen_masks.p + words : nullptr;
+        a.scratch = c->gen_scratch.p; a.scratch_stride = sub;
+        qk::ref_keygen_kernel<<<(unsigned)((a.n_frames + 127) / 128), 128, 0, s>>>(a);
+        c->kernel_launches += 1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    return QKDLDPC_OK;
+}
+
+int qkdldpc_run_trials(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_trials, const uint64_t *trial_seeds, uint64_t seed_offset,
+                       double qber, const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos, int32_t n_short,
+                       uint32_t *out_bits, int32_t *out_iters, uint8_t *out_flags, uint64_t *tally, double *accurate_qber_out) {
+    int rc = check_params(c, P, n_trials);
+    if (rc) return rc;
+    const int64_t tl = qkdldpc_tally_len(P->max_iterations);
+    double acc = 0.;
+    const size_t words = (size_t)(c->n + 31) / 32, tot = (size_t)n_trials * words;
+    CK(cudaSetDevice(c->device));
+    CK(c->st_alice.reserve(std::max<size_t>(tot, 1)));
+    CK(c->st_bob.reserve(std::max<size_t>(tot, 1)));
+    rc = qkdldpc_generate_trial_inputs_device(c, n_trials, trial_seeds, seed_offset, qber, punct_pos, n_punct, short_pos, n_short,
+                                              c->st_alice.p, c->st_bob.p, &acc);
+    if (rc) return rc;
+    if (accurate_qber_out) *accurate_qber_out = acc;
+    if (n_trials == 0) {
+        if (tally) memset(tally, 0, tl * sizeof(uint64_t));
+        return QKDLDPC_OK;
+    }
+    if (acc == 0.)   // run_trial throws here (simulation.cpp:556-557)
+        return fail(QKDLDPC_ERR_INVALID, "Key size '%d' is too small for QBER.", c->n);
+    CK(c->st_qber.reserve(1));
+    if (out_bits) CK(c->st_out.reserve(tot));
+    CK(c->st_iters.reserve(n_trials));
+    CK(c->st_flags.reserve(n_trials));
+    CK(c->st_tally.reserve(tl));
+    cudaStream_t s = c->stream;
+    CK(cudaMemcpyAsync(c->st_qber.p, &acc, sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = qkdldpc_decode_batch_device(c, P, n_trials, c->st_alice.p, c->st_bob.p, c->st_qber.p, 1, punct_pos, n_punct, short_pos, n_short,
+                                     out_bits ? c->st_out.p : nullptr, c->st_iters.p, c->st_flags.p,
+                                     reinterpret_cast<uint64_t *>(c->st_tally.p));
+    if (rc) return rc;
+    if (out_bits) CK(cudaMemcpyAsync(out_bits, c->st_out.p, tot * 4, cudaMemcpyDeviceToHost, s));
+    if (out_iters) CK(cudaMemcpyAsync(out_iters, c->st_iters.p, n_trials * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (out_flags) CK(cudaMemcpyAsync(out_flags, c->st_flags.p, n_trials, cudaMemcpyDeviceToHost, s));
+    if (tally) CK(cudaMemcpyAsync(tally, c->st_tally.p, tl * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return QKDLDPC_OK;
 }
 

@@ -49,4 +49,150 @@ __global__ void __launch_bounds__(128) gen_keys_kernel(int n, int words, int n_e
     for (int w = tid; w < words; w += blockDim.x) bob[f * words + w] = alice[f * words + w] ^ s_err[w];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Reference-compatible trial inputs ON THE DEVICE: the frames this kernel writes are bit-identical to what the
+// reference's run_trial builds on the CPU for the same per-trial seed (simulation.cpp:549-555, 743):
+//   prng = xoshiro256++ seeded through SplitMix64 with seeds[n] + combination index (XoshiroCpp v1.1);
+//   fill_random_bits   (array_and_matrix_operations.cpp:889-901): N draws, bit = draw >> 63 (libstdc++'s
+//                      uniform_int_distribution<int>(0,1) on a 64-bit engine: Lemire's method with range 2);
+//   inject_errors      (:905-933): std::shuffle of 0..N-1, flip the bits at the first floor(N*QBER) entries;
+//   QKD_LDPC_RATE_ADAPT (qkd_ldpc_algorithm.cpp:1148-1174): punctured positions (ascending) take one more draw per
+//                      party, shortened positions are 0, the others take the first payload bits in order.
+// libstdc++ 13's std::shuffle (bits/stl_algo.h:3742-3805) walks i = 1..N-1 swapping a[i] with a[j], j uniform in
+// [0, i], two positions per engine draw: x = uniform(0, (i+1)(i+2)-1) by Lemire's nearly-divisionless method
+// (bits/uniform_int_dist.h:257-281, 128-bit product, rejection below (2^64 - R) % R), j_i = x / (i+2),
+// j_{i+1} = x % (i+2); an even N first spends one draw on a[1] <-> a[draw >> 63].
+// Only the first K = floor(N*QBER) entries of the shuffled array are used, and they can be had WITHOUT the array:
+// before step i, a[i] still holds i (earlier steps only touched indices < i), so step i writes the value i into
+// a[j]; a step with i >= K therefore matters only when j < K (prefix[j] = i), whatever it moves out of the prefix
+// never comes back. Steps i < K are real swaps inside the prefix. One thread per frame, sequential like the CPU code.
+struct Xoshiro256pp {
+    u64 s0, s1, s2, s3;
+    __device__ __forceinline__ explicit Xoshiro256pp(u64 seed) {
+        u64 x = seed;
+        auto next = [&x]() {
+            x += 0x9e3779b97f4a7c15ull;
+            u64 z = x;
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            return z ^ (z >> 31);
+        };
+        s0 = next(); s1 = next(); s2 = next(); s3 = next();
+    }
+    static __device__ __forceinline__ u64 rotl(u64 v, int k) { return (v << k) | (v >> (64 - k)); }
+    __device__ __forceinline__ u64 operator()() {
+        const u64 r = rotl(s0 + s3, 23) + s0;
+        const u64 t = s1 << 17;
+        s2 ^= s0; s3 ^= s1; s1 ^= s2; s0 ^= s3; s2 ^= t;
+        s3 = rotl(s3, 45);
+        return r;
+    }
+    // std::uniform_int_distribution<uint64>{0, range - 1}: Lemire's nearly-divisionless method, as libstdc++ does it
+    __device__ __forceinline__ u64 below(u64 range) {
+        u64 d = (*this)();
+        u64 lo = d * range;
+        if (lo < range) {
+            const u64 threshold = (0ull - range) % range;
+            while (lo < threshold) {
+                d = (*this)();
+                lo = d * range;
+            }
+        }
+        return __umul64hi(d, range);
+    }
+};
+
+struct RefKeygenArgs {
+    int n, words, n_err;
+    long long n_frames;
+    const u64 *seeds;          // [n_frames] per-trial seeds (simulation.cpp:713-719)
+    u64 seed_offset;           // + combination index (simulation.cpp:743)
+    uint32_t *alice, *bob;     // [n_frames][words] output frames (extended frames when rate adaptation is on)
+    int rate_adapt;            // punctured / shortened masks present
+    const uint32_t *punct_mask, *short_mask;   // [words] packed positions (shortened excludes punctured)
+    uint32_t *scratch;         // thread-interleaved: [(2*words if rate_adapt) + n_err][threads of the launch]
+    long long scratch_stride;  // threads of the launch
+};
+
+__global__ void __launch_bounds__(128) ref_keygen_kernel(const RefKeygenArgs a) {
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= a.n_frames) return;
+    const long long T = a.scratch_stride;
+    uint32_t *raw_a = a.scratch + f;                                  // raw_a[w * T]  (rate adaptation only)
+    uint32_t *raw_b = raw_a + (a.rate_adapt ? (long long)a.words * T : 0);
+    uint32_t *prefix = a.scratch + (a.rate_adapt ? 2ll * a.words * T : 0) + f;   // prefix[j * T]
+    uint32_t *out_a = a.alice + f * a.words, *out_b = a.bob + f * a.words;
+    Xoshiro256pp g(a.seeds[f] + a.seed_offset);
+
+    // fill_random_bits
+    for (int w = 0; w < a.words; ++w) {
+        const int cnt = min(32, a.n - w * 32);
+        uint32_t word = 0;
+        for (int b = 0; b < cnt; ++b) word |= (uint32_t)(g() >> 63) << b;
+        if (a.rate_adapt) { raw_a[(long long)w * T] = word; raw_b[(long long)w * T] = word; }
+        else { out_a[w] = word; out_b[w] = word; }
+    }
+
+    // inject_errors: the first K entries of std::shuffle(0..N-1), without the array
+    const int K = a.n_err;
+    if (K > 0) {
+        for (int j = 0; j < K; ++j) prefix[(long long)j * T] = (uint32_t)j;
+        auto step = [&](uint32_t i, uint32_t j) {   // std::iter_swap(first + i, first + j), j <= i
+            if (i < (uint32_t)K) {
+                const uint32_t vi = prefix[(long long)i * T], vj = prefix[(long long)j * T];
+                prefix[(long long)i * T] = vj;
+                prefix[(long long)j * T] = vi;
+            } else if (j < (uint32_t)K) {
+                prefix[(long long)j * T] = i;
+            }
+        };
+        uint32_t i = 1;
+        const uint32_t N = (uint32_t)a.n;
+        if (N > 1 && (N % 2) == 0) {
+            step(1, (uint32_t)(g() >> 63));
+            i = 2;
+        }
+        for (; i < N; i += 2) {
+            const u64 b1 = (u64)i + 2;                       // __swap_range + 1
+            const u64 x = g.below(((u64)i + 1) * b1);
+            uint32_t p0, p1;
+            if (b1 * b1 <= 0xFFFFFFFFull) {                  // x < (i+1)(i+2) fits 32 bits: cheap division
+                p0 = (uint32_t)x / (uint32_t)b1;
+                p1 = (uint32_t)x % (uint32_t)b1;
+            } else {
+                p0 = (uint32_t)(x / b1);
+                p1 = (uint32_t)(x % b1);
+            }
+            step(i, p0);
+            step(i + 1, p1);
+        }
+        for (int j = 0; j < K; ++j) {
+            const uint32_t p = prefix[(long long)j * T];
+            if (a.rate_adapt) raw_b[(long long)(p >> 5) * T] ^= 1u << (p & 31);
+            else out_b[p >> 5] ^= 1u << (p & 31);
+        }
+    }
+    if (!a.rate_adapt) return;
+
+    // QKD_LDPC_RATE_ADAPT frame construction
+    int k = 0;   // payload index n of the reference loop
+    for (int w = 0; w < a.words; ++w) {
+        const uint32_t pm = a.punct_mask[w], sm = a.short_mask[w];
+        const int cnt = min(32, a.n - w * 32);
+        uint32_t wa = 0, wb = 0;
+        for (int b = 0; b < cnt; ++b) {
+            if ((pm >> b) & 1u) {
+                wa |= (uint32_t)(g() >> 63) << b;
+                wb |= (uint32_t)(g() >> 63) << b;
+            } else if (!((sm >> b) & 1u)) {
+                wa |= ((raw_a[(long long)(k >> 5) * T] >> (k & 31)) & 1u) << b;
+                wb |= ((raw_b[(long long)(k >> 5) * T] >> (k & 31)) & 1u) << b;
+                ++k;
+            }
+        }
+        out_a[w] = wa;
+        out_b[w] = wb;
+    }
+}
+
 }  // namespace qk

@@ -108,6 +108,9 @@ struct qkdldpc_code {
     DevBuf<int32_t> st_iters;
     DevBuf<uint8_t> st_flags;
     DevBuf<unsigned long long> st_tally;
+    // reference-compatible trial-input generator (gen_kernels.cuh)
+    DevBuf<uint64_t> gen_seeds;
+    DevBuf<uint32_t> gen_masks, gen_scratch;
     unsigned long long *h_done = nullptr;   // pinned
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll = nullptr;
     // captured step graph

@@ -217,6 +217,46 @@ class LdpcCode:
             ns_, vp(d_out_bits), vp(d_out_iters), vp(d_out_flags), vp(d_tally)), "qkdldpc_decode_batch_device")
         del pa, sa
 
+    def run_trials(self, trial_seeds, QBER: float, scaling_factors=(0.0, 0.0), cfg: Optional[DecoderConfig] = None,
+                   seed_offset: int = 0, punctured_bits: Sequence[int] = (), shortened_bits: Sequence[int] = (),
+                   want_bits: bool = True) -> BatchResult:
+        """The batched ``run_trial`` (simulation.cpp:540-577): inputs of every trial are generated ON THE DEVICE from
+        ``Xoshiro256++(trial_seeds[n] + seed_offset)`` exactly as the reference does on the CPU, then decoded.
+        ``QBER`` is the configured QBER; the accurate one is in ``result.info["accurate_qber"]``."""
+        cfg = cfg or DecoderConfig()
+        L = _cabi.lib()
+        seeds = np.ascontiguousarray(trial_seeds, np.uint64)
+        F = int(seeds.size)
+        p = cfg.to_params(scaling_factors)
+        pa, pp, np_ = self._poslist(punctured_bits)
+        sa, sp, ns_ = self._poslist(shortened_bits)
+        out_bits = np.zeros((F, self.words), np.uint32) if want_bits else None
+        iters = np.zeros(F, np.int32)
+        flags = np.zeros(F, np.uint8)
+        tally = np.zeros(int(L.qkdldpc_tally_len(p.max_iterations)), np.uint64)
+        acc = C.c_double()
+        _cabi.check(L.qkdldpc_run_trials(self._h, C.byref(p), F, seeds.ctypes.data, int(seed_offset), float(QBER), pp, np_, sp, ns_,
+                                         out_bits.ctypes.data if want_bits else None, iters.ctypes.data, flags.ctypes.data,
+                                         tally.ctypes.data, C.byref(acc)), "qkdldpc_run_trials")
+        del pa, sa
+        inf = self.info()
+        inf["accurate_qber"] = acc.value
+        return BatchResult(iters, flags, out_bits, tally, self.n, inf["last_batch_ms"], inf)
+
+    def generate_trial_inputs_device(self, trial_seeds, qber: float, d_alice: int, d_bob: int, seed_offset: int = 0,
+                                     punctured_bits: Sequence[int] = (), shortened_bits: Sequence[int] = ()) -> float:
+        """Reference-compatible trial inputs written to DEVICE buffers (``qkdldpc_generate_trial_inputs_device``);
+        returns the accurate QBER."""
+        seeds = np.ascontiguousarray(trial_seeds, np.uint64)
+        pa, pp, np_ = self._poslist(punctured_bits)
+        sa, sp, ns_ = self._poslist(shortened_bits)
+        acc = C.c_double()
+        _cabi.check(_cabi.lib().qkdldpc_generate_trial_inputs_device(
+            self._h, int(seeds.size), seeds.ctypes.data, int(seed_offset), float(qber), pp, np_, sp, ns_, C.c_void_p(d_alice),
+            C.c_void_p(d_bob), C.byref(acc)), "qkdldpc_generate_trial_inputs_device")
+        del pa, sa
+        return acc.value
+
     def generate_keys_device(self, n_frames: int, qber: float, seed: int, d_alice: int, d_bob: int) -> float:
         acc = C.c_double()
         _cabi.check(_cabi.lib().qkdldpc_generate_keys_device(self._h, int(n_frames), float(qber), int(seed),

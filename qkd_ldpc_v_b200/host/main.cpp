@@ -38,6 +38,7 @@ const char *kHelp =
     "  --concurrent K      combinations decoded concurrently per device (own handle and stream each); default: automatic\n"
     "                      (1 for large trial counts, up to 8 for rate-adaptation sweeps of ~100 trials)\n"
     "  --trials T          override trials_number of the config\n"
+    "  --host-keygen       generate the trial inputs on host threads and upload them; default: on the device, bit-identical\n"
     "  --quiet             no per-combination progress lines\n"
     "  --wait              wait for Enter before exiting, like the reference\n"
     "\n"
@@ -150,6 +151,7 @@ int main(int argc, char *argv[]) {
             else if (arg == "--chunk-frames") dev.chunk_frames = std::stoll(value());
             else if (arg == "--concurrent") dev.concurrent_combinations = std::stoi(value());
             else if (arg == "--trials") trials_override = std::stol(value());
+            else if (arg == "--host-keygen") dev.host_keygen = true;
             else if (arg == "--quiet") dev.verbose = false;
             else if (arg == "--wait") wait = true;
             else throw std::runtime_error("unknown option " + arg + " (see --help)");
@@ -163,6 +165,7 @@ int main(int argc, char *argv[]) {
         api.code_destroy = &qkdldpc_code_destroy;
         api.decode_batch = &qkdldpc_decode_batch;
         api.last_error = &qkdldpc_last_error;
+        api.run_trials = &qkdldpc_run_trials;
 
         std::vector<fs::path> config_paths;
         if (!config_file.empty()) config_paths.push_back(config_file);

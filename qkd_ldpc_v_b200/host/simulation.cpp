@@ -262,8 +262,32 @@ struct range_outcome {
 };
 range_outcome decode_trial_range(const config_data &cfg, const decoder_api &api, qkdldpc_code *code, const qkdldpc_params &P,
                                  const H_matrix &matrix, const sim_combination &comb, const std::vector<uint64_t> &seeds, size_t curr_sim,
-                                 size_t lo, size_t hi, size_t chunk, size_t gen_threads, std::vector<uint64_t> &tally) {
+                                 size_t lo, size_t hi, size_t chunk, size_t gen_threads, bool host_keygen, std::vector<uint64_t> &tally) {
     range_outcome out;
+    if (!host_keygen && api.run_trials) {
+        // inputs are generated on the device from the per-trial seeds (bit-identical to run_trial's, simulation.cpp:549-555):
+        // only 8 bytes per trial cross PCIe
+        const auto &mp = comb.matrix_params;
+        const bool ra = cfg.ENABLE_CODE_RATE_ADAPTATION;
+        std::vector<uint64_t> t(tally.size());
+        for (size_t pos = lo; pos < hi; pos += chunk) {
+            const size_t cnt = std::min(chunk, hi - pos);
+            double acc = 0.;
+            const auto t0 = std::chrono::steady_clock::now();
+            const int rc = api.run_trials(code, &P, static_cast<int64_t>(cnt), seeds.data() + pos, static_cast<uint64_t>(curr_sim), comb.config_QBER,
+                                          ra ? mp.punctured_bits.data() : nullptr, ra ? static_cast<int32_t>(mp.punctured_bits.size()) : 0,
+                                          ra ? mp.shortened_bits.data() : nullptr, ra ? static_cast<int32_t>(mp.shortened_bits.size()) : 0,
+                                          nullptr, nullptr, nullptr, t.data(), &acc);
+            out.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (rc != 0) {
+                const std::string msg = api.last_error();
+                throw std::runtime_error(msg.rfind("Key size", 0) == 0 ? msg : "qkdldpc_run_trials: " + msg);
+            }
+            for (size_t k = 0; k < tally.size(); ++k) tally[k] += t[k];
+            if (pos == lo) out.accurate_qber = acc;
+        }
+        return out;
+    }
     chunk_buffers cur, nxt;
     std::vector<uint64_t> t(tally.size());
     size_t pos = lo;
@@ -365,7 +389,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
                         for (size_t ci = next.fetch_add(1); ci < n_comb; ci = next.fetch_add(1)) {
                             const sim_combination &comb = in.combinations[ci];
                             const range_outcome o = decode_trial_range(cfg, api, codes[l], params_of(comb), matrix, comb, seeds, first_sim + ci,
-                                                                       0, trials, chunk, gen_threads, totals[ci]);
+                                                                       0, trials, chunk, gen_threads, dev.host_keygen, totals[ci]);
                             acc_qber[ci] = o.accurate_qber;
                             comb_ms[ci] = o.ms;
                         }
@@ -386,7 +410,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
                         try {
                             const size_t lo = trials * d / n_dev, hi = trials * (d + 1) / n_dev;   // contiguous trial range
                             outc[d] = decode_trial_range(cfg, api, codes[d], params_of(comb), matrix, comb, seeds, first_sim + ci, lo, hi, chunk,
-                                                         gen_threads, part[d]);
+                                                         gen_threads, dev.host_keygen, part[d]);
                         } catch (const std::exception &e) {
                             errors[d] = e.what();
                         }

@@ -69,6 +69,8 @@ struct device_options {
     int message_precision = 32;      // 32: float32 messages; 64: float64 parity mode
     int64_t chunk_frames = 65536;    // frames generated / uploaded per qkdldpc_decode_batch call and device
     int64_t pool_bytes = 0;          // 0 = library default
+    bool host_keygen = false;        // true: generate the trial inputs on host threads and upload them (cross-check path);
+                                     // false: generate them on the device, bit-identical (qkdldpc_run_trials)
     int concurrent_combinations = 0; // combinations decoded at the same time per device (own handle + stream each);
                                      // 0 = automatic: 1 for large trial counts, up to 8 for sweeps of small batches
     bool verbose = true;
@@ -81,6 +83,7 @@ struct decoder_api {
     decltype(&qkdldpc_code_destroy) code_destroy = nullptr;
     decltype(&qkdldpc_decode_batch) decode_batch = nullptr;
     decltype(&qkdldpc_last_error) last_error = nullptr;
+    decltype(&qkdldpc_run_trials) run_trials = nullptr;   // batched run_trial with inputs generated on the device
 };
 
 std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const std::vector<sim_input> &sim_in,

@@ -1,0 +1,110 @@
+"""GPU: trial inputs generated on the device (qkdldpc_generate_trial_inputs_device / qkdldpc_run_trials) must be
+bit-identical to the host generator, which drives the reference's own libstdc++ distributions and std::shuffle with the
+same xoshiro256++ stream (tests/test_host_rng.py pins the host generator against keys produced by the compiled
+reference). Covers even / odd / tiny block lengths, zero and large error counts, the rate-adaptation frame extension and
+the batched run_trial."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def q(built):
+    import qkd_ldpc_v_b200 as q
+    return q
+
+
+_handles = {}
+
+
+def handle(q, name, **kw):
+    key = (name, tuple(sorted(kw.items())))
+    if key not in _handles:
+        a = util.code_arrays(name)
+        _handles[key] = q.LdpcCode(a["n"], a["m"], a["row_ptr"], a["col_idx"], device=0, **kw)
+    return _handles[key]
+
+
+def device_keys(q, name, seeds, qber, offset=0, punct=(), short=()):
+    import torch
+    arr = util.code_arrays(name)
+    words = (arr["n"] + 31) // 32
+    da = torch.zeros((len(seeds), words), dtype=torch.int32, device="cuda:0")
+    db = torch.zeros_like(da)
+    acc = handle(q, name).generate_trial_inputs_device(seeds, qber, da.data_ptr(), db.data_ptr(), seed_offset=offset,
+                                                       punctured_bits=punct, shortened_bits=short)
+    torch.cuda.synchronize()
+    return da.cpu().numpy().view(np.uint32), db.cpu().numpy().view(np.uint32), acc
+
+
+@pytest.mark.parametrize("name,qber,frames", [("N6", 0.2, 64), ("N6", 0.5, 40), ("N7", 0.3, 64), ("N7", 0.15, 33), ("N100", 0.03, 200),
+                                              ("N100", 0.005, 50), ("K1_5", 0.02, 300), ("K1_5", 0.118, 100), ("K1_3", 0.0009, 64),
+                                              ("A79", 0.03, 150), ("A79", 0.002, 64), ("L100k", 0.06, 12)])
+def test_device_keys_equal_host_keys(q, name, qber, frames):
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays(name)
+    seeds = hostlib.trial_seeds(20251018, frames)
+    ha, hb, hacc = hostlib.gen_keys(seeds, arr["n"], qber)
+    da, db, dacc = device_keys(q, name, seeds, qber)
+    assert dacc == hacc
+    assert (da == ha).all(), "Alice keys differ"
+    assert (db == hb).all(), "Bob keys differ"
+    if hacc > 0:
+        flips = np.unpackbits((da ^ db).view(np.uint8), axis=1).sum(axis=1)
+        assert (flips == round(hacc * arr["n"])).all()       # exactly floor(N * QBER) errors per frame
+
+
+def test_seed_offset_is_added_to_every_seed(q):
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays("K1_4")
+    seeds = hostlib.trial_seeds(5, 100)
+    with np.errstate(over="ignore"):
+        shifted = seeds + np.uint64(12345)
+    ha, hb, _ = hostlib.gen_keys(shifted, arr["n"], 0.03)
+    da, db, _ = device_keys(q, "K1_4", seeds, 0.03, offset=12345)
+    assert (da == ha).all() and (db == hb).all()
+
+
+@pytest.mark.parametrize("name,qber,n_p,n_s", [("K1_5", 0.02, 60, 25), ("I80", 0.0196, 278, 29), ("I80", 0.0276, 54, 1072),
+                                               ("N100", 0.05, 7, 0), ("N100", 0.05, 0, 9)])
+def test_rate_adapted_frames_equal_host(q, name, qber, n_p, n_s):
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays(name)
+    rng = np.random.default_rng(n_p * 131 + n_s)
+    pos = rng.permutation(arr["n"])
+    p, s = np.sort(pos[:n_p]).astype(np.int32), np.sort(pos[n_p:n_p + n_s]).astype(np.int32)
+    seeds = hostlib.trial_seeds(99, 80)
+    ha, hb, hacc = hostlib.gen_keys_rate_adapt(seeds, arr["n"], qber, p, s)
+    da, db, dacc = device_keys(q, name, seeds, qber, punct=p, short=s)
+    assert dacc == hacc
+    assert (da == ha).all() and (db == hb).all()
+
+
+@pytest.mark.parametrize("alg,path", [(2, 0), (0, 0), (5, 1)])
+def test_run_trials_equals_decode_of_host_keys(q, alg, path):
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays("K1_5")
+    seeds = hostlib.trial_seeds(777, 500)
+    fac = {2: (0.75, 0.0), 0: (0.0, 0.0), 5: (0.3, 0.9)}[alg]
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32)
+    h = handle(q, "K1_5", decoder_path=path)
+    with np.errstate(over="ignore"):
+        a, b, acc = hostlib.gen_keys(seeds + np.uint64(3), arr["n"], 0.02)
+    r_host = h.QKD_LDPC_batch(a, b, acc, fac, cfg)
+    r_dev = h.run_trials(seeds, 0.02, fac, cfg, seed_offset=3)
+    assert r_dev.info["accurate_qber"] == acc
+    assert (r_dev.iterations_num == r_host.iterations_num).all() and (r_dev.flags == r_host.flags).all()
+    assert (r_dev.bob_solution == r_host.bob_solution).all() and (r_dev.tally == r_host.tally).all()
+
+
+def test_run_trials_rejects_qber_too_small_for_the_key(q):
+    """run_trial throws "Key size ... is too small for QBER." when floor(N * QBER) == 0 (simulation.cpp:556-557)."""
+    from qkd_ldpc_v_b200 import hostlib
+    from qkd_ldpc_v_b200._cabi import QkdLdpcError
+    with pytest.raises(QkdLdpcError, match="too small for QBER"):
+        handle(q, "N100").run_trials(hostlib.trial_seeds(1, 4), 0.001, (0.8, 0), q.DecoderConfig())
+    r = handle(q, "N100").run_trials(np.zeros(0, np.uint64), 0.05, (0.8, 0), q.DecoderConfig())
+    assert r.iterations_num.size == 0 and r.tally.sum() == 0

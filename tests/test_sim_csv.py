@@ -85,7 +85,8 @@ def test_csv_identical_minsum_fp64(built, tmp_path, alg):
     rname, ref_lines = _run_reference(tmp_path)
     # 400 trials per combination: qkdldpc_sim decodes several combinations concurrently (own handle + stream each);
     # alg 2 is also run strictly one combination at a time -- the CSV must not depend on it
-    oname, our_lines = _run_ours(tmp_path, 64, ["--concurrent", "1"] if alg == 2 else [])
+    # trial inputs are generated on the device by default (bit-identical to run_trial's); alg 3 uses the host generator
+    oname, our_lines = _run_ours(tmp_path, 64, {2: ["--concurrent", "1"], 3: ["--host-keygen"]}.get(alg, []))
     assert _strip_duration(rname) == _strip_duration(oname)
     assert len(ref_lines) == 1 + 3 + 2
     # the reference enumerates matrices in directory order; so do we (same directory) -> rows line up
