@@ -177,7 +177,7 @@ int main(int argc, char *argv[]) {
             print_config_info(cfg, config_paths[i].filename().string(), i + 1);
             const fs::path mdir = matrix_dir.empty() ? matrix_dir_for(root, cfg.MATRIX_FORMAT) : matrix_dir;
             const std::vector<fs::path> matrix_paths = get_file_paths_in_directory(mdir, ".mtrx");
-            const std::vector<sim_input> inputs = prepare_sim_inputs(cfg, matrix_paths, untp_cache);
+            const std::vector<sim_input> inputs = prepare_sim_inputs(cfg, matrix_paths, untp_cache, dev.verbose);
 
             const auto t0 = std::chrono::steady_clock::now();
             const std::vector<sim_result> results = QKD_LDPC_batch_simulation(cfg, inputs, api, dev);

@@ -119,7 +119,7 @@ void finish_adapted_params(const config_data &cfg, const H_matrix &matrix, H_mat
 // (untainted lists and random puncturing / shortening positions draw from it in matrix order).
 // ---------------------------------------------------------------------------------------------------------------
 std::vector<sim_input> prepare_sim_inputs(const config_data &cfg, const std::vector<fs::path> &matrix_paths,
-                                          const fs::path &untp_cache_dir) {
+                                          const fs::path &untp_cache_dir, bool print_warnings) {
     Xoshiro256pp prng(cfg.SIMULATION_SEED);
     std::vector<sim_input> inputs(matrix_paths.size());
     for (size_t i = 0; i < matrix_paths.size(); ++i) {
@@ -129,6 +129,7 @@ std::vector<sim_input> prepare_sim_inputs(const config_data &cfg, const std::vec
         const double code_rate = in.matrix.code_rate();
 
         std::vector<std::pair<double, H_matrix_params>> qber_params;
+        size_t skipped = 0;
         if (cfg.ENABLE_CODE_RATE_ADAPTATION) {
             if (cfg.ENABLE_UNTAINTED_PUNCTURING)
                 in.matrix.punctured_bits_untainted = get_punctured_bits_untainted(matrix_paths[i], prng, in.matrix, untp_cache_dir);
@@ -136,7 +137,8 @@ std::vector<sim_input> prepare_sim_inputs(const config_data &cfg, const std::vec
                 std::string warn;
                 H_matrix_params mp = adapt_code_rate(prng, in.matrix, qber, delta, efficiency, cfg.ENABLE_UNTAINTED_PUNCTURING, &warn);
                 if (mp.punctured_bits.empty() && mp.shortened_bits.empty()) {
-                    if (!warn.empty()) std::fprintf(stderr, "%s\n", warn.c_str());
+                    if (!warn.empty() && print_warnings) std::fprintf(stderr, "%s\n", warn.c_str());
+                    ++skipped;
                     return;   // combination skipped (simulation.cpp:413-415)
                 }
                 finish_adapted_params(cfg, in.matrix, mp);
@@ -169,6 +171,9 @@ std::vector<sim_input> prepare_sim_inputs(const config_data &cfg, const std::vec
             factors.push_back({});
         }
 
+        if (skipped > 0 && !print_warnings)
+            std::fprintf(stderr, "%s: %zu parameter combinations are outside the achievable rate range and will not be used\n",
+                         matrix_paths[i].filename().string().c_str(), skipped);
         in.combinations.reserve(qber_params.size() * factors.size());
         for (const auto &qp : qber_params)
             for (const auto &sf : factors) in.combinations.push_back({qp.first, qp.second, sf});

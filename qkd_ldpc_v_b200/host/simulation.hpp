@@ -58,7 +58,7 @@ double get_rate_based_scaling_factor_value(double code_rate, const std::vector<R
 
 // `untp_cache_dir`: where freshly generated `.untp` lists are written when the matrix directory is read-only.
 std::vector<sim_input> prepare_sim_inputs(const config_data &cfg, const std::vector<fs::path> &matrix_paths,
-                                          const fs::path &untp_cache_dir = {});
+                                          const fs::path &untp_cache_dir = {}, bool print_warnings = true);
 
 // Statistics of one combination from the tally vector of include/qkdldpc.h (length max_iterations + 5).
 // Same numbers as process_trials_results (simulation.cpp:580-624,683-689).

@@ -52,6 +52,27 @@ CONFIGS = {
 }
 
 
+def adaptive_r(coarse):
+    """`ADAPTIVE R.json` (schema v3, AOMSA, untainted puncturing) for the three irregular 10k codes of matrices_2.
+    coarse=True thins the QBER / delta / f_EC grids so that the CPU reference finishes in about a minute."""
+    q, d, e = (0.01, 0.1, 0.25) if coarse else (0.001, 0.05, 0.05)
+    rates = [(0.805, 0.0046, 0.0446, 0.7, 0.99), (0.655, 0.0338, 0.0738, 0.74, 0.94), (0.505, 0.0714, 0.1114, 0.72, 0.85)]
+    return dict(
+        {k: v for k, v in COMMON.items() if k != "matrix_format"}, matrix_format=3, simulation_seed=5555,
+        throughput_measurement_parameters=dict(consider_RTT=True, RTT=1.0), decoding_algorithm=5,
+        adaptive_min_sum_offset_parameters=dict(
+            use_beta_range=False, beta_range=dict(begin=0.01, end=1.0, step=0.01),
+            code_rate_beta_maps=[dict(code_rate=r, beta=b) for r, _, _, b, _ in rates], use_sigma_range=False,
+            sigma_range=dict(begin=0.01, end=1.0, step=0.01), code_rate_sigma_maps=[dict(code_rate=r, sigma=sg) for r, _, _, _, sg in rates]),
+        code_rate_QBER_maps=[dict(code_rate=r, QBER=dict(begin=b0, end=b1, step=q)) for r, b0, b1, _, _ in rates],
+        enable_code_rate_adaptation=True, enable_untainted_puncturing=True,
+        code_rate_adaptation_parameters_maps=[dict(code_rate=r, delta=dict(begin=0.05, end=0.3 if not coarse else 0.25, step=d),
+                                                   efficiency=dict(begin=1.0, end=2.0, step=e)) for r, *_ in rates])
+
+
+CONFIGS["adaptiveR"] = dict(codes=["I80", "I65", "I50"], trials=100, cfg=adaptive_r(False), ref_cfg=adaptive_r(True))
+
+
 def wilson(k, n, z=1.96):
     p = k / n
     d = 1 + z * z / n
@@ -63,7 +84,7 @@ def wilson(k, n, z=1.96):
 def to_v4(cfg):
     """The same run in the schema the reference's parser accepts today (config.cpp:89-403); the archived configs are
     schema v1, which only our parser reads."""
-    nm = cfg["min_sum_normalized_parameters"]
+    nm = cfg.get("min_sum_normalized_parameters")
     unused = dict(use_range=False, rng=dict(begin=0.1, end=1.0, step=0.1), maps=[dict(code_rate=0.99, v=0.5)])
     def block(prim, sec=None):
         b = {f"use_{prim}_range": unused["use_range"], f"{prim}_range": unused["rng"],
@@ -71,40 +92,48 @@ def to_v4(cfg):
         if sec:
             b.update({f"use_{sec}_range": False, f"{sec}_range": unused["rng"], f"code_rate_{sec}_maps": [{"code_rate": 0.99, sec: 0.5}]})
         return b
-    out = {k: v for k, v in cfg.items() if k not in ("use_min_sum_normalized_algorithm", "code_rate_QBER_maps", "interactive_mode")}
-    out["decoding_algorithm"] = 2 if cfg["use_min_sum_normalized_algorithm"] else 0
-    out["min_sum_normalized_parameters"] = nm
-    out["min_sum_offset_parameters"] = block("beta")
-    out["adaptive_min_sum_normalized_parameters"] = block("alpha", "nu")
-    out["adaptive_min_sum_offset_parameters"] = block("beta", "sigma")
-    out["code_rate_QBER_ranges"] = [dict(code_rate=m["code_rate"], QBER=dict(begin=m["QBER_begin"], end=m["QBER_end"], step=m["QBER_step"]))
-                                    for m in cfg["code_rate_QBER_maps"]]
-    out["enable_code_rate_adaptation"] = False
+    legacy_keys = ("use_min_sum_normalized_algorithm", "code_rate_QBER_maps", "interactive_mode", "enable_untainted_puncturing",
+                   "code_rate_adaptation_parameters_maps")
+    out = {k: v for k, v in cfg.items() if k not in legacy_keys}
+    if "decoding_algorithm" not in cfg:
+        out["decoding_algorithm"] = 2 if cfg["use_min_sum_normalized_algorithm"] else 0
+    out["min_sum_normalized_parameters"] = nm or block("alpha")
+    out.setdefault("min_sum_offset_parameters", block("beta"))
+    out.setdefault("adaptive_min_sum_normalized_parameters", block("alpha", "nu"))
+    out.setdefault("adaptive_min_sum_offset_parameters", block("beta", "sigma"))
+    out["code_rate_QBER_ranges"] = [dict(code_rate=m["code_rate"], QBER=m["QBER"] if "QBER" in m else
+                                         dict(begin=m["QBER_begin"], end=m["QBER_end"], step=m["QBER_step"])) for m in cfg["code_rate_QBER_maps"]]
+    out["enable_code_rate_adaptation"] = cfg.get("enable_code_rate_adaptation", False)
     out["code_rate_adaptation_parameters"] = dict(
-        enable_untainted_puncturing=False, use_adaptation_parameters_ranges=True,
-        code_rate_adaptation_parameters_ranges=[dict(code_rate=0.99, delta=dict(begin=0.05, end=0.1, step=0.05),
-                                                     efficiency=dict(begin=1.3, end=1.3, step=0.1))],
+        enable_untainted_puncturing=cfg.get("enable_untainted_puncturing", False), use_adaptation_parameters_ranges=True,
+        code_rate_adaptation_parameters_ranges=cfg.get("code_rate_adaptation_parameters_maps") or
+        [dict(code_rate=0.99, delta=dict(begin=0.05, end=0.1, step=0.05), efficiency=dict(begin=1.3, end=1.3, step=0.1))],
         code_rate_QBER_adaptation_parameters_maps=[])
     return out
 
 
-def setup(run_dir, spec, trials, legacy):
-    """legacy=True: the archived schema-v1 file (qkdldpc_sim); False: its v4 translation (the reference executable)."""
+def setup(run_dir, spec, trials, legacy, coarse=False):
+    """legacy=True: the archived legacy-schema file (qkdldpc_sim); False: its v4 translation (the reference executable).
+    coarse: the thinned parameter grid of configs whose full grid is too much CPU work for the reference arm."""
     os.makedirs(os.path.join(run_dir, "configs"))
-    mdir = os.path.join(run_dir, "sparse_matrices", "matrices_alist")
+    fmt = spec["cfg"]["matrix_format"]
+    mdir = os.path.join(run_dir, "sparse_matrices", {1: "matrices_alist", 3: "matrices_2"}[fmt])
     os.makedirs(mdir)
-    cfg = dict(spec["cfg"], trials_number=trials)
+    cfg = dict(spec["ref_cfg"] if coarse and "ref_cfg" in spec else spec["cfg"], trials_number=trials)
     with open(os.path.join(run_dir, "configs", "run.json"), "w") as f:
         json.dump(cfg if legacy else to_v4(cfg), f)
     for name in spec["codes"]:
-        util.write_alist(os.path.join(mdir, util.code_arrays(name)["file"]), name)
+        (util.write_alist if fmt == 1 else util.write_sparse2)(os.path.join(mdir, util.code_arrays(name)["file"]), name)
 
 
 def read_csv(directory):
+    """header, {(matrix, config QBER, delta, f_EC): row}"""
     files = [f for f in os.listdir(directory) if f.endswith(".csv")]
     assert len(files) == 1, files
     rows = [ln.split(";") for ln in open(os.path.join(directory, files[0])).read().splitlines()]
-    return rows[0], {r[1]: r for r in rows[1:]}
+    adapt = "DELTA" in rows[0]
+    i_d = rows[0].index("DELTA") if adapt else None
+    return rows[0], {(r[1], r[6]) + ((r[i_d], r[i_d + 1]) if adapt else ()): r for r in rows[1:]}
 
 
 def num(x):
@@ -124,14 +153,14 @@ def main():
 
     # reference executable vs qkdldpc_sim (float32 and float64) at the same trial count
     tmp_ref = tempfile.mkdtemp(prefix="cfgref_")
-    setup(tmp_ref, spec, args.ref_trials, legacy=False)
+    setup(tmp_ref, spec, args.ref_trials, legacy=False, coarse=True)
     t0 = time.perf_counter()
     with open(os.devnull) as nul:
         subprocess.run([REF_BIN], cwd=tmp_ref, stdin=nul, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
     t_ref = time.perf_counter() - t0
     hdr, ref = read_csv(os.path.join(tmp_ref, "results"))
     tmp = tempfile.mkdtemp(prefix="cfgpar_")
-    setup(tmp, spec, args.ref_trials, legacy=True)
+    setup(tmp, spec, args.ref_trials, legacy=True, coarse=True)
     report["runs"]["reference_cpu"] = {"seconds": t_ref, "threads": spec["cfg"]["threads_number"], "trials": args.ref_trials}
     for prec in (32, 64):
         out = os.path.join(tmp, f"results_gpu{prec}")
@@ -145,7 +174,7 @@ def main():
             o = ours[name]
             fails_ref = round(num(r[14]) * args.ref_trials)
             lo, hi = wilson(fails_ref, args.ref_trials)
-            rows.append({"matrix": name, "qber": num(r[6]), "fer_ref": num(r[14]), "fer_gpu": num(o[14]), "fer_ci95": [lo, hi],
+            rows.append({"matrix": name[0], "qber": num(r[6]), "fer_ref": num(r[14]), "fer_gpu": num(o[14]), "fer_ci95": [lo, hi],
                          "fer_inside_ci": lo - 1e-12 <= num(o[14]) <= hi + 1e-12, "iter_mean_ref": num(r[8]), "iter_mean_gpu": num(o[8]),
                          "row_identical": o == r})
         report["runs"][f"qkdldpc_sim_fp{prec}"] = {"seconds": dt, "trials": args.ref_trials, "gpus": args.gpus, "rows": rows,
@@ -161,9 +190,11 @@ def main():
         side = [f for f in os.listdir(out) if f.endswith(".gpu.json")][0]
         report["runs"]["qkdldpc_sim_full"] = {
             "seconds": dt, "trials": spec["trials"], "gpus": args.gpus,
-            "rows": [{"matrix": k, "qber": num(v[6]), "fer": num(v[14]), "iter_mean": num(v[8])} for k, v in ours.items()],
-            "sidecar": json.load(open(os.path.join(out, side)))["combinations"],
-            "reference_cpu_seconds_extrapolated": t_ref * spec["trials"] / args.ref_trials}
+            "combinations": len(ours),
+            "rows": [{"matrix": k[0], "qber": num(v[6]), "fer": num(v[14]), "iter_mean": num(v[8])} for k, v in list(ours.items())[:64]],
+            "sidecar": json.load(open(os.path.join(out, side)))["combinations"][:64],
+            # the reference's time scales with trials x combinations (the coarse grid of the reference arm has fewer)
+            "reference_cpu_seconds_extrapolated": t_ref * (spec["trials"] / args.ref_trials) * (len(ours) / max(1, len(ref)))}
     text = json.dumps(report, indent=1)
     print(text)
     if args.out:
