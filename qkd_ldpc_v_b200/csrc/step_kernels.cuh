@@ -111,7 +111,12 @@ struct RowState {
     }
     // Second pass (:64-70 / :400-408, :573-574, :759-767, :949-956). `kept` is what absorb() returned for this edge.
     __device__ __forceinline__ T emit(T kept, bool syn, T factor) const {
-        if constexpr (ALG <= 1) {
+        if constexpr (ALG == 0 && sizeof(T) == 4) {
+            // float SPA: 2 atanh(P / t) = ln((t + P) / (t - P)) -- one divide and one logarithm instead of a divide, a
+            // divide inside atanhf and a log1pf. Same special values as the reference's formula: t == 0 gives ln(-1) =
+            // NaN (0/0 -> NaN there), |P/t| == 1 gives +-inf (clamped), |P/t| > 1 by rounding gives NaN (quirk Q3).
+            return logf(__fdividef(kept + a, kept - a));
+        } else if constexpr (ALG <= 1) {
             return cn_two_atanh<T, ALG>(a / kept);
         } else {
             T sign_prod = syn ? (T)-1 : (T)1;
