@@ -54,6 +54,7 @@ def parse():
     p.add_argument("--path", type=int, default=0, choices=[0, 1, 2],
                    help="decoder path: 0 auto (on-chip min-sum when eligible), 1 streaming (messages in HBM), 2 on-chip")
     p.add_argument("--onchip-threads", type=int, default=0)
+    p.add_argument("--no-compaction", action="store_true", help="streaming path: do not compact the tail of a draining batch")
     p.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU-baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -217,7 +218,8 @@ def main():
     words = (n + 31) // 32
     F = args.frames
     code = q.LdpcCode(n, m, arr["row_ptr"], arr["col_idx"], device=local_rank, pool_slots=args.pool_slots,
-                      frames_per_lane_f32=args.frames_per_lane, decoder_path=args.path, onchip_threads=args.onchip_threads)
+                      frames_per_lane_f32=args.frames_per_lane, decoder_path=args.path, onchip_threads=args.onchip_threads,
+                      tail_compaction=-1 if args.no_compaction else 0)
     stream = torch.cuda.Stream(device=dev)      # a real stream: the decoder replays CUDA graphs on it
     torch.cuda.set_stream(stream)
     code.set_stream(stream.cuda_stream)

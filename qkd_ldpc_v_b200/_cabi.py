@@ -18,7 +18,7 @@ class Params(C.Structure):
 class Options(C.Structure):
     _fields_ = [("pool_bytes", C.c_int64), ("pool_slots", C.c_int32), ("steps_per_poll", C.c_int32),
                 ("frames_per_lane_f32", C.c_int32), ("use_graph", C.c_int32), ("decoder_path", C.c_int32),
-                ("onchip_threads", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("onchip_threads", C.c_int32), ("tail_compaction", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class Info(C.Structure):

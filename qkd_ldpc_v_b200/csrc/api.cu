@@ -276,7 +276,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         (oc_ok && ((e = up(c->oc_cn_ginfo, oc_cn_ginfo)) || (e = up(c->oc_cnT, oc_cnT)) || (e = up(c->oc_cn_row, oc_cn_row)) || (e = up(c->oc_vn_ginfo, oc_vn_ginfo)) ||
                    (e = up(c->oc_vn_bit, oc_vn_bit)) || (e = up(c->oc_vT, oc_vT)))) ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
-        (e = cudaMallocHost(&c->h_done, sizeof(unsigned long long))) || (e = cudaEventCreate(&c->ev0)) ||
+        (e = cudaMallocHost(&c->h_done, 2 * sizeof(unsigned long long))) || (e = cudaEventCreate(&c->ev0)) ||
         (e = cudaEventCreate(&c->ev1)) || (e = cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming))) {
         qkdldpc_code_destroy(c);
         return fail(QKDLDPC_ERR_CUDA, "graph upload failed: %s", cudaGetErrorString(e));
@@ -313,6 +313,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->st_alice.release(); c->st_bob.release(); c->st_out.release(); c->st_qber.release(); c->st_iters.release();
     c->st_flags.release(); c->st_tally.release();
     c->gen_seeds.release(); c->gen_masks.release(); c->gen_scratch.release();
+    c->compact_moves.release(); c->compact_plan.release();
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (c->h_done) cudaFreeHost(c->h_done);
     if (c->ev0) cudaEventDestroy(c->ev0);

@@ -111,7 +111,9 @@ struct qkdldpc_code {
     // reference-compatible trial-input generator (gen_kernels.cuh)
     DevBuf<uint64_t> gen_seeds;
     DevBuf<uint32_t> gen_masks, gen_scratch;
-    unsigned long long *h_done = nullptr;   // pinned
+    DevBuf<int2> compact_moves;        // tail compaction (sched_kernels.cuh)
+    DevBuf<int> compact_plan;
+    unsigned long long *h_done = nullptr;   // pinned [2]: frames handed out, frames finished
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll = nullptr;
     // captured step graph
     cudaGraphExec_t graph_exec = nullptr;

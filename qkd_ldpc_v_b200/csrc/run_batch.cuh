@@ -119,8 +119,11 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     const int64_t per_tile = (int64_t)c->nnz * FT * (int64_t)sizeof(T);
     // default 2 GiB: enough frames in flight to saturate HBM (>= 8k frames of a 10k code), small enough that a batch
     // refills every slot several times -- at converging operating points a pool as large as the batch leaves most lanes
-    // idle while each tile waits for its slowest frame
+    // idle while each tile waits for its slowest frame. Long codes (n = 100k: 157 MB of messages per 128-frame tile) get
+    // at least 32 tiles: the scheduler handles one tile per CTA, and with a dozen tiles its retire / refill work (bit
+    // transposes of n-bit frames) costs more than the decoding (measured 75 vs 55 ms per step at 13 tiles).
     int64_t budget = c->opt.pool_bytes > 0 ? c->opt.pool_bytes : (int64_t)2 << 30;
+    if (c->opt.pool_bytes <= 0) budget = std::max(budget, std::min<int64_t>(32 * per_tile, (int64_t)8 << 30));
     int64_t tiles = std::max<int64_t>(1, budget / std::max<int64_t>(per_tile, 1));
     if (c->opt.pool_slots > 0) tiles = std::max<int64_t>(1, (c->opt.pool_slots + FT - 1) / FT);
     tiles = std::min<int64_t>(tiles, tiles_needed);
@@ -202,14 +205,15 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     const int alg = P->algorithm;
     const bool fast = fast_minsum_ok(P);
     int launches_per_step = 0;
+    int cur_tiles = (int)tiles;   // shrinks when the tail of the batch is compacted (sched_kernels.cuh)
     auto one_step = [&](cudaStream_t st, bool prof) {
         EvPair *e = nullptr;
         if (prof) { e = next_ev(c, 0); cudaEventRecord(e->a, st); }
-        int nl = launch_cn<T, V>(c, alg, fast, (int)tiles, st, a);
+        int nl = launch_cn<T, V>(c, alg, fast, cur_tiles, st, a);
         if (prof) { cudaEventRecord(e->b, st); e = next_ev(c, 1); cudaEventRecord(e->a, st); }
-        nl += launch_vn<T, V>(c, fast, (int)tiles, st, a);
+        nl += launch_vn<T, V>(c, fast, cur_tiles, st, a);
         if (prof) { cudaEventRecord(e->b, st); e = next_ev(c, 2); cudaEventRecord(e->a, st); }
-        sched_kernel<T, V><<<(unsigned)tiles, kSchedThreads, 0, st>>>(a, b);
+        sched_kernel<T, V><<<(unsigned)cur_tiles, kSchedThreads, 0, st>>>(a, b);
         if (prof) cudaEventRecord(e->b, st);
         launches_per_step = nl + 1;
     };
@@ -220,8 +224,8 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     // (the legacy default stream cannot be captured: plain launches there)
     const bool use_graph = c->opt.use_graph >= 0 && !c->profiling && s != nullptr;
 
-    if (use_graph) {
-        // the captured launches embed every pointer and parameter of this batch: key the cache on all of them
+    // the captured launches embed every pointer and parameter of this batch: the cache is keyed on all of them
+    auto ensure_graph = [&]() -> int {
         unsigned long long h = 1469598103934665603ull;
         auto mixin = [&h](const void *p, size_t nbytes) {
             const unsigned char *q = static_cast<const unsigned char *>(p);
@@ -229,35 +233,42 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
         };
         mixin(&a, sizeof a);
         mixin(&b, sizeof b);
-        const int geo[6] = {(int)sizeof(T), V, alg, (int)tiles, spp, fast ? 1 : 0};
+        const int geo[6] = {(int)sizeof(T), V, alg, cur_tiles, spp, fast ? 1 : 0};
         mixin(geo, sizeof geo);
         char key[64];
         snprintf(key, sizeof key, "%016llx", h);
         if (c->graph_key != key) {
             if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+            c->graph_key.clear();
             cudaGraph_t g = nullptr;
             CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             for (int k = 0; k < spp; ++k) one_step(s, false);
-            CK(cudaMemcpyAsync(c->h_done, c->counters.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(c->h_done, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamEndCapture(s, &g));
             CK(cudaGraphInstantiate(&c->graph_exec, g, 0));
             cudaGraphDestroy(g);
             c->graph_key = key;
         }
+        return QKDLDPC_OK;
+    };
+    if (use_graph) {
+        const int rc = ensure_graph();
+        if (rc) return rc;
     }
 
-    *c->h_done = 0;
+    c->h_done[0] = c->h_done[1] = 0;   // [0] frames handed out by the queue, [1] frames finished
     // upper bound on steps: every generation of the pool needs at most max_iter steps (+1 for refills that
     // waited one step); guards against a hang if something is badly wrong
     const int64_t generations = (n_frames + (int64_t)slots - 1) / (int64_t)slots;
     const int64_t step_limit = (generations + 1) * ((int64_t)P->max_iterations + 2) + spp;
     int64_t steps = 0;
+    const bool compaction = c->opt.tail_compaction >= 0;
     while (true) {
         if (use_graph) {
             CK(cudaGraphLaunch(c->graph_exec, s));
         } else {
             for (int k = 0; k < spp; ++k) one_step(s, c->profiling);
-            CK(cudaMemcpyAsync(c->h_done, c->counters.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(c->h_done, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         }
         steps += spp;
         if (use_graph && launches_per_step == 0) {   // graph came from the cache: count its kernels once
@@ -268,10 +279,31 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
         c->decoder_steps += spp;
         CK(cudaEventRecord(c->ev_poll, s));
         CK(cudaEventSynchronize(c->ev_poll));
-        if (*c->h_done >= (unsigned long long)n_frames) break;
+        const unsigned long long handed_out = c->h_done[0], done = c->h_done[1];
+        if (done >= (unsigned long long)n_frames) break;
         if (steps > step_limit)
-            return fail(QKDLDPC_ERR_STATE, "decoder did not finish: %llu of %lld frames after %lld steps",
-                        *c->h_done, (long long)n_frames, (long long)steps);
+            return fail(QKDLDPC_ERR_STATE, "decoder did not finish: %llu of %lld frames after %lld steps", done, (long long)n_frames,
+                        (long long)steps);
+        // Tail compaction: the queue is empty and at most half of the slots of >= 4 tiles are still occupied
+        const long long remaining = (long long)n_frames - (long long)done;
+        if (compaction && handed_out >= (unsigned long long)n_frames && cur_tiles >= 4 && remaining * 2 <= (long long)cur_tiles * FT) {
+            CK(c->compact_moves.reserve((size_t)cur_tiles * FT));
+            CK(c->compact_plan.reserve(2));
+            auto *plan = reinterpret_cast<CompactPlan *>(c->compact_plan.p);
+            compact_plan_kernel<FT><<<1, 32, 0, s>>>(cur_tiles, c->slot_frame.p, c->compact_moves.p, plan);
+            const unsigned max_moves = (unsigned)std::min<long long>(remaining, 65535);
+            compact_msg_kernel<T, FT><<<dim3(max_moves, 8), 256, 0, s>>>(c->compact_moves.p, plan, a.msg, a.e_stride, (int)c->nnz);
+            compact_mask_kernel<V><<<dim3(max_moves, 4), 256, 0, s>>>(c->compact_moves.p, plan, n, m, a.bobmask, a.zmask, a.synd, a.par);
+            compact_finish_kernel<T, V><<<1, 1024, 0, s>>>(c->compact_moves.p, plan, cur_tiles, c->slot_frame.p, c->slot_iter.p, a.slot_llr,
+                                                          a.tile_active, a.tile_new);
+            c->kernel_launches += 4;
+            CK(cudaGetLastError());
+            cur_tiles = (int)std::max<long long>(1, (remaining + FT - 1) / FT);   // == plan->new_tiles (active == remaining)
+            if (use_graph) {
+                const int rc = ensure_graph();
+                if (rc) return rc;
+            }
+        }
     }
     CK(cudaEventRecord(c->ev1, s));
     CK(cudaEventSynchronize(c->ev1));

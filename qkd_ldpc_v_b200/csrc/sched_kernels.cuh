@@ -243,4 +243,101 @@ __global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, Bat
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tail compaction. Once the frame queue is empty the pool drains: every tile keeps running until its slowest frame is
+// done, and at a converging operating point that is a handful of stragglers (FER ~ 1 %: a third of the tiles hold
+// one frame that runs to max_iterations while the other 31 or 127 lanes idle). The host calls these kernels between two
+// steps when at most half of the slots are still occupied: occupied slots of the HIGH tiles move into free slots of the
+// first ceil(active / FT) tiles (sources and destinations are disjoint, so the move is in place and fully parallel)
+// and the step kernels are launched on the shrunk tile count from then on. A frame's state is its E messages, one bit
+// in each of the 2N + 2M mask words of its tile, and three slot words; results do not depend on where a frame sits.
+struct CompactPlan {
+    int n_moves;
+    int new_tiles;
+};
+
+// One thread walks the slot table (a few thousand entries, a few times per batch).
+template <int FT>
+__global__ void compact_plan_kernel(int tiles, const long long *slot_frame, int2 *moves, CompactPlan *plan) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int slots = tiles * FT;
+    int active = 0;
+    for (int s = 0; s < slots; ++s) active += slot_frame[s] >= 0;
+    const int new_tiles = max(1, (active + FT - 1) / FT);
+    int n = 0, dst = 0;
+    const int low = new_tiles * FT;
+    for (int src = low; src < slots; ++src) {
+        if (slot_frame[src] < 0) continue;
+        while (dst < low && slot_frame[dst] >= 0) ++dst;   // next free slot of the low tiles (exists: active <= low)
+        moves[n++] = make_int2(src, dst++);
+    }
+    plan->n_moves = n;
+    plan->new_tiles = new_tiles;
+}
+
+// grid = (moves, chunks): messages of the moved frames. Slot position p of a tile <-> message lane p (common.cuh).
+template <typename T, int FT>
+__global__ void __launch_bounds__(256) compact_msg_kernel(const int2 *moves, const CompactPlan *plan, T *msg, long long e_stride, int nnz) {
+    if ((int)blockIdx.x >= plan->n_moves) return;
+    const int2 mv = moves[blockIdx.x];
+    const T *src = msg + (long long)(mv.x / FT) * e_stride + (mv.x % FT);
+    T *dst = msg + (long long)(mv.y / FT) * e_stride + (mv.y % FT);
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < nnz; e += gridDim.y * blockDim.x) dst[(long long)e * FT] = src[(long long)e * FT];
+}
+
+// grid = (moves, chunks): one bit per mask word. Slot p <-> word v = p % V, bit l = p / V (sched_kernel).
+template <int V>
+__global__ void __launch_bounds__(256) compact_mask_kernel(const int2 *moves, const CompactPlan *plan, int n, int m, uint32_t *bobmask,
+                                                           uint32_t *zmask, uint32_t *synd, uint32_t *par) {
+    constexpr int FT = 32 * V;
+    if ((int)blockIdx.x >= plan->n_moves) return;
+    const int2 mv = moves[blockIdx.x];
+    const int st = mv.x / FT, sp = mv.x % FT, dt = mv.y / FT, dp = mv.y % FT;
+    const int sv = sp % V, sl = sp / V, dv = dp % V, dl = dp / V;
+    auto move_bit = [&](uint32_t *arr, int rows, int r) {
+        const uint32_t bit = (arr[((size_t)st * rows + r) * V + sv] >> sl) & 1u;
+        uint32_t *w = arr + ((size_t)dt * rows + r) * V + dv;
+        if (bit) atomicOr(w, 1u << dl);
+        else atomicAnd(w, ~(1u << dl));
+    };
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n + m; i += gridDim.y * blockDim.x) {
+        if (i < n) {
+            move_bit(bobmask, n, i);
+            move_bit(zmask, n, i);
+        } else {
+            move_bit(synd, m, i - n);
+            move_bit(par, m, i - n);
+        }
+    }
+}
+
+// Slot words of the moved frames, then the active / new masks of every tile of the old pool.
+template <typename T, int V>
+__global__ void compact_finish_kernel(const int2 *moves, const CompactPlan *plan, int old_tiles, long long *slot_frame, int32_t *slot_iter,
+                                      T *slot_llr, uint32_t *tile_active, uint32_t *tile_new) {
+    constexpr int FT = 32 * V;
+    const int nm = plan->n_moves;
+    for (int k = threadIdx.x; k < nm; k += blockDim.x) {   // single CTA: moves are disjoint
+        const int2 mv = moves[k];
+        slot_frame[mv.y] = slot_frame[mv.x];
+        slot_iter[mv.y] = slot_iter[mv.x];
+        slot_llr[mv.y] = slot_llr[mv.x];
+        slot_frame[mv.x] = -1;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < old_tiles * V; w += blockDim.x) {
+        const int tile = w / V, v = w % V;
+        uint32_t act = 0, nw = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int p = tile * FT + l * V + v;
+            if (slot_frame[p] >= 0) {
+                act |= 1u << l;
+                if (slot_iter[p] == -1) nw |= 1u << l;
+            }
+        }
+        tile_active[w] = act;
+        tile_new[w] = nw;
+    }
+}
+
 }  // namespace qk

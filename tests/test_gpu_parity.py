@@ -211,3 +211,23 @@ def test_rate_adaptation_against_reference(q, tmp_path, alg, pri, sec, point, un
     assert (r32.iterations_num == it).mean() >= 0.9
     both = r32.syndromes_match & ((fl & 1) != 0)
     assert (r32.keys_match[both] == ((fl[both] & 2) != 0)).all()
+
+
+@pytest.mark.parametrize("alg,prec,fpl,frames", [(0, 32, 1, 1500), (2, 32, 4, 3000), (5, 64, 0, 1200), (1, 32, 2, 1500)])
+def test_tail_compaction_does_not_change_results(q, alg, prec, fpl, frames):
+    """Streaming path: once the queue is empty the stragglers of a draining batch are moved into few tiles
+    (sched_kernels.cuh). Frames are independent, so every per-frame result and the tallies must be identical with the
+    compaction switched off -- at an operating point where some frames fail (they are the stragglers that get moved)."""
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays("K1_4")
+    seeds = hostlib.trial_seeds(31415, frames)
+    a, b, acc = hostlib.gen_keys(seeds, arr["n"], 0.038)
+    fac = {0: (0, 0), 1: (0, 0), 2: (0.75, 0), 5: (0.3, 0.9)}[alg]
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=prec)
+    kw = dict(decoder_path=1, frames_per_lane_f32=fpl)
+    on = handle(q, "K1_4", **kw).QKD_LDPC_batch(a, b, acc, fac, cfg)
+    off = handle(q, "K1_4", tail_compaction=-1, **kw).QKD_LDPC_batch(a, b, acc, fac, cfg)
+    assert 0 < (on.flags & 1).sum() < frames, "need both converging frames and stragglers"
+    assert (on.iterations_num == off.iterations_num).all() and (on.flags == off.flags).all()
+    assert (on.bob_solution == off.bob_solution).all() and (on.tally == off.tally).all()
+    assert on.info["decoder_steps"] <= off.info["decoder_steps"]
