@@ -313,7 +313,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->st_alice.release(); c->st_bob.release(); c->st_out.release(); c->st_qber.release(); c->st_iters.release();
     c->st_flags.release(); c->st_tally.release();
     c->gen_seeds.release(); c->gen_masks.release(); c->gen_scratch.release();
-    c->compact_moves.release(); c->compact_plan.release();
+    c->compact_moves.release(); c->compact_plan.release(); c->sched_work.release();
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (c->h_done) cudaFreeHost(c->h_done);
     if (c->ev0) cudaEventDestroy(c->ev0);

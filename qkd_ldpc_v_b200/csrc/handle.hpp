@@ -111,6 +111,7 @@ struct qkdldpc_code {
     // reference-compatible trial-input generator (gen_kernels.cuh)
     DevBuf<uint64_t> gen_seeds;
     DevBuf<uint32_t> gen_masks, gen_scratch;
+    DevBuf<unsigned char> sched_work;  // TileWork per tile (sched_kernels.cuh)
     DevBuf<int2> compact_moves;        // tail compaction (sched_kernels.cuh)
     DevBuf<int> compact_plan;
     unsigned long long *h_done = nullptr;   // pinned [2]: frames handed out, frames finished

@@ -198,8 +198,15 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     c->ev_used = 0;
     CK(cudaEventRecord(c->ev0, s));
     prep_kernel<T><<<(unsigned)n_frames, 256, 0, s>>>(n, m, c->row_ptr.p, c->col_idx.p, b);
-    sched_kernel<T, V><<<(unsigned)tiles, kSchedThreads, 0, s>>>(a, b);
-    c->kernel_launches += 2;
+    // scheduler work lists (one per tile) and the split of a tile's rows over the CTAs of sched_move_kernel
+    CK(c->sched_work.reserve((size_t)tiles * sizeof(TileWork<FT>)));
+    CK(cudaMemsetAsync(c->sched_work.p, 0, (size_t)tiles * sizeof(TileWork<FT>), s));
+    auto *work = reinterpret_cast<TileWork<FT> *>(c->sched_work.p);
+    const int rows_per_part = std::max(4096, ((std::max(n, m) + 63) / 64 + 31) / 32 * 32);   // multiple of 32, at most 64 parts
+    const unsigned move_parts = (unsigned)((std::max(n, m) + rows_per_part - 1) / rows_per_part);
+    sched_kernel<T, V><<<(unsigned)tiles, kSchedThreads, 0, s>>>(a, b, work);
+    sched_move_kernel<T, V><<<dim3((unsigned)tiles, move_parts), kSchedThreads, 0, s>>>(a, b, work, rows_per_part);
+    c->kernel_launches += 3;
     CK(cudaGetLastError());
 
     const int alg = P->algorithm;
@@ -213,9 +220,10 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
         if (prof) { cudaEventRecord(e->b, st); e = next_ev(c, 1); cudaEventRecord(e->a, st); }
         nl += launch_vn<T, V>(c, fast, cur_tiles, st, a);
         if (prof) { cudaEventRecord(e->b, st); e = next_ev(c, 2); cudaEventRecord(e->a, st); }
-        sched_kernel<T, V><<<(unsigned)cur_tiles, kSchedThreads, 0, st>>>(a, b);
+        sched_kernel<T, V><<<(unsigned)cur_tiles, kSchedThreads, 0, st>>>(a, b, work);
+        sched_move_kernel<T, V><<<dim3((unsigned)cur_tiles, move_parts), kSchedThreads, 0, st>>>(a, b, work, rows_per_part);
         if (prof) cudaEventRecord(e->b, st);
-        launches_per_step = nl + 1;
+        launches_per_step = nl + 2;
     };
 
     // steps between two host polls of the done counter: a frame needs at most max_iter steps, and the host
@@ -233,8 +241,9 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
         };
         mixin(&a, sizeof a);
         mixin(&b, sizeof b);
-        const int geo[6] = {(int)sizeof(T), V, alg, cur_tiles, spp, fast ? 1 : 0};
+        const int geo[8] = {(int)sizeof(T), V, alg, cur_tiles, spp, fast ? 1 : 0, rows_per_part, (int)move_parts};
         mixin(geo, sizeof geo);
+        mixin(&work, sizeof work);
         char key[64];
         snprintf(key, sizeof key, "%016llx", h);
         if (c->graph_key != key) {
@@ -273,7 +282,7 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
         steps += spp;
         if (use_graph && launches_per_step == 0) {   // graph came from the cache: count its kernels once
             for (int k = 0; k < kBuckets; ++k) launches_per_step += (c->cn_count[k] > 0) + (c->vn_count[k] > 0);
-            launches_per_step += 1;
+            launches_per_step += 2;
         }
         c->kernel_launches += (int64_t)launches_per_step * spp;
         c->decoder_steps += spp;

@@ -67,26 +67,39 @@ __global__ void __launch_bounds__(256) prep_kernel(int n, int m, const int *row_
     }
 }
 
-// K4: one CTA per tile, after every CN+VN step.
+// K4, part 1 (`sched_kernel`, one CTA per tile, after every CN+VN step):
 //  1. all-checks-satisfied test per slot: OR over rows of par (quirk Q9: non-adaptive variants test the decision
 //     of iteration t and return t; quirk Q10: adaptive variants test the INITIAL decision too, find success one
 //     iteration later (return t+1) and never test the decision of the last allowed iteration);
-//  2. retire finished frames: unpack the hard decision into out_bits, compare with Alice's key (arrays_equal,
-//     qkd_ldpc_algorithm.cpp:1087), write iterations / flags, update the tallies;
-//  3. refill free slots from the frame queue (continuous batching): transpose the new frame's key bits, syndrome
-//     and initial check values into the tile's bit masks, and publish the tile's active / new masks.
+//  2. decide which frames retire, hand every free slot the next frame of the queue (continuous batching), update the
+//     slot table and the tile's active / new masks, and leave the two work lists of the tile in global memory.
+// K4, part 2 (`sched_move_kernel`, several CTAs per tile, each owning a range of bit / check rows): the data movement,
+//     which for long codes is most of the scheduler's work and must not be serialised on one CTA per tile:
+//     retire -- unpack the hard decision into out_bits, compare with Alice's key (arrays_equal,
+//     qkd_ldpc_algorithm.cpp:1087); the last CTA of the tile to finish writes iterations / flags / tallies;
+//     refill -- transpose the new frames' key bits, syndromes and initial check values into the tile's bit masks.
+template <int FT>
+struct TileWork {
+    int nret, nnew;
+    int ticket;                 // CTAs of sched_move_kernel that have finished this tile (reset by the last one)
+    int ret[FT];                // retiring slots: slot | success << 8 | iterations << 9
+    int run[FT];                // decoder iterations those frames actually ran
+    long long ret_frame[FT];
+    unsigned int ret_diff[FT];  // != 0: decoded key differs from Alice's (OR over the CTAs of the tile)
+    int newslot[FT];
+    long long newframe[FT];
+};
+
 template <typename T, int V>
-__global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, BatchArgs<T> b) {
+__global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, BatchArgs<T> b, TileWork<32 * V> *work) {
     constexpr int FT = kWarp * V;
     __shared__ uint32_t s_unsat[V], s_act[V], s_newm[V];
-    __shared__ int s_ret[FT], s_nret;        // retiring slots: slot | success << 8 | iterations << 9
-    __shared__ int s_newslot[FT], s_nnew;
-    __shared__ long long s_newframe[FT];
+    __shared__ int s_nret, s_nnew;
     __shared__ int s_wfree[FT / 32 + 1];
     __shared__ u64 s_base;
-    __shared__ int s_run[FT];
 
     const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    TileWork<FT> &tw = work[tile];
     bool any_act = false;
 #pragma unroll
     for (int v = 0; v < V; ++v) any_act |= a.tile_active[tile * V + v] != 0;
@@ -131,39 +144,15 @@ __global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, Bat
             }
             if (done) {
                 const int idx = atomicAdd(&s_nret, 1);
-                s_ret[idx] = tid | (succ << 8) | (iters << 9);
-                s_run[idx] = it;
+                tw.ret[idx] = tid | (succ << 8) | (iters << 9);
+                tw.run[idx] = it;
+                tw.ret_frame[idx] = frame;
+                tw.ret_diff[idx] = 0u;
             } else {
                 b.slot_iter[(size_t)tile * FT + tid] = it;
             }
         }
     }
-    __syncthreads();
-
-    const int nret = s_nret;
-    for (int r = 0; r < nret; ++r) {
-        const int s = s_ret[r] & 255, succ = (s_ret[r] >> 8) & 1, iters = s_ret[r] >> 9;
-        const long long fr = b.slot_frame[(size_t)tile * FT + s];
-        const int v = s % V, l = s / V;
-        const uint32_t *zm = a.zmask + (size_t)tile * a.n * V + v;
-        uint32_t diff = 0;
-        for (int w = tid; w < b.words; w += blockDim.x) {
-            uint32_t word = 0;
-            const int i0 = w * 32;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k)
-                if (i0 + k < a.n) word |= ((zm[(size_t)(i0 + k) * V] >> l) & 1u) << k;
-            if (b.out_bits) b.out_bits[fr * b.words + w] = word;
-            diff |= word ^ b.alice_bits[fr * b.words + w];
-        }
-        const int keys_differ = __syncthreads_or(diff != 0);
-        if (tid == 0) {
-            if (b.out_iters) b.out_iters[fr] = iters;
-            if (b.out_flags) b.out_flags[fr] = (uint8_t)((succ ? 1u : 0u) | (keys_differ ? 0u : 2u));
-            tally_frame(b.tally, succ, !keys_differ, iters, s_run[r]);
-        }
-    }
-
     // refill: every free slot claims the next frame of the queue
     const bool is_free = tid < FT && (frame < 0 || done);
     const uint32_t fm = __ballot_sync(0xffffffffu, is_free);
@@ -175,7 +164,7 @@ __global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, Bat
         u64 base = (u64)b.n_frames;
         if (total > 0 && *(volatile u64 *)b.next_frame < (u64)b.n_frames) base = atomicAdd(b.next_frame, (u64)total);
         s_base = base;
-        if (nret) atomicAdd(b.n_done, (u64)nret);
+        if (s_nret) atomicAdd(b.n_done, (u64)s_nret);
     }
     __syncthreads();
     if (tid < FT) {
@@ -188,8 +177,8 @@ __global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, Bat
                 b.slot_iter[(size_t)tile * FT + tid] = -1;
                 a.slot_llr[(size_t)tile * FT + tid] = b.frame_llr[nf];
                 const int idx = atomicAdd(&s_nnew, 1);
-                s_newslot[idx] = tid;
-                s_newframe[idx] = nf;
+                tw.newslot[idx] = tid;
+                tw.newframe[idx] = nf;
                 atomicOr(&s_newm[sv], 1u << sl);
             }
         }
@@ -200,47 +189,102 @@ __global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, Bat
         a.tile_active[tile * V + tid] = s_act[tid];
         a.tile_new[tile * V + tid] = s_newm[tid];
     }
-    const int nnew = s_nnew;
-    if (nnew == 0) return;
+    if (tid == 0) {
+        tw.nret = s_nret;
+        tw.nnew = s_nnew;
+    }
+}
 
-    uint32_t *bm = a.bobmask + (size_t)tile * a.n * V;
-    for (int i = tid; i < a.n; i += blockDim.x) {
-        uint32_t mk[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) mk[v] = bm[(size_t)i * V + v];
-        for (int q = 0; q < nnew; ++q) {
-            const int s = s_newslot[q];
-            const uint32_t bit = (b.bob_bits[s_newframe[q] * b.words + (i >> 5)] >> (i & 31)) & 1u;
-            const int l = s / V;
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                if (v == s % V) mk[v] = (mk[v] & ~(1u << l)) | (bit << l);
+// grid = (tiles, parts): CTA (tile, p) owns bit rows [p * rows_per_part, ...) and the same range of check rows.
+template <typename T, int V>
+__global__ void __launch_bounds__(kSchedThreads) sched_move_kernel(StepArgs<T> a, BatchArgs<T> b, TileWork<32 * V> *work, int rows_per_part) {
+    constexpr int FT = kWarp * V;
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    TileWork<FT> &tw = work[tile];
+    const int nret = tw.nret, nnew = tw.nnew;
+    if (nret == 0 && nnew == 0) return;
+    const int r0 = blockIdx.y * rows_per_part;   // multiple of 32
+    __shared__ int s_last;
+
+    // retire
+    const int w0 = r0 >> 5, w1 = min(b.words, (r0 + rows_per_part) >> 5);
+    for (int r = 0; r < nret; ++r) {
+        const int s = tw.ret[r] & 255;
+        const long long fr = tw.ret_frame[r];
+        const int v = s % V, l = s / V;
+        const uint32_t *zm = a.zmask + (size_t)tile * a.n * V + v;
+        uint32_t diff = 0;
+        for (int w = w0 + tid; w < w1; w += blockDim.x) {
+            uint32_t word = 0;
+            const int i0 = w * 32;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k)
+                if (i0 + k < a.n) word |= ((zm[(size_t)(i0 + k) * V] >> l) & 1u) << k;
+            if (b.out_bits) b.out_bits[fr * b.words + w] = word;
+            diff |= word ^ b.alice_bits[fr * b.words + w];
         }
-#pragma unroll
-        for (int v = 0; v < V; ++v) bm[(size_t)i * V + v] = mk[v];
+        if (__syncthreads_or(diff != 0) && tid == 0) atomicOr(&tw.ret_diff[r], 1u);
     }
-    uint32_t *sy = a.synd + (size_t)tile * a.m * V;
-    uint32_t *pa = a.par + (size_t)tile * a.m * V;
-    for (int j = tid; j < a.m; j += blockDim.x) {
-        uint32_t ms[V], mp[V];
+
+    // refill
+    if (nnew > 0) {
+        uint32_t *bm = a.bobmask + (size_t)tile * a.n * V;
+        for (int i = r0 + tid; i < min(a.n, r0 + rows_per_part); i += blockDim.x) {
+            uint32_t mk[V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) { ms[v] = sy[(size_t)j * V + v]; mp[v] = pa[(size_t)j * V + v]; }
-        for (int q = 0; q < nnew; ++q) {
-            const int s = s_newslot[q];
-            const size_t off = s_newframe[q] * b.swords + (j >> 5);
-            const uint32_t sbit = (b.synd_all[off] >> (j & 31)) & 1u;
-            const uint32_t pbit = sbit;   // the VN-side init XORs the parity of the initial decision on top
-            const int l = s / V;
+            for (int v = 0; v < V; ++v) mk[v] = bm[(size_t)i * V + v];
+            for (int q = 0; q < nnew; ++q) {
+                const int s = tw.newslot[q];
+                const uint32_t bit = (b.bob_bits[tw.newframe[q] * b.words + (i >> 5)] >> (i & 31)) & 1u;
+                const int l = s / V;
 #pragma unroll
-            for (int v = 0; v < V; ++v)
-                if (v == s % V) {
-                    ms[v] = (ms[v] & ~(1u << l)) | (sbit << l);
-                    mp[v] = (mp[v] & ~(1u << l)) | (pbit << l);
-                }
+                for (int v = 0; v < V; ++v)
+                    if (v == s % V) mk[v] = (mk[v] & ~(1u << l)) | (bit << l);
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) bm[(size_t)i * V + v] = mk[v];
         }
+        uint32_t *sy = a.synd + (size_t)tile * a.m * V;
+        uint32_t *pa = a.par + (size_t)tile * a.m * V;
+        for (int j = r0 + tid; j < min(a.m, r0 + rows_per_part); j += blockDim.x) {
+            uint32_t ms[V], mp[V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) { sy[(size_t)j * V + v] = ms[v]; pa[(size_t)j * V + v] = mp[v]; }
+            for (int v = 0; v < V; ++v) { ms[v] = sy[(size_t)j * V + v]; mp[v] = pa[(size_t)j * V + v]; }
+            for (int q = 0; q < nnew; ++q) {
+                const int s = tw.newslot[q];
+                const size_t off = tw.newframe[q] * b.swords + (j >> 5);
+                const uint32_t sbit = (b.synd_all[off] >> (j & 31)) & 1u;
+                const uint32_t pbit = sbit;   // the VN-side init XORs the parity of the initial decision on top
+                const int l = s / V;
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (v == s % V) {
+                        ms[v] = (ms[v] & ~(1u << l)) | (sbit << l);
+                        mp[v] = (mp[v] & ~(1u << l)) | (pbit << l);
+                    }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) { sy[(size_t)j * V + v] = ms[v]; pa[(size_t)j * V + v] = mp[v]; }
+        }
     }
+
+    // the last CTA of the tile to get here publishes the per-frame results of the retired frames
+    if (nret == 0) return;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&tw.ticket, 1) == (int)gridDim.y - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int r = tid; r < nret; r += blockDim.x) {
+        const int succ = (tw.ret[r] >> 8) & 1, iters = tw.ret[r] >> 9;
+        const long long fr = tw.ret_frame[r];
+        const bool keys_differ = *(volatile unsigned int *)&tw.ret_diff[r] != 0u;
+        if (b.out_iters) b.out_iters[fr] = iters;
+        if (b.out_flags) b.out_flags[fr] = (uint8_t)((succ ? 1u : 0u) | (keys_differ ? 0u : 2u));
+        tally_frame(b.tally, succ, !keys_differ, iters, tw.run[r]);
+    }
+    if (tid == 0) tw.ticket = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
