@@ -177,6 +177,13 @@ QKDLDPC_API int qkdldpc_run_trials(qkdldpc_code *code, const qkdldpc_params *par
                        const int32_t *short_pos, int32_t n_short, uint32_t *out_bits, int32_t *out_iters,
                        uint8_t *out_flags, uint64_t *tally, double *accurate_qber_out);
 
+/* remove_bits (array_and_matrix_operations.cpp:259-287; called by QKD_LDPC / QKD_LDPC_RATE_ADAPT after the decoder,
+ * qkd_ldpc_algorithm.cpp:1092,1220): deletes the positions `bits_to_remove` (strictly ascending: the privacy-maintenance
+ * list, or punctured + shortened positions, H_matrix_params.bits_to_remove) from every frame. keys: HOST, n_frames packed
+ * frames of n bits; out_keys: HOST, n_frames packed frames of n - n_remove bits ((n - n_remove + 31) / 32 words each). */
+QKDLDPC_API int qkdldpc_remove_bits(qkdldpc_code *code, int64_t n_frames, const uint32_t *keys, const int32_t *bits_to_remove,
+                        int32_t n_remove, uint32_t *out_keys);
+
 /* Introspection used by benchmarks and tests. */
 typedef struct qkdldpc_info {
     int32_t n, m;

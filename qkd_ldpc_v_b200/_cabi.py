@@ -50,6 +50,7 @@ SYMBOLS = {
                                                        C.c_int32, _VP, _VP, C.POINTER(C.c_double)]),
     "qkdldpc_run_trials": (C.c_int, [_VP, C.POINTER(Params), C.c_int64, _VP, C.c_uint64, C.c_double, _VP, C.c_int32, _VP,
                                      C.c_int32, _VP, _VP, _VP, _VP, C.POINTER(C.c_double)]),
+    "qkdldpc_remove_bits": (C.c_int, [_VP, C.c_int64, _VP, _VP, C.c_int32, _VP]),
     "qkdldpc_code_info": (C.c_int, [_VP, C.POINTER(Info)]),
     "qkdldpc_code_set_profiling": (C.c_int, [_VP, C.c_int32]),
 }

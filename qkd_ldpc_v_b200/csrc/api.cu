@@ -272,7 +272,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     cudaError_t e = cudaSuccess;
     if ((e = up(c->row_ptr, rp)) || (e = up(c->col_idx, ci)) || (e = up(c->col_ptr, col_ptr)) ||
         (e = up(c->csc_edge, csc_edge)) || (e = up(c->csc_row, csc_row)) || (e = up(c->row_order, row_order)) ||
-        (e = up(c->col_order, col_order)) ||
+        (e = up(c->col_order, col_order)) || 
         (oc_ok && ((e = up(c->oc_cn_ginfo, oc_cn_ginfo)) || (e = up(c->oc_cnT, oc_cnT)) || (e = up(c->oc_cn_row, oc_cn_row)) || (e = up(c->oc_vn_ginfo, oc_vn_ginfo)) ||
                    (e = up(c->oc_vn_bit, oc_vn_bit)) || (e = up(c->oc_vT, oc_vT)))) ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
@@ -282,6 +282,17 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         return fail(QKDLDPC_ERR_CUDA, "graph upload failed: %s", cudaGetErrorString(e));
     }
     c->own_stream = true;
+    for (int k = 0; k < kSideStreams; ++k) {
+        if (cudaStreamCreateWithFlags(&c->side_streams[k], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) {
+            qkdldpc_code_destroy(c);
+            return fail(QKDLDPC_ERR_CUDA, "side stream creation failed");
+        }
+    }
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
+        qkdldpc_code_destroy(c);
+        return fail(QKDLDPC_ERR_CUDA, "event creation failed");
+    }
     c->oc_max_dc = max_dc;
     c->oc_groups_cn = (int)oc_cn_ginfo.size();
     c->oc_groups_vn = (int)oc_vn_ginfo.size();
@@ -313,12 +324,17 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->st_alice.release(); c->st_bob.release(); c->st_out.release(); c->st_qber.release(); c->st_iters.release();
     c->st_flags.release(); c->st_tally.release();
     c->gen_seeds.release(); c->gen_masks.release(); c->gen_scratch.release();
-    c->compact_moves.release(); c->compact_plan.release(); c->sched_work.release();
+    c->compact_moves.release(); c->compact_plan.release(); c->sched_work.release(); c->rb_kept.release();
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (c->h_done) cudaFreeHost(c->h_done);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_poll) cudaEventDestroy(c->ev_poll);
+    for (int k = 0; k < kSideStreams; ++k) {
+        if (c->side_streams[k]) { cudaStreamSynchronize(c->side_streams[k]); cudaStreamDestroy(c->side_streams[k]); }
+        if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -531,6 +547,45 @@ int qkdldpc_run_trials(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_trial
     if (out_flags) CK(cudaMemcpyAsync(out_flags, c->st_flags.p, n_trials, cudaMemcpyDeviceToHost, s));
     if (tally) CK(cudaMemcpyAsync(tally, c->st_tally.p, tl * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return QKDLDPC_OK;
+}
+
+int qkdldpc_remove_bits(qkdldpc_code *c, int64_t n_frames, const uint32_t *keys, const int32_t *bits_to_remove, int32_t n_remove,
+                        uint32_t *out_keys) {
+    if (!c) return fail(QKDLDPC_ERR_INVALID, "null code handle");
+    if (n_frames < 0 || n_remove < 0 || n_remove > c->n || (n_remove > 0 && !bits_to_remove))
+        return fail(QKDLDPC_ERR_INVALID, "bad remove_bits arguments");
+    const int n = c->n, words_in = (n + 31) / 32, n_keep = n - n_remove, words_out = (n_keep + 31) / 32;
+    if (n_frames == 0 || words_out == 0) return QKDLDPC_OK;
+    if (!keys || !out_keys) return fail(QKDLDPC_ERR_INVALID, "null key buffer");
+    std::vector<int> kept;
+    kept.reserve((size_t)n_keep);
+    for (int i = 0, r = 0; i < n; ++i) {
+        if (r < n_remove && bits_to_remove[r] == i) {
+            ++r;
+            if (r < n_remove && bits_to_remove[r] <= i) return fail(QKDLDPC_ERR_INVALID, "bits_to_remove must be strictly ascending");
+        } else {
+            kept.push_back(i);
+        }
+    }
+    if ((int)kept.size() != n_keep) return fail(QKDLDPC_ERR_INVALID, "bits_to_remove must be strictly ascending positions in [0, n)");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t tot_in = (size_t)n_frames * words_in, tot_out = (size_t)n_frames * words_out;
+    CK(c->st_alice.reserve(tot_in));
+    CK(c->st_out.reserve(tot_out));
+    CK(c->rb_kept.reserve(kept.size()));
+    CK(cudaMemcpyAsync(c->rb_kept.p, kept.data(), kept.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->st_alice.p, keys, tot_in * 4, cudaMemcpyHostToDevice, s));
+    for (int64_t f0 = 0; f0 < n_frames; f0 += 65535 * 1024ll) {   // gridDim.x limit is far away; keep the launch simple
+        const unsigned nf = (unsigned)std::min<int64_t>(n_frames - f0, 65535 * 1024ll);
+        qk::remove_bits_kernel<<<dim3(nf, (unsigned)((words_out + 7) / 8)), 256, 0, s>>>(words_in, n_keep, words_out, c->rb_kept.p,
+                                                                                      c->st_alice.p + f0 * words_in, c->st_out.p + f0 * words_out);
+        c->kernel_launches += 1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_keys, c->st_out.p, tot_out * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));   // also keeps `kept` alive until the upload is done
     return QKDLDPC_OK;
 }
 

@@ -195,4 +195,24 @@ __global__ void __launch_bounds__(128) ref_keygen_kernel(const RefKeygenArgs a) 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// remove_bits (array_and_matrix_operations.cpp:259-287): the step after the decoder in the protocol -- privacy
+// maintenance / removal of the punctured and shortened positions leaves the final key. `kept` lists the surviving
+// positions in ascending order; one warp packs 32 of them per ballot. grid = (frames, ceil(words_out / warps per CTA)).
+__global__ void __launch_bounds__(256) remove_bits_kernel(int words_in, int n_keep, int words_out, const int *kept, const uint32_t *in,
+                                                          uint32_t *out) {
+    const long long f = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= words_out) return;
+    const int k = w * 32 + lane;
+    uint32_t bit = 0;
+    if (k < n_keep) {
+        const int p = __ldg(kept + k);
+        bit = (in[f * words_in + (p >> 5)] >> (p & 31)) & 1u;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, bit != 0);
+    if (lane == 0) out[f * words_out + w] = word;
+}
+
 }  // namespace qk

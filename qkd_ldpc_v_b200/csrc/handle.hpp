@@ -57,6 +57,8 @@ struct DevBuf {
     }
 };
 
+constexpr int kSideStreams = 3;
+
 struct EvPair {
     cudaEvent_t a, b;
     int kind;   // 0 CN, 1 VN, 2 sched
@@ -71,6 +73,8 @@ struct qkdldpc_code {
     qkdldpc_options opt{};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side_streams[kSideStreams] = {nullptr, nullptr, nullptr};   // concurrent VN bucket kernels (run_batch.cuh)
+    cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {nullptr, nullptr, nullptr};
     // graph (device)
     DevBuf<int> row_ptr, col_idx, col_ptr, csc_edge, csc_row, row_order, col_order;
     int cn_first[5] = {0}, cn_count[5] = {0}, vn_first[5] = {0}, vn_count[5] = {0};   // degree buckets in row/col_order
@@ -111,6 +115,7 @@ struct qkdldpc_code {
     // reference-compatible trial-input generator (gen_kernels.cuh)
     DevBuf<uint64_t> gen_seeds;
     DevBuf<uint32_t> gen_masks, gen_scratch;
+    DevBuf<int> rb_kept;               // remove_bits: surviving positions
     DevBuf<unsigned char> sched_work;  // TileWork per tile (sched_kernels.cuh)
     DevBuf<int2> compact_moves;        // tail compaction (sched_kernels.cuh)
     DevBuf<int> compact_plan;

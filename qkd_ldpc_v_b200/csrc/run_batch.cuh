@@ -83,12 +83,42 @@ inline int launch_vn_bucket(const qkdldpc_code *c, bool fast, int tiles, cudaStr
     vn_kernel<T, V, DVMAX, false><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt);
     return 1;
 }
-// widest columns first: their warps run longest
+// The bucket kernels are latency-bound one by one (48-59 % of DRAM peak each, profiles/r01_c_ncu_summary.md): they touch
+// disjoint bits, so they run CONCURRENTLY -- the widest bucket stays on the main stream, the others fork onto side
+// streams and join back (also inside a captured graph, where this becomes parallel branches).
 template <typename T, int V>
 int launch_vn(const qkdldpc_code *c, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a) {
-    return launch_vn_bucket<T, V, 4>(c, fast, tiles, s, a) + launch_vn_bucket<T, V, 3>(c, fast, tiles, s, a) +
-           launch_vn_bucket<T, V, 2>(c, fast, tiles, s, a) + launch_vn_bucket<T, V, 1>(c, fast, tiles, s, a) +
-           launch_vn_bucket<T, V, 0>(c, fast, tiles, s, a);
+    int order[kBuckets], nb = 0;
+    for (int bk = kBuckets - 1; bk >= 0; --bk)
+        if (c->vn_count[bk] > 0) order[nb++] = bk;
+    auto launch_bucket = [&](int bk, cudaStream_t st) {
+        switch (bk) {
+            case 4: return launch_vn_bucket<T, V, 4>(c, fast, tiles, st, a);
+            case 3: return launch_vn_bucket<T, V, 3>(c, fast, tiles, st, a);
+            case 2: return launch_vn_bucket<T, V, 2>(c, fast, tiles, st, a);
+            case 1: return launch_vn_bucket<T, V, 1>(c, fast, tiles, st, a);
+            default: return launch_vn_bucket<T, V, 0>(c, fast, tiles, st, a);
+        }
+    };
+    const bool fork = nb > 1 && c->side_streams[0] != nullptr && s != nullptr;
+    if (!fork) {
+        int nl = 0;
+        for (int k = 0; k < nb; ++k) nl += launch_bucket(order[k], s);
+        return nl;
+    }
+    cudaEventRecord(c->ev_fork, s);
+    int nl = 0;
+    for (int k = 1; k < nb; ++k) {
+        cudaStream_t side = c->side_streams[(k - 1) % kSideStreams];
+        if (k - 1 < kSideStreams) cudaStreamWaitEvent(side, c->ev_fork, 0);
+        nl += launch_bucket(order[k], side);
+    }
+    nl += launch_bucket(order[0], s);
+    for (int k = 0; k < std::min(nb - 1, kSideStreams); ++k) {
+        cudaEventRecord(c->ev_join[k], c->side_streams[k]);
+        cudaStreamWaitEvent(s, c->ev_join[k], 0);
+    }
+    return nl;
 }
 
 inline EvPair *next_ev(qkdldpc_code *c, int kind) {

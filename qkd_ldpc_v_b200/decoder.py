@@ -257,6 +257,17 @@ class LdpcCode:
         del pa, sa
         return acc.value
 
+    def remove_bits(self, keys, bits_to_remove) -> np.ndarray:
+        """``remove_bits`` (array_and_matrix_operations.cpp:259-287) for a batch of packed frames: returns packed frames
+        of ``n - len(bits_to_remove)`` bits."""
+        k = self._as_packed(keys)
+        r = np.ascontiguousarray(bits_to_remove, np.int32)
+        words_out = (self.n - r.size + 31) // 32
+        out = np.zeros((k.shape[0], words_out), np.uint32)
+        _cabi.check(_cabi.lib().qkdldpc_remove_bits(self._h, k.shape[0], k.ctypes.data, r.ctypes.data if r.size else None, r.size,
+                                                    out.ctypes.data if out.size else None), "qkdldpc_remove_bits")
+        return out
+
     def generate_keys_device(self, n_frames: int, qber: float, seed: int, d_alice: int, d_bob: int) -> float:
         acc = C.c_double()
         _cabi.check(_cabi.lib().qkdldpc_generate_keys_device(self._h, int(n_frames), float(qber), int(seed),

@@ -108,3 +108,19 @@ def test_run_trials_rejects_qber_too_small_for_the_key(q):
         handle(q, "N100").run_trials(hostlib.trial_seeds(1, 4), 0.001, (0.8, 0), q.DecoderConfig())
     r = handle(q, "N100").run_trials(np.zeros(0, np.uint64), 0.05, (0.8, 0), q.DecoderConfig())
     assert r.iterations_num.size == 0 and r.tally.sum() == 0
+
+
+@pytest.mark.parametrize("name,n_remove", [("K1_5", 250), ("N100", 0), ("N100", 99), ("I80", 2077), ("N7", 3)])
+def test_remove_bits_equals_reference_semantics(q, name, n_remove):
+    """remove_bits (array_and_matrix_operations.cpp:259-287): delete the listed positions, keep the order of the rest."""
+    arr = util.code_arrays(name)
+    rng = np.random.default_rng(n_remove + 5)
+    bits = rng.integers(0, 2, (37, arr["n"]), dtype=np.uint8)
+    rm = np.sort(rng.permutation(arr["n"])[:n_remove]).astype(np.int32)
+    out = handle(q, name).remove_bits(bits, rm)
+    expect = np.delete(bits, rm, axis=1)
+    assert (q.unpack_bits(out, arr["n"] - n_remove) == expect).all()
+    from qkd_ldpc_v_b200._cabi import QkdLdpcError
+    if n_remove >= 2:
+        with pytest.raises(QkdLdpcError):
+            handle(q, name).remove_bits(bits, rm[::-1].copy())
