@@ -85,7 +85,7 @@ typedef struct qkdldpc_options {
     int32_t frames_per_lane_f32; /* 1, 2 or 4 (tile = 32 x this many frames); default 4 (128-bit accesses)    */
     int32_t use_graph;      /* 1 (default): replay one captured CUDA graph per poll interval; -1: plain launches */
     int32_t decoder_path;   /* 0 auto; 1 streaming kernels (messages in HBM); 2 on-chip min-sum (frame state in shared
-                               memory; float32 min-sum family, check degrees <= 32, n < 65535) or QKDLDPC_ERR_INVALID */
+                               memory; float32 min-sum family, check degrees <= 64, n < 65535) or QKDLDPC_ERR_INVALID */
     int32_t onchip_threads; /* CTA size of the on-chip kernel (multiple of 32, <= 768); 0 = derived from the code size */
     int32_t tail_compaction; /* streaming path: 0 (default) move the stragglers of a draining batch into few tiles; -1 never */
     int32_t reserved[2];

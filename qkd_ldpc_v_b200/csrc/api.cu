@@ -103,7 +103,12 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     // blocks of 4 edges per lane.
     int max_dc = 0;
     for (int j = 0; j < m; ++j) max_dc = std::max(max_dc, row_ptr[j + 1] - row_ptr[j]);
-    const bool oc_ok = n < 65535 && m < 65535 && max_dc <= 32;
+    // Record slots: a row of up to 32 edges owns one 16-byte record; a row of 33..64 edges owns two consecutive ones
+    // (edges 0..31 and 32..dc-1), so that every record still carries 32 sign bits and the variable phase is unchanged.
+    std::vector<int> slot0(m + 1, 0);
+    for (int j = 0; j < m; ++j) slot0[j + 1] = slot0[j] + ((row_ptr[j + 1] - row_ptr[j]) > 32 ? 2 : 1);
+    const int rec_slots = slot0[m];   // slots rec_slots and rec_slots + 1 are scratch (padding lanes)
+    const bool oc_ok = n < 65535 && rec_slots + 2 < 65535 && max_dc <= 64;
     std::vector<int2> oc_cn_ginfo, oc_vn_ginfo;
     std::vector<uint16_t> oc_cn_row, oc_vn_bit;
     std::vector<uint2> oc_cnT;
@@ -117,11 +122,14 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         // node whose neighbours collide least with the banks already used at each step. Measured effect on n=10240
         // codes: 9.9 -> 6.9 wavefronts per 32 record gathers (irregular R=0.8), 9.8 -> 4.5 (alist R=0.79).
         auto pack = [](const std::vector<int> &members, const std::vector<int> &ptr, const int *nbr, int ncol, int width,
-                       std::vector<std::vector<int>> &out) {
+                       std::vector<std::vector<int>> &out, const int *remap /* neighbour id -> storage slot, or null */) {
             const int d = ptr[members[0] + 1] - ptr[members[0]];
             std::vector<unsigned char> col((size_t)members.size() * d);
             for (size_t i = 0; i < members.size(); ++i)
-                for (int k = 0; k < d; ++k) col[i * d + k] = (unsigned char)(nbr[ptr[members[i]] + k] % ncol);
+                for (int k = 0; k < d; ++k) {
+                    const int id = nbr[ptr[members[i]] + k];
+                    col[i * d + k] = (unsigned char)((remap ? remap[id] : id) % ncol);
+                }
             std::vector<char> used(members.size(), 0);
             std::vector<int> cnt((size_t)d * ncol);
             size_t next_free = 0, left = members.size();
@@ -167,11 +175,11 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         // check phase: groups of 32 rows
         for (const auto &cls : degree_classes(m, rp)) {
             std::vector<std::vector<int>> groups;
-            pack(cls, rp, col_idx, 32, 32, groups);
+            pack(cls, rp, col_idx, 32, 32, groups, nullptr);
             const int dc = rp[cls[0] + 1] - rp[cls[0]], blocks = (dc + 3) / 4;
             for (const auto &gr : groups) {
                 oc_cn_ginfo.push_back(make_int2((int)oc_cnT.size(), dc));
-                for (int l = 0; l < 32; ++l) oc_cn_row.push_back(l < (int)gr.size() ? (uint16_t)gr[l] : (uint16_t)m);
+                for (int l = 0; l < 32; ++l) oc_cn_row.push_back(l < (int)gr.size() ? (uint16_t)slot0[gr[l]] : (uint16_t)rec_slots);
                 for (int kb = 0; kb < blocks; ++kb)
                     for (int l = 0; l < 32; ++l) {
                         uint32_t c[4] = {0, 0, 0, 0};
@@ -184,7 +192,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         // variable phase: octets (one quarter-warp each), four octets per group
         for (const auto &cls : degree_classes(n, col_ptr)) {
             std::vector<std::vector<int>> octets;
-            pack(cls, col_ptr, csc_row.data(), 8, 8, octets);
+            pack(cls, col_ptr, csc_row.data(), 8, 8, octets, slot0.data());
             const int dv = col_ptr[cls[0] + 1] - col_ptr[cls[0]], blocks = (dv + 3) / 4;
             for (size_t o = 0; o < octets.size(); o += 4) {
                 int lane_bit[32];
@@ -198,12 +206,13 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
                     for (int l = 0; l < 32; ++l) {
                         uint32_t e[4];
                         for (int j = 0; j < 4; ++j) {
-                            e[j] = (uint32_t)m << 9;   // padding: the scratch record
+                            e[j] = (uint32_t)rec_slots << 9;   // padding: the scratch record
                             const int k = kb * 4 + j;
                             if (lane_bit[l] >= 0 && k < dv) {
                                 const int p = col_ptr[lane_bit[l]] + k, r = csc_row[p];
                                 const int pos = csc_edge[p] - rp[r], dcr = rp[r + 1] - rp[r];
-                                e[j] = ((uint32_t)r << 9) | (uint32_t)(32 - dcr + pos);
+                                const int half = pos / 32, dch = (dcr <= 32) ? dcr : (half == 0 ? 32 : dcr - 32);
+                                e[j] = ((uint32_t)(slot0[r] + half) << 9) | (uint32_t)(32 - dch + pos % 32);
                             }
                         }
                         oc_vT.push_back(make_uint4(e[0], e[1], e[2], e[3]));
@@ -218,11 +227,14 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         size_t edges_cn = 0, edges_vn = 0;
         for (size_t g = 0; g < oc_cn_ginfo.size(); ++g) {
             const int dc = oc_cn_ginfo[g].y, blocks = (dc + 3) / 4;
-            if (dc < 1 || dc > 32 || (size_t)oc_cn_ginfo[g].x + (size_t)blocks * 32 > oc_cnT.size())
+            if (dc < 1 || dc > 64 || (size_t)oc_cn_ginfo[g].x + (size_t)blocks * 32 > oc_cnT.size())
                 return fail(QKDLDPC_ERR_STATE, "on-chip check table: bad group header %zu", g);
             for (int l = 0; l < 32; ++l) {
-                const int row = oc_cn_row[g * 32 + l];
-                if (row > m) return fail(QKDLDPC_ERR_STATE, "on-chip check table: row %d out of range", row);
+                const int slot = oc_cn_row[g * 32 + l];
+                if (slot > rec_slots) return fail(QKDLDPC_ERR_STATE, "on-chip check table: record slot %d out of range", slot);
+                const int row = slot == rec_slots ? m : (int)(std::upper_bound(slot0.begin(), slot0.end(), slot) - slot0.begin()) - 1;
+                if (row < m && (slot0[row] != slot || rp[row + 1] - rp[row] != dc))
+                    return fail(QKDLDPC_ERR_STATE, "on-chip check table: slot %d is not the first record of a row of %d edges", slot, dc);
                 for (int k = 0; k < dc; ++k) {
                     const uint2 w = oc_cnT[oc_cn_ginfo[g].x + (k / 4) * 32 + l];
                     const uint32_t c = (k % 4 == 0) ? (w.x & 0xFFFFu) : (k % 4 == 1) ? (w.x >> 16) : (k % 4 == 2) ? (w.y & 0xFFFFu) : (w.y >> 16);
@@ -243,9 +255,10 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
                     const uint4 w = oc_vT[oc_vn_ginfo[g].x + (k / 4) * 32 + l];
                     const uint32_t e = (k % 4 == 0) ? w.x : (k % 4 == 1) ? w.y : (k % 4 == 2) ? w.z : w.w;
                     const int r = (int)(e >> 9), sh = (int)(e & 511u);
-                    if (r > m || sh > 31) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: bad entry for bit %d", bit);
+                    if (r > rec_slots || sh > 31) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: bad entry for bit %d", bit);
                     if (bit < n && k < dv) {
-                        if (r != csc_row[col_ptr[bit] + k]) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: wrong check for bit %d", bit);
+                        const int p = col_ptr[bit] + k, row = csc_row[p], pos = csc_edge[p] - rp[row];
+                        if (r != slot0[row] + pos / 32) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: wrong check for bit %d", bit);
                         ++edges_vn;
                     }
                 }
@@ -294,6 +307,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         return fail(QKDLDPC_ERR_CUDA, "event creation failed");
     }
     c->oc_max_dc = max_dc;
+    c->oc_rec_slots = rec_slots;
     c->oc_groups_cn = (int)oc_cn_ginfo.size();
     c->oc_groups_vn = (int)oc_vn_ginfo.size();
     for (const auto &gi : oc_vn_ginfo) c->oc_vn_degree.push_back(gi.y);

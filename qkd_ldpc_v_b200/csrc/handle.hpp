@@ -80,7 +80,7 @@ struct qkdldpc_code {
     int cn_first[5] = {0}, cn_count[5] = {0}, vn_first[5] = {0}, vn_count[5] = {0};   // degree buckets in row/col_order
     // on-chip min-sum path (onchip_minsum.cuh): ELL index arrays per 32-node group; eligible == the graph fits
     bool oc_eligible = false;
-    int oc_groups_cn = 0, oc_groups_vn = 0, oc_max_dc = 0;
+    int oc_groups_cn = 0, oc_groups_vn = 0, oc_max_dc = 0, oc_rec_slots = 0;
     size_t oc_smem = 0;
     DevBuf<int2> oc_cn_ginfo, oc_vn_ginfo;
     DevBuf<uint16_t> oc_cn_row, oc_vn_bit;

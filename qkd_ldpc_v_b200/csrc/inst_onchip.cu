@@ -18,22 +18,22 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
     }
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return false;
-    return onchip_smem_bytes(c->n, c->m, c->oc_groups_cn) <= (size_t)dev_smem;
+    return onchip_smem_bytes(c->n, c->oc_rec_slots, c->oc_groups_cn) <= (size_t)dev_smem;
 }
 
 // threads == 0: pick the CTA size that puts the most warps on an SM (shared memory decides how many CTAs fit; ties go
 // to the smaller CTA -- measured: 3 x 512 beats 2 x 768 on n=10240 m=2048, 2 x 768 beats 2 x 512 on m=2201). A CTA
 // never has more lanes than the check phase has rows.
-template <int ALG>
+template <int ALG, bool WIDE>
 static cudaError_t pick_geometry(int m, int sms, size_t smem, long long n_frames, int *threads, int *grid) {
-    cudaError_t e = cudaFuncSetAttribute(onchip_minsum_kernel<ALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(onchip_minsum_kernel<ALG, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (*threads == 0) {
         const int cap = std::max(128, std::min(768, (m + 31) / 32 * 32));
         int best = 0;
         for (int t = 128; t <= cap; t += 128) {
             int k = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, onchip_minsum_kernel<ALG>, t, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, onchip_minsum_kernel<ALG, WIDE>, t, smem);
             if (e != cudaSuccess) return e;
             if (k * t > best) {
                 best = k * t;
@@ -43,16 +43,16 @@ static cudaError_t pick_geometry(int m, int sms, size_t smem, long long n_frames
         if (*threads == 0) return cudaErrorLaunchOutOfResources;
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onchip_minsum_kernel<ALG>, *threads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onchip_minsum_kernel<ALG, WIDE>, *threads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     *grid = (int)std::min<long long>(n_frames, (long long)per_sm * sms);   // persistent CTAs pull frames from a queue
     return cudaSuccess;
 }
 
-template <int ALG>
+template <int ALG, bool WIDE>
 static cudaError_t launch(const OnchipArgs &a, int grid, int threads, size_t smem, cudaStream_t s) {
-    onchip_minsum_kernel<ALG><<<(unsigned)grid, threads, smem, s>>>(a);
+    onchip_minsum_kernel<ALG, WIDE><<<(unsigned)grid, threads, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -104,7 +104,7 @@ int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const
     if (d_tally) CK(cudaMemsetAsync(d_tally, 0, (size_t)qkdldpc_tally_len(P->max_iterations) * sizeof(uint64_t), s));
 
     OnchipArgs a{};
-    a.n = n; a.m = m; a.words = words;
+    a.n = n; a.m = m; a.words = words; a.rec_slots = c->oc_rec_slots;
     a.n_groups_cn = c->oc_groups_cn; a.n_groups_vn = c->oc_groups_vn;
     a.cn_ginfo = c->oc_cn_ginfo.p; a.cn_row = c->oc_cn_row.p; a.cnT = c->oc_cnT.p;
     a.vn_ginfo = c->oc_vn_ginfo.p; a.vn_bit = c->oc_vn_bit.p; a.vT = c->oc_vT.p;
@@ -117,17 +117,18 @@ int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const
     a.thr = P->enable_threshold ? (float)P->threshold : INFINITY;
 
     int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(768, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
-    const size_t smem = onchip_smem_bytes(n, m, c->oc_groups_cn);
+    const size_t smem = onchip_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn);
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 
     int grid = 0;
     cudaError_t e;
+    const bool wide = c->oc_max_dc > 32;   // rows of 33..64 edges: two records per row, separate kernel instantiation
     switch (P->algorithm) {
-        case 2: e = pick_geometry<2>(m, sms, smem, n_frames, &threads, &grid); break;
-        case 3: e = pick_geometry<3>(m, sms, smem, n_frames, &threads, &grid); break;
-        case 4: e = pick_geometry<4>(m, sms, smem, n_frames, &threads, &grid); break;
-        default: e = pick_geometry<5>(m, sms, smem, n_frames, &threads, &grid); break;
+        case 2: e = wide ? pick_geometry<2, true>(m, sms, smem, n_frames, &threads, &grid) : pick_geometry<2, false>(m, sms, smem, n_frames, &threads, &grid); break;
+        case 3: e = wide ? pick_geometry<3, true>(m, sms, smem, n_frames, &threads, &grid) : pick_geometry<3, false>(m, sms, smem, n_frames, &threads, &grid); break;
+        case 4: e = wide ? pick_geometry<4, true>(m, sms, smem, n_frames, &threads, &grid) : pick_geometry<4, false>(m, sms, smem, n_frames, &threads, &grid); break;
+        default: e = wide ? pick_geometry<5, true>(m, sms, smem, n_frames, &threads, &grid) : pick_geometry<5, false>(m, sms, smem, n_frames, &threads, &grid); break;
     }
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel geometry failed: %s", cudaGetErrorString(e));
     if (c->oc_sched_warps != threads / 32) {   // the variable-phase schedule depends on the number of warps per CTA
@@ -154,10 +155,10 @@ int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const
 
     CK(cudaEventRecord(c->ev0, s));
     switch (P->algorithm) {
-        case 2: e = launch<2>(a, grid, threads, smem, s); break;
-        case 3: e = launch<3>(a, grid, threads, smem, s); break;
-        case 4: e = launch<4>(a, grid, threads, smem, s); break;
-        default: e = launch<5>(a, grid, threads, smem, s); break;
+        case 2: e = wide ? launch<2, true>(a, grid, threads, smem, s) : launch<2, false>(a, grid, threads, smem, s); break;
+        case 3: e = wide ? launch<3, true>(a, grid, threads, smem, s) : launch<3, false>(a, grid, threads, smem, s); break;
+        case 4: e = wide ? launch<4, true>(a, grid, threads, smem, s) : launch<4, false>(a, grid, threads, smem, s); break;
+        default: e = wide ? launch<5, true>(a, grid, threads, smem, s) : launch<5, false>(a, grid, threads, smem, s); break;
     }
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel launch failed: %s", cudaGetErrorString(e));
     c->kernel_launches += 1;

@@ -23,8 +23,8 @@
 // rows and bits are sorted by degree and a group never mixes degrees, so the inner loops carry no validity tests.
 //
 // Eligibility (host): float32 messages, min-sum family with the FAST precondition of run_batch.cuh (no NaN possible),
-// every check degree <= 32, n and m < 65535, state fits the 227 KB of shared memory. Everything else (SPA, float64,
-// n = 100k codes, very wide rows) takes the streaming path.
+// every check degree <= 64 (rows of 33..64 edges own two records), fewer than 65533 records, state fits the 227 KB of
+// shared memory. Everything else (SPA, float64, n = 100k codes) takes the streaming path.
 #pragma once
 #include "common.cuh"
 
@@ -34,6 +34,7 @@ typedef unsigned long long u64;
 
 struct OnchipArgs {
     int n, m, words;
+    int rec_slots;              // record slots in use (m + number of rows wider than 32 edges); + 2 scratch slots
     int n_groups_cn, n_groups_vn;
     // Index tables: one entry per (group, block of 4 edges, lane), so a lane fetches the indices of 4 edges with ONE
     // 8- or 16-byte load. A group holds 32 rows (bits) of ONE degree; which nodes share a group is chosen on the host
@@ -62,11 +63,11 @@ struct OnchipArgs {
     float primary, secondary, thr;   // thr = +inf when the clamp is disabled
 };
 
-// Shared-memory layout: rec[m+1] uint4 | L[n+1] float (padded to 16 B) | bob[words] | alice[words] | syn[groups_cn] | misc
+// Shared-memory layout: rec[rec_slots+2] uint4 | L[n+1] float (padded to 16 B) | bob[words] | alice[words] | syn[groups_cn] | misc
 __host__ __device__ inline size_t onchip_l_slots(int n) { return ((size_t)n + 1 + 3) / 4 * 4; }
-__host__ __device__ inline size_t onchip_smem_bytes(int n, int m, int groups_cn) {
+__host__ __device__ inline size_t onchip_smem_bytes(int n, int rec_slots, int groups_cn) {
     const size_t words = (size_t)(n + 31) / 32;
-    return ((size_t)m + 1) * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn) * 4 + 64;
+    return ((size_t)rec_slots + 2) * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn) * 4 + 64;
 }
 
 // Record of a row: x = bits(c1), y = bits(c2) (non-negative magnitudes), z = final sign of the message on edge k in bit
@@ -92,14 +93,20 @@ __host__ __device__ inline size_t onchip_smem_bytes(int n, int m, int groups_cn)
         m1 = fminf(m1, ab);                                                                                             \
     }
 
-template <int ALG>
+// A row of 33..64 edges owns two consecutive records (edges 0..31 and 32..dc-1) with the same c1 / c2; the record that
+// does not hold the first minimum carries kNoArg in w, which no table entry matches.
+constexpr uint32_t kNoArg = 0x100u;
+
+template <int ALG, bool WIDE>
 __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float *L, uint4 *rec, const uint32_t *synw,
                                                 float thr_b, int warp, int lane, int nwarps) {
     bool unsat = false;
     for (int g = warp; g < a.n_groups_cn; g += nwarps) {
         const int2 gi = __ldg(a.cn_ginfo + g);
-        const int dc = gi.y;
-        const uint32_t row = __ldg(a.cn_row + g * 32 + lane);
+        const int dc_row = gi.y;                                  // degree of the group's rows (warp-uniform)
+        const bool two = WIDE && dc_row > 32;                     // two records per row
+        const int dc = two ? 32 : dc_row;                         // edges covered by the first record
+        const uint32_t row = __ldg(a.cn_row + g * 32 + lane);     // first record slot of the lane's row
         const uint4 ro = rec[row];
         const uint2 *cp = a.cnT + gi.x + lane;
         float m1 = FLT_MAX, m2 = FLT_MAX;
@@ -123,9 +130,36 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float
             if (left > 1) QK_CN_EDGE(1, cw.x >> 16)
             if (left > 2) QK_CN_EDGE(2, cw.y & 0xFFFFu)
         }
+        uint32_t own_first = own;
+        if constexpr (WIDE) {
+            if (two) {                            // edges 32..dc_row-1: the row's second record (warp-uniform branch)
+                const int dc2 = dc_row - 32;
+                const uint4 ro2 = rec[row + 1];
+                zs = ro2.z << (32 - dc2);
+                const int arg_old2 = (int)ro2.w - (32 - dc2);   // kNoArg gives a value no edge index reaches
+                own = 0;
+                for (; kb + 4 <= dc_row; kb += 4) {
+                    const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+                    const int rel = arg_old2 - (kb - 32);
+                    const uint4 &ro = ro2;
+                    QK_CN_EDGE(0, cw.x & 0xFFFFu)
+                    QK_CN_EDGE(1, cw.x >> 16)
+                    QK_CN_EDGE(2, cw.y & 0xFFFFu)
+                    QK_CN_EDGE(3, cw.y >> 16)
+                }
+                if (kb < dc_row) {
+                    const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+                    const int rel = arg_old2 - (kb - 32), left = dc_row - kb;
+                    const uint4 &ro = ro2;
+                    QK_CN_EDGE(0, cw.x & 0xFFFFu)
+                    if (left > 1) QK_CN_EDGE(1, cw.x >> 16)
+                    if (left > 2) QK_CN_EDGE(2, cw.y & 0xFFFFu)
+                }
+            }
+        }
         const uint32_t syn = (synw[g] >> lane) & 1u;
         const bool viol = (((zacc >> 31) ^ syn) & 1u) != 0;    // check not satisfied by the current hard decision
-        unsat |= viol && row < (uint32_t)a.m;
+        unsat |= viol && row < (uint32_t)a.rec_slots;
         const float factor = (ALG >= 4 && viol) ? a.secondary : a.primary;   // (:749-757, :939-947)
         float c1, c2;
         if constexpr (ALG == 2 || ALG == 4) {
@@ -142,9 +176,16 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float
         uint4 rn;
         rn.x = __float_as_uint(c1);
         rn.y = __float_as_uint(c2);
-        rn.z = own ^ (0u - rowneg);
-        rn.w = (uint32_t)(arg + 32 - dc);
+        rn.z = own_first ^ (0u - rowneg);
+        rn.w = (!two || arg < 32) ? (uint32_t)(arg + 32 - dc) : kNoArg;
         rec[row] = rn;
+        if constexpr (WIDE) {
+            if (two) {
+                rn.z = own ^ (0u - rowneg);
+                rn.w = (arg >= 32) ? (uint32_t)(arg - 32 + 32 - (dc_row - 32)) : kNoArg;
+                rec[row + 1] = rn;
+            }
+        }
     }
     return unsat;
 }
@@ -164,7 +205,7 @@ __device__ __forceinline__ float onchip_llr(const OnchipArgs &a, const uint32_t 
 #define QK_VN_EDGE(ENT)                                                                                                 \
     {                                                                                                                   \
         const uint4 r = *reinterpret_cast<const uint4 *>(recb + ((ENT) >> 5));                                          \
-        const uint32_t mag = (((ENT) ^ r.w) & 31u) ? r.x : r.y;                                                         \
+        const uint32_t mag = (((ENT) ^ r.w) & 0x1FFu) ? r.x : r.y;   /* r.w == kNoArg never matches */                                                         \
         acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.z, (ENT)) & 0x80000000u));   /* r.z << sh */           \
     }
 
@@ -201,11 +242,11 @@ __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, float *L, c
 }
 #undef QK_VN_EDGE
 
-template <int ALG>
+template <int ALG, bool WIDE>
 __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *rec = reinterpret_cast<uint4 *>(smem_raw);
-    float *L = reinterpret_cast<float *>(rec + a.m + 1);
+    float *L = reinterpret_cast<float *>(rec + a.rec_slots + 2);
     uint32_t *bobw = reinterpret_cast<uint32_t *>(L + onchip_l_slots(a.n));
     uint32_t *alw = bobw + a.words;
     uint32_t *synw = alw + a.words;
@@ -252,9 +293,10 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
                 if (left > 2) s ^= alw[c2 >> 5] >> (c2 & 31u);
                 if (left > 3) s ^= alw[c3 >> 5] >> (c3 & 31u);
             }
-            const uint32_t sw = __ballot_sync(0xffffffffu, (s & 1u) != 0 && row < (uint32_t)a.m);
+            const uint32_t sw = __ballot_sync(0xffffffffu, (s & 1u) != 0 && row < (uint32_t)a.rec_slots);
             if (lane == 0) synw[g] = sw;
             rec[row] = make_uint4(0u, 0u, 0u, 0u);
+            if (WIDE && gi.y > 32) rec[row + 1] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();
 
@@ -263,7 +305,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
         for (int it = 1;; ++it) {
             // the check-node pass of iteration `it`; at it = max_iter + 1 it only serves as the syndrome test of the
             // last hard decision (non-adaptive variants, :424-445)
-            const bool unsat = onchip_cn_phase<ALG>(a, L, rec, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
+            const bool unsat = onchip_cn_phase<ALG, WIDE>(a, L, rec, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
             const bool any_unsat = __syncthreads_or(unsat) != 0;
             if (!kAdaptive) {
                 if (it > 1 && !any_unsat) { success = true; iters = run = it - 1; break; }   // z of iteration it-1 (:439-445)

@@ -68,9 +68,9 @@ def test_fp64_messages_against_reference_golden(q, case):
 
 
 def onchip_eligible(name, alg):
-    """float32 min-sum family, every check degree <= 32, n < 65535 (onchip_minsum.cuh)."""
+    """float32 min-sum family, every check degree <= 64, n < 65535 (onchip_minsum.cuh)."""
     arr = util.code_arrays(name)
-    return alg >= 2 and int(np.diff(arr["row_ptr"]).max()) <= 32 and arr["n"] < 65535
+    return alg >= 2 and int(np.diff(arr["row_ptr"]).max()) <= 64 and arr["n"] < 65535
 
 
 @pytest.mark.parametrize("path", [1, 2], ids=["streaming", "onchip"])
