@@ -140,3 +140,17 @@ def test_csv_fp32_fer(built, tmp_path):
         assert abs(float(fa[14].replace(",", ".")) - float(fb[14].replace(",", "."))) <= 0.005
         if float(fb[12].replace(",", ".")) >= 0.5:   # the mean over a handful of successes is noise
             assert abs(float(fa[8].replace(",", ".")) - float(fb[8].replace(",", "."))) <= 0.1
+
+
+def test_csv_trials_sharded_over_two_handles(built, tmp_path):
+    """>= 2048 trials per combination: qkdldpc_sim splits the trials of a combination into contiguous ranges, one per
+    device (here two handles on device 0, several chunks each) and sums the tallies; per-trial seeds are
+    seeds[n] + combination index whatever the partition (quirk Q16), so the CSV equals the reference's."""
+    cfg = dict(BASE, trials_number=2500, decoding_algorithm=2, matrix_format=1,
+               code_rate_QBER_ranges=[dict(code_rate=0.95, QBER=dict(begin=0.02, end=0.025, step=0.005))])
+    _setup(tmp_path, cfg, ["K1_5"])
+    _, ref_lines = _run_reference(tmp_path)
+    _, our_lines = _run_ours(tmp_path, 64, ["--devices", "0,0", "--chunk-frames", "700"])
+    assert our_lines == ref_lines
+    _, host_lines = _run_ours(tmp_path / "h", 64, ["--devices", "0,0", "--chunk-frames", "700", "--host-keygen", "--root", str(tmp_path)])
+    assert host_lines == ref_lines
