@@ -363,6 +363,10 @@ def main():
         cpu_baseline = {"value": n * cf / dt / 1e9, "unit": "Gbit/s", "cores": cores, "kind": kind,
                         "sample": f"{cf} frames of the same workload (reference RNG keys), decode only, {dt:.1f} s",
                         "mean_iterations": float(np.mean(it)), "fer": float(1.0 - np.mean((fl & 3) == 3))}
+        # and on ONE host thread (how the reference's authors run their throughput configs)
+        cf1 = max(4, cf // (2 * cores))
+        dt1, _, _, _ = cpu_reference_run(args.workload, cf1, 1)
+        cpu_baseline["single_thread"] = {"value": n * cf1 / dt1 / 1e9, "unit": "Gbit/s", "sample": f"{cf1} frames, {dt1:.1f} s"}
 
     if rank == 0:
         stats = q.stats_from_tally(tally, frames_total)
