@@ -154,3 +154,15 @@ def test_csv_trials_sharded_over_two_handles(built, tmp_path):
     assert our_lines == ref_lines
     _, host_lines = _run_ours(tmp_path / "h", 64, ["--devices", "0,0", "--chunk-frames", "700", "--host-keygen", "--root", str(tmp_path)])
     assert host_lines == ref_lines
+
+
+def test_example_program(built):
+    """example/qkdldpc_example.cpp = the reference's example (N = 6, Johnson ex. 2.5) through the C ABI: iteration counts
+    traced from the unmodified reference: SPA 1, SPA-lin 1, NMSA 1, OMSA 2, ANMSA 3, AOMSA 2."""
+    exe = os.path.join(ROOT, "qkd_ldpc_v_b200", "qkdldpc_example")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == 6
+    for line, it in zip(lines, (1, 1, 1, 2, 3, 2)):
+        assert f"iterations {it}," in line and "syndromes match, keys match" in line and line.endswith("0 0 1 0 1 1"), line
