@@ -177,6 +177,28 @@ QKDLDPC_API int qkdldpc_run_trials(qkdldpc_code *code, const qkdldpc_params *par
                        const int32_t *short_pos, int32_t n_short, uint32_t *out_bits, int32_t *out_iters,
                        uint8_t *out_flags, uint64_t *tally, double *accurate_qber_out);
 
+/* One parameter combination of a sweep (sim_combination, simulation.hpp:22-27, plus its running index). */
+typedef struct qkdldpc_combination {
+    double qber;               /* configured QBER (config_QBER); the accurate one is floor(n * qber) / n          */
+    double primary, secondary; /* decoding_scaling_factors of the combination                                    */
+    const int32_t *punct_pos;  /* H_matrix_params.punctured_bits (may be NULL with n_punct == 0)                  */
+    int32_t n_punct;
+    const int32_t *short_pos;  /* H_matrix_params.shortened_bits                                                  */
+    int32_t n_short;
+    uint64_t seed_offset;      /* curr_sim: added to every trial seed (simulation.cpp:743)                        */
+} qkdldpc_combination;
+
+/* The batched run_trial for SEVERAL combinations of one matrix in one call: the rate-adaptation
+ * sweeps of the reference run thousands of combinations x ~100 trials, and 100 frames do not fill a B200. All
+ * n_combinations x n_trials frames are generated and decoded by ONE launch each (per-frame QBER, scaling factors and
+ * punctured / shortened masks); when the on-chip decoder cannot be used (SPA, float64, long codes) the combinations are
+ * processed one after the other. params->primary / secondary are ignored. Outputs (HOST, each may be NULL):
+ * out_iters / out_flags: n_combinations x n_trials; tallies: n_combinations x qkdldpc_tally_len(); accurate_qber_out:
+ * n_combinations. Results are identical to n_combinations calls of qkdldpc_run_trials. */
+QKDLDPC_API int qkdldpc_run_trials_multi(qkdldpc_code *code, const qkdldpc_params *params, int32_t n_combinations,
+                             const qkdldpc_combination *combinations, int64_t n_trials, const uint64_t *trial_seeds,
+                             int32_t *out_iters, uint8_t *out_flags, uint64_t *tallies, double *accurate_qber_out);
+
 /* remove_bits (array_and_matrix_operations.cpp:259-287; called by QKD_LDPC / QKD_LDPC_RATE_ADAPT after the decoder,
  * qkd_ldpc_algorithm.cpp:1092,1220): deletes the positions `bits_to_remove` (strictly ascending: the privacy-maintenance
  * list, or punctured + shortened positions, H_matrix_params.bits_to_remove) from every frame. keys: HOST, n_frames packed

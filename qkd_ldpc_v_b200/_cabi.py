@@ -21,6 +21,11 @@ class Options(C.Structure):
                 ("onchip_threads", C.c_int32), ("tail_compaction", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
+class Combination(C.Structure):
+    _fields_ = [("qber", C.c_double), ("primary", C.c_double), ("secondary", C.c_double), ("punct_pos", C.c_void_p),
+                ("n_punct", C.c_int32), ("short_pos", C.c_void_p), ("n_short", C.c_int32), ("seed_offset", C.c_uint64)]
+
+
 class Info(C.Structure):
     _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("nnz", C.c_int64), ("device", C.c_int32),
                 ("frames_per_tile", C.c_int32), ("pool_tiles", C.c_int32), ("pool_bytes", C.c_int64),
@@ -50,6 +55,7 @@ SYMBOLS = {
                                                        C.c_int32, _VP, _VP, C.POINTER(C.c_double)]),
     "qkdldpc_run_trials": (C.c_int, [_VP, C.POINTER(Params), C.c_int64, _VP, C.c_uint64, C.c_double, _VP, C.c_int32, _VP,
                                      C.c_int32, _VP, _VP, _VP, _VP, C.POINTER(C.c_double)]),
+    "qkdldpc_run_trials_multi": (C.c_int, [_VP, C.POINTER(Params), C.c_int32, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP]),
     "qkdldpc_remove_bits": (C.c_int, [_VP, C.c_int64, _VP, _VP, C.c_int32, _VP]),
     "qkdldpc_code_info": (C.c_int, [_VP, C.POINTER(Info)]),
     "qkdldpc_code_set_profiling": (C.c_int, [_VP, C.c_int32]),

@@ -3,6 +3,7 @@
 #include "handle.hpp"
 #include "common.cuh"
 #include "gen_kernels.cuh"
+#include "onchip_minsum.cuh"
 
 namespace qkhost {
 template <typename T, int V>
@@ -18,6 +19,10 @@ int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const
                const double *d_qber, int qber_is_scalar, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short,
                uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally);
 bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P);
+int onchip_pack_masks(int n, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short, uint32_t *dst);
+int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int64_t frames_per_combo, const qk::OnchipCombo *combos,
+                     const uint32_t *masks, const uint32_t *d_alice, const uint32_t *d_bob, const double *d_qber, int qber_is_scalar,
+                     uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally);
 }  // namespace qkhost
 
 namespace {
@@ -337,7 +342,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->bitclass.release(); c->counters.release();
     c->st_alice.release(); c->st_bob.release(); c->st_out.release(); c->st_qber.release(); c->st_iters.release();
     c->st_flags.release(); c->st_tally.release();
-    c->gen_seeds.release(); c->gen_masks.release(); c->gen_scratch.release();
+    c->gen_seeds.release(); c->gen_masks.release(); c->gen_scratch.release(); c->gen_combos.release(); c->oc_combos.release();
     c->compact_moves.release(); c->compact_plan.release(); c->sched_work.release(); c->rb_kept.release();
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -469,57 +474,152 @@ int qkdldpc_generate_keys_device(qkdldpc_code *c, int64_t n_frames, double qber,
     return QKDLDPC_OK;
 }
 
-int qkdldpc_generate_trial_inputs_device(qkdldpc_code *c, int64_t n_frames, const uint64_t *trial_seeds, uint64_t seed_offset,
-                                         double qber, const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos,
-                                         int32_t n_short, uint32_t *d_alice_bits, uint32_t *d_bob_bits, double *accurate_qber_out) {
-    if (!c) return fail(QKDLDPC_ERR_INVALID, "null code handle");
-    if (!(qber >= 0.) || !(qber < 1.)) return fail(QKDLDPC_ERR_INVALID, "qber must be in [0, 1)");
-    if (n_frames < 0 || (n_frames > 0 && (!trial_seeds || !d_alice_bits || !d_bob_bits))) return fail(QKDLDPC_ERR_INVALID, "bad frame buffers");
-    if ((n_punct > 0 && !punct_pos) || (n_short > 0 && !short_pos) || n_punct < 0 || n_short < 0)
-        return fail(QKDLDPC_ERR_INVALID, "bad punctured/shortened position list");
+namespace {
+
+// Reference-compatible inputs for n_combos x trials frames (frame c * trials + t = trial t of combination c) into DEVICE
+// buffers. accurate[c] receives floor(n * qber_c) / n.
+int generate_inputs_multi(qkdldpc_code *c, int n_combos, const qkdldpc_combination *combos, int64_t trials, const uint64_t *trial_seeds,
+                          uint32_t *d_alice, uint32_t *d_bob, double *accurate) {
     const int n = c->n, words = (n + 31) / 32;
-    // inject_errors: num_errors = size_t(double(N) * QBER) (array_and_matrix_operations.cpp:913-914)
-    const int n_err = (int)(size_t)((double)n * qber);
-    if (accurate_qber_out) *accurate_qber_out = (double)n_err / (double)n;
+    std::vector<qk::RefKeygenCombo> table((size_t)n_combos);
+    std::vector<uint32_t> masks;
+    int max_err = 1;
+    bool any_ra = false;
+    for (int k = 0; k < n_combos; ++k) {
+        const qkdldpc_combination &cb = combos[k];
+        if (!(cb.qber >= 0.) || !(cb.qber < 1.)) return fail(QKDLDPC_ERR_INVALID, "qber must be in [0, 1)");
+        if ((cb.n_punct > 0 && !cb.punct_pos) || (cb.n_short > 0 && !cb.short_pos) || cb.n_punct < 0 || cb.n_short < 0)
+            return fail(QKDLDPC_ERR_INVALID, "bad punctured/shortened position list");
+        // inject_errors: num_errors = size_t(double(N) * QBER) (array_and_matrix_operations.cpp:913-914)
+        const int n_err = (int)(size_t)((double)n * cb.qber);
+        if (accurate) accurate[k] = (double)n_err / (double)n;
+        table[k].seed_offset = cb.seed_offset;
+        table[k].n_err = n_err;
+        table[k].rate_adapt = (cb.n_punct > 0 || cb.n_short > 0) ? 1 : 0;
+        max_err = std::max(max_err, n_err);
+        any_ra |= table[k].rate_adapt != 0;
+    }
+    const int64_t n_frames = (int64_t)n_combos * trials;
     if (n_frames == 0) return QKDLDPC_OK;
+    if (any_ra) {
+        masks.assign((size_t)n_combos * 2 * words, 0u);
+        for (int k = 0; k < n_combos; ++k) {
+            const int rc = onchip_pack_masks(n, combos[k].punct_pos, combos[k].n_punct, combos[k].short_pos, combos[k].n_short,
+                                             masks.data() + (size_t)k * 2 * words);
+            if (rc) return rc;
+        }
+    }
     CK(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
-    const bool ra = n_punct > 0 || n_short > 0;
-    CK(c->gen_seeds.reserve((size_t)n_frames));
-    CK(cudaMemcpyAsync(c->gen_seeds.p, trial_seeds, (size_t)n_frames * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    if (ra) {
-        std::vector<uint32_t> masks((size_t)2 * words, 0u);
-        for (int i = 0; i < n_punct; ++i) {
-            if (punct_pos[i] < 0 || punct_pos[i] >= n) return fail(QKDLDPC_ERR_INVALID, "punctured position out of range");
-            masks[punct_pos[i] >> 5] |= 1u << (punct_pos[i] & 31);
-        }
-        for (int i = 0; i < n_short; ++i) {
-            if (short_pos[i] < 0 || short_pos[i] >= n) return fail(QKDLDPC_ERR_INVALID, "shortened position out of range");
-            if (!((masks[short_pos[i] >> 5] >> (short_pos[i] & 31)) & 1u))   // punctured is tested first (:1150)
-                masks[(size_t)words + (short_pos[i] >> 5)] |= 1u << (short_pos[i] & 31);
-        }
-        CK(c->gen_masks.reserve(masks.size()));
-        CK(cudaMemcpyAsync(c->gen_masks.p, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        CK(cudaStreamSynchronize(s));   // the host vector dies at scope end
-    }
+    CK(c->gen_seeds.reserve((size_t)trials));
+    CK(c->gen_combos.reserve(table.size() * sizeof(qk::RefKeygenCombo)));
+    CK(c->gen_masks.reserve(std::max<size_t>(masks.size(), 1)));
+    CK(cudaMemcpyAsync(c->gen_seeds.p, trial_seeds, (size_t)trials * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->gen_combos.p, table.data(), table.size() * sizeof(qk::RefKeygenCombo), cudaMemcpyHostToDevice, s));
+    if (any_ra) CK(cudaMemcpyAsync(c->gen_masks.p, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     // one thread per frame; sub-batches bound the per-thread scratch (raw keys for rate adaptation + shuffle prefix)
-    const long long per_thread = (ra ? 2ll * words : 0ll) + std::max(n_err, 1);
+    const long long per_thread = (any_ra ? 2ll * words : 0ll) + max_err;
     const long long sub = std::max<long long>(128, std::min<long long>(n_frames, ((long long)256 << 20) / (per_thread * 4)) / 128 * 128);
     CK(c->gen_scratch.reserve((size_t)(per_thread * sub)));
     for (long long f0 = 0; f0 < n_frames; f0 += sub) {
         qk::RefKeygenArgs a{};
-        a.n = n; a.words = words; a.n_err = n_err;
+        a.n = n; a.words = words;
         a.n_frames = std::min<long long>(sub, n_frames - f0);
-        a.seeds = reinterpret_cast<const qk::u64 *>(c->gen_seeds.p) + f0;
-        a.seed_offset = seed_offset;
-        a.alice = d_alice_bits + f0 * words; a.bob = d_bob_bits + f0 * words;
-        a.rate_adapt = ra ? 1 : 0;
-        a.punct_mask = c->gen_masks.p; a.short_mask = ra ? c->gen_masks.p + words : nullptr;
+        a.first_frame = f0;
+        a.trials = trials;
+        a.seeds = reinterpret_cast<const qk::u64 *>(c->gen_seeds.p);
+        a.combos = reinterpret_cast<const qk::RefKeygenCombo *>(c->gen_combos.p);
+        a.alice = d_alice + f0 * words; a.bob = d_bob + f0 * words;
+        a.masks = c->gen_masks.p;
+        a.any_rate_adapt = any_ra ? 1 : 0;
+        a.max_err = max_err;
         a.scratch = c->gen_scratch.p; a.scratch_stride = sub;
         qk::ref_keygen_kernel<<<(unsigned)((a.n_frames + 127) / 128), 128, 0, s>>>(a);
         c->kernel_launches += 1;
     }
     CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));   // the host tables die at scope end
+    return QKDLDPC_OK;
+}
+
+}  // namespace
+
+int qkdldpc_generate_trial_inputs_device(qkdldpc_code *c, int64_t n_frames, const uint64_t *trial_seeds, uint64_t seed_offset,
+                                         double qber, const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos,
+                                         int32_t n_short, uint32_t *d_alice_bits, uint32_t *d_bob_bits, double *accurate_qber_out) {
+    if (!c) return fail(QKDLDPC_ERR_INVALID, "null code handle");
+    if (n_frames < 0 || (n_frames > 0 && (!trial_seeds || !d_alice_bits || !d_bob_bits))) return fail(QKDLDPC_ERR_INVALID, "bad frame buffers");
+    qkdldpc_combination cb{};
+    cb.qber = qber;
+    cb.punct_pos = punct_pos; cb.n_punct = n_punct;
+    cb.short_pos = short_pos; cb.n_short = n_short;
+    cb.seed_offset = seed_offset;
+    return generate_inputs_multi(c, 1, &cb, n_frames, trial_seeds, d_alice_bits, d_bob_bits, accurate_qber_out);
+}
+
+int qkdldpc_run_trials_multi(qkdldpc_code *c, const qkdldpc_params *P, int32_t n_combinations, const qkdldpc_combination *combos,
+                             int64_t n_trials, const uint64_t *trial_seeds, int32_t *out_iters, uint8_t *out_flags, uint64_t *tallies,
+                             double *accurate_qber_out) {
+    int rc = check_params(c, P, n_trials);
+    if (rc) return rc;
+    if (n_combinations < 0 || (n_combinations > 0 && !combos)) return fail(QKDLDPC_ERR_INVALID, "bad combination table");
+    const int64_t tl = qkdldpc_tally_len(P->max_iterations);
+    if (n_combinations == 0) return QKDLDPC_OK;
+    if (n_trials > 0 && !trial_seeds) return fail(QKDLDPC_ERR_INVALID, "null seed array");
+    qkdldpc_params Pk = *P;
+    Pk.primary = combos[0].primary;
+    Pk.secondary = combos[0].secondary;
+    bool onchip = c->opt.decoder_path != 1;
+    for (int k = 0; k < n_combinations && onchip; ++k) {   // every combination must satisfy the on-chip preconditions
+        Pk.primary = combos[k].primary;
+        Pk.secondary = combos[k].secondary;
+        onchip = onchip_usable(c, &Pk);
+    }
+    if (!onchip || n_trials == 0) {
+        // streaming path (SPA, float64, long codes): one combination after the other
+        for (int k = 0; k < n_combinations; ++k) {
+            Pk.primary = combos[k].primary;
+            Pk.secondary = combos[k].secondary;
+            rc = qkdldpc_run_trials(c, &Pk, n_trials, trial_seeds, combos[k].seed_offset, combos[k].qber, combos[k].punct_pos, combos[k].n_punct,
+                                    combos[k].short_pos, combos[k].n_short, nullptr, out_iters ? out_iters + (int64_t)k * n_trials : nullptr,
+                                    out_flags ? out_flags + (int64_t)k * n_trials : nullptr, tallies ? tallies + (int64_t)k * tl : nullptr,
+                                    accurate_qber_out ? accurate_qber_out + k : nullptr);
+            if (rc) return rc;
+        }
+        return QKDLDPC_OK;
+    }
+    CK(cudaSetDevice(c->device));
+    const int words = (c->n + 31) / 32;
+    const int64_t n_frames = (int64_t)n_combinations * n_trials;
+    const size_t tot = (size_t)n_frames * words;
+    CK(c->st_alice.reserve(tot));
+    CK(c->st_bob.reserve(tot));
+    std::vector<double> acc((size_t)n_combinations, 0.);
+    rc = generate_inputs_multi(c, n_combinations, combos, n_trials, trial_seeds, c->st_alice.p, c->st_bob.p, acc.data());
+    if (rc) return rc;
+    std::vector<qk::OnchipCombo> table((size_t)n_combinations);
+    std::vector<uint32_t> masks((size_t)n_combinations * 2 * words, 0u);
+    for (int k = 0; k < n_combinations; ++k) {
+        if (acc[k] == 0.) return fail(QKDLDPC_ERR_INVALID, "Key size '%d' is too small for QBER.", c->n);   // simulation.cpp:556-557
+        if (accurate_qber_out) accurate_qber_out[k] = acc[k];
+        table[k].qber = acc[k];
+        table[k].primary = (float)combos[k].primary;
+        table[k].secondary = (float)combos[k].secondary;
+        table[k].has_cls = (combos[k].n_punct > 0 || combos[k].n_short > 0) ? 1 : 0;
+        rc = onchip_pack_masks(c->n, combos[k].punct_pos, combos[k].n_punct, combos[k].short_pos, combos[k].n_short,
+                               masks.data() + (size_t)k * 2 * words);
+        if (rc) return rc;
+    }
+    CK(c->st_iters.reserve(n_frames));
+    CK(c->st_flags.reserve(n_frames));
+    CK(c->st_tally.reserve((size_t)n_combinations * tl));
+    rc = run_onchip_multi(c, P, n_combinations, n_trials, table.data(), masks.data(), c->st_alice.p, c->st_bob.p, nullptr, 1, nullptr,
+                          c->st_iters.p, c->st_flags.p, c->st_tally.p);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    if (out_iters) CK(cudaMemcpyAsync(out_iters, c->st_iters.p, n_frames * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (out_flags) CK(cudaMemcpyAsync(out_flags, c->st_flags.p, n_frames, cudaMemcpyDeviceToHost, s));
+    if (tallies) CK(cudaMemcpyAsync(tallies, c->st_tally.p, (size_t)n_combinations * tl * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return QKDLDPC_OK;
 }

@@ -102,39 +102,52 @@ struct Xoshiro256pp {
     }
 };
 
-struct RefKeygenArgs {
-    int n, words, n_err;
-    long long n_frames;
-    const u64 *seeds;          // [n_frames] per-trial seeds (simulation.cpp:713-719)
-    u64 seed_offset;           // + combination index (simulation.cpp:743)
-    uint32_t *alice, *bob;     // [n_frames][words] output frames (extended frames when rate adaptation is on)
+// One parameter combination of a sweep: frames [c * trials, (c+1) * trials) of a launch belong to combination c and use
+// trial seeds seeds[0 .. trials) + seed_offset (the reference's seeds[n] + curr_sim, simulation.cpp:743).
+struct RefKeygenCombo {
+    u64 seed_offset;
+    int n_err;                 // floor(n * QBER)
     int rate_adapt;            // punctured / shortened masks present
-    const uint32_t *punct_mask, *short_mask;   // [words] packed positions (shortened excludes punctured)
-    uint32_t *scratch;         // thread-interleaved: [(2*words if rate_adapt) + n_err][threads of the launch]
+};
+
+struct RefKeygenArgs {
+    int n, words;
+    long long n_frames, first_frame;   // frames of this launch; global index of its first frame
+    long long trials;          // frames per combination
+    const u64 *seeds;          // [trials] per-trial seeds (simulation.cpp:713-719)
+    const RefKeygenCombo *combos;
+    uint32_t *alice, *bob;     // [n_frames][words] output frames of this launch (extended frames with rate adaptation)
+    const uint32_t *masks;     // [combo][2][words] packed punctured / shortened positions (shortened excludes punctured)
+    int any_rate_adapt;        // the scratch holds raw-key words (some combination is rate-adapted)
+    int max_err;               // prefix entries per thread in the scratch
+    uint32_t *scratch;         // thread-interleaved: [(2*words if any_rate_adapt) + max_err][threads of the launch]
     long long scratch_stride;  // threads of the launch
 };
 
 __global__ void __launch_bounds__(128) ref_keygen_kernel(const RefKeygenArgs a) {
     const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= a.n_frames) return;
+    const long long gf = a.first_frame + f, combo = gf / a.trials;
+    const RefKeygenCombo cb = a.combos[combo];
+    const int rate_adapt = cb.rate_adapt;
     const long long T = a.scratch_stride;
     uint32_t *raw_a = a.scratch + f;                                  // raw_a[w * T]  (rate adaptation only)
-    uint32_t *raw_b = raw_a + (a.rate_adapt ? (long long)a.words * T : 0);
-    uint32_t *prefix = a.scratch + (a.rate_adapt ? 2ll * a.words * T : 0) + f;   // prefix[j * T]
+    uint32_t *raw_b = raw_a + (a.any_rate_adapt ? (long long)a.words * T : 0);
+    uint32_t *prefix = a.scratch + (a.any_rate_adapt ? 2ll * a.words * T : 0) + f;   // prefix[j * T]
     uint32_t *out_a = a.alice + f * a.words, *out_b = a.bob + f * a.words;
-    Xoshiro256pp g(a.seeds[f] + a.seed_offset);
+    Xoshiro256pp g(a.seeds[gf % a.trials] + cb.seed_offset);
 
     // fill_random_bits
     for (int w = 0; w < a.words; ++w) {
         const int cnt = min(32, a.n - w * 32);
         uint32_t word = 0;
         for (int b = 0; b < cnt; ++b) word |= (uint32_t)(g() >> 63) << b;
-        if (a.rate_adapt) { raw_a[(long long)w * T] = word; raw_b[(long long)w * T] = word; }
+        if (rate_adapt) { raw_a[(long long)w * T] = word; raw_b[(long long)w * T] = word; }
         else { out_a[w] = word; out_b[w] = word; }
     }
 
     // inject_errors: the first K entries of std::shuffle(0..N-1), without the array
-    const int K = a.n_err;
+    const int K = cb.n_err;
     if (K > 0) {
         for (int j = 0; j < K; ++j) prefix[(long long)j * T] = (uint32_t)j;
         auto step = [&](uint32_t i, uint32_t j) {   // std::iter_swap(first + i, first + j), j <= i
@@ -168,16 +181,17 @@ __global__ void __launch_bounds__(128) ref_keygen_kernel(const RefKeygenArgs a) 
         }
         for (int j = 0; j < K; ++j) {
             const uint32_t p = prefix[(long long)j * T];
-            if (a.rate_adapt) raw_b[(long long)(p >> 5) * T] ^= 1u << (p & 31);
+            if (rate_adapt) raw_b[(long long)(p >> 5) * T] ^= 1u << (p & 31);
             else out_b[p >> 5] ^= 1u << (p & 31);
         }
     }
-    if (!a.rate_adapt) return;
+    if (!rate_adapt) return;
+    const uint32_t *punct_mask = a.masks + combo * 2 * a.words, *short_mask = punct_mask + a.words;
 
     // QKD_LDPC_RATE_ADAPT frame construction
     int k = 0;   // payload index n of the reference loop
     for (int w = 0; w < a.words; ++w) {
-        const uint32_t pm = a.punct_mask[w], sm = a.short_mask[w];
+        const uint32_t pm = punct_mask[w], sm = short_mask[w];
         const int cnt = min(32, a.n - w * 32);
         uint32_t wa = 0, wb = 0;
         for (int b = 0; b < cnt; ++b) {

@@ -87,6 +87,7 @@ struct qkdldpc_code {
     DevBuf<uint2> oc_cnT;
     DevBuf<uint4> oc_vT;
     DevBuf<uint32_t> oc_cls;
+    DevBuf<unsigned char> oc_combos;  // OnchipCombo table of the current launch
     // variable-phase groups as built by code_create; the device copies (oc_vn_ginfo / oc_vn_bit) are re-laid out in
     // schedule order for the number of warps per CTA of the launch (inst_onchip.cu)
     std::vector<int> oc_vn_degree;
@@ -114,6 +115,7 @@ struct qkdldpc_code {
     DevBuf<unsigned long long> st_tally;
     // reference-compatible trial-input generator (gen_kernels.cuh)
     DevBuf<uint64_t> gen_seeds;
+    DevBuf<unsigned char> gen_combos;  // RefKeygenCombo table of the current launch
     DevBuf<uint32_t> gen_masks, gen_scratch;
     DevBuf<int> rb_kept;               // remove_bits: surviving positions
     DevBuf<unsigned char> sched_work;  // TileWork per tile (sched_kernels.cuh)

@@ -78,42 +78,50 @@ static std::vector<int> vn_schedule(const std::vector<int> &group_degree, int nw
     return sched;
 }
 
-int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const uint32_t *d_alice, const uint32_t *d_bob,
-               const double *d_qber, int qber_is_scalar, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short,
-               uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally) {
-    const int n = c->n, m = c->m, words = (n + 31) / 32;
-    cudaStream_t s = c->stream;
-    CK(c->oc_cls.reserve((size_t)2 * words));
-    CK(c->counters.reserve(2));
-    // punctured / shortened position masks (H_matrix_params, array_and_matrix_operations.hpp:44-48)
-    const bool has_cls = n_punct > 0 || n_short > 0;
-    if (has_cls) {
-        std::vector<uint32_t> cls((size_t)2 * words, 0u);
-        for (int i = 0; i < n_punct; ++i) {
-            if (punct[i] < 0 || punct[i] >= n) return fail(QKDLDPC_ERR_INVALID, "punctured position out of range");
-            cls[punct[i] >> 5] |= 1u << (punct[i] & 31);
-        }
-        for (int i = 0; i < n_short; ++i) {
-            if (shortd[i] < 0 || shortd[i] >= n) return fail(QKDLDPC_ERR_INVALID, "shortened position out of range");
-            cls[(size_t)words + (shortd[i] >> 5)] |= 1u << (shortd[i] & 31);   // in both lists: punctured wins (:1150 tested first)
-        }
-        CK(cudaMemcpyAsync(c->oc_cls.p, cls.data(), cls.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-        CK(cudaStreamSynchronize(s));   // the host vector dies at scope end
+// Packed punctured / shortened masks of one combination into dst[0 .. 2*words): [punctured | shortened without punctured].
+int onchip_pack_masks(int n, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short, uint32_t *dst) {
+    const int words = (n + 31) / 32;
+    for (int i = 0; i < n_punct; ++i) {
+        if (punct[i] < 0 || punct[i] >= n) return fail(QKDLDPC_ERR_INVALID, "punctured position out of range");
+        dst[punct[i] >> 5] |= 1u << (punct[i] & 31);
     }
+    for (int i = 0; i < n_short; ++i) {
+        if (shortd[i] < 0 || shortd[i] >= n) return fail(QKDLDPC_ERR_INVALID, "shortened position out of range");
+        if (!((dst[shortd[i] >> 5] >> (shortd[i] & 31)) & 1u))   // in both lists: punctured wins (:1150 is tested first)
+            dst[(size_t)words + (shortd[i] >> 5)] |= 1u << (shortd[i] & 31);
+    }
+    return QKDLDPC_OK;
+}
+
+// One launch over n_combos x frames_per_combo frames. `combos` / `masks` are HOST tables ([n_combos], [n_combos][2][words]);
+// d_tally holds n_combos tally vectors.
+int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int64_t frames_per_combo, const OnchipCombo *combos,
+                     const uint32_t *masks, const uint32_t *d_alice, const uint32_t *d_bob, const double *d_qber, int qber_is_scalar,
+                     uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally) {
+    const int n = c->n, m = c->m, words = (n + 31) / 32;
+    const int64_t n_frames = (int64_t)n_combos * frames_per_combo;
+    const int tl = (int)qkdldpc_tally_len(P->max_iterations);
+    cudaStream_t s = c->stream;
+    CK(c->oc_cls.reserve((size_t)n_combos * 2 * words));
+    CK(c->oc_combos.reserve((size_t)n_combos * sizeof(OnchipCombo)));
+    CK(c->counters.reserve(2));
+    CK(cudaMemcpyAsync(c->oc_cls.p, masks, (size_t)n_combos * 2 * words * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->oc_combos.p, combos, (size_t)n_combos * sizeof(OnchipCombo), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));   // the caller's host tables may die after this call returns early on an error below
     CK(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), s));
-    if (d_tally) CK(cudaMemsetAsync(d_tally, 0, (size_t)qkdldpc_tally_len(P->max_iterations) * sizeof(uint64_t), s));
+    if (d_tally) CK(cudaMemsetAsync(d_tally, 0, (size_t)n_combos * tl * sizeof(uint64_t), s));
 
     OnchipArgs a{};
     a.n = n; a.m = m; a.words = words; a.rec_slots = c->oc_rec_slots;
     a.n_groups_cn = c->oc_groups_cn; a.n_groups_vn = c->oc_groups_vn;
     a.cn_ginfo = c->oc_cn_ginfo.p; a.cn_row = c->oc_cn_row.p; a.cnT = c->oc_cnT.p;
     a.vn_ginfo = c->oc_vn_ginfo.p; a.vn_bit = c->oc_vn_bit.p; a.vT = c->oc_vT.p;
-    a.cls_punct = c->oc_cls.p; a.cls_short = c->oc_cls.p + words; a.has_cls = has_cls ? 1 : 0;
+    a.combos = reinterpret_cast<const OnchipCombo *>(c->oc_combos.p); a.frames_per_combo = frames_per_combo;
+    a.cls_masks = c->oc_cls.p; a.tally_len = tl;
     a.n_frames = n_frames; a.alice_bits = d_alice; a.bob_bits = d_bob; a.qber = d_qber; a.qber_is_scalar = qber_is_scalar;
     a.out_bits = d_out_bits; a.out_iters = d_out_iters; a.out_flags = d_out_flags; a.tally = d_tally;
     a.next_frame = c->counters.p;
     a.max_iter = P->max_iterations;
-    a.primary = (float)P->primary; a.secondary = (float)P->secondary;
     a.thr = P->enable_threshold ? (float)P->threshold : INFINITY;
 
     int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(768, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
@@ -175,6 +183,23 @@ int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const
     c->pool_bytes = (int64_t)grid * (int64_t)smem;   // bytes of on-chip decoder state in flight
     CK(cudaGetLastError());
     return QKDLDPC_OK;
+}
+
+// The single-combination call of qkdldpc_decode_batch_device.
+int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const uint32_t *d_alice, const uint32_t *d_bob,
+               const double *d_qber, int qber_is_scalar, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short,
+               uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally) {
+    const int words = (c->n + 31) / 32;
+    std::vector<uint32_t> masks((size_t)2 * words, 0u);
+    const int rc = onchip_pack_masks(c->n, punct, n_punct, shortd, n_short, masks.data());
+    if (rc) return rc;
+    OnchipCombo cb{};
+    cb.qber = -1.;   // LLR magnitude from the caller's qber array
+    cb.primary = (float)P->primary;
+    cb.secondary = (float)P->secondary;
+    cb.has_cls = (n_punct > 0 || n_short > 0) ? 1 : 0;
+    return run_onchip_multi(c, P, 1, n_frames, &cb, masks.data(), d_alice, d_bob, d_qber, qber_is_scalar, d_out_bits, d_out_iters,
+                            d_out_flags, d_tally);
 }
 
 }  // namespace qkhost

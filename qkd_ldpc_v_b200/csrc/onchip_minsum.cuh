@@ -32,6 +32,13 @@ namespace qk {
 
 typedef unsigned long long u64;
 
+struct OnchipCombo {
+    double qber;              // accurate QBER of the combination; < 0: take the per-frame / scalar `qber` array instead
+    float primary, secondary; // decoding_scaling_factors
+    int has_cls;              // rate adaptation: punctured / shortened masks present
+    int pad;
+};
+
 struct OnchipArgs {
     int n, m, words;
     int rec_slots;              // record slots in use (m + number of rows wider than 32 edges); + 2 scratch slots
@@ -47,9 +54,12 @@ struct OnchipArgs {
     const uint16_t *vn_bit;     // [groups*32] bit handled by (group, lane); padding lanes hold n (a scratch L slot)
     const uint4 *vT;            // [off + kb*32 + lane] 4 x uint32: row << 9 | sh of checks 4kb..4kb+3 of that bit,
                                 //                      sh = 32 - dc(row) + position in the row (padding: scratch row m)
-    const uint32_t *cls_punct;  // [words] packed: punctured positions (all zero without rate adaptation)
-    const uint32_t *cls_short;  // [words] packed: shortened positions
-    int has_cls;
+    // One launch may span several parameter COMBINATIONS of a sweep (frames [c * frames_per_combo, (c+1) * ...) belong to
+    // combination c): scaling factors, QBER, punctured / shortened masks and the tally vector are per combination.
+    const OnchipCombo *combos;  // [n_combos]
+    long long frames_per_combo; // frames of one combination (n_frames when there is a single one)
+    const uint32_t *cls_masks;  // [n_combos][2][words] packed punctured / shortened positions (shortened excludes punctured)
+    int tally_len;
     long long n_frames;
     const uint32_t *alice_bits, *bob_bits;
     const double *qber;
@@ -60,19 +70,27 @@ struct OnchipArgs {
     u64 *tally;
     u64 *next_frame;
     int max_iter;
-    float primary, secondary, thr;   // thr = +inf when the clamp is disabled
+    float thr;                  // +inf when the clamp is disabled
 };
 
 // Shared-memory layout: rec[rec_slots+2] uint4 | L[n+1] float (padded to 16 B) | bob[words] | alice[words] | syn[groups_cn] | misc
 __host__ __device__ inline size_t onchip_l_slots(int n) { return ((size_t)n + 1 + 3) / 4 * 4; }
 __host__ __device__ inline size_t onchip_smem_bytes(int n, int rec_slots, int groups_cn) {
     const size_t words = (size_t)(n + 31) / 32;
-    return ((size_t)rec_slots + 2) * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn) * 4 + 64;
+    return ((size_t)rec_slots + 2) * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn) * 4 + 96;   // + frame id, FrameCtx
 }
 
 // Record of a row: x = bits(c1), y = bits(c2) (non-negative magnitudes), z = final sign of the message on edge k in bit
 // (dc-1-k), w = 32 - dc + position of the first minimum. A reader that knows sh = 32 - dc + k gets the sign with
 // (z << sh) & 0x80000000 and the magnitude with (sh == w) ? c2 : c1.
+
+// Per-frame parameters (shared memory, written by thread 0 when the CTA takes a frame).
+struct FrameCtx {
+    float lp, primary, secondary;
+    int has_cls;
+    const uint32_t *cls_punct, *cls_short;
+    u64 *tally;
+};
 
 // One edge of a check node: gather L of the bit, rebuild the bit-to-check message with the OLD record, update the
 // running min1 / min2 / argmin / sign state.  `rel` = old argmin - index of the first edge of the current block.
@@ -98,8 +116,8 @@ __host__ __device__ inline size_t onchip_smem_bytes(int n, int rec_slots, int gr
 constexpr uint32_t kNoArg = 0x100u;
 
 template <int ALG, bool WIDE>
-__device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float *L, uint4 *rec, const uint32_t *synw,
-                                                float thr_b, int warp, int lane, int nwarps) {
+__device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const FrameCtx *ctx, const float *L, uint4 *rec,
+                                                const uint32_t *synw, float thr_b, int warp, int lane, int nwarps) {
     bool unsat = false;
     for (int g = warp; g < a.n_groups_cn; g += nwarps) {
         const int2 gi = __ldg(a.cn_ginfo + g);
@@ -160,7 +178,7 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float
         const uint32_t syn = (synw[g] >> lane) & 1u;
         const bool viol = (((zacc >> 31) ^ syn) & 1u) != 0;    // check not satisfied by the current hard decision
         unsat |= viol && row < (uint32_t)a.rec_slots;
-        const float factor = (ALG >= 4 && viol) ? a.secondary : a.primary;   // (:749-757, :939-947)
+        const float factor = (ALG >= 4 && viol) ? ctx->secondary : ctx->primary;   // (:749-757, :939-947)
         float c1, c2;
         if constexpr (ALG == 2 || ALG == 4) {
             c1 = factor * m1;
@@ -191,12 +209,12 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const float
 }
 #undef QK_CN_EDGE
 
-__device__ __forceinline__ float onchip_llr(const OnchipArgs &a, const uint32_t *bobw, uint32_t bit, float lp) {
+__device__ __forceinline__ float onchip_llr(const FrameCtx *ctx, const uint32_t *bobw, uint32_t bit, float lp) {
     const uint32_t w = bit >> 5, s = bit & 31u;
     float v = ((bobw[w] >> s) & 1u) ? -lp : lp;                // qkd_ldpc_algorithm.cpp:1043-1049
-    if (a.has_cls) {
-        if ((__ldg(a.cls_punct + w) >> s) & 1u) v = 1e-4f;     // punctured: ALMOST_ZERO (:1155)
-        else if ((__ldg(a.cls_short + w) >> s) & 1u) v = FLT_MAX;   // shortened: largest finite value (:1164)
+    if (ctx->has_cls) {
+        if ((__ldg(ctx->cls_punct + w) >> s) & 1u) v = 1e-4f;  // punctured: ALMOST_ZERO (:1155)
+        else if ((__ldg(ctx->cls_short + w) >> s) & 1u) v = FLT_MAX;   // shortened: largest finite value (:1164)
     }
     return v;
 }
@@ -209,8 +227,8 @@ __device__ __forceinline__ float onchip_llr(const OnchipArgs &a, const uint32_t 
         acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.z, (ENT)) & 0x80000000u));   /* r.z << sh */           \
     }
 
-__device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, float *L, const uint4 *rec, const uint32_t *bobw, float lp, int warp,
-                                                int lane, int nwarps) {
+__device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *L, const uint4 *rec, const uint32_t *bobw,
+                                                float lp, int warp, int lane, int nwarps) {
     const unsigned char *recb = reinterpret_cast<const unsigned char *>(rec);
     // groups come in SCHEDULE order: entry g is handled by warp g % nwarps, and the host dealt the groups to the warps
     // longest-first so that all warps of the CTA finish the phase together (inst_onchip.cu)
@@ -218,7 +236,7 @@ __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, float *L, c
         const int2 gi = __ldg(a.vn_ginfo + g);
         const int dv = gi.y;
         const uint32_t bit = __ldg(a.vn_bit + g * 32 + lane);
-        float acc = onchip_llr(a, bobw, bit < (uint32_t)a.n ? bit : 0u, lp);
+        float acc = onchip_llr(ctx, bobw, bit < (uint32_t)a.n ? bit : 0u, lp);
         const uint4 *ep = a.vT + gi.x + lane;
         int kb = 0;
         // ascending check order, starting from the LLR (std::accumulate, :414-417)
@@ -252,7 +270,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
     uint32_t *synw = alw + a.words;
     uint32_t *tail = synw + a.n_groups_cn;
     long long *s_frame = reinterpret_cast<long long *>(tail + ((2 * a.words + a.n_groups_cn) & 1));
-    float *s_lp = reinterpret_cast<float *>(s_frame + 1);
+    FrameCtx *ctx = reinterpret_cast<FrameCtx *>(s_frame + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     constexpr bool kAdaptive = (ALG >= 4);
@@ -264,21 +282,29 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
             const long long f = (long long)atomicAdd(a.next_frame, 1ull);
             *s_frame = f;
             if (f < a.n_frames) {
-                const double q = a.qber_is_scalar ? a.qber[0] : a.qber[f];
-                *s_lp = (float)log((1. - q) / q);
+                const long long combo = f / a.frames_per_combo;
+                const OnchipCombo cb = a.combos[combo];
+                const double q = cb.qber >= 0. ? cb.qber : (a.qber_is_scalar ? a.qber[0] : a.qber[f]);
+                ctx->lp = (float)log((1. - q) / q);
+                ctx->primary = cb.primary;
+                ctx->secondary = cb.secondary;
+                ctx->has_cls = cb.has_cls;
+                ctx->cls_punct = a.cls_masks + combo * 2 * a.words;
+                ctx->cls_short = ctx->cls_punct + a.words;
+                ctx->tally = a.tally ? a.tally + combo * a.tally_len : nullptr;
             }
         }
         __syncthreads();
         const long long f = *s_frame;
         if (f >= a.n_frames) break;
-        const float lp = *s_lp;
+        const float lp = ctx->lp;
         for (int w = tid; w < a.words; w += blockDim.x) {
             bobw[w] = a.bob_bits[f * a.words + w];
             alw[w] = a.alice_bits[f * a.words + w];
         }
         __syncthreads();
         // L = a-priori LLR; Alice's syndrome (calculate_syndrome, array_and_matrix_operations.cpp:936-950); records = 0
-        for (int i = tid; i <= a.n; i += blockDim.x) L[i] = (i < a.n) ? onchip_llr(a, bobw, (uint32_t)i, lp) : 1.f;
+        for (int i = tid; i <= a.n; i += blockDim.x) L[i] = (i < a.n) ? onchip_llr(ctx, bobw, (uint32_t)i, lp) : 1.f;
         for (int g = warp; g < a.n_groups_cn; g += nwarps) {
             const int2 gi = __ldg(a.cn_ginfo + g);
             const uint32_t row = __ldg(a.cn_row + g * 32 + lane);
@@ -305,7 +331,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
         for (int it = 1;; ++it) {
             // the check-node pass of iteration `it`; at it = max_iter + 1 it only serves as the syndrome test of the
             // last hard decision (non-adaptive variants, :424-445)
-            const bool unsat = onchip_cn_phase<ALG, WIDE>(a, L, rec, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
+            const bool unsat = onchip_cn_phase<ALG, WIDE>(a, ctx, L, rec, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
             const bool any_unsat = __syncthreads_or(unsat) != 0;
             if (!kAdaptive) {
                 if (it > 1 && !any_unsat) { success = true; iters = run = it - 1; break; }   // z of iteration it-1 (:439-445)
@@ -313,7 +339,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
             } else {
                 if (!any_unsat) { success = true; iters = it; run = it - 1; break; }         // exit test before the VN step (:770-776)
             }
-            onchip_vn_phase(a, L, rec, bobw, lp, warp, lane, nwarps);
+            onchip_vn_phase(a, ctx, L, rec, bobw, lp, warp, lane, nwarps);
             __syncthreads();
             if (kAdaptive && it == a.max_iter) break;          // the decision of the last iteration is never tested (Q10)
         }
@@ -332,14 +358,15 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
         if (tid == 0) {
             if (a.out_iters) a.out_iters[f] = iters;
             if (a.out_flags) a.out_flags[f] = (uint8_t)((success ? 1u : 0u) | (keys_differ ? 0u : 2u));
-            if (a.tally) {
-                atomicAdd(a.tally + 0, 1ull);
+            u64 *tally = ctx->tally;
+            if (tally) {
+                atomicAdd(tally + 0, 1ull);
                 if (success) {
-                    atomicAdd(a.tally + 1, 1ull);
-                    if (!keys_differ) atomicAdd(a.tally + 2, 1ull);
-                    atomicAdd(a.tally + 4 + iters, 1ull);
+                    atomicAdd(tally + 1, 1ull);
+                    if (!keys_differ) atomicAdd(tally + 2, 1ull);
+                    atomicAdd(tally + 4 + iters, 1ull);
                 }
-                atomicAdd(a.tally + 3, (u64)run);
+                atomicAdd(tally + 3, (u64)run);
             }
         }
     }

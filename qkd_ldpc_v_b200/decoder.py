@@ -243,6 +243,33 @@ class LdpcCode:
         inf["accurate_qber"] = acc.value
         return BatchResult(iters, flags, out_bits, tally, self.n, inf["last_batch_ms"], inf)
 
+    def run_trials_multi(self, trial_seeds, combinations, cfg: Optional[DecoderConfig] = None):
+        """Several combinations of a sweep in one call (``qkdldpc_run_trials_multi``). ``combinations``: list of dicts with
+        keys QBER, primary, secondary, punctured_bits, shortened_bits, seed_offset. Returns (iterations [C][T],
+        flags [C][T], tallies [C][tally_len], accurate_qber [C])."""
+        cfg = cfg or DecoderConfig()
+        L = _cabi.lib()
+        seeds = np.ascontiguousarray(trial_seeds, np.uint64)
+        T, Cn = int(seeds.size), len(combinations)
+        p = cfg.to_params((0.0, 0.0))
+        table = (_cabi.Combination * max(Cn, 1))()
+        keep = []
+        for k, cb in enumerate(combinations):
+            pa, pp, np_ = self._poslist(cb.get("punctured_bits", ()))
+            sa, sp, ns_ = self._poslist(cb.get("shortened_bits", ()))
+            keep += [pa, sa]
+            table[k] = _cabi.Combination(float(cb["QBER"]), float(cb.get("primary", 0.0)), float(cb.get("secondary", 0.0)), pp, np_, sp,
+                                         ns_, int(cb.get("seed_offset", 0)))
+        tl = int(L.qkdldpc_tally_len(p.max_iterations))
+        iters = np.zeros((Cn, T), np.int32)
+        flags = np.zeros((Cn, T), np.uint8)
+        tallies = np.zeros((Cn, tl), np.uint64)
+        acc = np.zeros(Cn, np.float64)
+        _cabi.check(L.qkdldpc_run_trials_multi(self._h, C.byref(p), Cn, C.byref(table), T, seeds.ctypes.data, iters.ctypes.data,
+                                               flags.ctypes.data, tallies.ctypes.data, acc.ctypes.data), "qkdldpc_run_trials_multi")
+        del keep
+        return iters, flags, tallies, acc
+
     def generate_trial_inputs_device(self, trial_seeds, qber: float, d_alice: int, d_bob: int, seed_offset: int = 0,
                                      punctured_bits: Sequence[int] = (), shortened_bits: Sequence[int] = ()) -> float:
         """Reference-compatible trial inputs written to DEVICE buffers (``qkdldpc_generate_trial_inputs_device``);

@@ -166,6 +166,7 @@ int main(int argc, char *argv[]) {
         api.decode_batch = &qkdldpc_decode_batch;
         api.last_error = &qkdldpc_last_error;
         api.run_trials = &qkdldpc_run_trials;
+        api.run_trials_multi = &qkdldpc_run_trials_multi;
 
         std::vector<fs::path> config_paths;
         if (!config_file.empty()) config_paths.push_back(config_file);

@@ -386,17 +386,55 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
         };
 
         if (sweep_mode) {
+            // Few trials per combination. With device-side input generation whole batches of combinations go through ONE
+            // generate + ONE decode launch (qkdldpc_run_trials_multi); otherwise (host-generated inputs) the lanes pull
+            // single combinations from a queue and decode them concurrently.
+            const bool multi = !dev.host_keygen && api.run_trials_multi != nullptr;
+            const size_t per_call = multi ? std::max<size_t>(1, std::min<size_t>(512, (size_t)65536 / std::max<size_t>(trials, 1))) : 1;
             std::atomic<size_t> next{0};
             std::vector<std::thread> workers;
             for (size_t l = 0; l < lanes; ++l)
                 workers.emplace_back([&, l] {
                     try {
-                        for (size_t ci = next.fetch_add(1); ci < n_comb; ci = next.fetch_add(1)) {
-                            const sim_combination &comb = in.combinations[ci];
-                            const range_outcome o = decode_trial_range(cfg, api, codes[l], params_of(comb), matrix, comb, seeds, first_sim + ci,
-                                                                       0, trials, chunk, gen_threads, dev.host_keygen, totals[ci]);
-                            acc_qber[ci] = o.accurate_qber;
-                            comb_ms[ci] = o.ms;
+                        for (size_t c0 = next.fetch_add(per_call); c0 < n_comb; c0 = next.fetch_add(per_call)) {
+                            const size_t cnt = std::min(per_call, n_comb - c0);
+                            if (!multi) {
+                                const sim_combination &comb = in.combinations[c0];
+                                const range_outcome o = decode_trial_range(cfg, api, codes[l], params_of(comb), matrix, comb, seeds, first_sim + c0,
+                                                                           0, trials, chunk, gen_threads, dev.host_keygen, totals[c0]);
+                                acc_qber[c0] = o.accurate_qber;
+                                comb_ms[c0] = o.ms;
+                                continue;
+                            }
+                            std::vector<qkdldpc_combination> table(cnt);
+                            for (size_t k = 0; k < cnt; ++k) {
+                                const sim_combination &comb = in.combinations[c0 + k];
+                                const auto &mp = comb.matrix_params;
+                                const bool ra = cfg.ENABLE_CODE_RATE_ADAPTATION;
+                                table[k].qber = comb.config_QBER;
+                                table[k].primary = comb.scaling_factors.primary;
+                                table[k].secondary = comb.scaling_factors.secondary;
+                                table[k].punct_pos = ra ? mp.punctured_bits.data() : nullptr;
+                                table[k].n_punct = ra ? static_cast<int32_t>(mp.punctured_bits.size()) : 0;
+                                table[k].short_pos = ra ? mp.shortened_bits.data() : nullptr;
+                                table[k].n_short = ra ? static_cast<int32_t>(mp.shortened_bits.size()) : 0;
+                                table[k].seed_offset = static_cast<uint64_t>(first_sim + c0 + k);
+                            }
+                            std::vector<uint64_t> tl(cnt * tally_len);
+                            std::vector<double> acc(cnt);
+                            const auto t0 = std::chrono::steady_clock::now();
+                            const int rc = api.run_trials_multi(codes[l], &P0, static_cast<int32_t>(cnt), table.data(), static_cast<int64_t>(trials),
+                                                                seeds.data(), nullptr, nullptr, tl.data(), acc.data());
+                            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                            if (rc != 0) {
+                                const std::string msg = api.last_error();
+                                throw std::runtime_error(msg.rfind("Key size", 0) == 0 ? msg : "qkdldpc_run_trials_multi: " + msg);
+                            }
+                            for (size_t k = 0; k < cnt; ++k) {
+                                std::copy(tl.begin() + k * tally_len, tl.begin() + (k + 1) * tally_len, totals[c0 + k].begin());
+                                acc_qber[c0 + k] = acc[k];
+                                comb_ms[c0 + k] = ms / static_cast<double>(cnt);   // the call's time, shared equally
+                            }
                         }
                     } catch (const std::exception &e) {
                         errors[l] = e.what();

@@ -84,6 +84,7 @@ struct decoder_api {
     decltype(&qkdldpc_decode_batch) decode_batch = nullptr;
     decltype(&qkdldpc_last_error) last_error = nullptr;
     decltype(&qkdldpc_run_trials) run_trials = nullptr;   // batched run_trial with inputs generated on the device
+    decltype(&qkdldpc_run_trials_multi) run_trials_multi = nullptr;   // ... for several combinations in one call
 };
 
 std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const std::vector<sim_input> &sim_in,

@@ -124,3 +124,28 @@ def test_remove_bits_equals_reference_semantics(q, name, n_remove):
     if n_remove >= 2:
         with pytest.raises(QkdLdpcError):
             handle(q, name).remove_bits(bits, rm[::-1].copy())
+
+
+@pytest.mark.parametrize("alg,name", [(5, "I80"), (2, "K1_5"), (0, "K1_5")])
+def test_run_trials_multi_equals_one_call_per_combination(q, alg, name):
+    """qkdldpc_run_trials_multi: a whole sweep (different QBER, scaling factors, punctured / shortened lists, seed offsets)
+    in ONE generate + ONE decode launch; alg 0 exercises the fallback (one combination after the other)."""
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays(name)
+    rng = np.random.default_rng(alg)
+    seeds = hostlib.trial_seeds(4321, 70)
+    combos = []
+    for k in range(9):
+        pos = rng.permutation(arr["n"])
+        n_p, n_s = (0, 0) if k % 3 == 0 else (int(arr["n"] * 0.02 * (k % 3)), int(arr["n"] * 0.01 * k))
+        combos.append(dict(QBER=0.012 + 0.002 * k, primary=0.6 + 0.02 * k, secondary=0.9 - 0.03 * k, seed_offset=1000 + k,
+                           punctured_bits=np.sort(pos[:n_p]).astype(np.int32), shortened_bits=np.sort(pos[n_p:n_p + n_s]).astype(np.int32)))
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32, max_iterations=60)
+    h = handle(q, name)
+    it, fl, tl, acc = h.run_trials_multi(seeds, combos, cfg)
+    for k, cb in enumerate(combos):
+        r = h.run_trials(seeds, cb["QBER"], (cb["primary"], cb["secondary"]), cfg, seed_offset=cb["seed_offset"],
+                         punctured_bits=cb["punctured_bits"], shortened_bits=cb["shortened_bits"], want_bits=False)
+        assert (it[k] == r.iterations_num).all() and (fl[k] == r.flags).all(), k
+        assert (tl[k] == r.tally).all() and acc[k] == r.info["accurate_qber"], k
+    assert 0 < (fl & 1).sum() < fl.size
