@@ -162,11 +162,13 @@ class LdpcCode:
     # -- the hot path ---------------------------------------------------------------------------------------
     def QKD_LDPC_batch(self, alice_bit_array, bob_bit_array, QBER, scaling_factors=(0.0, 0.0),
                        cfg: Optional[DecoderConfig] = None, punctured_bits: Sequence[int] = (),
-                       shortened_bits: Sequence[int] = (), want_bits: bool = True) -> BatchResult:
+                       shortened_bits: Sequence[int] = (), want_bits: bool = True, out=None) -> BatchResult:
         """Batched ``QKD_LDPC`` / ``QKD_LDPC_RATE_ADAPT`` with HOST buffers (copies inside).
 
         alice_bit_array / bob_bit_array: packed uint32 [F][W] (or 0/1 arrays [F][n], packed here). With
         punctured / shortened lists the frames must already be the EXTENDED ones. QBER: scalar or [F].
+        out: optional (bits uint32 [F][W], iterations int32 [F], flags uint8 [F]) arrays to receive the results, e.g.
+        views of pinned memory (the default allocates fresh pageable arrays on every call).
         """
         cfg = cfg or DecoderConfig()
         L = _cabi.lib()
@@ -182,9 +184,16 @@ class LdpcCode:
         p = cfg.to_params(scaling_factors)
         pa, pp, np_ = self._poslist(punctured_bits)
         sa, sp, ns_ = self._poslist(shortened_bits)
-        out_bits = np.zeros((F, self.words), np.uint32) if want_bits else None
-        iters = np.zeros(F, np.int32)
-        flags = np.zeros(F, np.uint8)
+        if out is not None:
+            out_bits, iters, flags = out
+            want_bits = out_bits is not None
+            if (want_bits and (out_bits.dtype != np.uint32 or out_bits.shape != (F, self.words) or not out_bits.flags.c_contiguous)) or \
+                    iters.dtype != np.int32 or iters.shape != (F,) or flags.dtype != np.uint8 or flags.shape != (F,):
+                raise ValueError("out buffers must be (uint32 [F][W] or None, int32 [F], uint8 [F])")
+        else:
+            out_bits = np.zeros((F, self.words), np.uint32) if want_bits else None
+            iters = np.zeros(F, np.int32)
+            flags = np.zeros(F, np.uint8)
         tally = np.zeros(int(L.qkdldpc_tally_len(p.max_iterations)), np.uint64)
         _cabi.check(L.qkdldpc_decode_batch(self._h, C.byref(p), F, a.ctypes.data, b.ctypes.data, q.ctypes.data, scalar,
                                            pp, np_, sp, ns_, out_bits.ctypes.data if want_bits else None,
