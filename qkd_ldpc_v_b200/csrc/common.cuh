@@ -67,9 +67,18 @@ __device__ __forceinline__ void st_msg(T *p, const Vec<T, V> &x) {
 // threshold_matrix (array_and_matrix_operations.cpp:953-972): NaN passes through.
 template <typename T>
 __device__ __forceinline__ T clamp_msg(T x, T thr) {
-    if (x > thr) return thr;
-    if (x < -thr) return -thr;
-    return x;
+    if constexpr (sizeof(T) == 4) {
+        // NaN-propagating min / max (FMNMX.NAN): the same result as the compare chain below for every input,
+        // +-inf, -0 and NaN included, without the two branches
+        float r;
+        asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(-thr));
+        asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(thr));
+        return r;
+    } else {
+        if (x > thr) return thr;
+        if (x < -thr) return -thr;
+        return x;
+    }
 }
 
 // Per-batch launch arguments shared by the step kernels.

@@ -95,6 +95,13 @@ struct qkdldpc_code {
     std::vector<uint16_t> oc_vn_bit_host;
     int oc_sched_warps = 0;   // oc_cls: [2][words] punctured / shortened bit masks of the current batch
     int oc_threads = 0;               // CTA size of the last on-chip launch
+    // on-chip sum-product path (onchip_spa.cuh): one message word per edge; check phase shares oc_cn_* with min-sum
+    bool sp_eligible = false;
+    int sp_groups_sv = 0, sp_msg_words = 0;
+    DevBuf<int> sp_cn_moff;
+    DevBuf<int2> sp_sv_ginfo;
+    DevBuf<uint16_t> sp_sv_bit;
+    DevBuf<uint2> sp_svT;
     int last_path = 0;                // 1 streaming, 2 on-chip (of the last batch)
     // pool (device, raw bytes reinterpreted per precision)
     DevBuf<unsigned char> msg;

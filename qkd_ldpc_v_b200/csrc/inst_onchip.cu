@@ -6,8 +6,20 @@ namespace qkhost {
 
 using namespace qk;
 
+cudaError_t onchip_spa_geometry(int alg, int groups_cn, int sms, size_t smem, long long n_frames, int *threads, int *grid);
+cudaError_t onchip_spa_launch(int alg, const OnchipArgs &a, int grid, int threads, size_t smem, cudaStream_t s);
+
 bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
-    if (!c->oc_eligible || P->message_precision != 32 || P->algorithm < 2) return false;
+    if (P->message_precision != 32) return false;
+    if (P->algorithm < 2) {
+        // sum-product kernel (onchip_spa.cuh): one float per edge must fit; NaN / inf messages are handled as in the
+        // streaming kernels, so there is no precondition on the parameters
+        int dev_smem = 0;
+        if (!c->sp_eligible || cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess)
+            return false;
+        return onchip_spa_smem_bytes(c->n, c->sp_msg_words, c->oc_groups_cn) <= (size_t)dev_smem;
+    }
+    if (!c->oc_eligible) return false;
     // same precondition as the FAST streaming kernels (fast_minsum_ok, run_batch.cuh): no message can become NaN / inf
     if (P->enable_threshold) {
         if (!std::isfinite(P->threshold)) return false;
@@ -93,6 +105,24 @@ int onchip_pack_masks(int n, const int32_t *punct, int n_punct, const int32_t *s
     return QKDLDPC_OK;
 }
 
+// Bookkeeping after the (single) kernel of an on-chip batch has been enqueued on c->stream after ev0.
+static int onchip_finish(qkdldpc_code *c, int grid, int threads, size_t smem) {
+    c->kernel_launches += 1;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_batch_ms = ms;
+    c->last_cn_ms = c->last_vn_ms = c->last_sched_ms = 0;
+    c->last_path = 2;
+    c->frames_per_tile = 1;
+    c->oc_threads = threads;
+    c->pool_tiles = grid;
+    c->pool_bytes = (int64_t)grid * (int64_t)smem;   // bytes of on-chip decoder state in flight
+    CK(cudaGetLastError());
+    return QKDLDPC_OK;
+}
+
 // One launch over n_combos x frames_per_combo frames. `combos` / `masks` are HOST tables ([n_combos], [n_combos][2][words]);
 // d_tally holds n_combos tally vectors.
 int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int64_t frames_per_combo, const OnchipCombo *combos,
@@ -124,13 +154,24 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     a.max_iter = P->max_iterations;
     a.thr = P->enable_threshold ? (float)P->threshold : INFINITY;
 
-    int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(768, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
-    const size_t smem = onchip_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn);
+    const bool spa = P->algorithm < 2;
+    int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(spa ? 1024 : 768, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
+    const size_t smem = spa ? onchip_spa_smem_bytes(n, c->sp_msg_words, c->oc_groups_cn) : onchip_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn);
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 
     int grid = 0;
     cudaError_t e;
+    if (spa) {
+        a.cn_moff = c->sp_cn_moff.p; a.sv_ginfo = c->sp_sv_ginfo.p; a.sv_bit = c->sp_sv_bit.p; a.svT = c->sp_svT.p;
+        a.n_groups_sv = c->sp_groups_sv; a.msg_words = c->sp_msg_words;
+        e = onchip_spa_geometry(P->algorithm, c->oc_groups_cn, sms, smem, n_frames, &threads, &grid);
+        if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip sum-product kernel geometry failed: %s", cudaGetErrorString(e));
+        CK(cudaEventRecord(c->ev0, s));
+        e = onchip_spa_launch(P->algorithm, a, grid, threads, smem, s);
+        if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip sum-product kernel launch failed: %s", cudaGetErrorString(e));
+        return onchip_finish(c, grid, threads, smem);
+    }
     const bool wide = c->oc_max_dc > 32;   // rows of 33..64 edges: two records per row, separate kernel instantiation
     switch (P->algorithm) {
         case 2: e = wide ? pick_geometry<2, true>(m, sms, smem, n_frames, &threads, &grid) : pick_geometry<2, false>(m, sms, smem, n_frames, &threads, &grid); break;
@@ -169,20 +210,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         default: e = wide ? launch<5, true>(a, grid, threads, smem, s) : launch<5, false>(a, grid, threads, smem, s); break;
     }
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel launch failed: %s", cudaGetErrorString(e));
-    c->kernel_launches += 1;
-    CK(cudaEventRecord(c->ev1, s));
-    CK(cudaEventSynchronize(c->ev1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    c->last_batch_ms = ms;
-    c->last_cn_ms = c->last_vn_ms = c->last_sched_ms = 0;
-    c->last_path = 2;
-    c->frames_per_tile = 1;
-    c->oc_threads = threads;
-    c->pool_tiles = grid;
-    c->pool_bytes = (int64_t)grid * (int64_t)smem;   // bytes of on-chip decoder state in flight
-    CK(cudaGetLastError());
-    return QKDLDPC_OK;
+    return onchip_finish(c, grid, threads, smem);
 }
 
 // The single-combination call of qkdldpc_decode_batch_device.

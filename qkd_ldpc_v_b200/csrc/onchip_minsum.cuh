@@ -54,6 +54,13 @@ struct OnchipArgs {
     const uint16_t *vn_bit;     // [groups*32] bit handled by (group, lane); padding lanes hold n (a scratch L slot)
     const uint4 *vT;            // [off + kb*32 + lane] 4 x uint32: row << 9 | sh of checks 4kb..4kb+3 of that bit,
                                 //                      sh = 32 - dc(row) + position in the row (padding: scratch row m)
+    // Sum-product kernel only (onchip_spa.cuh): one float per edge in shared memory, word cn_moff[group] + k * 32 + lane
+    // for edge k of the row handled by (group, lane); the variable phase has its own groups and addresses the words directly.
+    const int *cn_moff;         // [groups_cn] first message word of the group
+    const int2 *sv_ginfo;       // [groups_sv] {offset into svT (in uint2), degree of the group's bits}
+    const uint16_t *sv_bit;     // [groups_sv*32] bit handled by (group, lane); padding lanes hold n
+    const uint2 *svT;           // [off + kb*32 + lane] 4 x uint16: message word of checks 4kb..4kb+3 of that bit (padding: 0)
+    int n_groups_sv, msg_words;
     // One launch may span several parameter COMBINATIONS of a sweep (frames [c * frames_per_combo, (c+1) * ...) belong to
     // combination c): scaling factors, QBER, punctured / shortened masks and the tally vector are per combination.
     const OnchipCombo *combos;  // [n_combos]
@@ -79,6 +86,13 @@ __host__ __device__ inline size_t onchip_smem_bytes(int n, int rec_slots, int gr
     const size_t words = (size_t)(n + 31) / 32;
     return ((size_t)rec_slots + 2) * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn) * 4 + 96;   // + frame id, FrameCtx
 }
+
+// The sum-product kernel (onchip_spa.cuh): msg[msg_words] float instead of the records, the rest alike.
+__host__ __device__ inline size_t onchip_spa_smem_bytes(int n, int msg_words, int groups_cn) {
+    const size_t words = (size_t)(n + 31) / 32;
+    return ((size_t)msg_words + 3) / 4 * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn) * 4 + 96;
+}
+constexpr size_t kOnchipSmemMax = 227 * 1024;   // opt-in shared memory per CTA on sm_100
 
 // Record of a row: x = bits(c1), y = bits(c2) (non-negative magnitudes), z = final sign of the message on edge k in bit
 // (dc-1-k), w = 32 - dc + position of the first minimum. A reader that knows sh = 32 - dc + k gets the sign with

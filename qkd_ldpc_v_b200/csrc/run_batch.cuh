@@ -211,8 +211,8 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     a.tile_active = c->tile_active.p; a.tile_new = c->tile_new.p;
     a.slot_llr = reinterpret_cast<T *>(c->slot_llr.p);
     a.e_stride = (int64_t)c->nnz * FT;
-    a.primary = (T)P->primary; a.secondary = (T)P->secondary; a.thr = (T)P->threshold;
-    a.enable_thr = P->enable_threshold != 0;
+    a.primary = (T)P->primary; a.secondary = (T)P->secondary; a.enable_thr = P->enable_threshold != 0;
+    a.thr = a.enable_thr ? (T)P->threshold : (T)INFINITY;   // the kernels clamp unconditionally; +inf is a no-op
 
     BatchArgs<T> b{};
     b.n_frames = n_frames; b.words = words; b.swords = swords;

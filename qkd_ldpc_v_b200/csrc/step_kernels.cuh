@@ -112,10 +112,21 @@ struct RowState {
     // Second pass (:64-70 / :400-408, :573-574, :759-767, :949-956). `kept` is what absorb() returned for this edge.
     __device__ __forceinline__ T emit(T kept, bool syn, T factor) const {
         if constexpr (ALG == 0 && sizeof(T) == 4) {
-            // float SPA: 2 atanh(P / t) = ln((t + P) / (t - P)) -- one divide and one logarithm instead of a divide, a
-            // divide inside atanhf and a log1pf. Same special values as the reference's formula: t == 0 gives ln(-1) =
-            // NaN (0/0 -> NaN there), |P/t| == 1 gives +-inf (clamped), |P/t| > 1 by rounding gives NaN (quirk Q3).
-            return logf(__fdividef(kept + a, kept - a));
+            // float SPA: 2 atanh(P / t) = ln((|t| + P') / (|t| - P')) with P' = P * sgn(t): one approximate reciprocal
+            // and one MUFU logarithm instead of a divide, a divide inside atanhf and a log1pf (the accurate logf alone
+            // was 28 of the 77 instructions per edge). Special values follow the reference's formula (quirk Q3):
+            //   P' == |t| != 0 (all other tanh saturated to 1)  ->  x / +0 = +inf -> ln = +inf  (atanh(1), clamped)
+            //   P' == -|t|                                     ->  0 / 2|t| = 0  -> ln = -inf  (atanh(-1), clamped)
+            //   t == 0                                         ->  P / -P = -1, or 0 * inf -> NaN  (0/0 there)
+            // |P| <= |t| always holds (a running product of factors <= 1 never grows), so the quotient is never
+            // negative for another reason. Folding sgn(t) into P keeps the +0 denominator's sign from flipping the
+            // infinity when t < 0.
+            const float ps = __uint_as_float(__float_as_uint(a) ^ (__float_as_uint(kept) & 0x80000000u));
+            const float at = fabsf(kept);
+            float r, l;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(at - ps));
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"((at + ps) * r));
+            return l * 0.693147182464599609375f;
         } else if constexpr (ALG <= 1) {
             return cn_two_atanh<T, ALG>(a / kept);
         } else {
@@ -224,7 +235,7 @@ cn_kernel(const StepArgs<T> a, const int first, const int count) {
                 c1 = (d1 < 0.f) ? 0.f : d1;
                 c2 = (d2 < 0.f) ? 0.f : d2;
             }
-            if (a.enable_thr) { c1 = fminf(c1, a.thr); c2 = fminf(c2, a.thr); }   // magnitudes: clamp is symmetric
+            c1 = fminf(c1, a.thr); c2 = fminf(c2, a.thr);   // magnitudes: clamp is symmetric (thr = +inf when disabled)
             const uint32_t rs = sx[v] & 0x80000000u;
             o1[v] = __float_as_uint(c1) ^ rs;
             // a message that is exactly 0 has min1 == 0, takes the "== min1" output and counts as negative for its
@@ -266,7 +277,7 @@ cn_kernel(const StepArgs<T> a, const int first, const int count) {
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         T c = st[v].emit(x[k].v[v], syn[v], factor[v]);
-                        o.v[v] = a.enable_thr ? clamp_msg(c, a.thr) : c;   // threshold_matrix(check_to_bit_msg), :73-74
+                        o.v[v] = clamp_msg(c, a.thr);   // threshold_matrix(check_to_bit_msg), :73-74; +inf = off
                     }
                     st_msg<T, V>(base + (size_t)k * FT, o);
                 }
@@ -284,7 +295,7 @@ cn_kernel(const StepArgs<T> a, const int first, const int count) {
                     T kept = x.v[v];
                     if constexpr (ALG <= 1) kept = cn_tanh_half<T, ALG>(kept);
                     T c = st[v].emit(kept, syn[v], factor[v]);
-                    o.v[v] = a.enable_thr ? clamp_msg(c, a.thr) : c;
+                    o.v[v] = clamp_msg(c, a.thr);
                 }
                 st_msg<T, V>(base + (size_t)k * FT, o);
             }
@@ -307,10 +318,8 @@ __device__ __forceinline__ Vec<T, V> vn_out(const StepArgs<T> &a, const Vec<T, V
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         T s = L.v[v] - c.v[v];
-        if (a.enable_thr) {
-            if constexpr (FAST) s = fminf(fmaxf(s, -a.thr), a.thr);
-            else s = clamp_msg(s, a.thr);
-        }
+        if constexpr (FAST) s = fminf(fmaxf(s, -a.thr), a.thr);   // thr = +inf when the clamp is disabled
+        else s = clamp_msg(s, a.thr);
         if constexpr (HASNEW) s = isnew[v] ? llr.v[v] : s;
         o.v[v] = s;
     }

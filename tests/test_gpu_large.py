@@ -47,9 +47,9 @@ def test_operating_point(built, name, alg, qber, pri, sec, frames, seed, bar):
     it_ref, fl_ref, bits_ref = cpu.qkd_ldpc_batch(oc, alg, ab, bb, acc, primary=pri, secondary=sec, precision=64)
     with q.LdpcCode(arr["n"], arr["m"], arr["row_ptr"], arr["col_idx"], device=0, pool_slots=2048) as code:
         cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32)
-        r = code.QKD_LDPC_batch(a, b, acc, (pri, sec), cfg)   # auto path: on-chip for the min-sum family, else streaming
-        assert r.info["last_path"] == (2 if alg >= 2 else 1)
-        if alg >= 2:   # the two float32 paths are the same arithmetic: identical per-frame results
+        r = code.QKD_LDPC_batch(a, b, acc, (pri, sec), cfg)   # auto path: on-chip (all six algorithms fit these codes)
+        assert r.info["last_path"] == 2
+        if True:       # the two float32 paths are the same arithmetic: identical per-frame results
             with q.LdpcCode(arr["n"], arr["m"], arr["row_ptr"], arr["col_idx"], device=0, pool_slots=2048, decoder_path=1) as sc:
                 rs = sc.QKD_LDPC_batch(a, b, acc, (pri, sec), cfg)
             assert rs.info["last_path"] == 1

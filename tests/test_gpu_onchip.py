@@ -127,7 +127,8 @@ def test_rate_adaptation_paths_agree(q, tmp_path, alg):
 
 
 def test_ineligible_requests(q):
-    """SPA, float64 and n = 100k codes cannot run on chip: an explicit request fails, the automatic choice streams.
+    """float64 and n = 100k codes cannot run on chip, nor can the sum-product variants on a code whose per-edge messages
+    exceed the shared memory (n = 10240, E = 60430): an explicit request fails, the automatic choice streams.
     (Rows of 33..64 edges are fine: they take two records, see K1_hi in the parity test above.)"""
     from qkd_ldpc_v_b200._cabi import QkdLdpcError
     a, b, acc = keys("L100k", 3, 8, 0.06)
@@ -137,10 +138,15 @@ def test_ineligible_requests(q):
     r = handle(q, "L100k").QKD_LDPC_batch(a, b, acc, (0.72, 0), cfg)
     assert r.info["last_path"] == 1
     a, b, acc = keys("K1_5", 3, 40, 0.02)
-    for c in (q.DecoderConfig(decoding_algorithm=0, message_precision=32), q.DecoderConfig(decoding_algorithm=2, message_precision=64)):
-        with pytest.raises(QkdLdpcError):
-            handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(a, b, acc, (0.8, 0), c)
-        assert handle(q, "K1_5").QKD_LDPC_batch(a, b, acc, (0.8, 0), c).info["last_path"] == 1
+    c = q.DecoderConfig(decoding_algorithm=2, message_precision=64)
+    with pytest.raises(QkdLdpcError):
+        handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(a, b, acc, (0.8, 0), c)
+    assert handle(q, "K1_5").QKD_LDPC_batch(a, b, acc, (0.8, 0), c).info["last_path"] == 1
+    a, b, acc = keys("I80", 3, 40, 0.015)
+    c = q.DecoderConfig(decoding_algorithm=0, message_precision=32, max_iterations=30)
+    with pytest.raises(QkdLdpcError):
+        handle(q, "I80", decoder_path=2).QKD_LDPC_batch(a, b, acc, (0, 0), c)
+    assert handle(q, "I80").QKD_LDPC_batch(a, b, acc, (0, 0), c).info["last_path"] == 1
 
 
 @pytest.mark.parametrize("threads", [32, 64, 256, 512])

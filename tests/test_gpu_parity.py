@@ -68,9 +68,20 @@ def test_fp64_messages_against_reference_golden(q, case):
 
 
 def onchip_eligible(name, alg):
-    """float32 min-sum family, every check degree <= 64, n < 65535 (onchip_minsum.cuh)."""
+    """float32 min-sum family: every check degree <= 64, n < 65535 (onchip_minsum.cuh). Sum-product variants: in
+    addition one float per edge (padded to whole 32-row groups per degree) plus the bit totals fit the 227 KB of shared
+    memory and 65535 message words (onchip_spa.cuh)."""
     arr = util.code_arrays(name)
-    return alg >= 2 and int(np.diff(arr["row_ptr"]).max()) <= 64 and arr["n"] < 65535
+    dc = np.diff(arr["row_ptr"])
+    if int(dc.max()) > 64 or arr["n"] >= 65535:
+        return False
+    if alg >= 2:
+        return True
+    deg, cnt = np.unique(dc, return_counts=True)
+    groups = (cnt + 31) // 32
+    words = int((groups * 32 * deg).sum())
+    smem = (words + 3) // 4 * 16 + (arr["n"] + 4) // 4 * 16 + (2 * ((arr["n"] + 31) // 32) + int(groups.sum())) * 4 + 96
+    return words <= 65535 and smem <= 227 * 1024
 
 
 @pytest.mark.parametrize("path", [1, 2], ids=["streaming", "onchip"])
@@ -125,13 +136,14 @@ def test_small_pool_refill_equals_big_pool(q):
     seeds = hostlib.trial_seeds(4242, 1000)
     a, b, acc = hostlib.gen_keys(seeds, arr["n"], 0.03)
     cfg = q.DecoderConfig(decoding_algorithm=0, message_precision=32)
-    big = handle(q, "K1_4").QKD_LDPC_batch(a, b, acc, (0, 0), cfg)
-    small = handle(q, "K1_4", pool_slots=32, frames_per_lane_f32=1, steps_per_poll=3).QKD_LDPC_batch(a, b, acc, (0, 0),
-                                                                                                  cfg)
+    big = handle(q, "K1_4", decoder_path=1).QKD_LDPC_batch(a, b, acc, (0, 0), cfg)
+    small = handle(q, "K1_4", pool_slots=32, frames_per_lane_f32=1, steps_per_poll=3, decoder_path=1).QKD_LDPC_batch(
+        a, b, acc, (0, 0), cfg)
+    assert big.info["last_path"] == 1 and small.info["last_path"] == 1
     assert (big.iterations_num == small.iterations_num).all()
     assert (big.flags == small.flags).all() and (big.bob_solution == small.bob_solution).all()
     assert (big.tally == small.tally).all()
-    nog = handle(q, "K1_4", pool_slots=64, use_graph=-1).QKD_LDPC_batch(a, b, acc, (0, 0), cfg)
+    nog = handle(q, "K1_4", pool_slots=64, use_graph=-1, decoder_path=1).QKD_LDPC_batch(a, b, acc, (0, 0), cfg)
     assert (big.iterations_num == nog.iterations_num).all() and (big.bob_solution == nog.bob_solution).all()
 
 
@@ -170,6 +182,56 @@ def test_adaptive_bob_already_correct(q):
                                               precision=prec)
             assert (r.iterations_num == it).all() and (r.flags == fl).all() and (r.bits() == bits).all()
             assert (r.iterations_num[:20] == 1).all()
+
+
+@pytest.mark.parametrize("alg", [0, 1])
+@pytest.mark.parametrize("name,qber", [("K1_5", 0.02), ("K1_4", 0.03), ("A82", 0.0162), ("N100", 0.05)])
+def test_onchip_spa_equals_streaming(q, name, qber, alg):
+    """The on-chip sum-product kernel rebuilds b2c = clamp(L - c2b) from the bit totals instead of storing it; operands
+    and order are those of the streaming kernels, so iterations, flags and words must be identical."""
+    from qkd_ldpc_v_b200 import hostlib
+    if not onchip_eligible(name, alg):
+        pytest.skip("code not eligible for the on-chip sum-product kernel")
+    arr = util.code_arrays(name)
+    frames = 600 if arr["n"] > 5000 else 2000
+    a, b, acc = hostlib.gen_keys(hostlib.trial_seeds(99 + alg, frames), arr["n"], qber)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32, max_iterations=60)
+    r1 = handle(q, name, decoder_path=1).QKD_LDPC_batch(a, b, acc, (0, 0), cfg)
+    r2 = handle(q, name, decoder_path=2).QKD_LDPC_batch(a, b, acc, (0, 0), cfg)
+    assert r1.info["last_path"] == 1 and r2.info["last_path"] == 2
+    assert (r1.iterations_num == r2.iterations_num).all()
+    assert (r1.flags == r2.flags).all() and (r1.bob_solution == r2.bob_solution).all()
+    assert (r1.tally == r2.tally).all()
+    assert 0.2 < r1.syndromes_match.mean()          # a meaningful operating point, not all-fail
+    for t in (128, 1024):                            # CTA size does not change the arithmetic
+        r3 = handle(q, name, decoder_path=2, onchip_threads=t).QKD_LDPC_batch(a, b, acc, (0, 0), cfg)
+        assert (r3.iterations_num == r2.iterations_num).all() and (r3.bob_solution == r2.bob_solution).all()
+
+
+@pytest.mark.parametrize("fpl", [1, 2, 4])
+def test_spa_saturated_rows(q, fpl):
+    """Float SPA with |LLR| > 18: tanhf saturates to exactly +-1, every row product is +-1 and P / t = +-1 on every
+    edge, so every check-to-bit message is atanh(+-1) = +-inf, tamed only by the clamp (quirk Q3). The CUDA check node
+    computes ln((|t| + P') / (|t| - P')) instead of 2 atanh(P / t): the +0 denominator must give +inf for t < 0 too,
+    not NaN. Compared with the float32 oracle (glibc tanhf / atanhf saturate the same way)."""
+    arr = util.code_arrays("K1_5")
+    oc = util.oracle_code("K1_5")
+    rng = np.random.default_rng(77)
+    alice = rng.integers(0, 2, (96, arr["n"]), dtype=np.uint8)
+    bob = alice.copy()
+    for f in range(96):
+        bob[f, rng.choice(arr["n"], 1 + f % 12, replace=False)] ^= 1
+    qber = 1e-9                                    # ln((1 - q) / q) = 20.7 -> tanhf(10.36) == 1.0f
+    cfg = q.DecoderConfig(decoding_algorithm=0, message_precision=32, max_iterations=30)
+    r = handle(q, "K1_5", frames_per_lane_f32=fpl, decoder_path=1).QKD_LDPC_batch(alice, bob, qber, (0, 0), cfg)
+    it, fl, bits = cpu.qkd_ldpc_batch(oc, 0, alice, bob, qber, max_iter=30, primary=0, secondary=0, precision=32)
+    if fpl == 1:   # the on-chip kernel shares the check-node arithmetic
+        r2 = handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(alice, bob, qber, (0, 0), cfg)
+        assert (r2.flags == r.flags).all() and (r2.iterations_num == r.iterations_num).all()
+    assert (r.flags == fl).all(), "a saturated row must not poison the frame with NaN"
+    assert (r.iterations_num == it).mean() >= 0.97
+    ok = (fl & 1) != 0
+    assert ok.mean() > 0.5 and (r.bits()[ok] == bits[ok]).all()
 
 
 @pytest.mark.parametrize("alg,pri,sec,point,untainted", [
