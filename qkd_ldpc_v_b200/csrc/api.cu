@@ -120,9 +120,8 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     std::vector<uint4> oc_vT;
     // sum-product on-chip path (onchip_spa.cuh): message word of edge k of the row at (group g, lane l) = moff[g] + 32 k + l
     std::vector<int> sp_cn_moff, row_word0(m, 0), row_lane(m, 0);
-    std::vector<int2> sp_sv_ginfo;
-    std::vector<uint16_t> sp_sv_bit;
-    std::vector<uint2> sp_svT;
+    std::vector<uint4> sp_items;         // variable phase: one 16-byte entry per (item, lane), see onchip_spa.cuh
+    std::vector<int> sp_group_item0;     // first item of every variable-phase group, then the total
     int sp_msg_words = 0;
     bool sp_ok = false;
     if (oc_ok) {
@@ -239,7 +238,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         }
         // sum-product variable phase: groups of 32 bits of one degree; a 4-byte gather of the lanes' k-th messages is
         // conflict-free when the 32 rows sit in 32 different lanes of their check groups (bank = word mod 32 = lane)
-        sp_ok = sp_msg_words > 0 && sp_msg_words <= 65535 &&
+        sp_ok = sp_msg_words > 0 && sp_msg_words <= 65534 &&   // word sp_msg_words is the always-zero padding word
                 qk::onchip_spa_smem_bytes(n, sp_msg_words, (int)oc_cn_ginfo.size()) <= qk::kOnchipSmemMax;
         if (sp_ok) {
             for (const auto &cls : degree_classes(n, col_ptr)) {
@@ -247,20 +246,22 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
                 pack(cls, col_ptr, csc_row.data(), 32, 32, groups, row_lane.data());
                 const int dv = col_ptr[cls[0] + 1] - col_ptr[cls[0]], blocks = (dv + 3) / 4;
                 for (const auto &gr : groups) {
-                    sp_sv_ginfo.push_back(make_int2((int)sp_svT.size(), dv));
-                    for (int l = 0; l < 32; ++l) sp_sv_bit.push_back(l < (int)gr.size() ? (uint16_t)gr[l] : (uint16_t)n);
+                    sp_group_item0.push_back((int)(sp_items.size() / 32));
                     for (int kb = 0; kb < blocks; ++kb)
                         for (int l = 0; l < 32; ++l) {
-                            uint32_t e[4] = {0, 0, 0, 0};   // padding: word 0 (read and ignored)
+                            uint32_t e[4] = {(uint32_t)sp_msg_words, (uint32_t)sp_msg_words, (uint32_t)sp_msg_words, (uint32_t)sp_msg_words};
                             if (l < (int)gr.size())
                                 for (int j = 0; j < 4 && kb * 4 + j < dv; ++j) {
                                     const int p = col_ptr[gr[l]] + kb * 4 + j, r = csc_row[p];
                                     e[j] = (uint32_t)(row_word0[r] + 32 * (csc_edge[p] - rp[r]));
                                 }
-                            sp_svT.push_back(make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16)));
+                            const uint32_t bit = l < (int)gr.size() ? (uint32_t)gr[l] : (uint32_t)n;
+                            const uint32_t flags = (kb == 0 ? 0x10000u : 0u) | (kb == blocks - 1 ? 0x20000u : 0u);
+                            sp_items.push_back(make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), bit | flags, 0u));
                         }
                 }
             }
+            sp_group_item0.push_back((int)(sp_items.size() / 32));
         }
     }
 
@@ -311,33 +312,39 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
             return fail(QKDLDPC_ERR_STATE, "on-chip tables cover %zu / %zu of %lld edges", edges_cn, edges_vn, (long long)nnz);
     }
     if (sp_ok) {
-        // the sum-product tables: every message word < msg_words, every edge owns exactly one word, both phases agree
+        // the sum-product tables: every message word <= msg_words (the zero word), every edge owns exactly one word and
+        // appears once, in ascending check order, between the first and the last item of its bit
         std::vector<char> seen((size_t)sp_msg_words, 0);
+        std::vector<int> next_k((size_t)n, 0);
         size_t edges_sv = 0;
         if (sp_cn_moff.size() != oc_cn_ginfo.size()) return fail(QKDLDPC_ERR_STATE, "sum-product table: group count");
         for (size_t g = 0; g < oc_cn_ginfo.size(); ++g)
             if (sp_cn_moff[g] % 32 != 0 || sp_cn_moff[g] + oc_cn_ginfo[g].y * 32 > sp_msg_words)
                 return fail(QKDLDPC_ERR_STATE, "sum-product table: bad message offset of group %zu", g);
-        for (size_t g = 0; g < sp_sv_ginfo.size(); ++g) {
-            const int dv = sp_sv_ginfo[g].y, blocks = (dv + 3) / 4;
-            if (dv < 1 || (size_t)sp_sv_ginfo[g].x + (size_t)blocks * 32 > sp_svT.size())
-                return fail(QKDLDPC_ERR_STATE, "sum-product variable table: bad group header %zu", g);
-            for (int l = 0; l < 32; ++l) {
-                const int bit = sp_sv_bit[g * 32 + l];
-                if (bit > n) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: bit %d out of range", bit);
-                for (int k = 0; k < blocks * 4; ++k) {
-                    const uint2 w = sp_svT[sp_sv_ginfo[g].x + (k / 4) * 32 + l];
-                    const int word = (int)((k % 4 == 0) ? (w.x & 0xFFFFu) : (k % 4 == 1) ? (w.x >> 16) : (k % 4 == 2) ? (w.y & 0xFFFFu) : (w.y >> 16));
-                    if (word >= sp_msg_words) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: word %d out of range", word);
-                    if (bit < n && k < dv) {
-                        const int p = col_ptr[bit] + k, row = csc_row[p];
-                        if (word != row_word0[row] + 32 * (csc_edge[p] - rp[row]) || seen[word])
-                            return fail(QKDLDPC_ERR_STATE, "sum-product variable table: wrong word for bit %d", bit);
-                        seen[word] = 1;
-                        ++edges_sv;
-                    }
+        for (size_t i = 0; i < sp_items.size(); ++i) {
+            const uint4 it = sp_items[i];
+            const int bit = (int)(it.z & 0xFFFFu);
+            const bool first = (it.z & 0x10000u) != 0, last = (it.z & 0x20000u) != 0;
+            if (bit > n) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: bit %d out of range", bit);
+            const int word[4] = {(int)(it.x & 0xFFFFu), (int)(it.x >> 16), (int)(it.y & 0xFFFFu), (int)(it.y >> 16)};
+            if (bit < n && first != (next_k[bit] == 0)) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: first flag of bit %d", bit);
+            for (int j = 0; j < 4; ++j) {
+                if (word[j] > sp_msg_words) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: word %d out of range", word[j]);
+                if (bit == n) continue;
+                const int k = next_k[bit], dv = col_ptr[bit + 1] - col_ptr[bit];
+                if (k >= dv) {
+                    if (word[j] != sp_msg_words) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: padding of bit %d", bit);
+                    continue;
                 }
+                const int p = col_ptr[bit] + k, row = csc_row[p];
+                if (word[j] != row_word0[row] + 32 * (csc_edge[p] - rp[row]) || seen[word[j]])
+                    return fail(QKDLDPC_ERR_STATE, "sum-product variable table: wrong word for bit %d", bit);
+                seen[word[j]] = 1;
+                next_k[bit] = k + 1;
+                ++edges_sv;
             }
+            if (bit < n && last != (next_k[bit] == col_ptr[bit + 1] - col_ptr[bit]))
+                return fail(QKDLDPC_ERR_STATE, "sum-product variable table: last flag of bit %d", bit);
         }
         if (edges_sv != (size_t)nnz) return fail(QKDLDPC_ERR_STATE, "sum-product tables cover %zu of %lld edges", edges_sv, (long long)nnz);
     }
@@ -362,8 +369,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         (e = up(c->col_order, col_order)) || 
         (oc_ok && ((e = up(c->oc_cn_ginfo, oc_cn_ginfo)) || (e = up(c->oc_cnT, oc_cnT)) || (e = up(c->oc_cn_row, oc_cn_row)) || (e = up(c->oc_vn_ginfo, oc_vn_ginfo)) ||
                    (e = up(c->oc_vn_bit, oc_vn_bit)) || (e = up(c->oc_vT, oc_vT)))) ||
-        (sp_ok && ((e = up(c->sp_cn_moff, sp_cn_moff)) || (e = up(c->sp_sv_ginfo, sp_sv_ginfo)) || (e = up(c->sp_sv_bit, sp_sv_bit)) ||
-                   (e = up(c->sp_svT, sp_svT)))) ||
+        (sp_ok && ((e = up(c->sp_cn_moff, sp_cn_moff)) || (e = up(c->sp_sv_items, sp_items)))) ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
         (e = cudaMallocHost(&c->h_done, 2 * sizeof(unsigned long long))) || (e = cudaEventCreate(&c->ev0)) ||
         (e = cudaEventCreate(&c->ev1)) || (e = cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming))) {
@@ -391,7 +397,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     c->oc_vn_bit_host = oc_vn_bit;
     c->oc_eligible = oc_ok;
     c->sp_eligible = sp_ok;
-    c->sp_groups_sv = (int)sp_sv_ginfo.size();
+    c->sp_group_item0 = sp_group_item0;
     c->sp_msg_words = sp_msg_words;
     for (int k = 0; k < 5; ++k) {
         c->cn_first[k] = cn_first[k]; c->cn_count[k] = cn_count[k];
@@ -410,7 +416,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->row_order.release(); c->col_order.release();
     c->oc_cn_ginfo.release(); c->oc_vn_ginfo.release(); c->oc_cnT.release(); c->oc_cn_row.release(); c->oc_vn_bit.release(); c->oc_vT.release();
     c->oc_cls.release();
-    c->sp_cn_moff.release(); c->sp_sv_ginfo.release(); c->sp_sv_bit.release(); c->sp_svT.release();
+    c->sp_cn_moff.release(); c->sp_sv_items.release(); c->sp_sv_chunk.release();
     c->msg.release(); c->bobmask.release(); c->zmask.release(); c->synd.release(); c->par.release();
     c->tile_active.release(); c->tile_new.release(); c->slot_llr.release(); c->slot_frame.release();
     c->slot_iter.release(); c->frame_llr.release(); c->synd_all.release();

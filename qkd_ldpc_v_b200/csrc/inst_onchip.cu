@@ -163,10 +163,26 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     int grid = 0;
     cudaError_t e;
     if (spa) {
-        a.cn_moff = c->sp_cn_moff.p; a.sv_ginfo = c->sp_sv_ginfo.p; a.sv_bit = c->sp_sv_bit.p; a.svT = c->sp_svT.p;
-        a.n_groups_sv = c->sp_groups_sv; a.msg_words = c->sp_msg_words;
         e = onchip_spa_geometry(P->algorithm, c->oc_groups_cn, sms, smem, n_frames, &threads, &grid);
         if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip sum-product kernel geometry failed: %s", cudaGetErrorString(e));
+        if (c->sp_chunk_warps != threads / 32) {
+            // variable phase: warp w owns a contiguous run of items; boundaries fall between groups, runs balanced greedily
+            const int nw = threads / 32, groups = (int)c->sp_group_item0.size() - 1, total = c->sp_group_item0.back();
+            std::vector<int> chunk(nw + 1, total);   // chunk[nw] = total
+            chunk[0] = 0;
+            int g = 0;   // sp_group_item0[g] <= target < sp_group_item0[g + 1]
+            for (int w = 1; w < nw; ++w) {
+                const int target = (int)((long long)total * w / nw);
+                while (g + 1 < groups && c->sp_group_item0[g + 1] <= target) ++g;
+                const int lo = c->sp_group_item0[g], hi = c->sp_group_item0[g + 1];
+                chunk[w] = std::max(chunk[w - 1], (target - lo <= hi - target) ? lo : hi);   // the nearer group boundary
+            }
+            CK(c->sp_sv_chunk.reserve(chunk.size()));
+            CK(cudaMemcpyAsync(c->sp_sv_chunk.p, chunk.data(), chunk.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+            c->sp_chunk_warps = nw;
+        }
+        a.cn_moff = c->sp_cn_moff.p; a.sv_items = c->sp_sv_items.p; a.sv_chunk = c->sp_sv_chunk.p; a.msg_words = c->sp_msg_words;
         CK(cudaEventRecord(c->ev0, s));
         e = onchip_spa_launch(P->algorithm, a, grid, threads, smem, s);
         if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip sum-product kernel launch failed: %s", cudaGetErrorString(e));

@@ -19,7 +19,8 @@
 //       pass 2  c2b = clamp(2 atanh(P / t)) stored in place (:64-74)
 //   VN  thread per bit: L = llr + sum of the bit's c2b in ascending check order (:76-84)
 // The check-phase tables (groups of 32 rows of one degree, bit indices in blocks of 4) are the ones of the min-sum
-// kernel; the variable phase has its own groups, packed so that the 32 lanes' k-th messages lie in different banks.
+// kernel; the variable phase has its own groups, packed so that the 32 lanes' k-th messages lie in different banks,
+// stored as a flat list of 4-check items.
 #pragma once
 #include "onchip_minsum.cuh"
 #include "step_kernels.cuh"
@@ -27,98 +28,117 @@
 namespace qk {
 
 // Shared-memory layout (onchip_spa_smem_bytes, onchip_minsum.cuh):
-//   msg[msg_words] float | L[n+1] float (padded to 16 B) | bob[words] | alice[words] | syn[groups_cn] | misc
+//   L[n+1] float (padded to 16 B) | msg[msg_words + 1] float (padded; the last word stays 0) | bob[words] | alice[words] | syn[groups_cn] | misc
 
-#define QK_SPA_CN_EDGE(J, COL)                                                                                          \
-    {                                                                                                                   \
-        const float Lv = L[(COL)];                                                                                      \
-        zpar ^= (Lv <= 0.f) ? 1u : 0u;                    /* hard decision (:80-83); NaN decides 0 (quirk Q2) */         \
-        float *w = mp + (kb + (J)) * 32;                                                                                \
-        /* clamp(L - c2b) (:109-123); first iteration: zero message and thr_b = +inf leave the unclamped LLR (:21-29) */ \
-        *w = st.absorb(clamp_msg(Lv - *w, thr_b));        /* tanh(m / 2), in place (:58-62) */                           \
-    }
-#define QK_SPA_CN_EMIT(J)                                                                                               \
-    {                                                                                                                   \
-        float *w = mp + (kb + (J)) * 32;                                                                                \
-        *w = clamp_msg(st.emit(*w, syn != 0, 0.f), a.thr);   /* 2 atanh(P / t), threshold_matrix (:64-74) */             \
-    }
+// Pass 1 of a check node for a block of edges: all gathers first (independent loads in flight together), then the
+// arithmetic, then the stores -- the in-place update would otherwise serialise the edges of a block.
+#define QK_SPA_LOAD(J, COL) const float Lv##J = L[(COL)]; const float c##J = mp[(kb + (J)) * 32];
+/* hard decision (:80-83), NaN decides 0 (quirk Q2); clamp(L - c2b) (:109-123) -- first iteration: zero message and     */
+/* thr_b = +inf leave the unclamped LLR (:21-29); tanh(m / 2) kept in place (:58-62), P *= t in edge order               */
+#define QK_SPA_ABSORB(J)                                                                                                \
+    zpar ^= (Lv##J <= 0.f) ? 1u : 0u;                                                                                   \
+    const float t##J = st.absorb(clamp_msg(Lv##J - c##J, thr_b));
+#define QK_SPA_STORE(J) mp[(kb + (J)) * 32] = t##J;
+/* pass 2: 2 atanh(P / t), threshold_matrix (:64-74) */
+#define QK_SPA_EMIT(J) const float e##J = clamp_msg(st.emit(mp[(kb + (J)) * 32], syn != 0, 0.f), a.thr);
+#define QK_SPA_ESTORE(J) mp[(kb + (J)) * 32] = e##J;
 
 template <int ALG>
-__device__ __forceinline__ bool onchip_spa_cn_phase(const OnchipArgs &a, const float *L, float *msg, const uint32_t *synw,
-                                                    float thr_b, int warp, int lane, int nwarps) {
+__device__ __forceinline__ bool onchip_spa_cn_phase(const OnchipArgs &a, const float *__restrict__ L, float *__restrict__ msg,
+                                                    const uint32_t *synw, float thr_b, int warp, int lane, int nwarps) {
     bool unsat = false;
     for (int g = warp; g < a.n_groups_cn; g += nwarps) {
         const int2 gi = __ldg(a.cn_ginfo + g);
         const int dc = gi.y;                                      // degree of the group's rows (warp-uniform)
         const uint32_t row = __ldg(a.cn_row + g * 32 + lane);     // record slot of the min-sum kernel: only its validity is used
         const uint2 *cp = a.cnT + gi.x + lane;
-        float *mp = msg + __ldg(a.cn_moff + g) + lane;
+        float *__restrict__ mp = msg + __ldg(a.cn_moff + g) + lane;
         const uint32_t syn = (synw[g] >> lane) & 1u;
         RowState<float, ALG> st;
         st.init(syn != 0);                                        // P = syndrome ? -1 : 1 (:56-57)
         uint32_t zpar = 0;
         int kb = 0;
-#pragma unroll 1
+        uint2 cw = __ldg(cp);                                     // indices of the first block; the next block is
+#pragma unroll 1                                                  // fetched while the current one is processed
         for (; kb + 4 <= dc; kb += 4) {
-            const uint2 cw = __ldg(cp + (kb >> 2) * 32);
-            QK_SPA_CN_EDGE(0, cw.x & 0xFFFFu)
-            QK_SPA_CN_EDGE(1, cw.x >> 16)
-            QK_SPA_CN_EDGE(2, cw.y & 0xFFFFu)
-            QK_SPA_CN_EDGE(3, cw.y >> 16)
+            const uint2 nx = __ldg(cp + (((kb + 4 < dc) ? kb + 4 : kb) >> 2) * 32);
+            QK_SPA_LOAD(0, cw.x & 0xFFFFu) QK_SPA_LOAD(1, cw.x >> 16) QK_SPA_LOAD(2, cw.y & 0xFFFFu) QK_SPA_LOAD(3, cw.y >> 16)
+            QK_SPA_ABSORB(0) QK_SPA_ABSORB(1) QK_SPA_ABSORB(2) QK_SPA_ABSORB(3)
+            QK_SPA_STORE(0) QK_SPA_STORE(1) QK_SPA_STORE(2) QK_SPA_STORE(3)
+            cw = nx;
         }
         if (kb < dc) {                            // warp-uniform tail of 1..3 edges
-            const uint2 cw = __ldg(cp + (kb >> 2) * 32);
             const int left = dc - kb;
-            QK_SPA_CN_EDGE(0, cw.x & 0xFFFFu)
-            if (left > 1) QK_SPA_CN_EDGE(1, cw.x >> 16)
-            if (left > 2) QK_SPA_CN_EDGE(2, cw.y & 0xFFFFu)
+            QK_SPA_LOAD(0, cw.x & 0xFFFFu)
+            QK_SPA_ABSORB(0)
+            QK_SPA_STORE(0)
+            if (left > 1) {
+                QK_SPA_LOAD(1, cw.x >> 16)
+                QK_SPA_ABSORB(1)
+                QK_SPA_STORE(1)
+            }
+            if (left > 2) {
+                QK_SPA_LOAD(2, cw.y & 0xFFFFu)
+                QK_SPA_ABSORB(2)
+                QK_SPA_STORE(2)
+            }
         }
         unsat |= ((zpar ^ syn) & 1u) != 0 && row < (uint32_t)a.rec_slots;
 #pragma unroll 1
         for (kb = 0; kb + 4 <= dc; kb += 4) {
-            QK_SPA_CN_EMIT(0)
-            QK_SPA_CN_EMIT(1)
-            QK_SPA_CN_EMIT(2)
-            QK_SPA_CN_EMIT(3)
+            QK_SPA_EMIT(0) QK_SPA_EMIT(1) QK_SPA_EMIT(2) QK_SPA_EMIT(3)
+            QK_SPA_ESTORE(0) QK_SPA_ESTORE(1) QK_SPA_ESTORE(2) QK_SPA_ESTORE(3)
         }
         if (kb < dc) {
             const int left = dc - kb;
-            QK_SPA_CN_EMIT(0)
-            if (left > 1) QK_SPA_CN_EMIT(1)
-            if (left > 2) QK_SPA_CN_EMIT(2)
+            { QK_SPA_EMIT(0) QK_SPA_ESTORE(0) }
+            if (left > 1) { QK_SPA_EMIT(1) QK_SPA_ESTORE(1) }
+            if (left > 2) { QK_SPA_EMIT(2) QK_SPA_ESTORE(2) }
         }
     }
     return unsat;
 }
-#undef QK_SPA_CN_EDGE
-#undef QK_SPA_CN_EMIT
+#undef QK_SPA_LOAD
+#undef QK_SPA_ABSORB
+#undef QK_SPA_STORE
+#undef QK_SPA_EMIT
+#undef QK_SPA_ESTORE
 
-__device__ __forceinline__ void onchip_spa_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *L, const float *msg,
-                                                    const uint32_t *bobw, float lp, int warp, int lane, int nwarps) {
-    for (int g = warp; g < a.n_groups_sv; g += nwarps) {
-        const int2 gi = __ldg(a.sv_ginfo + g);
-        const int dv = gi.y;
-        const uint32_t bit = __ldg(a.sv_bit + g * 32 + lane);
-        float acc = onchip_llr(ctx, bobw, bit < (uint32_t)a.n ? bit : 0u, lp);
-        const uint2 *ep = a.svT + gi.x + lane;
-        int kb = 0;
-        // ascending check order, starting from the LLR (std::accumulate, :78)
-#pragma unroll 2
-        for (; kb + 4 <= dv; kb += 4) {
-            const uint2 ew = __ldg(ep + (kb >> 2) * 32);
-            acc = acc + msg[ew.x & 0xFFFFu];
-            acc = acc + msg[ew.x >> 16];
-            acc = acc + msg[ew.y & 0xFFFFu];
-            acc = acc + msg[ew.y >> 16];
+// Variable phase. The work is a flat list of ITEMS, one per (group of 32 bits, block of 4 checks): a lane's 16-byte
+// entry {4 x uint16 message word, bit id | first << 16 | last << 17} is everything it needs, so there is no group
+// header to chase and the next item is fetched while the current one is processed. Warp w owns the contiguous items
+// [sv_chunk[w], sv_chunk[w+1]) (whole groups, balanced on the host). Blocks of fewer than 4 checks are padded with the
+// message word that is always 0.0f (x + 0.0f == x for every x that can occur here), so a block is 4 unconditional adds
+// in ascending check order, starting from the LLR (std::accumulate, :78).
+__device__ __forceinline__ void onchip_spa_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *__restrict__ L, const float *__restrict__ msg,
+                                                    const uint32_t *__restrict__ bobw, float lp, int warp, int lane) {
+    int i = __ldg(a.sv_chunk + warp);
+    const int end = __ldg(a.sv_chunk + warp + 1);
+    if (i >= end) return;
+    const int has_cls = ctx->has_cls;
+    const uint32_t *cls_punct = ctx->cls_punct, *cls_short = ctx->cls_short;
+    const uint4 *p = a.sv_items + (size_t)i * 32 + lane;
+    uint4 it = __ldg(p);
+    float acc = 0.f;
+    for (; i < end; ++i) {
+        p += (i + 1 < end) ? 32 : 0;
+        const uint4 nx = __ldg(p);
+        const uint32_t bit = it.z & 0xFFFFu;                       // padding lanes: n (the scratch slot L[n])
+        if (it.z & 0x10000u) {                                     // first block of the bit: start from the LLR
+            const uint32_t bi = bit < (uint32_t)a.n ? bit : 0u, w = bi >> 5, sh = bi & 31u;
+            acc = ((bobw[w] >> sh) & 1u) ? -lp : lp;               // qkd_ldpc_algorithm.cpp:1043-1049
+            if (has_cls) {
+                if ((__ldg(cls_punct + w) >> sh) & 1u) acc = 1e-4f;            // punctured: ALMOST_ZERO (:1155)
+                else if ((__ldg(cls_short + w) >> sh) & 1u) acc = FLT_MAX;     // shortened: largest finite value (:1164)
+            }
         }
-        if (kb < dv) {                            // warp-uniform tail of 1..3 checks
-            const uint2 ew = __ldg(ep + (kb >> 2) * 32);
-            const int left = dv - kb;
-            acc = acc + msg[ew.x & 0xFFFFu];
-            if (left > 1) acc = acc + msg[ew.x >> 16];
-            if (left > 2) acc = acc + msg[ew.y & 0xFFFFu];
-        }
-        L[bit] = acc;                             // padding lanes write the scratch slot L[n]
+        const float m0 = msg[it.x & 0xFFFFu], m1 = msg[it.x >> 16], m2 = msg[it.y & 0xFFFFu], m3 = msg[it.y >> 16];
+        acc = acc + m0;
+        acc = acc + m1;
+        acc = acc + m2;
+        acc = acc + m3;
+        if (it.z & 0x20000u) L[bit] = acc;                         // last block of the bit
+        it = nx;
     }
 }
 
@@ -126,9 +146,9 @@ template <int ALG>
 __global__ void __launch_bounds__(1024, 1) onchip_spa_kernel(const OnchipArgs a) {
     static_assert(ALG == 0 || ALG == 1, "sum-product variants only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *msg = reinterpret_cast<float *>(smem_raw);
-    float *L = msg + (a.msg_words + 3) / 4 * 4;
-    uint32_t *bobw = reinterpret_cast<uint32_t *>(L + onchip_l_slots(a.n));
+    float *L = reinterpret_cast<float *>(smem_raw);          // offset 0: the gather address is one shift-add
+    float *msg = L + onchip_l_slots(a.n);
+    uint32_t *bobw = reinterpret_cast<uint32_t *>(msg + (a.msg_words + 4) / 4 * 4);
     uint32_t *alw = bobw + a.words;
     uint32_t *synw = alw + a.words;
     uint32_t *tail = synw + a.n_groups_cn;
@@ -164,7 +184,7 @@ __global__ void __launch_bounds__(1024, 1) onchip_spa_kernel(const OnchipArgs a)
             bobw[w] = a.bob_bits[f * a.words + w];
             alw[w] = a.alice_bits[f * a.words + w];
         }
-        for (int i = tid; i < a.msg_words; i += blockDim.x) msg[i] = 0.f;
+        for (int i = tid; i <= a.msg_words; i += blockDim.x) msg[i] = 0.f;   // + the always-zero word msg[msg_words]
         __syncthreads();
         // L = a-priori LLR; Alice's syndrome (calculate_syndrome, array_and_matrix_operations.cpp:936-950)
         for (int i = tid; i <= a.n; i += blockDim.x) L[i] = (i < a.n) ? onchip_llr(ctx, bobw, (uint32_t)i, lp) : 1.f;
@@ -196,7 +216,7 @@ __global__ void __launch_bounds__(1024, 1) onchip_spa_kernel(const OnchipArgs a)
             const bool any_unsat = __syncthreads_or(unsat) != 0;
             if (it > 1 && !any_unsat) { success = true; iters = run = it - 1; break; }   // z of iteration it-1
             if (it > a.max_iter) break;
-            onchip_spa_vn_phase(a, ctx, L, msg, bobw, lp, warp, lane, nwarps);
+            onchip_spa_vn_phase(a, ctx, L, msg, bobw, lp, warp, lane);
             __syncthreads();
         }
 
