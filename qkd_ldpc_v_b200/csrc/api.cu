@@ -238,8 +238,10 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         }
         // sum-product variable phase: groups of 32 bits of one degree; a 4-byte gather of the lanes' k-th messages is
         // conflict-free when the 32 rows sit in 32 different lanes of their check groups (bank = word mod 32 = lane)
-        sp_ok = sp_msg_words > 0 && sp_msg_words <= 65534 &&   // word sp_msg_words is the always-zero padding word
-                qk::onchip_spa_smem_bytes(n, sp_msg_words, (int)oc_cn_ginfo.size()) <= qk::kOnchipSmemMax;
+        // shared-memory words: L[l_slots] first, then the messages, then the always-zero padding word
+        const int l_slots = (int)qk::onchip_l_slots(n), zero_word = l_slots + sp_msg_words;
+        sp_ok = sp_msg_words > 0 &&
+                qk::onchip_spa_smem_bytes(n, sp_msg_words, (int)oc_cn_ginfo.size(), (n + 31) / 32) <= qk::kOnchipSmemMax;   // lower bound
         if (sp_ok) {
             for (const auto &cls : degree_classes(n, col_ptr)) {
                 std::vector<std::vector<int>> groups;
@@ -249,19 +251,23 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
                     sp_group_item0.push_back((int)(sp_items.size() / 32));
                     for (int kb = 0; kb < blocks; ++kb)
                         for (int l = 0; l < 32; ++l) {
-                            uint32_t e[4] = {(uint32_t)sp_msg_words, (uint32_t)sp_msg_words, (uint32_t)sp_msg_words, (uint32_t)sp_msg_words};
+                            uint32_t e[4] = {(uint32_t)zero_word, (uint32_t)zero_word, (uint32_t)zero_word, (uint32_t)zero_word};
                             if (l < (int)gr.size())
                                 for (int j = 0; j < 4 && kb * 4 + j < dv; ++j) {
                                     const int p = col_ptr[gr[l]] + kb * 4 + j, r = csc_row[p];
-                                    e[j] = (uint32_t)(row_word0[r] + 32 * (csc_edge[p] - rp[r]));
+                                    e[j] = (uint32_t)(l_slots + row_word0[r] + 32 * (csc_edge[p] - rp[r]));
                                 }
                             const uint32_t bit = l < (int)gr.size() ? (uint32_t)gr[l] : (uint32_t)n;
                             const uint32_t flags = (kb == 0 ? 0x10000u : 0u) | (kb == blocks - 1 ? 0x20000u : 0u);
-                            sp_items.push_back(make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), bit | flags, 0u));
+                            sp_items.push_back(make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), bit | flags,
+                                                          (uint32_t)sp_group_item0.size() - 1u));
                         }
                 }
             }
             sp_group_item0.push_back((int)(sp_items.size() / 32));
+            // the final word: every shared-memory word index must fit 16 bits, and the true group count enters the size
+            sp_ok = qk::onchip_spa_smem_bytes(n, sp_msg_words, (int)oc_cn_ginfo.size(), (int)sp_group_item0.size() - 1) <= qk::kOnchipSmemMax &&
+                    zero_word <= 65535;
         }
     }
 
@@ -314,7 +320,8 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     if (sp_ok) {
         // the sum-product tables: every message word <= msg_words (the zero word), every edge owns exactly one word and
         // appears once, in ascending check order, between the first and the last item of its bit
-        std::vector<char> seen((size_t)sp_msg_words, 0);
+        const int l_slots = (int)qk::onchip_l_slots(n), zero_word = l_slots + sp_msg_words;
+        std::vector<char> seen((size_t)zero_word + 1, 0);
         std::vector<int> next_k((size_t)n, 0);
         size_t edges_sv = 0;
         if (sp_cn_moff.size() != oc_cn_ginfo.size()) return fail(QKDLDPC_ERR_STATE, "sum-product table: group count");
@@ -326,18 +333,21 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
             const int bit = (int)(it.z & 0xFFFFu);
             const bool first = (it.z & 0x10000u) != 0, last = (it.z & 0x20000u) != 0;
             if (bit > n) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: bit %d out of range", bit);
+            const int grp = (int)it.w;
+            if (grp < 0 || grp + 1 >= (int)sp_group_item0.size() || (int)(i / 32) < sp_group_item0[grp] || (int)(i / 32) >= sp_group_item0[grp + 1])
+                return fail(QKDLDPC_ERR_STATE, "sum-product variable table: group of item %zu", i / 32);
             const int word[4] = {(int)(it.x & 0xFFFFu), (int)(it.x >> 16), (int)(it.y & 0xFFFFu), (int)(it.y >> 16)};
             if (bit < n && first != (next_k[bit] == 0)) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: first flag of bit %d", bit);
             for (int j = 0; j < 4; ++j) {
-                if (word[j] > sp_msg_words) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: word %d out of range", word[j]);
+                if (word[j] < l_slots || word[j] > zero_word) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: word %d out of range", word[j]);
                 if (bit == n) continue;
                 const int k = next_k[bit], dv = col_ptr[bit + 1] - col_ptr[bit];
                 if (k >= dv) {
-                    if (word[j] != sp_msg_words) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: padding of bit %d", bit);
+                    if (word[j] != zero_word) return fail(QKDLDPC_ERR_STATE, "sum-product variable table: padding of bit %d", bit);
                     continue;
                 }
                 const int p = col_ptr[bit] + k, row = csc_row[p];
-                if (word[j] != row_word0[row] + 32 * (csc_edge[p] - rp[row]) || seen[word[j]])
+                if (word[j] != l_slots + row_word0[row] + 32 * (csc_edge[p] - rp[row]) || seen[word[j]])
                     return fail(QKDLDPC_ERR_STATE, "sum-product variable table: wrong word for bit %d", bit);
                 seen[word[j]] = 1;
                 next_k[bit] = k + 1;
@@ -369,7 +379,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         (e = up(c->col_order, col_order)) || 
         (oc_ok && ((e = up(c->oc_cn_ginfo, oc_cn_ginfo)) || (e = up(c->oc_cnT, oc_cnT)) || (e = up(c->oc_cn_row, oc_cn_row)) || (e = up(c->oc_vn_ginfo, oc_vn_ginfo)) ||
                    (e = up(c->oc_vn_bit, oc_vn_bit)) || (e = up(c->oc_vT, oc_vT)))) ||
-        (sp_ok && ((e = up(c->sp_cn_moff, sp_cn_moff)) || (e = up(c->sp_sv_items, sp_items)))) ||
+        (sp_ok && ((e = up(c->sp_cn_moff, sp_cn_moff)) || (e = up(c->sp_sv_items, sp_items)) || (e = up(c->sp_sv_group_item0, sp_group_item0)))) ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
         (e = cudaMallocHost(&c->h_done, 2 * sizeof(unsigned long long))) || (e = cudaEventCreate(&c->ev0)) ||
         (e = cudaEventCreate(&c->ev1)) || (e = cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming))) {
@@ -398,6 +408,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     c->oc_eligible = oc_ok;
     c->sp_eligible = sp_ok;
     c->sp_group_item0 = sp_group_item0;
+    c->sp_groups_sv = sp_ok ? (int)sp_group_item0.size() - 1 : 0;
     c->sp_msg_words = sp_msg_words;
     for (int k = 0; k < 5; ++k) {
         c->cn_first[k] = cn_first[k]; c->cn_count[k] = cn_count[k];
@@ -416,7 +427,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->row_order.release(); c->col_order.release();
     c->oc_cn_ginfo.release(); c->oc_vn_ginfo.release(); c->oc_cnT.release(); c->oc_cn_row.release(); c->oc_vn_bit.release(); c->oc_vT.release();
     c->oc_cls.release();
-    c->sp_cn_moff.release(); c->sp_sv_items.release(); c->sp_sv_chunk.release();
+    c->sp_cn_moff.release(); c->sp_sv_items.release(); c->sp_sv_chunk.release(); c->sp_sv_group_item0.release();
     c->msg.release(); c->bobmask.release(); c->zmask.release(); c->synd.release(); c->par.release();
     c->tile_active.release(); c->tile_new.release(); c->slot_llr.release(); c->slot_frame.release();
     c->slot_iter.release(); c->frame_llr.release(); c->synd_all.release();

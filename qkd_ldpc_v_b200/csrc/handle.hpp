@@ -98,7 +98,8 @@ struct qkdldpc_code {
     // on-chip sum-product path (onchip_spa.cuh): one message word per edge; check phase shares oc_cn_* with min-sum
     bool sp_eligible = false;
     int sp_msg_words = 0, sp_chunk_warps = 0;
-    DevBuf<int> sp_cn_moff, sp_sv_chunk;
+    DevBuf<int> sp_cn_moff, sp_sv_chunk, sp_sv_group_item0;
+    int sp_groups_sv = 0;
     DevBuf<uint4> sp_sv_items;
     std::vector<int> sp_group_item0;  // first item of every variable-phase group (+ total): chunk boundaries lie on these
     int last_path = 0;                // 1 streaming, 2 on-chip (of the last batch)

@@ -17,7 +17,7 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
         int dev_smem = 0;
         if (!c->sp_eligible || cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess)
             return false;
-        return onchip_spa_smem_bytes(c->n, c->sp_msg_words, c->oc_groups_cn) <= (size_t)dev_smem;
+        return onchip_spa_smem_bytes(c->n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv) <= (size_t)dev_smem;
     }
     if (!c->oc_eligible) return false;
     // same precondition as the FAST streaming kernels (fast_minsum_ok, run_batch.cuh): no message can become NaN / inf
@@ -156,7 +156,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
 
     const bool spa = P->algorithm < 2;
     int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(spa ? 1024 : 768, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
-    const size_t smem = spa ? onchip_spa_smem_bytes(n, c->sp_msg_words, c->oc_groups_cn) : onchip_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn);
+    const size_t smem = spa ? onchip_spa_smem_bytes(n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv) : onchip_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn);
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 
@@ -183,6 +183,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
             c->sp_chunk_warps = nw;
         }
         a.cn_moff = c->sp_cn_moff.p; a.sv_items = c->sp_sv_items.p; a.sv_chunk = c->sp_sv_chunk.p; a.msg_words = c->sp_msg_words;
+        a.sv_group_item0 = c->sp_sv_group_item0.p; a.n_groups_sv = c->sp_groups_sv;
         CK(cudaEventRecord(c->ev0, s));
         e = onchip_spa_launch(P->algorithm, a, grid, threads, smem, s);
         if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip sum-product kernel launch failed: %s", cudaGetErrorString(e));

@@ -57,8 +57,11 @@ struct OnchipArgs {
     // Sum-product kernel only (onchip_spa.cuh): one float per edge in shared memory, word cn_moff[group] + k * 32 + lane
     // for edge k of the row handled by (group, lane); the variable phase has its own groups and addresses the words directly.
     const int *cn_moff;         // [groups_cn] first message word of the group
-    const uint4 *sv_items;      // [items*32] variable phase: {4 x uint16 message word, bit | first << 16 | last << 17, 0}
+    const uint4 *sv_items;      // [items*32] variable phase: {4 x uint16 shared-memory WORD of the message (L starts at word
+                                //            0, the messages follow), bit | first << 16 | last << 17, variable group}
     const int *sv_chunk;        // [warps per CTA + 1] items [sv_chunk[w], sv_chunk[w+1]) belong to warp w
+    const int *sv_group_item0;  // [groups_sv] first item of the group
+    int n_groups_sv;
     int msg_words;              // word msg_words is kept at 0.0f (padding of short blocks)
     // One launch may span several parameter COMBINATIONS of a sweep (frames [c * frames_per_combo, (c+1) * ...) belong to
     // combination c): scaling factors, QBER, punctured / shortened masks and the tally vector are per combination.
@@ -87,9 +90,9 @@ __host__ __device__ inline size_t onchip_smem_bytes(int n, int rec_slots, int gr
 }
 
 // The sum-product kernel (onchip_spa.cuh): msg[msg_words] float instead of the records, the rest alike.
-__host__ __device__ inline size_t onchip_spa_smem_bytes(int n, int msg_words, int groups_cn) {
+__host__ __device__ inline size_t onchip_spa_smem_bytes(int n, int msg_words, int groups_cn, int groups_sv) {
     const size_t words = (size_t)(n + 31) / 32;
-    return ((size_t)msg_words + 4) / 4 * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn) * 4 + 96;
+    return ((size_t)msg_words + 4) / 4 * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn + (size_t)groups_sv) * 4 + 96;
 }
 constexpr size_t kOnchipSmemMax = 227 * 1024;   // opt-in shared memory per CTA on sm_100
 

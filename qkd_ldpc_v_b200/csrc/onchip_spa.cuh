@@ -28,7 +28,9 @@
 namespace qk {
 
 // Shared-memory layout (onchip_spa_smem_bytes, onchip_minsum.cuh):
-//   L[n+1] float (padded to 16 B) | msg[msg_words + 1] float (padded; the last word stays 0) | bob[words] | alice[words] | syn[groups_cn] | misc
+//   L[n+1] float (padded to 16 B) | msg[msg_words + 1] float (padded; the last word stays 0) | bob[words] | alice[words] |
+//   syn[groups_cn] | bobg[groups_sv] | misc.  Every word of it has an index < 65536 (227 KB / 4), which is what the
+//   variable-phase table stores.
 
 // Pass 1 of a check node for a block of edges: all gathers first (independent loads in flight together), then the
 // arithmetic, then the stores -- the in-place update would otherwise serialise the edges of a block.
@@ -105,40 +107,41 @@ __device__ __forceinline__ bool onchip_spa_cn_phase(const OnchipArgs &a, const f
 #undef QK_SPA_ESTORE
 
 // Variable phase. The work is a flat list of ITEMS, one per (group of 32 bits, block of 4 checks): a lane's 16-byte
-// entry {4 x uint16 message word, bit id | first << 16 | last << 17} is everything it needs, so there is no group
-// header to chase and the next item is fetched while the current one is processed. Warp w owns the contiguous items
+// entry {4 x uint16 shared-memory word of the message, bit id | first << 16 | last << 17, group} is everything it needs,
+// so there is no group header to chase, and the entries are fetched two items ahead. Warp w owns the contiguous items
 // [sv_chunk[w], sv_chunk[w+1]) (whole groups, balanced on the host). Blocks of fewer than 4 checks are padded with the
 // message word that is always 0.0f (x + 0.0f == x for every x that can occur here), so a block is 4 unconditional adds
-// in ascending check order, starting from the LLR (std::accumulate, :78).
-__device__ __forceinline__ void onchip_spa_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *__restrict__ L, const float *__restrict__ msg,
-                                                    const uint32_t *__restrict__ bobw, float lp, int warp, int lane) {
+// in ascending check order, starting from the LLR (std::accumulate, :78). Bob's bits are kept in group order
+// (bobg[group], bit = lane), so the LLR sign is one broadcast load away.
+__device__ __forceinline__ void onchip_spa_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *__restrict__ smf,
+                                                    const uint32_t *__restrict__ bobg, float lp, int warp, int lane) {
     int i = __ldg(a.sv_chunk + warp);
     const int end = __ldg(a.sv_chunk + warp + 1);
     if (i >= end) return;
     const int has_cls = ctx->has_cls;
     const uint32_t *cls_punct = ctx->cls_punct, *cls_short = ctx->cls_short;
-    const uint4 *p = a.sv_items + (size_t)i * 32 + lane;
-    uint4 it = __ldg(p);
+    const uint4 *items = a.sv_items + lane;
+    uint4 it = __ldg(items + (size_t)i * 32);
+    uint4 nx = __ldg(items + (size_t)min(i + 1, end - 1) * 32);
     float acc = 0.f;
     for (; i < end; ++i) {
-        p += (i + 1 < end) ? 32 : 0;
-        const uint4 nx = __ldg(p);
+        const uint4 nx2 = __ldg(items + (size_t)min(i + 2, end - 1) * 32);
         const uint32_t bit = it.z & 0xFFFFu;                       // padding lanes: n (the scratch slot L[n])
-        if (it.z & 0x10000u) {                                     // first block of the bit: start from the LLR
+        float llr = ((bobg[it.w] >> lane) & 1u) ? -lp : lp;        // qkd_ldpc_algorithm.cpp:1043-1049
+        if (has_cls) {                                             // rate adaptation (warp-uniform)
             const uint32_t bi = bit < (uint32_t)a.n ? bit : 0u, w = bi >> 5, sh = bi & 31u;
-            acc = ((bobw[w] >> sh) & 1u) ? -lp : lp;               // qkd_ldpc_algorithm.cpp:1043-1049
-            if (has_cls) {
-                if ((__ldg(cls_punct + w) >> sh) & 1u) acc = 1e-4f;            // punctured: ALMOST_ZERO (:1155)
-                else if ((__ldg(cls_short + w) >> sh) & 1u) acc = FLT_MAX;     // shortened: largest finite value (:1164)
-            }
+            if ((__ldg(cls_punct + w) >> sh) & 1u) llr = 1e-4f;                // punctured: ALMOST_ZERO (:1155)
+            else if ((__ldg(cls_short + w) >> sh) & 1u) llr = FLT_MAX;         // shortened: largest finite value (:1164)
         }
-        const float m0 = msg[it.x & 0xFFFFu], m1 = msg[it.x >> 16], m2 = msg[it.y & 0xFFFFu], m3 = msg[it.y >> 16];
+        acc = (it.z & 0x10000u) ? llr : acc;                       // first block of the bit: start from the LLR
+        const float m0 = smf[it.x & 0xFFFFu], m1 = smf[it.x >> 16], m2 = smf[it.y & 0xFFFFu], m3 = smf[it.y >> 16];
         acc = acc + m0;
         acc = acc + m1;
         acc = acc + m2;
         acc = acc + m3;
-        if (it.z & 0x20000u) L[bit] = acc;                         // last block of the bit
+        if (it.z & 0x20000u) smf[bit] = acc;                       // last block of the bit: L[bit]
         it = nx;
+        nx = nx2;
     }
 }
 
@@ -151,8 +154,9 @@ __global__ void __launch_bounds__(1024, 1) onchip_spa_kernel(const OnchipArgs a)
     uint32_t *bobw = reinterpret_cast<uint32_t *>(msg + (a.msg_words + 4) / 4 * 4);
     uint32_t *alw = bobw + a.words;
     uint32_t *synw = alw + a.words;
-    uint32_t *tail = synw + a.n_groups_cn;
-    long long *s_frame = reinterpret_cast<long long *>(tail + ((2 * a.words + a.n_groups_cn) & 1));
+    uint32_t *bobg = synw + a.n_groups_cn;
+    uint32_t *tail = bobg + a.n_groups_sv;
+    long long *s_frame = reinterpret_cast<long long *>(tail + ((2 * a.words + a.n_groups_cn + a.n_groups_sv) & 1));
     FrameCtx *ctx = reinterpret_cast<FrameCtx *>(s_frame + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -186,8 +190,14 @@ __global__ void __launch_bounds__(1024, 1) onchip_spa_kernel(const OnchipArgs a)
         }
         for (int i = tid; i <= a.msg_words; i += blockDim.x) msg[i] = 0.f;   // + the always-zero word msg[msg_words]
         __syncthreads();
-        // L = a-priori LLR; Alice's syndrome (calculate_syndrome, array_and_matrix_operations.cpp:936-950)
+        // L = a-priori LLR; Bob's bits in variable-group order; Alice's syndrome (calculate_syndrome,
+        // array_and_matrix_operations.cpp:936-950)
         for (int i = tid; i <= a.n; i += blockDim.x) L[i] = (i < a.n) ? onchip_llr(ctx, bobw, (uint32_t)i, lp) : 1.f;
+        for (int g = warp; g < a.n_groups_sv; g += nwarps) {
+            const uint32_t bit = __ldg(a.sv_items + (size_t)__ldg(a.sv_group_item0 + g) * 32 + lane).z & 0xFFFFu;
+            const uint32_t bw = __ballot_sync(0xffffffffu, bit < (uint32_t)a.n && ((bobw[(bit < (uint32_t)a.n ? bit : 0u) >> 5] >> (bit & 31u)) & 1u));
+            if (lane == 0) bobg[g] = bw;
+        }
         for (int g = warp; g < a.n_groups_cn; g += nwarps) {
             const int2 gi = __ldg(a.cn_ginfo + g);
             const uint32_t row = __ldg(a.cn_row + g * 32 + lane);
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(1024, 1) onchip_spa_kernel(const OnchipArgs a)
             const bool any_unsat = __syncthreads_or(unsat) != 0;
             if (it > 1 && !any_unsat) { success = true; iters = run = it - 1; break; }   // z of iteration it-1
             if (it > a.max_iter) break;
-            onchip_spa_vn_phase(a, ctx, L, msg, bobw, lp, warp, lane);
+            onchip_spa_vn_phase(a, ctx, L, bobg, lp, warp, lane);
             __syncthreads();
         }
 

@@ -80,8 +80,10 @@ def onchip_eligible(name, alg):
     deg, cnt = np.unique(dc, return_counts=True)
     groups = (cnt + 31) // 32
     words = int((groups * 32 * deg).sum())
-    smem = (words + 3) // 4 * 16 + (arr["n"] + 4) // 4 * 16 + (2 * ((arr["n"] + 31) // 32) + int(groups.sum())) * 4 + 96
-    return words <= 65535 and smem <= 227 * 1024
+    vgroups = int(((np.unique(np.diff(arr["col_ptr"]), return_counts=True)[1] + 31) // 32).sum())
+    smem = ((words + 4) // 4 * 16 + (arr["n"] + 4) // 4 * 16 +
+            (2 * ((arr["n"] + 31) // 32) + int(groups.sum()) + vgroups) * 4 + 96)
+    return smem <= 227 * 1024
 
 
 @pytest.mark.parametrize("path", [1, 2], ids=["streaming", "onchip"])
