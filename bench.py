@@ -52,7 +52,7 @@ def parse():
     p.add_argument("--pool-slots", type=int, default=0)
     p.add_argument("--frames-per-lane", type=int, default=0)
     p.add_argument("--path", type=int, default=0, choices=[0, 1, 2],
-                   help="decoder path: 0 auto (on-chip min-sum when eligible), 1 streaming (messages in HBM), 2 on-chip")
+                   help="decoder path: 0 auto (on-chip kernels when eligible), 1 streaming (messages in HBM), 2 on-chip")
     p.add_argument("--onchip-threads", type=int, default=0)
     p.add_argument("--no-compaction", action="store_true", help="streaming path: do not compact the tail of a draining batch")
     p.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU-baseline sample (0 = auto)")
@@ -299,14 +299,16 @@ def main():
         k_ms = batch_ms / args.steps
         k_bytes = cn_bytes + vn_bytes
         ach_k = k_bytes / (k_ms * 1e-3) / 1e9
-        tr = traffic_db.get("onchip_minsum_kernel", {}).get("dram_bytes_per_frame")
+        kname = "onchip_minsum_kernel" if alg >= 2 else "onchip_spa_kernel"
+        tr = traffic_db.get(kname, {}).get("dram_bytes_per_frame")
         roofline = {
-            "bound": "hbm", "kernel": f"onchip_minsum_kernel<ALG={alg}>", "achieved": ach_k, "peak": peak, "unit": "GB/s",
+            "bound": "hbm", "kernel": f"{kname}<ALG={alg}>", "achieved": ach_k, "peak": peak, "unit": "GB/s",
             "frac": ach_k / peak, "traffic": (tr * F if tr is not None else None), "peak_source": peak_src,
             "bytes_per_launch": k_bytes, "ms_per_launch": k_ms, "launches_per_step": 1,
             "whole_step_frac": (k_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak,
             "note": "algorithmic bytes = (16*E + 4*N) per frame-iteration (SURVEY.md 8d); this kernel keeps them on chip "
-                    "(4N + 16M bytes of shared memory per frame), DRAM traffic is the packed keys only -- see `traffic`",
+                    + ("(4N + 16M bytes of shared memory per frame)" if alg >= 2 else "(4N + 4E bytes of shared memory per frame)")
+                    + ", DRAM traffic is the packed keys only -- see `traffic`",
         }
     else:
         kern = {"cn": (cn_bytes, cn_ms / args.steps), "vn": (vn_bytes, vn_ms / args.steps)}
@@ -384,7 +386,9 @@ def main():
                        "max_iterations": MAX_ITER, "threshold": THRESHOLD, "accurate_qber": acc_q,
                        "frames_per_tile": inf["frames_per_tile"], "pool_tiles": inf["pool_tiles"],
                        "pool_bytes": inf["pool_bytes"],
-                       "decoder_path": "on-chip min-sum (frame state in shared memory)" if onchip else "streaming (messages in HBM)",
+                       "decoder_path": (("on-chip min-sum" if alg >= 2 else "on-chip sum-product") + " (frame state in shared memory)")
+                                       if onchip else "streaming (messages in HBM)",
+                       "onchip_threads": inf.get("onchip_threads") if onchip else None,
                        "l2_policy": ("inputs larger than L2: %.0f MB of packed keys in + decisions out per step, read once; decoder "
                                      "state is in shared memory" % (3 * F * words * 4 / 1e6)) if onchip else
                                     ("inputs larger than L2 (message pool %.1f GB >> 126 MB)" % (inf["pool_bytes"] / 1e9)),

@@ -41,18 +41,36 @@ __device__ __forceinline__ Vec<T, V> lane_llr(const StepArgs<T> &a, int tile, in
 
 // tanh / atanh flavours.
 //  ALG 0, double messages: libm-accurate double evaluation (parity mode).
-//  ALG 0, float messages:  CUDA's float tanhf / atanhf (<= 2-3 ulp) on the FMA/ALU pipes. An earlier version evaluated
+//  ALG 0, float messages:  float tanh (spa_tanh_half_f32, <= 3 ulp) and a fused divide + logarithm for 2 atanh (RowState::emit).
+//         An earlier version evaluated
 //         them in double on the float value (bit-equal to the f32 oracle) but spent 92 % of the SPA step in FP64
 //         transcendentals (2.1 s of a 2.3 s step); the float versions keep >= 99 % equal iteration counts against the
 //         float64 reference (tests/test_gpu_large.py) at a tenth of the time.
 //  ALG 1: the reference's piecewise-linear tables (qkd_ldpc_algorithm.cpp:146-172), written branch-free: slope and
 //         intercept are selected with the same `<` comparisons (a NaN fails them all and lands in the last segment,
 //         like the reference's else-chain), then one multiply and one add -- the same two roundings as the C++ code.
+// tanh(m / 2) in float32, <= 3 ulp: 1 - 2 / (exp(2|h|) + 1) with the sign of h for |h| >= 0.6 (exp2 and reciprocal on the
+// MUFU unit; exp = +inf gives exactly 1), an odd minimax polynomial h + h u p(u), u = h^2, below (coefficients fitted
+// for this file: tools/fit_tanh_poly.py). Both branches are evaluated and selected, NaN falls through to the polynomial.
+__device__ __forceinline__ float spa_tanh_half_f32(float m) {
+    const float h = 0.5f * m, ah = fabsf(h);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ah * 2.885390043f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    const float big = copysignf(fmaf(-2.f, r, 1.f), h);
+    const float u = h * h;
+    float p = fmaf(u, 0.015640417113900185f, -0.052231062203645706f);
+    p = fmaf(u, p, 0.13313519954681396f);
+    p = fmaf(u, p, -0.33332622051239014f);
+    const float small = fmaf(h, p * u, h);
+    return (ah >= 0.6f) ? big : small;
+}
+
 template <typename T, int ALG>
 __device__ __forceinline__ T cn_tanh_half(T x) {
     const T h = x / (T)2;
     if constexpr (ALG == 0) {
-        if constexpr (sizeof(T) == 4) return tanhf(h);
+        if constexpr (sizeof(T) == 4) return spa_tanh_half_f32(x);
         else return (T)tanh((double)h);
     } else {
         const T ax = fabs(h);

@@ -126,10 +126,12 @@ def test_remove_bits_equals_reference_semantics(q, name, n_remove):
             handle(q, name).remove_bits(bits, rm[::-1].copy())
 
 
-@pytest.mark.parametrize("alg,name", [(5, "I80"), (2, "K1_5"), (0, "K1_5")])
+@pytest.mark.parametrize("alg,name", [(5, "I80"), (2, "K1_5"), (0, "K1_5"), (1, "A82"), (0, "I80")])
 def test_run_trials_multi_equals_one_call_per_combination(q, alg, name):
     """qkdldpc_run_trials_multi: a whole sweep (different QBER, scaling factors, punctured / shortened lists, seed offsets)
-    in ONE generate + ONE decode launch; alg 0 exercises the fallback (one combination after the other)."""
+    in ONE generate + ONE decode launch (on-chip min-sum and sum-product kernels); SPA on the irregular n = 10240 code
+    does not fit on chip and exercises the fallback (one combination after the other). The streaming path must give the
+    same per-frame results."""
     from qkd_ldpc_v_b200 import hostlib
     arr = util.code_arrays(name)
     rng = np.random.default_rng(alg)
@@ -148,4 +150,10 @@ def test_run_trials_multi_equals_one_call_per_combination(q, alg, name):
                          punctured_bits=cb["punctured_bits"], shortened_bits=cb["shortened_bits"], want_bits=False)
         assert (it[k] == r.iterations_num).all() and (fl[k] == r.flags).all(), k
         assert (tl[k] == r.tally).all() and acc[k] == r.info["accurate_qber"], k
+        if k % 4 == 1:
+            rs = handle(q, name, decoder_path=1).run_trials(seeds, cb["QBER"], (cb["primary"], cb["secondary"]), cfg,
+                                                            seed_offset=cb["seed_offset"], punctured_bits=cb["punctured_bits"],
+                                                            shortened_bits=cb["shortened_bits"], want_bits=False)
+            assert rs.info["last_path"] == 1
+            assert (it[k] == rs.iterations_num).all() and (fl[k] == rs.flags).all(), k
     assert 0 < (fl & 1).sum() < fl.size
