@@ -84,8 +84,9 @@ typedef struct qkdldpc_options {
     int32_t steps_per_poll; /* decoder iterations launched between two host checks of the done counter       */
     int32_t frames_per_lane_f32; /* 1, 2 or 4 (tile = 32 x this many frames); 0 = auto: 4, SPA variants 2   */
     int32_t use_graph;      /* 1 (default): replay one captured CUDA graph per poll interval; -1: plain launches */
-    int32_t decoder_path;   /* 0 auto; 1 streaming kernels (messages in HBM); 2 on-chip min-sum (frame state in shared
-                               memory; float32 min-sum family, check degrees <= 64, n < 65535) or QKDLDPC_ERR_INVALID */
+    int32_t decoder_path;   /* 0 auto; 1 streaming kernels (messages in HBM); 2 on-chip kernels (frame state in shared
+                               memory; float32 messages, check degrees <= 64, n < 65535; SPA variants: 4 E + 4 n bytes
+                               must fit 227 KB) or QKDLDPC_ERR_INVALID when the code / parameters are not eligible */
     int32_t onchip_threads; /* CTA size of the on-chip kernels (multiple of 32; min-sum <= 768, sum-product <= 1024); 0 = auto */
     int32_t tail_compaction; /* streaming path: 0 (default) move the stragglers of a draining batch into few tiles; -1 never */
     int32_t reserved[2];
