@@ -187,7 +187,7 @@ def test_adaptive_bob_already_correct(q):
 
 
 @pytest.mark.parametrize("alg", [0, 1])
-@pytest.mark.parametrize("name,qber", [("K1_5", 0.02), ("K1_4", 0.03), ("A82", 0.0162), ("N100", 0.05)])
+@pytest.mark.parametrize("name,qber", [("K1_5", 0.02), ("K1_4", 0.03), ("K1_hi", 0.005), ("A82", 0.0162), ("N100", 0.05)])
 def test_onchip_spa_equals_streaming(q, name, qber, alg):
     """The on-chip sum-product kernel rebuilds b2c = clamp(L - c2b) from the bit totals instead of storing it; operands
     and order are those of the streaming kernels, so iterations, flags and words must be identical."""
