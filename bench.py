@@ -69,6 +69,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = None
 
     def start(self):
         try:
@@ -82,23 +83,38 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        """Start of the timed region. nvidia-smi needs about a second to deliver its first sample, so the process is
+        started before the warm-up; only samples taken after this mark are used."""
+        self.t_begin = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.time()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        window = "timed region"
+        rows = [r for t, r in self.rows if self.t_begin is None or t >= self.t_begin]
+        if not rows and self.rows:
+            # a timed region shorter than the sampling period: the GPU ran the same steps during the warm-up just
+            # before it, so the last samples before the end of the region stand in (and the window says so)
+            rows = [r for t, r in self.rows if t <= t_end][-3:]
+            window = "warm-up + timed region (timed region shorter than the 100 ms sampling period)"
+        self.rows = rows
+        self.window = window
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [nm for k, nm in enumerate(names) if any(len(r) >= 8 and r[4 + k].lower() == "active" for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": self.window, "reasons": reasons}
 
 
 def measured_peak():
@@ -249,14 +265,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     # ---- timed region: device-resident inputs, CUDA events on the launching stream, per-kernel events on ----------
     code.set_profiling(True)
-    sampler = ClockSampler(local_rank)
     l0 = code.info()["kernel_launches"]
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     cn_ms = vn_ms = sc_ms = batch_ms = 0.0
