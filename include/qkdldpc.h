@@ -158,6 +158,14 @@ QKDLDPC_API int qkdldpc_decode_batch_device(qkdldpc_code *code, const qkdldpc_pa
 QKDLDPC_API int qkdldpc_generate_keys_device(qkdldpc_code *code, int64_t n_frames, double qber, uint64_t seed,
                                  uint32_t *d_alice_bits, uint32_t *d_bob_bits, double *accurate_qber_out);
 
+/* Throughput entry point (north_star: "throughput is measured on synthetic keys"): generates n_frames synthetic key pairs
+ * on the device as qkdldpc_generate_keys_device does, decodes them with `params`, and returns the tally vector (HOST,
+ * qkdldpc_tally_len() entries, may be NULL) and the decode time in seconds (CUDA events around the decode of the
+ * device-resident frames; key generation excluded). No reference equivalent: the CPU program times each run_trial
+ * (simulation.cpp:559-568). */
+QKDLDPC_API int qkdldpc_bench_synthetic(qkdldpc_code *code, const qkdldpc_params *params, int64_t n_frames, double qber,
+                            uint64_t seed, uint64_t *tally, double *seconds_out);
+
 /* Trial inputs generated ON THE DEVICE, bit-identical to what the reference's run_trial builds on the CPU for the
  * same per-trial seed (simulation.cpp:549-555): prng = Xoshiro256++(trial_seeds[f] + seed_offset) -- seed_offset is the
  * running combination index the reference adds (simulation.cpp:743) --, fill_random_bits, inject_errors (libstdc++'s

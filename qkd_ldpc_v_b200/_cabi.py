@@ -51,6 +51,8 @@ SYMBOLS = {
                                               C.c_int32, _VP, C.c_int32, _VP, _VP, _VP, _VP]),
     "qkdldpc_generate_keys_device": (C.c_int, [_VP, C.c_int64, C.c_double, C.c_uint64, _VP, _VP,
                                                C.POINTER(C.c_double)]),
+    "qkdldpc_bench_synthetic": (C.c_int, [_VP, C.POINTER(Params), C.c_int64, C.c_double, C.c_uint64, _VP,
+                                          C.POINTER(C.c_double)]),
     "qkdldpc_generate_trial_inputs_device": (C.c_int, [_VP, C.c_int64, _VP, C.c_uint64, C.c_double, _VP, C.c_int32, _VP,
                                                        C.c_int32, _VP, _VP, C.POINTER(C.c_double)]),
     "qkdldpc_run_trials": (C.c_int, [_VP, C.POINTER(Params), C.c_int64, _VP, C.c_uint64, C.c_double, _VP, C.c_int32, _VP,

@@ -756,6 +756,49 @@ int qkdldpc_run_trials(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_trial
     return QKDLDPC_OK;
 }
 
+// synthetic keys generated on the device, decoded, timed -- the throughput entry point.
+int qkdldpc_bench_synthetic(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, double qber, uint64_t seed,
+                            uint64_t *tally, double *seconds_out) {
+    int rc = check_params(c, P, n_frames);
+    if (rc) return rc;
+    const int64_t tl = qkdldpc_tally_len(P->max_iterations);
+    if (seconds_out) *seconds_out = 0.;
+    if (n_frames == 0) {
+        if (tally) memset(tally, 0, tl * sizeof(uint64_t));
+        return QKDLDPC_OK;
+    }
+    const size_t words = (size_t)(c->n + 31) / 32, tot = (size_t)n_frames * words;
+    CK(cudaSetDevice(c->device));
+    CK(c->st_alice.reserve(tot));
+    CK(c->st_bob.reserve(tot));
+    double acc = 0.;
+    rc = qkdldpc_generate_keys_device(c, n_frames, qber, seed, c->st_alice.p, c->st_bob.p, &acc);
+    if (rc) return rc;
+    if (acc == 0.) return fail(QKDLDPC_ERR_INVALID, "Key size '%d' is too small for QBER.", c->n);
+    CK(c->st_qber.reserve(1));
+    CK(c->st_iters.reserve(n_frames));
+    CK(c->st_flags.reserve(n_frames));
+    CK(c->st_tally.reserve(tl));
+    cudaStream_t s = c->stream;
+    CK(cudaMemcpyAsync(c->st_qber.p, &acc, sizeof(double), cudaMemcpyHostToDevice, s));
+    cudaEvent_t t0 = nullptr, t1 = nullptr;   // the handle's own events are used inside the decode call
+    CK(cudaEventCreate(&t0));
+    CK(cudaEventCreate(&t1));
+    cudaEventRecord(t0, s);
+    rc = qkdldpc_decode_batch_device(c, P, n_frames, c->st_alice.p, c->st_bob.p, c->st_qber.p, 1, nullptr, 0, nullptr, 0, nullptr,
+                                     c->st_iters.p, c->st_flags.p, reinterpret_cast<uint64_t *>(c->st_tally.p));
+    cudaEventRecord(t1, s);
+    cudaEventSynchronize(t1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    if (rc) return rc;
+    if (seconds_out) *seconds_out = (double)ms * 1e-3;   // decode only: keys resident in device memory, CUDA events
+    if (tally) CK(cudaMemcpy(tally, c->st_tally.p, tl * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return QKDLDPC_OK;
+}
+
 int qkdldpc_remove_bits(qkdldpc_code *c, int64_t n_frames, const uint32_t *keys, const int32_t *bits_to_remove, int32_t n_remove,
                         uint32_t *out_keys) {
     if (!c) return fail(QKDLDPC_ERR_INVALID, "null code handle");

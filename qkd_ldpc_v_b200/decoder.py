@@ -311,6 +311,15 @@ class LdpcCode:
                     "qkdldpc_generate_keys_device")
         return acc.value
 
+    def bench_synthetic(self, n_frames: int, qber: float, scaling_factors, config: "DecoderConfig", seed: int = 1):
+        """qkdldpc_bench_synthetic: synthetic keys generated on the device, decoded, timed. Returns (tally, seconds)."""
+        P = config.to_params(scaling_factors)
+        tally = np.zeros(tally_len(config.max_iterations), np.uint64)
+        sec = C.c_double()
+        _cabi.check(_cabi.lib().qkdldpc_bench_synthetic(self._h, C.byref(P), int(n_frames), float(qber), int(seed),
+                                                        tally.ctypes.data, C.byref(sec)), "qkdldpc_bench_synthetic")
+        return tally, sec.value
+
     def _as_packed(self, x) -> np.ndarray:
         x = np.asarray(x)
         if x.dtype == np.uint32 and x.ndim == 2 and x.shape[1] == self.words:

@@ -157,3 +157,24 @@ def test_run_trials_multi_equals_one_call_per_combination(q, alg, name):
             assert rs.info["last_path"] == 1
             assert (it[k] == rs.iterations_num).all() and (fl[k] == rs.flags).all(), k
     assert 0 < (fl & 1).sum() < fl.size
+
+
+@pytest.mark.parametrize("alg,fac", [(2, (0.75, 0.0)), (0, (0.0, 0.0))])
+def test_bench_synthetic_entry_point(q, alg, fac):
+    """qkdldpc_bench_synthetic: device-generated synthetic keys, decode, tally + seconds. The tally must
+    be the one decode_batch_device gives on the same synthetic keys (same seed), and the time must be positive."""
+    import torch
+    arr = util.code_arrays("K1_5")
+    h = handle(q, "K1_5")
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32)
+    frames, qber, seed = 700, 0.02, 12345
+    tally, sec = h.bench_synthetic(frames, qber, fac, cfg, seed=seed)
+    assert sec > 0 and tally[0] == frames and 0 < tally[1] <= frames
+    words = (arr["n"] + 31) // 32
+    d_a = torch.empty((frames, words), dtype=torch.int32, device="cuda:0")
+    d_b = torch.empty_like(d_a)
+    acc = h.generate_keys_device(frames, qber, seed, d_a.data_ptr(), d_b.data_ptr())
+    r = h.QKD_LDPC_batch(d_a.cpu().numpy().view(np.uint32), d_b.cpu().numpy().view(np.uint32), acc, fac, cfg)
+    assert (r.tally == tally).all()
+    t0, s0 = h.bench_synthetic(0, qber, fac, cfg)
+    assert s0 == 0 and t0.sum() == 0
