@@ -102,6 +102,20 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     int cn_first[5], cn_count[5], vn_first[5], vn_count[5];
     group(m, rp, qk::cn_bucket_of, row_order, cn_first, cn_count);
     group(n, col_ptr, qk::vn_bucket_of, col_order, vn_first, vn_count);
+    // ELL records of the two narrow variable-node buckets (dv <= 4, dv <= 8): the edge and check ids of item i of bucket b
+    // at [base_b + i * W_b, + W_b), -1 padded, so that vn_kernel_ell needs no col_ptr / csc_edge / csc_row lookups
+    std::vector<int> vn_ell_edge, vn_ell_row;
+    for (int b = 0; b < 2; ++b) {
+        const int W = qk::vn_bucket_max(b);
+        for (int i = 0; i < vn_count[b]; ++i) {
+            const int bit = col_order[vn_first[b] + i], dv = col_ptr[bit + 1] - col_ptr[bit];
+            for (int k = 0; k < W; ++k) {
+                vn_ell_edge.push_back(k < dv ? csc_edge[col_ptr[bit] + k] : -1);
+                vn_ell_row.push_back(k < dv ? csc_row[col_ptr[bit] + k] : -1);
+            }
+        }
+    }
+    if (vn_ell_edge.empty()) { vn_ell_edge.assign(4, -1); vn_ell_row.assign(4, -1); }
 
     // On-chip path layout (onchip_minsum.cuh): rows and bits are split into degree classes; inside a class the nodes are
     // packed into groups of 32 lanes by a greedy conflict-aware heuristic (below); index tables are stored per group in
@@ -376,7 +390,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     cudaError_t e = cudaSuccess;
     if ((e = up(c->row_ptr, rp)) || (e = up(c->col_idx, ci)) || (e = up(c->col_ptr, col_ptr)) ||
         (e = up(c->csc_edge, csc_edge)) || (e = up(c->csc_row, csc_row)) || (e = up(c->row_order, row_order)) ||
-        (e = up(c->col_order, col_order)) || 
+        (e = up(c->col_order, col_order)) || (e = up(c->vn_ell_edge, vn_ell_edge)) || (e = up(c->vn_ell_row, vn_ell_row)) ||
         (oc_ok && ((e = up(c->oc_cn_ginfo, oc_cn_ginfo)) || (e = up(c->oc_cnT, oc_cnT)) || (e = up(c->oc_cn_row, oc_cn_row)) || (e = up(c->oc_vn_ginfo, oc_vn_ginfo)) ||
                    (e = up(c->oc_vn_bit, oc_vn_bit)) || (e = up(c->oc_vT, oc_vT)))) ||
         (sp_ok && ((e = up(c->sp_cn_moff, sp_cn_moff)) || (e = up(c->sp_sv_items, sp_items)) || (e = up(c->sp_sv_group_item0, sp_group_item0)))) ||
@@ -424,7 +438,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     c->row_ptr.release(); c->col_idx.release(); c->col_ptr.release(); c->csc_edge.release(); c->csc_row.release();
-    c->row_order.release(); c->col_order.release();
+    c->row_order.release(); c->col_order.release(); c->vn_ell_edge.release(); c->vn_ell_row.release();
     c->oc_cn_ginfo.release(); c->oc_vn_ginfo.release(); c->oc_cnT.release(); c->oc_cn_row.release(); c->oc_vn_bit.release(); c->oc_vT.release();
     c->oc_cls.release();
     c->sp_cn_moff.release(); c->sp_sv_items.release(); c->sp_sv_chunk.release(); c->sp_sv_group_item0.release();

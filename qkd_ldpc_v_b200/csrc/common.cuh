@@ -93,6 +93,7 @@ struct StepArgs {
     const int *csc_row;    // [nnz]  ... -> check id
     const int *row_order;  // [m]    rows grouped by degree bucket
     const int *col_order;  // [n]    bits grouped by degree bucket
+    const int *vn_ell_edge, *vn_ell_row;   // narrow VN buckets (dv <= 4, dv <= 8): DVMAX edge / check ids per item, -1 padded
     const uint8_t *bitclass;  // [n] 0 payload, 1 punctured, 2 shortened
     // pool (device)
     T *msg;

@@ -77,6 +77,7 @@ struct qkdldpc_code {
     cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {nullptr, nullptr, nullptr};
     // graph (device)
     DevBuf<int> row_ptr, col_idx, col_ptr, csc_edge, csc_row, row_order, col_order;
+    DevBuf<int> vn_ell_edge, vn_ell_row;   // ELL records of the two narrow VN buckets (step_kernels.cuh: vn_kernel_ell)
     int cn_first[5] = {0}, cn_count[5] = {0}, vn_first[5] = {0}, vn_count[5] = {0};   // degree buckets in row/col_order
     // on-chip min-sum path (onchip_minsum.cuh): ELL index arrays per 32-node group; eligible == the graph fits
     bool oc_eligible = false;

@@ -74,14 +74,26 @@ inline int launch_vn_bucket(const qkdldpc_code *c, bool fast, int tiles, cudaStr
     if (cnt == 0) return 0;
     constexpr int threads = vn_threads(sizeof(T), V, DVMAX);
     const dim3 grid(ceil_div(cnt, threads / 32), (unsigned)tiles);
-    if constexpr (sizeof(T) == 4) {
-        if (fast) {
-            vn_kernel<T, V, DVMAX, true><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt);
-            return 1;
+    if constexpr (DVMAX == 4 || DVMAX == 8) {   // narrow buckets: ELL records, two waves of loads (vn_kernel_ell)
+        const int ell_base = (B == 0) ? 0 : c->vn_count[0] * vn_bucket_max(0);
+        if constexpr (sizeof(T) == 4) {
+            if (fast) {
+                vn_kernel_ell<T, V, DVMAX, true><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base);
+                return 1;
+            }
         }
+        vn_kernel_ell<T, V, DVMAX, false><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base);
+        return 1;
+    } else {
+        if constexpr (sizeof(T) == 4) {
+            if (fast) {
+                vn_kernel<T, V, DVMAX, true><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt);
+                return 1;
+            }
+        }
+        vn_kernel<T, V, DVMAX, false><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt);
+        return 1;
     }
-    vn_kernel<T, V, DVMAX, false><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt);
-    return 1;
 }
 // The bucket kernels are latency-bound one by one (48-59 % of DRAM peak each, profiles/r01_c_ncu_summary.md): they touch
 // disjoint bits, so they run CONCURRENTLY -- the widest bucket stays on the main stream, the others fork onto side
@@ -205,6 +217,7 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     a.row_ptr = c->row_ptr.p; a.col_idx = c->col_idx.p; a.col_ptr = c->col_ptr.p;
     a.csc_edge = c->csc_edge.p; a.csc_row = c->csc_row.p;
     a.row_order = c->row_order.p; a.col_order = c->col_order.p;
+    a.vn_ell_edge = c->vn_ell_edge.p; a.vn_ell_row = c->vn_ell_row.p;
     a.bitclass = c->bitclass.p;
     a.msg = reinterpret_cast<T *>(c->msg.p);
     a.bobmask = c->bobmask.p; a.zmask = c->zmask.p; a.synd = c->synd.p; a.par = c->par.p;

@@ -436,4 +436,118 @@ vn_kernel(const StepArgs<T> a, const int first, const int count) {
     else vn_body<T, V, DVMAX, FAST, false>(a, tile, bit, lane, lane_act, act, newm);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K3 for the narrow buckets (DVMAX = 4, 8): the same arithmetic as vn_body, with the loads arranged in TWO dependent
+// round trips instead of six. A bit of 3-4 edges moves only 3-4 KB, so the kernel lives or dies by how many loads are in
+// flight: vn_body chases col_order -> col_ptr -> (bitclass -> bobmask) -> csc_edge -> messages -> csc_row -> RED one after
+// the other (ncu: 75 % of all stall samples sit on those six waits, 4.3 TB/s on the n = 102400 code, while a bare
+// scattered 512-byte read-modify-write kernel reaches 5.7 TB/s, tools/microbench/scatter_chunks.cu). Here everything
+// that depends only on (tile, item) is fetched at once -- tile masks, slot LLR magnitudes, the bit id and the item's
+// ELL record of edge and check ids (vn_ell_edge / vn_ell_row, -1 = padding) -- and everything that needs the bit id or
+// the edge ids in a second wave (bit class, Bob's mask word unconditionally, the messages).
+template <typename T, int V, int DVMAX, bool FAST, bool HASNEW>
+__device__ __forceinline__ void vn_body_ell(const StepArgs<T> &a, int tile, int bit, int lane, bool lane_act,
+                                            const uint32_t (&act)[V], const uint32_t (&newm)[V], const int (&e)[DVMAX],
+                                            const int (&r)[DVMAX], const Vec<T, V> &lp) {
+    constexpr int FT = kWarp * V;
+    T *tbase = a.msg + (size_t)tile * a.e_stride + lane * V;
+    // second wave of loads
+    const uint8_t cls = __ldg(a.bitclass + bit);
+    const Vec<uint32_t, V> bm = *reinterpret_cast<const Vec<uint32_t, V> *>(a.bobmask + ((size_t)tile * a.n + bit) * V);
+    Vec<T, V> c[DVMAX];
+#pragma unroll
+    for (int k = 0; k < DVMAX; ++k)
+        if (lane_act && e[k] >= 0) c[k] = ld_msg<T, V>(tbase + (size_t)e[k] * FT);
+    // a-priori LLR (lane_llr)
+    Vec<T, V> llr;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const T pay = ((bm.v[v] >> lane) & 1u) ? -lp.v[v] : lp.v[v];
+        llr.v[v] = (cls == 0) ? pay : ((cls == 1) ? (T)1e-4 : Lim<T>::max());
+    }
+    Vec<T, V> L = llr;
+    bool isnew[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) isnew[v] = HASNEW && ((newm[v] >> lane) & 1u);
+    if (lane_act) {
+#pragma unroll
+        for (int k = 0; k < DVMAX; ++k)
+            if (e[k] >= 0) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    if constexpr (HASNEW) c[k].v[v] = isnew[v] ? (T)0 : c[k].v[v];
+                    L.v[v] = L.v[v] + c[k].v[v];
+                }
+            }
+#pragma unroll
+        for (int k = 0; k < DVMAX; ++k)
+            if (e[k] >= 0) st_msg<T, V>(tbase + (size_t)e[k] * FT, vn_out<T, V, FAST, HASNEW>(a, L, c[k], llr, isnew));
+    }
+    uint32_t zw = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const uint32_t w = __ballot_sync(0xffffffffu, lane_act && (L.v[v] <= (T)0)) & act[v];
+        if (lane == v) zw = w;
+    }
+    if (lane < V) {
+        a.zmask[((size_t)tile * a.n + bit) * V + lane] = zw;
+        if (zw != 0) {
+#pragma unroll
+            for (int k = 0; k < DVMAX; ++k)
+                if (r[k] >= 0) atomicXor(a.par + ((size_t)tile * a.m + r[k]) * V + lane, zw);
+        }
+    }
+}
+
+// dv <= 4, float32: 6 CTAs of 256 threads per SM (<= 42 registers) -- occupancy is bytes in flight here
+#ifndef QK_VN4_CTAS
+#define QK_VN4_CTAS 6
+#endif
+#ifndef QK_VN8_CTAS
+#define QK_VN8_CTAS 1
+#endif
+__host__ __device__ constexpr int vn_ell_min_ctas(int elem_bytes, int V, int DVMAX) {
+    return (elem_bytes == 4 && DVMAX == 4) ? QK_VN4_CTAS : (elem_bytes == 4 && DVMAX == 8) ? QK_VN8_CTAS : 1;
+}
+template <typename T, int V, int DVMAX, bool FAST>
+__global__ void __launch_bounds__(vn_threads(sizeof(T), V, DVMAX), vn_ell_min_ctas(sizeof(T), V, DVMAX))
+vn_kernel_ell(const StepArgs<T> a, const int first, const int count, const int ell_base) {
+    static_assert(DVMAX == 4 || DVMAX == 8, "ELL records exist for the two narrow buckets");
+    constexpr int FT = kWarp * V;
+    const int tile = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= count) return;
+    // first wave of loads: nothing here depends on another load
+    uint32_t act[V], newm[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        act[v] = a.tile_active[tile * V + v];
+        newm[v] = a.tile_new[tile * V + v];
+    }
+    const int bit = __ldg(a.col_order + first + idx);
+    int e[DVMAX], r[DVMAX];
+    {
+        const int4 *pe = reinterpret_cast<const int4 *>(a.vn_ell_edge + ell_base + (size_t)idx * DVMAX);
+        const int4 *pr = reinterpret_cast<const int4 *>(a.vn_ell_row + ell_base + (size_t)idx * DVMAX);
+#pragma unroll
+        for (int j = 0; j < DVMAX / 4; ++j) {
+            const int4 x = __ldg(pe + j), y = __ldg(pr + j);
+            e[4 * j] = x.x; e[4 * j + 1] = x.y; e[4 * j + 2] = x.z; e[4 * j + 3] = x.w;
+            r[4 * j] = y.x; r[4 * j + 1] = y.y; r[4 * j + 2] = y.z; r[4 * j + 3] = y.w;
+        }
+    }
+    const Vec<T, V> lp = *reinterpret_cast<const Vec<T, V> *>(a.slot_llr + (size_t)tile * FT + lane * V);
+    bool any_act = false, any_new = false, lane_act = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        any_act |= act[v] != 0;
+        any_new |= newm[v] != 0;
+        lane_act |= (act[v] >> lane) & 1u;
+    }
+    if (!any_act) return;
+    if (any_new) vn_body_ell<T, V, DVMAX, FAST, true>(a, tile, bit, lane, lane_act, act, newm, e, r, lp);
+    else vn_body_ell<T, V, DVMAX, FAST, false>(a, tile, bit, lane, lane_act, act, newm, e, r, lp);
+}
+
 }  // namespace qk
