@@ -4,6 +4,7 @@ qkdldpc_sim (C++ host + libqkdldpc_cuda) run the SAME legacy-schema config on th
 are compared field by field and both runs are timed.
 
 Two of BASELINE.json's configs, restricted to the matrices whose graphs ship in tests/golden/codes.npz:
+  nopt_spa / nopt_spalin  `NOPT_R=0,82_SPA.json`, `NOPT_R=0,82_SPA_LIN_APPROX.json` (schema v2), 30 000 trials on A82
   config1k    `config 1k.json`      (schema v1 => SPA), 1k alist codes R = 0.47 / 0.66 / 0.76 / 0.92 at that file's QBERs
   config10k   `config 10k NMSA.json` (schema v1 => NMSA), 10k alist codes R = 0.79 / 0.82 at that file's alpha / QBER
 The reference arm is run with --ref-trials (CPU time!), qkdldpc_sim additionally with the config's full trial count.
@@ -70,6 +71,24 @@ def adaptive_r(coarse):
                                                    efficiency=dict(begin=1.0, end=2.0, step=e)) for r, *_ in rates])
 
 
+def nopt(alg):
+    """`NOPT_R=0,82_SPA.json` / `NOPT_R=0,82_SPA_LIN_APPROX.json` (schema v2: decoding_algorithm + every parameter block;
+    30 000 trials, seed 777, the FER ~ 0.01 operating point QBER 1.62 % of the alist n = 10240 R = 0.82 code). The files
+    say threads_number = 1; the reference arm here uses all cores of the box (results do not depend on it, quirk Q16)."""
+    rng = dict(begin=0.01, end=1.0, step=0.01)
+    return dict(
+        COMMON, simulation_seed=777, decoding_algorithm=alg,
+        min_sum_normalized_parameters=dict(use_alpha_range=False, alpha_range=rng, code_rate_alpha_maps=[dict(code_rate=0.995, alpha=0.8)]),
+        min_sum_offset_parameters=dict(use_beta_range=False, beta_range=rng, code_rate_beta_maps=[dict(code_rate=0.995, beta=1.26)]),
+        adaptive_min_sum_normalized_parameters=dict(use_alpha_range=False, alpha_range=rng, code_rate_alpha_maps=[dict(code_rate=0.995, alpha=0.88)],
+                                                    use_nu_range=False, nu_range=rng, code_rate_nu_maps=[dict(code_rate=0.995, nu=0.79)]),
+        adaptive_min_sum_offset_parameters=dict(use_beta_range=False, beta_range=rng, code_rate_beta_maps=[dict(code_rate=0.995, beta=0.91)],
+                                                use_sigma_range=False, sigma_range=rng, code_rate_sigma_maps=[dict(code_rate=0.995, sigma=1.11)]),
+        code_rate_QBER_maps=[dict(code_rate=0.825, QBER_begin=0.0162, QBER_end=0.0162, QBER_step=0.0005)])
+
+
+CONFIGS["nopt_spa"] = dict(codes=["A82"], trials=30000, cfg=nopt(0))
+CONFIGS["nopt_spalin"] = dict(codes=["A82"], trials=30000, cfg=nopt(1))
 CONFIGS["adaptiveR"] = dict(codes=["I80", "I65", "I50"], trials=100, cfg=adaptive_r(False), ref_cfg=adaptive_r(True))
 
 
