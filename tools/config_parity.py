@@ -5,6 +5,7 @@ are compared field by field and both runs are timed.
 
 Two of BASELINE.json's configs, restricted to the matrices whose graphs ship in tests/golden/codes.npz:
   nopt_spa / nopt_spalin  `NOPT_R=0,82_SPA.json`, `NOPT_R=0,82_SPA_LIN_APPROX.json` (schema v2), 30 000 trials on A82
+  config100k / config100k_nmsa  `config 100k.json` (schema v1 => SPA as shipped; NMSA variant), the n = 102400 R = 0.49 code
   config1k    `config 1k.json`      (schema v1 => SPA), 1k alist codes R = 0.47 / 0.66 / 0.76 / 0.92 at that file's QBERs
   config10k   `config 10k NMSA.json` (schema v1 => NMSA), 10k alist codes R = 0.79 / 0.82 at that file's alpha / QBER
 The reference arm is run with --ref-trials (CPU time!), qkdldpc_sim additionally with the config's full trial count.
@@ -87,6 +88,21 @@ def nopt(alg):
         code_rate_QBER_maps=[dict(code_rate=0.825, QBER_begin=0.0162, QBER_end=0.0162, QBER_step=0.0005)])
 
 
+def config_100k(nmsa):
+    """`config 100k.json` (schema v1; SPA as shipped, NMSA as BASELINE.json describes it) on the one n = 102400 code of the
+    golden set (R = 0.49 -> QBER 8.4 %, alpha 0.72), 100 trials, seed 9012025."""
+    return dict(
+        COMMON, simulation_seed=9012025, use_min_sum_normalized_algorithm=nmsa,
+        min_sum_normalized_parameters=dict(use_alpha_range=False, alpha_range=dict(begin=0.01, end=1.0, step=0.01),
+                                           code_rate_alpha_maps=[dict(code_rate=0.36, alpha=0.55), dict(code_rate=0.58, alpha=0.72),
+                                                                 dict(code_rate=0.95, alpha=0.76)]),
+        code_rate_QBER_maps=[dict(code_rate=0.475, QBER_begin=0.089, QBER_end=0.089, QBER_step=0.001),
+                             dict(code_rate=0.495, QBER_begin=0.084, QBER_end=0.084, QBER_step=0.001),
+                             dict(code_rate=0.515, QBER_begin=0.079, QBER_end=0.079, QBER_step=0.001)])
+
+
+CONFIGS["config100k"] = dict(codes=["L100k"], trials=100, cfg=config_100k(False))
+CONFIGS["config100k_nmsa"] = dict(codes=["L100k"], trials=100, cfg=config_100k(True))
 CONFIGS["nopt_spa"] = dict(codes=["A82"], trials=30000, cfg=nopt(0))
 CONFIGS["nopt_spalin"] = dict(codes=["A82"], trials=30000, cfg=nopt(1))
 CONFIGS["adaptiveR"] = dict(codes=["I80", "I65", "I50"], trials=100, cfg=adaptive_r(False), ref_cfg=adaptive_r(True))
