@@ -67,6 +67,21 @@ struct EvPair {
 }  // namespace qkhost
 using namespace qkhost;
 
+namespace qkhost {
+// Host tables of the on-chip kernels as built by build_onchip_tables (onchip_tables.cu).
+struct OnchipTables {
+    bool oc_ok = false, sp_ok = false;   // min-sum / sum-product kernel can address this graph
+    int max_dc = 0, rec_slots = 0, sp_msg_words = 0;
+    std::vector<int> slot0;              // first record slot of every row (+ total)
+    std::vector<int2> cn_ginfo, vn_ginfo;
+    std::vector<uint16_t> cn_row, vn_bit;
+    std::vector<uint2> cnT;
+    std::vector<uint4> vT;
+    std::vector<int> sp_cn_moff, sp_group_item0;
+    std::vector<uint4> sp_items;
+};
+}  // namespace qkhost
+
 struct qkdldpc_code {
     int n = 0, m = 0, device = 0;
     int64_t nnz = 0;
