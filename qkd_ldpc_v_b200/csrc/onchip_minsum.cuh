@@ -45,7 +45,7 @@ struct OnchipArgs {
     int n_groups_cn, n_groups_vn;
     // Index tables: one entry per (group, block of 4 edges, lane), so a lane fetches the indices of 4 edges with ONE
     // 8- or 16-byte load. A group holds 32 rows (bits) of ONE degree; which nodes share a group is chosen on the host
-    // so that the lanes' shared-memory gathers fall into different banks (conflict-aware grouping, api.cu).
+    // so that the lanes' shared-memory gathers fall into different banks (conflict-aware grouping, onchip_tables.cu).
     const int2 *cn_ginfo;       // [groups] {offset into cnT (in uint2), degree of the group's rows}
     const uint16_t *cn_row;     // [groups*32] row handled by (group, lane); padding lanes hold m (a scratch record slot)
     const uint2 *cnT;           // [off + kb*32 + lane] 4 x uint16: bit index of edges 4kb..4kb+3 of that row (padding: 0)
