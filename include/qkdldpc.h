@@ -200,7 +200,7 @@ typedef struct qkdldpc_combination {
 /* The batched run_trial for SEVERAL combinations of one matrix in one call: the rate-adaptation
  * sweeps of the reference run thousands of combinations x ~100 trials, and 100 frames do not fill a B200. All
  * n_combinations x n_trials frames are generated and decoded by ONE launch each (per-frame QBER, scaling factors and
- * punctured / shortened masks); when the on-chip decoder cannot be used (SPA, float64, long codes) the combinations are
+ * punctured / shortened masks); when no on-chip kernel can be used (float64, long codes, SPA on a graph too large for shared memory) the combinations are
  * processed one after the other. params->primary / secondary are ignored. Outputs (HOST, each may be NULL):
  * out_iters / out_flags: n_combinations x n_trials; tallies: n_combinations x qkdldpc_tally_len(); accurate_qber_out:
  * n_combinations. Results are identical to n_combinations calls of qkdldpc_run_trials. */

@@ -24,7 +24,7 @@
 //
 // Eligibility (host): float32 messages, min-sum family with the FAST precondition of run_batch.cuh (no NaN possible),
 // every check degree <= 64 (rows of 33..64 edges own two records), fewer than 65533 records, state fits the 227 KB of
-// shared memory. Everything else (SPA, float64, n = 100k codes) takes the streaming path.
+// shared memory. SPA / SPA-lin-approx have their own on-chip kernel (onchip_spa.cuh); float64 and n = 100k codes stream.
 #pragma once
 #include "common.cuh"
 
