@@ -111,10 +111,24 @@ __global__ void __launch_bounds__(kSchedThreads) sched_kernel(StepArgs<T> a, Bat
         uint32_t acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = 0;
-        const uint32_t *par = a.par + (size_t)tile * a.m * V;
-        for (int j = tid; j < a.m; j += blockDim.x) {
+        // one CTA reads the tile's m x V parity words: on the long codes (m = 52301: 837 KB) this is latency-bound unless
+        // many loads are in flight, so each thread issues 8 independent 4V-byte loads per round
+        const Vec<uint32_t, V> *par = reinterpret_cast<const Vec<uint32_t, V> *>(a.par + (size_t)tile * a.m * V);
+        const int stride = blockDim.x;
+        int j = tid;
+        for (; j + 7 * stride < a.m; j += 8 * stride) {
+            Vec<uint32_t, V> x[8];
 #pragma unroll
-            for (int v = 0; v < V; ++v) acc[v] |= par[(size_t)j * V + v];
+            for (int u = 0; u < 8; ++u) x[u] = par[j + u * stride];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] |= x[u].v[v];
+        }
+        for (; j < a.m; j += stride) {
+            const Vec<uint32_t, V> x = par[j];
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] |= x.v[v];
         }
 #pragma unroll
         for (int v = 0; v < V; ++v) {
