@@ -220,24 +220,38 @@ __global__ void __launch_bounds__(kSchedThreads) sched_move_kernel(StepArgs<T> a
     const int r0 = blockIdx.y * rows_per_part;   // multiple of 32
     __shared__ int s_last;
 
-    // retire
+    // retire: a warp owns 32 consecutive bits; every lane reads its bit's V mask words ONCE (coalesced) and the warp
+    // peels off one ballot per retiring frame -- n * 4V bytes per tile and step, however many frames retire (reading the
+    // masks once per retiring frame cost 32 B of sector traffic per bit and frame: 3.3 MB per frame on the n = 102400 code)
     const int w0 = r0 >> 5, w1 = min(b.words, (r0 + rows_per_part) >> 5);
-    for (int r = 0; r < nret; ++r) {
-        const int s = tw.ret[r] & 255;
-        const long long fr = tw.ret_frame[r];
-        const int v = s % V, l = s / V;
-        const uint32_t *zm = a.zmask + (size_t)tile * a.n * V + v;
-        uint32_t diff = 0;
-        for (int w = w0 + tid; w < w1; w += blockDim.x) {
-            uint32_t word = 0;
-            const int i0 = w * 32;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k)
-                if (i0 + k < a.n) word |= ((zm[(size_t)(i0 + k) * V] >> l) & 1u) << k;
-            if (b.out_bits) b.out_bits[fr * b.words + w] = word;
-            diff |= word ^ b.alice_bits[fr * b.words + w];
+    __shared__ unsigned int s_diff[FT];
+    if (nret > 0) {
+        for (int r = tid; r < nret; r += blockDim.x) s_diff[r] = 0u;
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+        const Vec<uint32_t, V> *zmv = reinterpret_cast<const Vec<uint32_t, V> *>(a.zmask + (size_t)tile * a.n * V);
+        for (int w = w0 + warp; w < w1; w += nwarps) {
+            const int i = w * 32 + lane;
+            Vec<uint32_t, V> z;
+#pragma unroll
+            for (int v = 0; v < V; ++v) z.v[v] = 0u;
+            if (i < a.n) z = zmv[i];
+            for (int r = 0; r < nret; ++r) {
+                const int s = tw.ret[r] & 255, sv = s % V, l = s / V;
+                uint32_t zw = z.v[0];
+#pragma unroll
+                for (int v = 1; v < V; ++v) zw = (sv == v) ? z.v[v] : zw;
+                const uint32_t word = __ballot_sync(0xffffffffu, (zw >> l) & 1u);
+                if (lane == 0) {
+                    const long long fr = tw.ret_frame[r];
+                    if (b.out_bits) b.out_bits[fr * b.words + w] = word;
+                    if (word ^ b.alice_bits[fr * b.words + w]) atomicOr(&s_diff[r], 1u);
+                }
+            }
         }
-        if (__syncthreads_or(diff != 0) && tid == 0) atomicOr(&tw.ret_diff[r], 1u);
+        __syncthreads();
+        for (int r = tid; r < nret; r += blockDim.x)
+            if (s_diff[r]) atomicOr(&tw.ret_diff[r], 1u);
     }
 
     // refill
