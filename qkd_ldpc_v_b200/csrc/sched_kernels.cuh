@@ -254,45 +254,65 @@ __global__ void __launch_bounds__(kSchedThreads) sched_move_kernel(StepArgs<T> a
             if (s_diff[r]) atomicOr(&tw.ret_diff[r], 1u);
     }
 
-    // refill
+    // refill: transpose the new frames' key bits / syndromes into the tile's mask words. A warp owns 32 consecutive rows,
+    // i.e. ONE packed word of every new frame: lane q fetches the word of new frame q (32 frames per round) and the warp
+    // hands the words round by shuffle, instead of every lane loading every frame's word itself.
     if (nnew > 0) {
+        const int lane = tid & 31;
         uint32_t *bm = a.bobmask + (size_t)tile * a.n * V;
-        for (int i = r0 + tid; i < min(a.n, r0 + rows_per_part); i += blockDim.x) {
+        for (int i0 = r0 + (tid & ~31); i0 < min(a.n, r0 + rows_per_part); i0 += blockDim.x) {
+            const int i = i0 + lane;
+            const bool live = i < a.n;
             uint32_t mk[V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) mk[v] = bm[(size_t)i * V + v];
-            for (int q = 0; q < nnew; ++q) {
-                const int s = tw.newslot[q];
-                const uint32_t bit = (b.bob_bits[tw.newframe[q] * b.words + (i >> 5)] >> (i & 31)) & 1u;
-                const int l = s / V;
+            for (int v = 0; v < V; ++v) mk[v] = live ? bm[(size_t)i * V + v] : 0u;
+            for (int qb = 0; qb < nnew; qb += 32) {
+                const int mine = qb + lane;
+                const uint32_t myword = mine < nnew ? b.bob_bits[tw.newframe[mine] * b.words + (i0 >> 5)] : 0u;
+                const int myslot = mine < nnew ? tw.newslot[mine] : 0;
+                const int cnt = min(32, nnew - qb);
+                for (int q = 0; q < cnt; ++q) {
+                    const uint32_t bit = (__shfl_sync(0xffffffffu, myword, q) >> lane) & 1u;
+                    const int s = __shfl_sync(0xffffffffu, myslot, q), l = s / V;
 #pragma unroll
-                for (int v = 0; v < V; ++v)
-                    if (v == s % V) mk[v] = (mk[v] & ~(1u << l)) | (bit << l);
+                    for (int v = 0; v < V; ++v)
+                        if (v == s % V) mk[v] = (mk[v] & ~(1u << l)) | (bit << l);
+                }
             }
+            if (live) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) bm[(size_t)i * V + v] = mk[v];
+                for (int v = 0; v < V; ++v) bm[(size_t)i * V + v] = mk[v];
+            }
         }
         uint32_t *sy = a.synd + (size_t)tile * a.m * V;
         uint32_t *pa = a.par + (size_t)tile * a.m * V;
-        for (int j = r0 + tid; j < min(a.m, r0 + rows_per_part); j += blockDim.x) {
+        for (int j0 = r0 + (tid & ~31); j0 < min(a.m, r0 + rows_per_part); j0 += blockDim.x) {
+            const int j = j0 + lane;
+            const bool live = j < a.m;
             uint32_t ms[V], mp[V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) { ms[v] = sy[(size_t)j * V + v]; mp[v] = pa[(size_t)j * V + v]; }
-            for (int q = 0; q < nnew; ++q) {
-                const int s = tw.newslot[q];
-                const size_t off = tw.newframe[q] * b.swords + (j >> 5);
-                const uint32_t sbit = (b.synd_all[off] >> (j & 31)) & 1u;
-                const uint32_t pbit = sbit;   // the VN-side init XORs the parity of the initial decision on top
-                const int l = s / V;
+            for (int v = 0; v < V; ++v) { ms[v] = live ? sy[(size_t)j * V + v] : 0u; mp[v] = live ? pa[(size_t)j * V + v] : 0u; }
+            for (int qb = 0; qb < nnew; qb += 32) {
+                const int mine = qb + lane;
+                const uint32_t myword = mine < nnew ? b.synd_all[tw.newframe[mine] * b.swords + (j0 >> 5)] : 0u;
+                const int myslot = mine < nnew ? tw.newslot[mine] : 0;
+                const int cnt = min(32, nnew - qb);
+                for (int q = 0; q < cnt; ++q) {
+                    const uint32_t sbit = (__shfl_sync(0xffffffffu, myword, q) >> lane) & 1u;
+                    const uint32_t pbit = sbit;   // the VN-side init XORs the parity of the initial decision on top
+                    const int s = __shfl_sync(0xffffffffu, myslot, q), l = s / V;
 #pragma unroll
-                for (int v = 0; v < V; ++v)
-                    if (v == s % V) {
-                        ms[v] = (ms[v] & ~(1u << l)) | (sbit << l);
-                        mp[v] = (mp[v] & ~(1u << l)) | (pbit << l);
-                    }
+                    for (int v = 0; v < V; ++v)
+                        if (v == s % V) {
+                            ms[v] = (ms[v] & ~(1u << l)) | (sbit << l);
+                            mp[v] = (mp[v] & ~(1u << l)) | (pbit << l);
+                        }
+                }
             }
+            if (live) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) { sy[(size_t)j * V + v] = ms[v]; pa[(size_t)j * V + v] = mp[v]; }
+                for (int v = 0; v < V; ++v) { sy[(size_t)j * V + v] = ms[v]; pa[(size_t)j * V + v] = mp[v]; }
+            }
         }
     }
 
