@@ -92,7 +92,8 @@ __host__ __device__ inline size_t onchip_smem_bytes(int n, int rec_slots, int gr
 // The sum-product kernel (onchip_spa.cuh): msg[msg_words] float instead of the records, the rest alike.
 __host__ __device__ inline size_t onchip_spa_smem_bytes(int n, int msg_words, int groups_cn, int groups_sv) {
     const size_t words = (size_t)(n + 31) / 32;
-    return ((size_t)msg_words + 4) / 4 * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn + (size_t)groups_sv) * 4 + 96;
+    return ((size_t)msg_words + 4) / 4 * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn + (size_t)groups_sv) * 4 + 96 +
+           384;   // + the piecewise-linear tanh table of SPA-lin-approx (LinLut, 360 B)
 }
 constexpr size_t kOnchipSmemMax = 227 * 1024;   // opt-in shared memory per CTA on sm_100
 

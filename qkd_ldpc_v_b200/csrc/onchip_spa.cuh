@@ -29,8 +29,49 @@ namespace qk {
 
 // Shared-memory layout (onchip_spa_smem_bytes, onchip_minsum.cuh):
 //   L[n+1] float (padded to 16 B) | msg[msg_words + 1] float (padded; the last word stays 0) | bob[words] | alice[words] |
-//   syn[groups_cn] | bobg[groups_sv] | misc.  Every word of it has an index < 65536 (227 KB / 4), which is what the
+//   syn[groups_cn] | bobg[groups_sv] | frame id, FrameCtx (64 B) | LinLut (SPA-lin-approx only).  Every word of it has an index < 65536 (227 KB / 4), which is what the
 //   variable-phase table stores.
+
+// SPA-lin-approx: the reference's piecewise-linear tanh (qkd_ldpc_algorithm.cpp:146-160) by table instead of a chain of
+// 7 compares and 14 selects. |h| is bucketed by its exponent and two mantissa bits (quarter octaves from 0.5 to 8, one
+// bucket below, one above that also takes NaN): all breakpoints but 0.9 and 1.2 fall on bucket borders, so a bucket holds
+// at most one breakpoint `thr` and the pair of (slope, intercept) on either side of it. The selected slope and intercept
+// are the reference's constants and the arithmetic is its one multiply and one add, so the result is bit-identical to
+// cn_tanh_half<float, 1> (the streaming kernels keep the select chain; tests compare the two paths frame by frame).
+constexpr int kLinBuckets = 18;
+struct LinLut {
+    float thr[kLinBuckets];        // breakpoint inside the bucket, +inf when there is none
+    float2 ab[2 * kLinBuckets];    // [2 * bucket + (|h| >= thr)] = {slope, intercept}
+};
+__device__ __forceinline__ void spa_lin_lut_fill(LinLut *lut, int tid) {
+    if (tid >= kLinBuckets) return;
+    const float T[7] = {0.5f, 0.9f, 1.2f, 1.75f, 2.5f, 3.5f, 8.f};
+    const float A[8] = {0.9242f, 0.6355f, 0.3912f, 0.1958f, 0.0603f, 0.0115f, 0.0004f, 0.f};
+    const float B[8] = {0.f, 0.1444f, 0.3642f, 0.5986f, 0.8358f, 0.9577f, 0.9967f, 1.f};
+    float lo, hi;                  // the bucket covers [lo, hi)
+    if (tid == 0) { lo = 0.f; hi = 0.5f; }
+    else if (tid == kLinBuckets - 1) { lo = 8.f; hi = __int_as_float(0x7f800000); }
+    else {
+        const int e = (tid - 1) / 4 - 1, q = (tid - 1) % 4;
+        const float scale = (e < 0) ? 0.5f : (float)(1 << e);
+        lo = scale * (1.f + 0.25f * (float)q);
+        hi = scale * (1.f + 0.25f * (float)(q + 1));
+    }
+    int seg = 0;                   // segment of `lo`: number of breakpoints <= lo
+    for (int k = 0; k < 7; ++k) seg += (T[k] <= lo) ? 1 : 0;
+    const bool inside = seg < 7 && T[seg] > lo && T[seg] < hi;
+    lut->thr[tid] = inside ? T[seg] : __int_as_float(0x7f800000);
+    lut->ab[2 * tid] = make_float2(A[seg], B[seg]);
+    lut->ab[2 * tid + 1] = make_float2(A[inside ? seg + 1 : seg], B[inside ? seg + 1 : seg]);
+}
+__device__ __forceinline__ float spa_tanh_lin_lut(const LinLut *lut, float x) {
+    const float h = x / 2.f, ax = fabsf(h);
+    const int idx = min(max((int)(__float_as_uint(ax) >> 21), 503), 520) - 503;   // 0.5 = 504 << 21, 8.0 = 520 << 21
+    const float thr = lut->thr[idx];
+    const float2 ab = lut->ab[2 * idx + ((ax >= thr) ? 1 : 0)];
+    const float r = ab.x * fminf(ax, 8.f) + ab.y;      // |h| >= 8 and NaN: 0 * 8 + 1, as `if (!(ax < 8)) r = 1`
+    return (h < 0.f) ? -r : r;
+}
 
 // Pass 1 of a check node for a block of edges: all gathers first (independent loads in flight together), then the
 // arithmetic, then the stores -- the in-place update would otherwise serialise the edges of a block.
@@ -39,15 +80,27 @@ namespace qk {
 /* thr_b = +inf leave the unclamped LLR (:21-29); tanh(m / 2) kept in place (:58-62), P *= t in edge order               */
 #define QK_SPA_ABSORB(J)                                                                                                \
     zpar ^= (Lv##J <= 0.f) ? 1u : 0u;                                                                                   \
-    const float t##J = st.absorb(clamp_msg(Lv##J - c##J, thr_b));
+    const float t##J = spa_absorb<ALG>(st, lut, clamp_msg(Lv##J - c##J, thr_b));
 #define QK_SPA_STORE(J) mp[(kb + (J)) * 32] = t##J;
 /* pass 2: 2 atanh(P / t), threshold_matrix (:64-74) */
 #define QK_SPA_EMIT(J) const float e##J = clamp_msg(st.emit(mp[(kb + (J)) * 32], syn != 0, 0.f), a.thr);
 #define QK_SPA_ESTORE(J) mp[(kb + (J)) * 32] = e##J;
 
 template <int ALG>
+__device__ __forceinline__ float spa_absorb(RowState<float, ALG> &st, const LinLut *lut, float b2c) {
+    if constexpr (ALG == 1) {
+        const float t = spa_tanh_lin_lut(lut, b2c);
+        st.a *= t;                                                // RowState::absorb with the tabulated tanh
+        return t;
+    } else {
+        return st.absorb(b2c);
+    }
+}
+
+template <int ALG>
 __device__ __forceinline__ bool onchip_spa_cn_phase(const OnchipArgs &a, const float *__restrict__ L, float *__restrict__ msg,
-                                                    const uint32_t *synw, float thr_b, int warp, int lane, int nwarps) {
+                                                    const uint32_t *synw, const LinLut *lut, float thr_b, int warp, int lane,
+                                                    int nwarps) {
     bool unsat = false;
     for (int g = warp; g < a.n_groups_cn; g += nwarps) {
         const int2 gi = __ldg(a.cn_ginfo + g);
@@ -158,9 +211,11 @@ __global__ void __launch_bounds__(1024, 1) onchip_spa_kernel(const OnchipArgs a)
     uint32_t *tail = bobg + a.n_groups_sv;
     long long *s_frame = reinterpret_cast<long long *>(tail + ((2 * a.words + a.n_groups_cn + a.n_groups_sv) & 1));
     FrameCtx *ctx = reinterpret_cast<FrameCtx *>(s_frame + 1);
+    LinLut *lut = reinterpret_cast<LinLut *>(reinterpret_cast<unsigned char *>(s_frame) + 64);   // 8-byte aligned, inside the tail
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const float inf = __int_as_float(0x7f800000);
+    if constexpr (ALG == 1) spa_lin_lut_fill(lut, tid);   // visible to all warps after the first barrier below
 
     for (;;) {
         __syncthreads();   // previous frame fully written out before the state is reused
@@ -222,7 +277,7 @@ __global__ void __launch_bounds__(1024, 1) onchip_spa_kernel(const OnchipArgs a)
         for (int it = 1;; ++it) {
             // the check-node pass of iteration `it`; at it = max_iter + 1 it only serves as the syndrome test of the
             // last hard decision (:101-107)
-            const bool unsat = onchip_spa_cn_phase<ALG>(a, L, msg, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
+            const bool unsat = onchip_spa_cn_phase<ALG>(a, L, msg, synw, lut, it == 1 ? inf : a.thr, warp, lane, nwarps);
             const bool any_unsat = __syncthreads_or(unsat) != 0;
             if (it > 1 && !any_unsat) { success = true; iters = run = it - 1; break; }   // z of iteration it-1
             if (it > a.max_iter) break;

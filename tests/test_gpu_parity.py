@@ -82,7 +82,7 @@ def onchip_eligible(name, alg):
     words = int((groups * 32 * deg).sum())
     vgroups = int(((np.unique(np.diff(arr["col_ptr"]), return_counts=True)[1] + 31) // 32).sum())
     smem = ((words + 4) // 4 * 16 + (arr["n"] + 4) // 4 * 16 +
-            (2 * ((arr["n"] + 31) // 32) + int(groups.sum()) + vgroups) * 4 + 96)
+            (2 * ((arr["n"] + 31) // 32) + int(groups.sum()) + vgroups) * 4 + 96 + 384)
     return smem <= 227 * 1024
 
 
