@@ -36,6 +36,11 @@ WORKLOADS = {
     "A82_spa_q0162": ("A82", 0, 0.0, 0.0, 0.0162, "n=10240 m=1801 alist R=0.82 (E=40960), SPA, QBER 1.62%"),
     "A82_spalin_q0162": ("A82", 1, 0.0, 0.0, 0.0162, "n=10240 m=1801 alist R=0.82, SPA-lin-approx, QBER 1.62%"),
     "L100k_nmsa_q060": ("L100k", 2, 0.72, 0.0, 0.06, "n=102400 m=52301 alist R=0.49 (E=307200), NMSA alpha=0.72, QBER 6%"),
+    "L100k_spa_q084": ("L100k", 0, 0.0, 0.0, 0.084, "n=102400 m=52301 alist R=0.49 (E=307200), SPA, QBER 8.4% (config 100k.json as shipped)"),
+    "A82_omsa_q0154": ("A82", 3, 0.81, 0.0, 0.0154, "n=10240 m=1801 alist R=0.82, OMSA beta=0.81, QBER 1.54%"),
+    "A82_anmsa_q0161": ("A82", 4, 0.80, 0.71, 0.0161, "n=10240 m=1801 alist R=0.82, ANMSA alpha=0.8 nu=0.71, QBER 1.61%"),
+    "A82_aomsa_q0161": ("A82", 5, 0.68, 1.25, 0.0161, "n=10240 m=1801 alist R=0.82, AOMSA beta=0.68 sigma=1.25, QBER 1.61%"),
+    "I80_aomsa_q015": ("I80", 5, 0.70, 0.99, 0.015, "n=10240 m=2048 irregular R=0.8 (E=60430), AOMSA beta=0.70 sigma=0.99, QBER 1.5% (ADAPTIVE R.json family)"),
 }
 MAX_ITER, THRESHOLD = 100, 100.0
 
@@ -48,7 +53,8 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="I80_nmsa_q030", choices=sorted(WORKLOADS))
     p.add_argument("--frames", type=int, default=32768, help="frames per GPU per step")
-    p.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    p.add_argument("--precision", type=int, default=0, choices=[0, 32, 64],
+                   help="message precision: 0 = the library's policy (float64 state for OMSA / ANMSA / AOMSA and SPA on n > 65536)")
     p.add_argument("--pool-slots", type=int, default=0)
     p.add_argument("--frames-per-lane", type=int, default=0)
     p.add_argument("--path", type=int, default=0, choices=[0, 1, 2],
@@ -299,7 +305,8 @@ def main():
     value = n * frames_total * args.steps / (elapsed_ms * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel (algorithmic bytes: SURVEY.md 8d) ---------------------------
-    sz = 4 if args.precision == 32 else 8
+    prec = inf["last_precision"]
+    sz = 4 if prec == 32 else 8
     it_rank = iters_executed / world         # frame-iterations one rank executed in one step
     cn_bytes, vn_bytes = 2 * sz * nnz * it_rank, (2 * sz * nnz + sz * n) * it_rank   # per step, all launches
     peak, peak_src = measured_peak()
@@ -316,7 +323,7 @@ def main():
         k_ms = batch_ms / args.steps
         k_bytes = cn_bytes + vn_bytes
         ach_k = k_bytes / (k_ms * 1e-3) / 1e9
-        kname = "onchip_minsum_kernel" if alg >= 2 else "onchip_spa_kernel"
+        kname = ("onchip_minsum_kernel" if prec == 32 else "onchip_minsum64_kernel") if alg >= 2 else "onchip_spa_kernel"
         tr = traffic_db.get(kname, {}).get("dram_bytes_per_frame")
         roofline = {
             "bound": "hbm", "kernel": f"{kname}<ALG={alg}>", "achieved": ach_k, "peak": peak, "unit": "GB/s",
@@ -324,7 +331,8 @@ def main():
             "bytes_per_launch": k_bytes, "ms_per_launch": k_ms, "launches_per_step": 1,
             "whole_step_frac": (k_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9) / peak,
             "note": "algorithmic bytes = (16*E + 4*N) per frame-iteration (SURVEY.md 8d); this kernel keeps them on chip "
-                    + ("(4N + 16M bytes of shared memory per frame)" if alg >= 2 else "(4N + 4E bytes of shared memory per frame)")
+                    + (("(4N + 16M bytes of shared memory per frame)" if prec == 32 else "(8N + 24M bytes of shared memory per frame)")
+                       if alg >= 2 else "(4N + 4E bytes of shared memory per frame)")
                     + ", DRAM traffic is the packed keys only -- see `traffic`",
         }
     else:
@@ -397,7 +405,7 @@ def main():
         out = {
             "metric": "decoded key Gbit/s", "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == 32 else "f64",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if prec == 32 else "f64",
             "data": "synthetic",
             "config": {"workload": desc, "workload_id": args.workload, "frames_per_step_per_gpu": F,
                        "max_iterations": MAX_ITER, "threshold": THRESHOLD, "accurate_qber": acc_q,

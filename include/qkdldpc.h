@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define QKDLDPC_VERSION 100 /* 0.1.0 */
+#define QKDLDPC_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define QKDLDPC_API __attribute__((visibility("default")))
@@ -73,9 +73,17 @@ typedef struct qkdldpc_params {
     double secondary;          /* nu (ANMSA) or sigma (AOMSA)               = scaling_factors.secondary      */
     int32_t enable_threshold;  /* = CFG.ENABLE_DECODING_ALG_MSG_LLR_THRESHOLD                               */
     double threshold;          /* = CFG.DECODING_ALG_MSG_LLR_THRESHOLD (> 0)                                */
-    int32_t message_precision; /* 32: float32 messages (production); 64: float64 messages (parity mode,
-                                  bit-identical to the reference for the min-sum family)                   */
+    int32_t message_precision; /* 0: automatic (the precision policy below); 32: float32 messages; 64: float64
+                                  messages (bit-identical to the reference for the min-sum family and SPA-lin)  */
 } qkdldpc_params;
+
+/* Precision policy of message_precision == 0 (qkdldpc_effective_precision): the narrowest state that meets the parity
+ * bar against the reference's double arithmetic (>= 99 % equal iteration counts, FER inside its 95 % interval):
+ *   OMSA, ANMSA, AOMSA            -> 64  (offset / adaptive min-sum is chaotic near threshold: float32 agrees on 95.7 ..
+ *                                         99.2 % of the iteration counts only; the float64 on-chip kernel is exact)
+ *   SPA, SPA-lin-approx, n > 65536 -> 64  (float32 has an error floor on the n = 102400 codes near capacity)
+ *   everything else               -> 32  (NMSA: 99.9 - 100 %; SPA / SPA-lin on n <= 65536: 99.9 %)                   */
+QKDLDPC_API int32_t qkdldpc_effective_precision(int32_t algorithm, int32_t n, int32_t message_precision);
 
 /* Tuning knobs of a handle (all optional; 0 = library default). */
 typedef struct qkdldpc_options {
@@ -89,7 +97,11 @@ typedef struct qkdldpc_options {
                                must fit 227 KB) or QKDLDPC_ERR_INVALID when the code / parameters are not eligible */
     int32_t onchip_threads; /* CTA size of the on-chip kernels (multiple of 32; min-sum <= 768, sum-product <= 1024); 0 = auto */
     int32_t tail_compaction; /* streaming path: 0 (default) move the stragglers of a draining batch into few tiles; -1 never */
-    int32_t reserved[2];
+    int32_t compaction_max_ctas; /* tail compaction: cap of the copy kernels' grid (0 = 65535); they stride over the moves */
+    int32_t copy_chunks;    /* qkdldpc_decode_batch (host buffers): number of chunks the batch is cut into so that the
+                               host-to-device copy of chunk k+1 and the device-to-host copy of chunk k-1 overlap the
+                               decoding of chunk k; 0 = auto, 1 = no overlap (copy, decode, copy back)                  */
+    int32_t reserved[4];
 } qkdldpc_options;
 
 QKDLDPC_API int qkdldpc_version(void);
@@ -229,6 +241,8 @@ typedef struct qkdldpc_info {
     double last_cn_ms, last_vn_ms, last_sched_ms; /* only filled when profiling is enabled */
     int32_t last_path;         /* decoder path of the last batch: 1 streaming, 2 on-chip */
     int32_t onchip_threads;    /* CTA size of the last on-chip launch */
+    int32_t last_precision;    /* message precision the last batch ran in (32 / 64), after the precision policy */
+    int32_t reserved;
 } qkdldpc_info;
 QKDLDPC_API int qkdldpc_code_info(const qkdldpc_code *code, qkdldpc_info *info);
 /* When enabled, every kernel of the step loop is bracketed by CUDA events (slow; for bench roofline numbers). */

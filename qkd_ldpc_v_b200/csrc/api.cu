@@ -35,8 +35,8 @@ int check_params(const qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frame
     if (P->algorithm < 0 || P->algorithm > 5) return fail(QKDLDPC_ERR_INVALID, "algorithm %d not in 0..5", P->algorithm);
     if (P->max_iterations < 1 || P->max_iterations > (1 << 20))
         return fail(QKDLDPC_ERR_INVALID, "max_iterations %d out of range", P->max_iterations);
-    if (P->message_precision != 32 && P->message_precision != 64)
-        return fail(QKDLDPC_ERR_INVALID, "message_precision must be 32 or 64");
+    if (P->message_precision != 0 && P->message_precision != 32 && P->message_precision != 64)
+        return fail(QKDLDPC_ERR_INVALID, "message_precision must be 0 (automatic), 32 or 64");
     if (P->enable_threshold && !(P->threshold > 0)) return fail(QKDLDPC_ERR_INVALID, "threshold must be > 0");
     if (n_frames < 0) return fail(QKDLDPC_ERR_INVALID, "negative frame count");
     return QKDLDPC_OK;
@@ -49,6 +49,13 @@ extern "C" {
 int qkdldpc_version(void) { return QKDLDPC_VERSION; }
 const char *qkdldpc_last_error(void) { return last_error().c_str(); }
 int64_t qkdldpc_tally_len(int32_t max_iterations) { return (int64_t)max_iterations + 5; }
+
+int32_t qkdldpc_effective_precision(int32_t algorithm, int32_t n, int32_t message_precision) {
+    if (message_precision != 0) return message_precision;
+    if (algorithm >= 3) return 64;               // OMSA, ANMSA, AOMSA
+    if (algorithm <= 1 && n > 65536) return 64;  // SPA / SPA-lin-approx on long codes
+    return 32;
+}
 
 int qkdldpc_device_count(void) {
     int n = 0;
@@ -236,6 +243,10 @@ int qkdldpc_decode_batch_device(qkdldpc_code *c, const qkdldpc_params *P, int64_
                                 uint8_t *d_out_flags, uint64_t *d_tally) {
     int rc = check_params(c, P, n_frames);
     if (rc) return rc;
+    qkdldpc_params Pe = *P;   // the precision policy resolved (message_precision == 0)
+    Pe.message_precision = qkdldpc_effective_precision(P->algorithm, c->n, P->message_precision);
+    P = &Pe;
+    c->last_precision = Pe.message_precision;
     if (n_frames == 0) {
         CK(cudaSetDevice(c->device));
         if (d_tally)
@@ -426,6 +437,9 @@ int qkdldpc_run_trials_multi(qkdldpc_code *c, const qkdldpc_params *P, int32_t n
     const int64_t tl = qkdldpc_tally_len(P->max_iterations);
     if (n_combinations == 0) return QKDLDPC_OK;
     if (n_trials > 0 && !trial_seeds) return fail(QKDLDPC_ERR_INVALID, "null seed array");
+    qkdldpc_params Pe = *P;   // the precision policy resolved (message_precision == 0)
+    Pe.message_precision = qkdldpc_effective_precision(P->algorithm, c->n, P->message_precision);
+    P = &Pe;
     qkdldpc_params Pk = *P;
     Pk.primary = combos[0].primary;
     Pk.secondary = combos[0].secondary;
@@ -463,8 +477,8 @@ int qkdldpc_run_trials_multi(qkdldpc_code *c, const qkdldpc_params *P, int32_t n
         if (acc[k] == 0.) return fail(QKDLDPC_ERR_INVALID, "Key size '%d' is too small for QBER.", c->n);   // simulation.cpp:556-557
         if (accurate_qber_out) accurate_qber_out[k] = acc[k];
         table[k].qber = acc[k];
-        table[k].primary = (float)combos[k].primary;
-        table[k].secondary = (float)combos[k].secondary;
+        table[k].primary = combos[k].primary;
+        table[k].secondary = combos[k].secondary;
         table[k].has_cls = (combos[k].n_punct > 0 || combos[k].n_short > 0) ? 1 : 0;
         rc = onchip_pack_masks(c->n, combos[k].punct_pos, combos[k].n_punct, combos[k].short_pos, combos[k].n_short,
                                masks.data() + (size_t)k * 2 * words);
@@ -473,6 +487,7 @@ int qkdldpc_run_trials_multi(qkdldpc_code *c, const qkdldpc_params *P, int32_t n
     CK(c->st_iters.reserve(n_frames));
     CK(c->st_flags.reserve(n_frames));
     CK(c->st_tally.reserve((size_t)n_combinations * tl));
+    c->last_precision = Pe.message_precision;
     rc = run_onchip_multi(c, P, n_combinations, n_trials, table.data(), masks.data(), c->st_alice.p, c->st_bob.p, nullptr, 1, nullptr,
                           c->st_iters.p, c->st_flags.p, c->st_tally.p);
     if (rc) return rc;
@@ -614,6 +629,8 @@ int qkdldpc_code_info(const qkdldpc_code *c, qkdldpc_info *info) {
     info->last_batch_ms = c->last_batch_ms;
     info->last_path = c->last_path;
     info->onchip_threads = c->oc_threads;
+    info->last_precision = c->last_precision;
+    info->reserved = 0;
     info->last_cn_ms = c->last_cn_ms; info->last_vn_ms = c->last_vn_ms; info->last_sched_ms = c->last_sched_ms;
     return QKDLDPC_OK;
 }

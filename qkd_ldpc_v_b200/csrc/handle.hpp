@@ -57,6 +57,21 @@ struct DevBuf {
     }
 };
 
+// Precondition of the branch-free min-sum arithmetic (FAST streaming kernels, both on-chip min-sum kernels): no message
+// can become NaN or infinite -- a finite clamp guarantees it; without the clamp it holds when no factor can scale a
+// message up (offset variants subtract; normalized variants need factors <= 1) -- and every factor in use is finite and
+// non-negative: the kernels clamp magnitudes with min(c, thr), which would miss the -thr side of threshold_matrix
+// (array_and_matrix_operations.cpp:953-972) for a negative factor. Anything else takes the EXACT streaming kernels.
+inline bool minsum_factors_ok(const qkdldpc_params *P) {
+    if (P->algorithm < 2) return false;
+    const bool two = P->algorithm >= 4;
+    if (!(P->primary >= 0) || !std::isfinite(P->primary)) return false;
+    if (two && (!(P->secondary >= 0) || !std::isfinite(P->secondary))) return false;
+    if (P->enable_threshold) return std::isfinite(P->threshold);
+    if (P->algorithm == 3 || P->algorithm == 5) return true;
+    return P->primary <= 1.0 && (!two || P->secondary <= 1.0);
+}
+
 constexpr int kSideStreams = 3;
 
 struct EvPair {
@@ -119,6 +134,7 @@ struct qkdldpc_code {
     DevBuf<uint4> sp_sv_items;
     std::vector<int> sp_group_item0;  // first item of every variable-phase group (+ total): chunk boundaries lie on these
     int last_path = 0;                // 1 streaming, 2 on-chip (of the last batch)
+    int last_precision = 0;           // 32 / 64: message precision of the last batch after the policy
     // pool (device, raw bytes reinterpreted per precision)
     DevBuf<unsigned char> msg;
     DevBuf<uint32_t> bobmask, zmask, synd, par, tile_active, tile_new;

@@ -1,6 +1,7 @@
 // On-chip min-sum path: host-side launcher (one persistent kernel per batch) and the four kernel instantiations.
 #include "handle.hpp"
 #include "onchip_minsum.cuh"
+#include "onchip_minsum64.cuh"
 
 namespace qkhost {
 
@@ -10,7 +11,7 @@ cudaError_t onchip_spa_geometry(int alg, int groups_cn, int sms, size_t smem, lo
 cudaError_t onchip_spa_launch(int alg, const OnchipArgs &a, int grid, int threads, size_t smem, cudaStream_t s);
 
 bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
-    if (P->message_precision != 32) return false;
+    if (P->message_precision != 32 && !(P->message_precision == 64 && P->algorithm >= 2)) return false;
     if (P->algorithm < 2) {
         // sum-product kernel (onchip_spa.cuh): one float per edge must fit; NaN / inf messages are handled as in the
         // streaming kernels, so there is no precondition on the parameters
@@ -20,32 +21,42 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
         return onchip_spa_smem_bytes(c->n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv) <= (size_t)dev_smem;
     }
     if (!c->oc_eligible) return false;
-    // same precondition as the FAST streaming kernels (fast_minsum_ok, run_batch.cuh): no message can become NaN / inf
-    if (P->enable_threshold) {
-        if (!std::isfinite(P->threshold)) return false;
-    } else if (P->algorithm == 3 || P->algorithm == 5) {
-        if (!(P->primary >= 0 && P->secondary >= 0)) return false;
-    } else if (!(P->primary <= 1.0 && (P->algorithm != 4 || P->secondary <= 1.0))) {
-        return false;
-    }
+    // same precondition as the FAST streaming kernels (minsum_factors_ok, handle.hpp): no message can become NaN / inf,
+    // and the factors are finite and non-negative (the magnitude clamp min(c, thr) covers only the positive side)
+    if (!minsum_factors_ok(P)) return false;
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return false;
+    if (P->message_precision == 64) return onchip64_smem_bytes(c->n, c->oc_rec_slots, c->oc_groups_cn) <= (size_t)dev_smem;
     return onchip_smem_bytes(c->n, c->oc_rec_slots, c->oc_groups_cn) <= (size_t)dev_smem;
 }
 
 // threads == 0: pick the CTA size that puts the most warps on an SM (shared memory decides how many CTAs fit; ties go
 // to the smaller CTA -- measured: 3 x 512 beats 2 x 768 on n=10240 m=2048, 2 x 768 beats 2 x 512 on m=2201). A CTA
 // never has more lanes than the check phase has rows.
+typedef void (*OnchipKernel)(const OnchipArgs);
+
 template <int ALG, bool WIDE>
-static cudaError_t pick_geometry(int m, int sms, size_t smem, long long n_frames, int *threads, int *grid) {
-    cudaError_t e = cudaFuncSetAttribute(onchip_minsum_kernel<ALG, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static OnchipKernel kernel_of(bool f64) {
+    return f64 ? (OnchipKernel)onchip_minsum64_kernel<ALG, WIDE> : (OnchipKernel)onchip_minsum_kernel<ALG, WIDE>;
+}
+static OnchipKernel kernel_of(int alg, bool wide, bool f64) {
+    switch (alg) {
+        case 2: return wide ? kernel_of<2, true>(f64) : kernel_of<2, false>(f64);
+        case 3: return wide ? kernel_of<3, true>(f64) : kernel_of<3, false>(f64);
+        case 4: return wide ? kernel_of<4, true>(f64) : kernel_of<4, false>(f64);
+        default: return wide ? kernel_of<5, true>(f64) : kernel_of<5, false>(f64);
+    }
+}
+
+static cudaError_t pick_geometry(OnchipKernel kern, int max_threads, int m, int sms, size_t smem, long long n_frames, int *threads, int *grid) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (*threads == 0) {
-        const int cap = std::max(128, std::min(768, (m + 31) / 32 * 32));
+        const int cap = std::max(128, std::min(max_threads, (m + 31) / 32 * 32));
         int best = 0;
         for (int t = 128; t <= cap; t += 128) {
             int k = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, onchip_minsum_kernel<ALG, WIDE>, t, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, kern, t, smem);
             if (e != cudaSuccess) return e;
             if (k * t > best) {
                 best = k * t;
@@ -55,17 +66,11 @@ static cudaError_t pick_geometry(int m, int sms, size_t smem, long long n_frames
         if (*threads == 0) return cudaErrorLaunchOutOfResources;
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, onchip_minsum_kernel<ALG, WIDE>, *threads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, *threads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     *grid = (int)std::min<long long>(n_frames, (long long)per_sm * sms);   // persistent CTAs pull frames from a queue
     return cudaSuccess;
-}
-
-template <int ALG, bool WIDE>
-static cudaError_t launch(const OnchipArgs &a, int grid, int threads, size_t smem, cudaStream_t s) {
-    onchip_minsum_kernel<ALG, WIDE><<<(unsigned)grid, threads, smem, s>>>(a);
-    return cudaGetLastError();
 }
 
 // Variable-phase schedule for `nwarps` warps per CTA: warp w handles entries w, w + nwarps, ... of the returned list.
@@ -153,10 +158,14 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     a.next_frame = c->counters.p;
     a.max_iter = P->max_iterations;
     a.thr = P->enable_threshold ? (float)P->threshold : INFINITY;
+    a.thr64 = P->enable_threshold ? P->threshold : (double)INFINITY;
 
-    const bool spa = P->algorithm < 2;
-    int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(spa ? 1024 : 768, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
-    const size_t smem = spa ? onchip_spa_smem_bytes(n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv) : onchip_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn);
+    const bool spa = P->algorithm < 2, f64 = P->message_precision == 64;
+    const int max_threads = (spa || f64) ? 1024 : 768;
+    int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(max_threads, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
+    const size_t smem = spa   ? onchip_spa_smem_bytes(n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv)
+                        : f64 ? onchip64_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn)
+                              : onchip_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn);
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 
@@ -190,12 +199,8 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         return onchip_finish(c, grid, threads, smem);
     }
     const bool wide = c->oc_max_dc > 32;   // rows of 33..64 edges: two records per row, separate kernel instantiation
-    switch (P->algorithm) {
-        case 2: e = wide ? pick_geometry<2, true>(m, sms, smem, n_frames, &threads, &grid) : pick_geometry<2, false>(m, sms, smem, n_frames, &threads, &grid); break;
-        case 3: e = wide ? pick_geometry<3, true>(m, sms, smem, n_frames, &threads, &grid) : pick_geometry<3, false>(m, sms, smem, n_frames, &threads, &grid); break;
-        case 4: e = wide ? pick_geometry<4, true>(m, sms, smem, n_frames, &threads, &grid) : pick_geometry<4, false>(m, sms, smem, n_frames, &threads, &grid); break;
-        default: e = wide ? pick_geometry<5, true>(m, sms, smem, n_frames, &threads, &grid) : pick_geometry<5, false>(m, sms, smem, n_frames, &threads, &grid); break;
-    }
+    const OnchipKernel kern = kernel_of(P->algorithm, wide, f64);
+    e = pick_geometry(kern, max_threads, m, sms, smem, n_frames, &threads, &grid);
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel geometry failed: %s", cudaGetErrorString(e));
     if (c->oc_sched_warps != threads / 32) {   // the variable-phase schedule depends on the number of warps per CTA
         const std::vector<int> sched = vn_schedule(c->oc_vn_degree, threads / 32);
@@ -220,12 +225,8 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     a.vn_bit = c->oc_vn_bit.p;
 
     CK(cudaEventRecord(c->ev0, s));
-    switch (P->algorithm) {
-        case 2: e = wide ? launch<2, true>(a, grid, threads, smem, s) : launch<2, false>(a, grid, threads, smem, s); break;
-        case 3: e = wide ? launch<3, true>(a, grid, threads, smem, s) : launch<3, false>(a, grid, threads, smem, s); break;
-        case 4: e = wide ? launch<4, true>(a, grid, threads, smem, s) : launch<4, false>(a, grid, threads, smem, s); break;
-        default: e = wide ? launch<5, true>(a, grid, threads, smem, s) : launch<5, false>(a, grid, threads, smem, s); break;
-    }
+    kern<<<(unsigned)grid, threads, smem, s>>>(a);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel launch failed: %s", cudaGetErrorString(e));
     return onchip_finish(c, grid, threads, smem);
 }
@@ -240,8 +241,8 @@ int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const
     if (rc) return rc;
     OnchipCombo cb{};
     cb.qber = -1.;   // LLR magnitude from the caller's qber array
-    cb.primary = (float)P->primary;
-    cb.secondary = (float)P->secondary;
+    cb.primary = P->primary;
+    cb.secondary = P->secondary;
     cb.has_cls = (n_punct > 0 || n_short > 0) ? 1 : 0;
     return run_onchip_multi(c, P, 1, n_frames, &cb, masks.data(), d_alice, d_bob, d_qber, qber_is_scalar, d_out_bits, d_out_iters,
                             d_out_flags, d_tally);

@@ -33,9 +33,9 @@ namespace qk {
 typedef unsigned long long u64;
 
 struct OnchipCombo {
-    double qber;              // accurate QBER of the combination; < 0: take the per-frame / scalar `qber` array instead
-    float primary, secondary; // decoding_scaling_factors
-    int has_cls;              // rate adaptation: punctured / shortened masks present
+    double qber;               // accurate QBER of the combination; < 0: take the per-frame / scalar `qber` array instead
+    double primary, secondary; // decoding_scaling_factors (the float32 kernels round them to float)
+    int has_cls;               // rate adaptation: punctured / shortened masks present
     int pad;
 };
 
@@ -80,6 +80,7 @@ struct OnchipArgs {
     u64 *next_frame;
     int max_iter;
     float thr;                  // +inf when the clamp is disabled
+    double thr64;               // the same for the float64 kernel (onchip_minsum64.cuh)
 };
 
 // Shared-memory layout: rec[rec_slots+2] uint4 | L[n+1] float (padded to 16 B) | bob[words] | alice[words] | syn[groups_cn] | misc
@@ -228,7 +229,9 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
 
 __device__ __forceinline__ float onchip_llr(const FrameCtx *ctx, const uint32_t *bobw, uint32_t bit, float lp) {
     const uint32_t w = bit >> 5, s = bit & 31u;
-    float v = ((bobw[w] >> s) & 1u) ? -lp : lp;                // qkd_ldpc_algorithm.cpp:1043-1049
+    // qkd_ldpc_algorithm.cpp:1043-1049; `0 - lp` instead of `-lp`: never -0 (QBER 0.5 gives lp = 0), which the
+    // bit tricks of the check phase rely on -- the decision (L <= 0) is the reference's either way
+    float v = ((bobw[w] >> s) & 1u) ? 0.f - lp : lp;
     if (ctx->has_cls) {
         if ((__ldg(ctx->cls_punct + w) >> s) & 1u) v = 1e-4f;  // punctured: ALMOST_ZERO (:1155)
         else if ((__ldg(ctx->cls_short + w) >> s) & 1u) v = FLT_MAX;   // shortened: largest finite value (:1164)
@@ -303,8 +306,8 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
                 const OnchipCombo cb = a.combos[combo];
                 const double q = cb.qber >= 0. ? cb.qber : (a.qber_is_scalar ? a.qber[0] : a.qber[f]);
                 ctx->lp = (float)log((1. - q) / q);
-                ctx->primary = cb.primary;
-                ctx->secondary = cb.secondary;
+                ctx->primary = (float)cb.primary;
+                ctx->secondary = (float)cb.secondary;
                 ctx->has_cls = cb.has_cls;
                 ctx->cls_punct = a.cls_masks + combo * 2 * a.words;
                 ctx->cls_short = ctx->cls_punct + a.words;

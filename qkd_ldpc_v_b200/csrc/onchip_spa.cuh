@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(1024, 1) onchip_spa_kernel(const OnchipArgs a)
                 const OnchipCombo cb = a.combos[combo];
                 const double q = cb.qber >= 0. ? cb.qber : (a.qber_is_scalar ? a.qber[0] : a.qber[f]);
                 ctx->lp = (float)log((1. - q) / q);
-                ctx->primary = cb.primary;
-                ctx->secondary = cb.secondary;
+                ctx->primary = (float)cb.primary;
+                ctx->secondary = (float)cb.secondary;
                 ctx->has_cls = cb.has_cls;
                 ctx->cls_punct = a.cls_masks + combo * 2 * a.words;
                 ctx->cls_short = ctx->cls_punct + a.words;

@@ -15,10 +15,7 @@ using namespace qk;
 // a finite clamp guarantees it; without the clamp it holds when no factor can scale a message up (offset
 // variants subtract; normalized variants need factors <= 1). SPA can produce NaN (0/0, quirk Q3) -> never fast.
 inline bool fast_minsum_ok(const qkdldpc_params *P) {
-    if (P->message_precision != 32 || P->algorithm < 2) return false;
-    if (P->enable_threshold) return std::isfinite(P->threshold);
-    if (P->algorithm == 3 || P->algorithm == 5) return P->primary >= 0 && P->secondary >= 0;
-    return P->primary <= 1.0 && (P->algorithm != 4 || P->secondary <= 1.0);
+    return P->message_precision == 32 && minsum_factors_ok(P);   // handle.hpp: also rejects negative / non-finite factors
 }
 
 inline unsigned ceil_div(int a, int b) { return (unsigned)((a + b - 1) / b); }
@@ -294,11 +291,20 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
             c->graph_key.clear();
             cudaGraph_t g = nullptr;
             CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            // from here to EndCapture nothing may return early: a failure would leave the handle's stream (and the forked
+            // side streams) in capture mode and every later call on the handle would fail
             for (int k = 0; k < spp; ++k) one_step(s, false);
-            CK(cudaMemcpyAsync(c->h_done, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamEndCapture(s, &g));
-            CK(cudaGraphInstantiate(&c->graph_exec, g, 0));
-            cudaGraphDestroy(g);
+            cudaError_t ce = cudaGetLastError();   // launch errors of the captured kernels
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->h_done, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+            const cudaError_t ee = cudaStreamEndCapture(s, &g);   // always: ends the capture even when it is invalidated
+            if (ce == cudaSuccess) ce = ee;
+            if (ce == cudaSuccess) ce = cudaGraphInstantiate(&c->graph_exec, g, 0);
+            if (g) cudaGraphDestroy(g);
+            if (ce != cudaSuccess) {
+                c->graph_exec = nullptr;
+                cudaGetLastError();
+                return fail(QKDLDPC_ERR_CUDA, "capture of the step graph failed: %s", cudaGetErrorString(ce));
+            }
             c->graph_key = key;
         }
         return QKDLDPC_OK;
@@ -343,7 +349,10 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
             CK(c->compact_plan.reserve(2));
             auto *plan = reinterpret_cast<CompactPlan *>(c->compact_plan.p);
             compact_plan_kernel<FT><<<1, 32, 0, s>>>(cur_tiles, c->slot_frame.p, c->compact_moves.p, plan);
-            const unsigned max_moves = (unsigned)std::min<long long>(remaining, 65535);
+            // both copy kernels stride over plan->n_moves, so a capped grid still moves every frame (a pool of many
+            // thousand tiles of a short code can hold more than 65535 stragglers)
+            const long long move_cap = c->opt.compaction_max_ctas > 0 ? c->opt.compaction_max_ctas : 65535;
+            const unsigned max_moves = (unsigned)std::max<long long>(1, std::min<long long>(remaining, move_cap));
             compact_msg_kernel<T, FT><<<dim3(max_moves, 8), 256, 0, s>>>(c->compact_moves.p, plan, a.msg, a.e_stride, (int)c->nnz);
             compact_mask_kernel<V><<<dim3(max_moves, 4), 256, 0, s>>>(c->compact_moves.p, plan, n, m, a.bobmask, a.zmask, a.synd, a.par);
             compact_finish_kernel<T, V><<<1, 1024, 0, s>>>(c->compact_moves.p, plan, cur_tiles, c->slot_frame.p, c->slot_iter.p, a.slot_llr,

@@ -370,11 +370,13 @@ __global__ void compact_plan_kernel(int tiles, const long long *slot_frame, int2
 // grid = (moves, chunks): messages of the moved frames. Slot position p of a tile <-> message lane p (common.cuh).
 template <typename T, int FT>
 __global__ void __launch_bounds__(256) compact_msg_kernel(const int2 *moves, const CompactPlan *plan, T *msg, long long e_stride, int nnz) {
-    if ((int)blockIdx.x >= plan->n_moves) return;
-    const int2 mv = moves[blockIdx.x];
-    const T *src = msg + (long long)(mv.x / FT) * e_stride + (mv.x % FT);
-    T *dst = msg + (long long)(mv.y / FT) * e_stride + (mv.y % FT);
-    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < nnz; e += gridDim.y * blockDim.x) dst[(long long)e * FT] = src[(long long)e * FT];
+    const int nm = plan->n_moves;
+    for (int k = blockIdx.x; k < nm; k += gridDim.x) {   // grid-stride: the launch may hold fewer CTAs than there are moves
+        const int2 mv = moves[k];
+        const T *src = msg + (long long)(mv.x / FT) * e_stride + (mv.x % FT);
+        T *dst = msg + (long long)(mv.y / FT) * e_stride + (mv.y % FT);
+        for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < nnz; e += gridDim.y * blockDim.x) dst[(long long)e * FT] = src[(long long)e * FT];
+    }
 }
 
 // grid = (moves, chunks): one bit per mask word. Slot p <-> word v = p % V, bit l = p / V (sched_kernel).
@@ -382,23 +384,25 @@ template <int V>
 __global__ void __launch_bounds__(256) compact_mask_kernel(const int2 *moves, const CompactPlan *plan, int n, int m, uint32_t *bobmask,
                                                            uint32_t *zmask, uint32_t *synd, uint32_t *par) {
     constexpr int FT = 32 * V;
-    if ((int)blockIdx.x >= plan->n_moves) return;
-    const int2 mv = moves[blockIdx.x];
-    const int st = mv.x / FT, sp = mv.x % FT, dt = mv.y / FT, dp = mv.y % FT;
-    const int sv = sp % V, sl = sp / V, dv = dp % V, dl = dp / V;
-    auto move_bit = [&](uint32_t *arr, int rows, int r) {
-        const uint32_t bit = (arr[((size_t)st * rows + r) * V + sv] >> sl) & 1u;
-        uint32_t *w = arr + ((size_t)dt * rows + r) * V + dv;
-        if (bit) atomicOr(w, 1u << dl);
-        else atomicAnd(w, ~(1u << dl));
-    };
-    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n + m; i += gridDim.y * blockDim.x) {
-        if (i < n) {
-            move_bit(bobmask, n, i);
-            move_bit(zmask, n, i);
-        } else {
-            move_bit(synd, m, i - n);
-            move_bit(par, m, i - n);
+    const int nm = plan->n_moves;
+    for (int k = blockIdx.x; k < nm; k += gridDim.x) {   // grid-stride over the moves, as in compact_msg_kernel
+        const int2 mv = moves[k];
+        const int st = mv.x / FT, sp = mv.x % FT, dt = mv.y / FT, dp = mv.y % FT;
+        const int sv = sp % V, sl = sp / V, dv = dp % V, dl = dp / V;
+        auto move_bit = [&](uint32_t *arr, int rows, int r) {
+            const uint32_t bit = (arr[((size_t)st * rows + r) * V + sv] >> sl) & 1u;
+            uint32_t *w = arr + ((size_t)dt * rows + r) * V + dv;
+            if (bit) atomicOr(w, 1u << dl);
+            else atomicAnd(w, ~(1u << dl));
+        };
+        for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n + m; i += gridDim.y * blockDim.x) {
+            if (i < n) {
+                move_bit(bobmask, n, i);
+                move_bit(zmask, n, i);
+            } else {
+                move_bit(synd, m, i - n);
+                move_bit(par, m, i - n);
+            }
         }
     }
 }

