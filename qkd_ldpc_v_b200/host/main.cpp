@@ -32,8 +32,9 @@ const char *kHelp =
     "                      is read-only (default: next to the matrix)\n"
     "  --gpus N            shard the trials of every combination over CUDA devices 0..N-1 (default 1)\n"
     "  --devices a,b,...   explicit device list\n"
-    "  --precision 32|64   float32 messages (default) or float64 parity mode (bit-identical to the CPU reference\n"
-    "                      for the min-sum family)\n"
+    "  --precision 0|32|64 0 (default): the library's policy -- float64 state for OMSA / ANMSA / AOMSA and for sum-product\n"
+    "                      decoding of codes longer than 65536 bits, float32 otherwise; 32 / 64 force float32 messages /\n"
+    "                      float64 messages (bit-identical to the CPU reference for the min-sum family)\n"
     "  --chunk-frames K    frames per decode call and device (default 65536)\n"
     "  --concurrent K      combinations decoded concurrently per device (own handle and stream each); default: automatic\n"
     "                      (1 for large trial counts, up to 8 for rate-adaptation sweeps of ~100 trials)\n"
@@ -156,7 +157,8 @@ int main(int argc, char *argv[]) {
             else if (arg == "--wait") wait = true;
             else throw std::runtime_error("unknown option " + arg + " (see --help)");
         }
-        if (dev.message_precision != 32 && dev.message_precision != 64) throw std::runtime_error("--precision must be 32 or 64");
+        if (dev.message_precision != 0 && dev.message_precision != 32 && dev.message_precision != 64)
+            throw std::runtime_error("--precision must be 0, 32 or 64");
         if (results_dir.empty()) results_dir = root / "results";
 
         if (qkdldpc_device_count() <= 0) throw std::runtime_error("no CUDA device available: the decoder has no CPU fallback");

@@ -361,11 +361,11 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
         const std::string name = in.matrix_path.filename().string();
         const CsrGraph g = to_csr_checked(matrix, name);
         if (P0.message_precision == 32 && P0.algorithm <= 1 && matrix.n() > 65536)
-            // measured on the n = 102400 codes at config 100k.json's operating points (profiles/r01_g_config_parity.md):
-            // a few percent of the frames that float64 decodes never converge in float32 (also in a float build of the
-            // reference), so the FER is not the reference's
+            // float32 FORCED where the precision policy would pick float64. Measured on the n = 102400 codes at config
+            // 100k.json's operating points (profiles/r01_g_config_parity.md): a few percent of the frames that float64 decodes
+            // never converge in float32 (also in a float build of the reference), so the FER is not the reference's
             std::fprintf(stderr, "note: %s: sum-product decoding with float32 messages has an error floor on codes this long; "
-                                 "use --precision 64 for the reference's FER\n", name.c_str());
+                                 "the default (--precision 0) uses float64 here\n", name.c_str());
         const size_t n_comb = in.combinations.size();
 
         std::vector<qkdldpc_code *> codes(lanes, nullptr);   // lane l runs on device l % n_dev

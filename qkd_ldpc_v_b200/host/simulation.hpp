@@ -66,7 +66,7 @@ void process_tally(const uint64_t *tally, size_t max_iterations, size_t trials_n
 
 struct device_options {
     std::vector<int> devices{0};     // CUDA devices to shard the trials over (contiguous trial ranges per device)
-    int message_precision = 32;      // 32: float32 messages; 64: float64 parity mode
+    int message_precision = 0;       // 0: the library's precision policy (include/qkdldpc.h); 32 / 64: forced
     int64_t chunk_frames = 65536;    // frames generated / uploaded per qkdldpc_decode_batch call and device
     int64_t pool_bytes = 0;          // 0 = library default
     bool host_keygen = false;        // true: generate the trial inputs on host threads and upload them (cross-check path);
