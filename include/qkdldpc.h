@@ -207,6 +207,9 @@ typedef struct qkdldpc_combination {
     const int32_t *short_pos;  /* H_matrix_params.shortened_bits                                                  */
     int32_t n_short;
     uint64_t seed_offset;      /* curr_sim: added to every trial seed (simulation.cpp:743)                        */
+    const int32_t *remove_pos; /* H_matrix_params.bits_to_remove (strictly ascending; may be NULL with n_remove == 0):  */
+    int32_t n_remove;          /* when given, remove_bits runs on the device after the decoder, as the last step of     */
+    int32_t reserved;          /* QKD_LDPC / QKD_LDPC_RATE_ADAPT (qkd_ldpc_algorithm.cpp:1089-1092, 1218-1220)          */
 } qkdldpc_combination;
 
 /* The batched run_trial for SEVERAL combinations of one matrix in one call: the rate-adaptation
@@ -219,6 +222,18 @@ typedef struct qkdldpc_combination {
 QKDLDPC_API int qkdldpc_run_trials_multi(qkdldpc_code *code, const qkdldpc_params *params, int32_t n_combinations,
                              const qkdldpc_combination *combinations, int64_t n_trials, const uint64_t *trial_seeds,
                              int32_t *out_iters, uint8_t *out_flags, uint64_t *tallies, double *accurate_qber_out);
+
+/* The same call with the protocol's last step included: every combination that carries a removal list (remove_pos /
+ * n_remove: the privacy-maintenance positions, or the punctured + shortened positions of rate adaptation) has its frames'
+ * final keys built on the device by remove_bits -- Alice's (extended) key and bob_solution without the listed positions
+ * (alice_bit_array_pm / bob_bit_array_pm, qkd_ldpc_algorithm.cpp:1089-1092; ..._rb, :1216-1220) -- inside the call, as the
+ * reference's timed region around QKD_LDPC* includes it (simulation.cpp:559-568). out_alice_keys / out_bob_keys: NULL, or
+ * n_combinations HOST pointers (entries may be NULL) receiving n_trials packed frames of n - n_remove bits each.
+ * qkdldpc_run_trials_multi is this call with both NULL. */
+QKDLDPC_API int qkdldpc_run_trials_multi_keys(qkdldpc_code *code, const qkdldpc_params *params, int32_t n_combinations,
+                                  const qkdldpc_combination *combinations, int64_t n_trials, const uint64_t *trial_seeds,
+                                  int32_t *out_iters, uint8_t *out_flags, uint64_t *tallies, double *accurate_qber_out,
+                                  uint32_t *const *out_alice_keys, uint32_t *const *out_bob_keys);
 
 /* remove_bits (array_and_matrix_operations.cpp:259-287; called by QKD_LDPC / QKD_LDPC_RATE_ADAPT after the decoder,
  * qkd_ldpc_algorithm.cpp:1092,1220): deletes the positions `bits_to_remove` (strictly ascending: the privacy-maintenance

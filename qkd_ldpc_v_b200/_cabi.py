@@ -24,7 +24,8 @@ class Options(C.Structure):
 
 class Combination(C.Structure):
     _fields_ = [("qber", C.c_double), ("primary", C.c_double), ("secondary", C.c_double), ("punct_pos", C.c_void_p),
-                ("n_punct", C.c_int32), ("short_pos", C.c_void_p), ("n_short", C.c_int32), ("seed_offset", C.c_uint64)]
+                ("n_punct", C.c_int32), ("short_pos", C.c_void_p), ("n_short", C.c_int32), ("seed_offset", C.c_uint64),
+                ("remove_pos", C.c_void_p), ("n_remove", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -60,6 +61,7 @@ SYMBOLS = {
     "qkdldpc_run_trials": (C.c_int, [_VP, C.POINTER(Params), C.c_int64, _VP, C.c_uint64, C.c_double, _VP, C.c_int32, _VP,
                                      C.c_int32, _VP, _VP, _VP, _VP, C.POINTER(C.c_double)]),
     "qkdldpc_run_trials_multi": (C.c_int, [_VP, C.POINTER(Params), C.c_int32, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP]),
+    "qkdldpc_run_trials_multi_keys": (C.c_int, [_VP, C.POINTER(Params), C.c_int32, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "qkdldpc_remove_bits": (C.c_int, [_VP, C.c_int64, _VP, _VP, C.c_int32, _VP]),
     "qkdldpc_code_info": (C.c_int, [_VP, C.POINTER(Info)]),
     "qkdldpc_code_set_profiling": (C.c_int, [_VP, C.c_int32]),

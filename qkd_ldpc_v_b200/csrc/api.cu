@@ -19,12 +19,12 @@ extern template int run_batch<float, 1>(qkdldpc_code *, const qkdldpc_params *, 
 extern template int run_batch<double, 2>(qkdldpc_code *, const qkdldpc_params *, int64_t, const uint32_t *, const uint32_t *, const double *, int, const int32_t *, int, const int32_t *, int, uint32_t *, int32_t *, uint8_t *, unsigned long long *);
 int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const uint32_t *d_alice, const uint32_t *d_bob,
                const double *d_qber, int qber_is_scalar, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short,
-               uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally);
+               uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally, const HostPipe *pipe);
 bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P);
 int onchip_pack_masks(int n, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short, uint32_t *dst);
 int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int64_t frames_per_combo, const qk::OnchipCombo *combos,
                      const uint32_t *masks, const uint32_t *d_alice, const uint32_t *d_bob, const double *d_qber, int qber_is_scalar,
-                     uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally);
+                     uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally, const HostPipe *pipe);
 }  // namespace qkhost
 
 namespace {
@@ -211,7 +211,9 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->st_flags.release(); c->st_tally.release();
     c->gen_seeds.release(); c->gen_masks.release(); c->gen_scratch.release(); c->gen_combos.release(); c->oc_combos.release();
     c->compact_moves.release(); c->compact_plan.release(); c->sched_work.release(); c->rb_kept.release();
+    c->rb_info.release(); c->st_keys_a.release(); c->st_keys_b.release();
     for (auto &p : c->ev_pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto &ev : c->pipe_ev) cudaEventDestroy(ev);
     if (c->h_done) cudaFreeHost(c->h_done);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -236,11 +238,30 @@ int qkdldpc_code_set_stream(qkdldpc_code *c, void *cuda_stream) {
     return QKDLDPC_OK;
 }
 
+// pipe != nullptr: the frames are still in HOST memory (qkdldpc_decode_batch) and d_alice_bits / d_bob_bits / d_out_* are
+// staging buffers; the on-chip path then copies piece by piece while it decodes (inst_onchip.cu). *used_pipe tells the
+// caller whether that happened (otherwise it has to copy in before and out after, as for the streaming path).
+static int decode_device_impl(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames,
+                              const uint32_t *d_alice_bits, const uint32_t *d_bob_bits, const double *d_qber,
+                              int32_t qber_is_scalar, const int32_t *punct_pos, int32_t n_punct,
+                              const int32_t *short_pos, int32_t n_short, uint32_t *d_out_bits, int32_t *d_out_iters,
+                              uint8_t *d_out_flags, uint64_t *d_tally, const HostPipe *pipe, bool *used_pipe);
+
 int qkdldpc_decode_batch_device(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames,
                                 const uint32_t *d_alice_bits, const uint32_t *d_bob_bits, const double *d_qber,
                                 int32_t qber_is_scalar, const int32_t *punct_pos, int32_t n_punct,
                                 const int32_t *short_pos, int32_t n_short, uint32_t *d_out_bits, int32_t *d_out_iters,
                                 uint8_t *d_out_flags, uint64_t *d_tally) {
+    return decode_device_impl(c, P, n_frames, d_alice_bits, d_bob_bits, d_qber, qber_is_scalar, punct_pos, n_punct, short_pos, n_short,
+                              d_out_bits, d_out_iters, d_out_flags, d_tally, nullptr, nullptr);
+}
+
+static int decode_device_impl(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames,
+                              const uint32_t *d_alice_bits, const uint32_t *d_bob_bits, const double *d_qber,
+                              int32_t qber_is_scalar, const int32_t *punct_pos, int32_t n_punct,
+                              const int32_t *short_pos, int32_t n_short, uint32_t *d_out_bits, int32_t *d_out_iters,
+                              uint8_t *d_out_flags, uint64_t *d_tally, const HostPipe *pipe, bool *used_pipe) {
+    if (used_pipe) *used_pipe = false;
     int rc = check_params(c, P, n_frames);
     if (rc) return rc;
     qkdldpc_params Pe = *P;   // the precision policy resolved (message_precision == 0)
@@ -263,10 +284,17 @@ int qkdldpc_decode_batch_device(qkdldpc_code *c, const qkdldpc_params *P, int64_
     const bool oc = onchip_usable(c, P);
     if (c->opt.decoder_path == 2 && !oc)
         return fail(QKDLDPC_ERR_INVALID, "on-chip path requested but not usable for this code / these parameters");
-    if (oc && c->opt.decoder_path != 1)
+    if (oc && c->opt.decoder_path != 1) {
+        if (used_pipe) *used_pipe = pipe != nullptr;
         return run_onchip(c, P, n_frames, d_alice_bits, d_bob_bits, d_qber, qber_is_scalar, punct_pos, n_punct, short_pos,
-                          n_short, d_out_bits, d_out_iters, d_out_flags, tl);
+                          n_short, d_out_bits, d_out_iters, d_out_flags, tl, pipe);
+    }
     c->last_path = 1;
+    if (pipe) {   // streaming path: the step loop needs every frame's syndrome up front -- copy in first, the caller copies out
+        const size_t tot = (size_t)n_frames * ((size_t)(c->n + 31) / 32);
+        CK(cudaMemcpyAsync(const_cast<uint32_t *>(d_alice_bits), pipe->h_alice, tot * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(const_cast<uint32_t *>(d_bob_bits), pipe->h_bob, tot * 4, cudaMemcpyHostToDevice, c->stream));
+    }
 #define RUN(T, V)                                                                                                   \
     return run_batch<T, V>(c, P, n_frames, d_alice_bits, d_bob_bits, d_qber, qber_is_scalar, punct_pos, n_punct,    \
                            short_pos, n_short, d_out_bits, d_out_iters, d_out_flags, tl)
@@ -310,16 +338,20 @@ int qkdldpc_decode_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_fra
     CK(c->st_flags.reserve(n_frames));
     CK(c->st_tally.reserve(tl));
     cudaStream_t s = c->stream;
-    CK(cudaMemcpyAsync(c->st_alice.p, alice_bits, tot * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->st_bob.p, bob_bits, tot * 4, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c->st_qber.p, qber, nq * sizeof(double), cudaMemcpyHostToDevice, s));
-    rc = qkdldpc_decode_batch_device(c, P, n_frames, c->st_alice.p, c->st_bob.p, c->st_qber.p, qber_is_scalar,
-                                     punct_pos, n_punct, short_pos, n_short, out_bits ? c->st_out.p : nullptr,
-                                     c->st_iters.p, c->st_flags.p, reinterpret_cast<uint64_t *>(c->st_tally.p));
+    // copy / compute overlap (on-chip paths): the batch is cut into pieces, see onchip_launch_all (inst_onchip.cu)
+    HostPipe pipe{alice_bits, bob_bits, out_bits, out_iters, out_flags, 1};
+    pipe.chunks = c->opt.copy_chunks > 0 ? std::min(c->opt.copy_chunks, kMaxPipeChunks) : (n_frames >= 4096 ? 8 : (n_frames >= 1024 ? 2 : 1));
+    bool piped = false;
+    rc = decode_device_impl(c, P, n_frames, c->st_alice.p, c->st_bob.p, c->st_qber.p, qber_is_scalar, punct_pos, n_punct, short_pos,
+                            n_short, out_bits ? c->st_out.p : nullptr, c->st_iters.p, c->st_flags.p,
+                            reinterpret_cast<uint64_t *>(c->st_tally.p), &pipe, &piped);
     if (rc) return rc;
-    if (out_bits) CK(cudaMemcpyAsync(out_bits, c->st_out.p, tot * 4, cudaMemcpyDeviceToHost, s));
-    if (out_iters) CK(cudaMemcpyAsync(out_iters, c->st_iters.p, n_frames * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (out_flags) CK(cudaMemcpyAsync(out_flags, c->st_flags.p, n_frames, cudaMemcpyDeviceToHost, s));
+    if (!piped) {
+        if (out_bits) CK(cudaMemcpyAsync(out_bits, c->st_out.p, tot * 4, cudaMemcpyDeviceToHost, s));
+        if (out_iters) CK(cudaMemcpyAsync(out_iters, c->st_iters.p, n_frames * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (out_flags) CK(cudaMemcpyAsync(out_flags, c->st_flags.p, n_frames, cudaMemcpyDeviceToHost, s));
+    }
     if (tally) CK(cudaMemcpyAsync(tally, c->st_tally.p, tl * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return QKDLDPC_OK;
@@ -415,6 +447,77 @@ int generate_inputs_multi(qkdldpc_code *c, int n_combos, const qkdldpc_combinati
 
 }  // namespace
 
+namespace {
+
+// remove_bits for the frames of a (multi-combination) launch, on the device: plan = every combination's surviving
+// positions back to back + where its final keys go.
+struct RemovePlan {
+    std::vector<int> kept;
+    std::vector<qk::RemoveCombo> info;
+    long long total_words = 0;   // output words per party
+    int max_words_out = 0;
+    bool any = false;
+};
+
+int plan_removal(int n, int64_t trials, int n_combos, const qkdldpc_combination *combos, RemovePlan &pl) {
+    pl.info.assign((size_t)n_combos, qk::RemoveCombo{0, 0, 0, 0, 0});
+    for (int k = 0; k < n_combos; ++k) {
+        const qkdldpc_combination &cb = combos[k];
+        if (cb.n_remove < 0 || cb.n_remove > n || (cb.n_remove > 0 && !cb.remove_pos)) return fail(QKDLDPC_ERR_INVALID, "bad removal list");
+        if (cb.n_remove == 0) continue;
+        qk::RemoveCombo &rc = pl.info[k];
+        rc.kept_off = (int)pl.kept.size();
+        for (int i = 0, r = 0; i < n; ++i) {
+            if (r < cb.n_remove && cb.remove_pos[r] == i) {
+                ++r;
+                if (r < cb.n_remove && cb.remove_pos[r] <= i) return fail(QKDLDPC_ERR_INVALID, "bits_to_remove must be strictly ascending");
+            } else {
+                pl.kept.push_back(i);
+            }
+        }
+        rc.n_keep = (int)pl.kept.size() - rc.kept_off;
+        if (rc.n_keep != n - cb.n_remove) return fail(QKDLDPC_ERR_INVALID, "bits_to_remove must be strictly ascending positions in [0, n)");
+        rc.words_out = (rc.n_keep + 31) / 32;
+        rc.out_off = pl.total_words;
+        pl.total_words += (long long)rc.words_out * trials;
+        pl.max_words_out = std::max(pl.max_words_out, rc.words_out);
+        pl.any = true;
+    }
+    return QKDLDPC_OK;
+}
+
+// Final keys of Alice (from d_alice) and Bob (from d_solution) into c->st_keys_a / st_keys_b; copies them to the host
+// pointers of combinations [0, n_combos) where given.
+int run_removal(qkdldpc_code *c, const RemovePlan &pl, int64_t trials, int n_combos, const uint32_t *d_alice, const uint32_t *d_solution,
+                uint32_t *const *out_a, uint32_t *const *out_b) {
+    if (!pl.any || trials == 0 || pl.max_words_out == 0) return QKDLDPC_OK;
+    cudaStream_t s = c->stream;
+    const int words_in = (c->n + 31) / 32;
+    CK(c->rb_kept.reserve(pl.kept.size()));
+    CK(c->rb_info.reserve(pl.info.size() * sizeof(qk::RemoveCombo)));
+    CK(c->st_keys_a.reserve((size_t)pl.total_words));
+    CK(c->st_keys_b.reserve((size_t)pl.total_words));
+    CK(cudaMemcpyAsync(c->rb_kept.p, pl.kept.data(), pl.kept.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->rb_info.p, pl.info.data(), pl.info.size() * sizeof(qk::RemoveCombo), cudaMemcpyHostToDevice, s));
+    const dim3 grid((unsigned)((int64_t)n_combos * trials), (unsigned)((pl.max_words_out + 7) / 8));
+    const auto *info = reinterpret_cast<const qk::RemoveCombo *>(c->rb_info.p);
+    qk::remove_bits_multi_kernel<<<grid, 256, 0, s>>>(words_in, (long long)trials, c->rb_kept.p, info, d_alice, c->st_keys_a.p);
+    qk::remove_bits_multi_kernel<<<grid, 256, 0, s>>>(words_in, (long long)trials, c->rb_kept.p, info, d_solution, c->st_keys_b.p);
+    c->kernel_launches += 2;
+    CK(cudaGetLastError());
+    for (int k = 0; k < n_combos; ++k) {
+        const qk::RemoveCombo &rc = pl.info[k];
+        const size_t bytes = (size_t)rc.words_out * trials * 4;
+        if (bytes == 0) continue;
+        if (out_a && out_a[k]) CK(cudaMemcpyAsync(out_a[k], c->st_keys_a.p + rc.out_off, bytes, cudaMemcpyDeviceToHost, s));
+        if (out_b && out_b[k]) CK(cudaMemcpyAsync(out_b[k], c->st_keys_b.p + rc.out_off, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));   // the plan's host tables may die after this
+    return QKDLDPC_OK;
+}
+
+}  // namespace
+
 int qkdldpc_generate_trial_inputs_device(qkdldpc_code *c, int64_t n_frames, const uint64_t *trial_seeds, uint64_t seed_offset,
                                          double qber, const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos,
                                          int32_t n_short, uint32_t *d_alice_bits, uint32_t *d_bob_bits, double *accurate_qber_out) {
@@ -428,9 +531,21 @@ int qkdldpc_generate_trial_inputs_device(qkdldpc_code *c, int64_t n_frames, cons
     return generate_inputs_multi(c, 1, &cb, n_frames, trial_seeds, d_alice_bits, d_bob_bits, accurate_qber_out);
 }
 
+static int run_trials_impl(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_trials, const uint64_t *trial_seeds, uint64_t seed_offset,
+                           double qber, const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos, int32_t n_short,
+                           bool keep_bits_on_device, uint32_t *out_bits, int32_t *out_iters, uint8_t *out_flags, uint64_t *tally,
+                           double *accurate_qber_out);
+
 int qkdldpc_run_trials_multi(qkdldpc_code *c, const qkdldpc_params *P, int32_t n_combinations, const qkdldpc_combination *combos,
                              int64_t n_trials, const uint64_t *trial_seeds, int32_t *out_iters, uint8_t *out_flags, uint64_t *tallies,
                              double *accurate_qber_out) {
+    return qkdldpc_run_trials_multi_keys(c, P, n_combinations, combos, n_trials, trial_seeds, out_iters, out_flags, tallies, accurate_qber_out,
+                                         nullptr, nullptr);
+}
+
+int qkdldpc_run_trials_multi_keys(qkdldpc_code *c, const qkdldpc_params *P, int32_t n_combinations, const qkdldpc_combination *combos,
+                                  int64_t n_trials, const uint64_t *trial_seeds, int32_t *out_iters, uint8_t *out_flags, uint64_t *tallies,
+                                  double *accurate_qber_out, uint32_t *const *out_alice_keys, uint32_t *const *out_bob_keys) {
     int rc = check_params(c, P, n_trials);
     if (rc) return rc;
     if (n_combinations < 0 || (n_combinations > 0 && !combos)) return fail(QKDLDPC_ERR_INVALID, "bad combination table");
@@ -454,14 +569,24 @@ int qkdldpc_run_trials_multi(qkdldpc_code *c, const qkdldpc_params *P, int32_t n
         for (int k = 0; k < n_combinations; ++k) {
             Pk.primary = combos[k].primary;
             Pk.secondary = combos[k].secondary;
-            rc = qkdldpc_run_trials(c, &Pk, n_trials, trial_seeds, combos[k].seed_offset, combos[k].qber, combos[k].punct_pos, combos[k].n_punct,
-                                    combos[k].short_pos, combos[k].n_short, nullptr, out_iters ? out_iters + (int64_t)k * n_trials : nullptr,
-                                    out_flags ? out_flags + (int64_t)k * n_trials : nullptr, tallies ? tallies + (int64_t)k * tl : nullptr,
-                                    accurate_qber_out ? accurate_qber_out + k : nullptr);
+            RemovePlan pl;
+            rc = plan_removal(c->n, n_trials, 1, combos + k, pl);
+            if (rc) return rc;
+            rc = run_trials_impl(c, &Pk, n_trials, trial_seeds, combos[k].seed_offset, combos[k].qber, combos[k].punct_pos, combos[k].n_punct,
+                                 combos[k].short_pos, combos[k].n_short, pl.any, nullptr, out_iters ? out_iters + (int64_t)k * n_trials : nullptr,
+                                 out_flags ? out_flags + (int64_t)k * n_trials : nullptr, tallies ? tallies + (int64_t)k * tl : nullptr,
+                                 accurate_qber_out ? accurate_qber_out + k : nullptr);
+            if (rc) return rc;
+            // the combination's frames are still in the staging buffers: Alice's (extended) keys and bob_solution
+            rc = run_removal(c, pl, n_trials, 1, c->st_alice.p, c->st_out.p, out_alice_keys ? out_alice_keys + k : nullptr,
+                             out_bob_keys ? out_bob_keys + k : nullptr);
             if (rc) return rc;
         }
         return QKDLDPC_OK;
     }
+    RemovePlan pl;
+    rc = plan_removal(c->n, n_trials, n_combinations, combos, pl);
+    if (rc) return rc;
     CK(cudaSetDevice(c->device));
     const int words = (c->n + 31) / 32;
     const int64_t n_frames = (int64_t)n_combinations * n_trials;
@@ -488,8 +613,11 @@ int qkdldpc_run_trials_multi(qkdldpc_code *c, const qkdldpc_params *P, int32_t n
     CK(c->st_flags.reserve(n_frames));
     CK(c->st_tally.reserve((size_t)n_combinations * tl));
     c->last_precision = Pe.message_precision;
-    rc = run_onchip_multi(c, P, n_combinations, n_trials, table.data(), masks.data(), c->st_alice.p, c->st_bob.p, nullptr, 1, nullptr,
-                          c->st_iters.p, c->st_flags.p, c->st_tally.p);
+    if (pl.any) CK(c->st_out.reserve(tot));   // bob_solution stays on the device for remove_bits
+    rc = run_onchip_multi(c, P, n_combinations, n_trials, table.data(), masks.data(), c->st_alice.p, c->st_bob.p, nullptr, 1,
+                          pl.any ? c->st_out.p : nullptr, c->st_iters.p, c->st_flags.p, c->st_tally.p, nullptr);
+    if (rc) return rc;
+    rc = run_removal(c, pl, n_trials, n_combinations, c->st_alice.p, c->st_out.p, out_alice_keys, out_bob_keys);
     if (rc) return rc;
     cudaStream_t s = c->stream;
     if (out_iters) CK(cudaMemcpyAsync(out_iters, c->st_iters.p, n_frames * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -502,6 +630,16 @@ int qkdldpc_run_trials_multi(qkdldpc_code *c, const qkdldpc_params *P, int32_t n
 int qkdldpc_run_trials(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_trials, const uint64_t *trial_seeds, uint64_t seed_offset,
                        double qber, const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos, int32_t n_short,
                        uint32_t *out_bits, int32_t *out_iters, uint8_t *out_flags, uint64_t *tally, double *accurate_qber_out) {
+    return run_trials_impl(c, P, n_trials, trial_seeds, seed_offset, qber, punct_pos, n_punct, short_pos, n_short, false, out_bits, out_iters,
+                           out_flags, tally, accurate_qber_out);
+}
+
+// keep_bits_on_device: decode with bob_solution written to the staging buffer even when the caller wants no host copy
+// (remove_bits follows on the device).
+static int run_trials_impl(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_trials, const uint64_t *trial_seeds, uint64_t seed_offset,
+                           double qber, const int32_t *punct_pos, int32_t n_punct, const int32_t *short_pos, int32_t n_short,
+                           bool keep_bits_on_device, uint32_t *out_bits, int32_t *out_iters, uint8_t *out_flags, uint64_t *tally,
+                           double *accurate_qber_out) {
     int rc = check_params(c, P, n_trials);
     if (rc) return rc;
     const int64_t tl = qkdldpc_tally_len(P->max_iterations);
@@ -521,14 +659,14 @@ int qkdldpc_run_trials(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_trial
     if (acc == 0.)   // run_trial throws here (simulation.cpp:556-557)
         return fail(QKDLDPC_ERR_INVALID, "Key size '%d' is too small for QBER.", c->n);
     CK(c->st_qber.reserve(1));
-    if (out_bits) CK(c->st_out.reserve(tot));
+    if (out_bits || keep_bits_on_device) CK(c->st_out.reserve(tot));
     CK(c->st_iters.reserve(n_trials));
     CK(c->st_flags.reserve(n_trials));
     CK(c->st_tally.reserve(tl));
     cudaStream_t s = c->stream;
     CK(cudaMemcpyAsync(c->st_qber.p, &acc, sizeof(double), cudaMemcpyHostToDevice, s));
     rc = qkdldpc_decode_batch_device(c, P, n_trials, c->st_alice.p, c->st_bob.p, c->st_qber.p, 1, punct_pos, n_punct, short_pos, n_short,
-                                     out_bits ? c->st_out.p : nullptr, c->st_iters.p, c->st_flags.p,
+                                     (out_bits || keep_bits_on_device) ? c->st_out.p : nullptr, c->st_iters.p, c->st_flags.p,
                                      reinterpret_cast<uint64_t *>(c->st_tally.p));
     if (rc) return rc;
     if (out_bits) CK(cudaMemcpyAsync(out_bits, c->st_out.p, tot * 4, cudaMemcpyDeviceToHost, s));

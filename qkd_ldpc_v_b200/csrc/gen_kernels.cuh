@@ -229,4 +229,27 @@ __global__ void __launch_bounds__(256) remove_bits_kernel(int words_in, int n_ke
     if (lane == 0) out[f * words_out + w] = word;
 }
 
+// The same for the frames of a multi-combination launch (frame f = combination f / trials, trial f % trials): every
+// combination has its own list of surviving positions (kept[kept_off .. + n_keep)) and its own output region.
+struct RemoveCombo {
+    int kept_off, n_keep, words_out, pad;
+    long long out_off;   // first output word of the combination
+};
+__global__ void __launch_bounds__(256) remove_bits_multi_kernel(int words_in, long long trials, const int *kept, const RemoveCombo *info,
+                                                                const uint32_t *in, uint32_t *out) {
+    const long long f = blockIdx.x;
+    const RemoveCombo rc = info[f / trials];
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= rc.words_out) return;       // also: combinations without a removal list (words_out == 0)
+    const int k = w * 32 + lane;
+    uint32_t bit = 0;
+    if (k < rc.n_keep) {
+        const int p = __ldg(kept + rc.kept_off + k);
+        bit = (in[f * words_in + (p >> 5)] >> (p & 31)) & 1u;
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, bit != 0);
+    if (lane == 0) out[rc.out_off + (f % trials) * rc.words_out + w] = word;
+}
+
 }  // namespace qk

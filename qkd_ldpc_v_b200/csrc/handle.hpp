@@ -74,6 +74,17 @@ inline bool minsum_factors_ok(const qkdldpc_params *P) {
 
 constexpr int kSideStreams = 3;
 
+// Host side of a pipelined on-chip batch (qkdldpc_decode_batch with host buffers): the batch is cut into `chunks` pieces;
+// the host-to-device copy of piece k+1 and the device-to-host copy of piece k-1 run on copy streams while piece k decodes.
+struct HostPipe {
+    const uint32_t *h_alice, *h_bob;
+    uint32_t *h_out_bits;
+    int32_t *h_out_iters;
+    uint8_t *h_out_flags;
+    int chunks;
+};
+constexpr int kMaxPipeChunks = 16;
+
 struct EvPair {
     cudaEvent_t a, b;
     int kind;   // 0 CN, 1 VN, 2 sched
@@ -157,6 +168,8 @@ struct qkdldpc_code {
     DevBuf<unsigned char> gen_combos;  // RefKeygenCombo table of the current launch
     DevBuf<uint32_t> gen_masks, gen_scratch;
     DevBuf<int> rb_kept;               // remove_bits: surviving positions
+    DevBuf<unsigned char> rb_info;     // RemoveCombo table of the current launch (gen_kernels.cuh)
+    DevBuf<uint32_t> st_keys_a, st_keys_b;   // final keys after remove_bits (Alice / Bob)
     DevBuf<unsigned char> sched_work;  // TileWork per tile (sched_kernels.cuh)
     DevBuf<int2> compact_moves;        // tail compaction (sched_kernels.cuh)
     DevBuf<int> compact_plan;
@@ -171,6 +184,7 @@ struct qkdldpc_code {
     double last_batch_ms = 0, last_cn_ms = 0, last_vn_ms = 0, last_sched_ms = 0;
     bool profiling = false;
     std::vector<EvPair> ev_pool;
+    std::vector<cudaEvent_t> pipe_ev;   // pipelined host batches: [2k] copy-in of chunk k done, [2k+1] kernel of chunk k done
     size_t ev_used = 0;
 };
 

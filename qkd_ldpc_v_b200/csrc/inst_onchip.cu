@@ -128,22 +128,91 @@ static int onchip_finish(qkdldpc_code *c, int grid, int threads, size_t smem) {
     return QKDLDPC_OK;
 }
 
+// The launch(es) of one on-chip batch on c->stream. Without a HostPipe: ONE persistent kernel over frames that are already
+// in device memory. With one: the batch is cut into pipe->chunks pieces, each its own launch with its own frame queue, on
+// two alternating compute streams -- so the CTAs of piece k+1 take over the SM slots that the draining piece k frees (no
+// tail between pieces) -- with the piece's packed keys copied in on a copy stream before it and its results copied out on a
+// second copy stream after it. Tallies are atomic adds into one vector, so the pieces share it.
+template <typename Launch>
+static int onchip_launch_all(qkdldpc_code *c, const OnchipArgs &a, int grid, int threads, size_t smem, int64_t n_frames, const HostPipe *pipe,
+                             Launch launch) {
+    cudaStream_t s = c->stream;
+    const int K = pipe ? std::max(1, std::min(pipe->chunks, kMaxPipeChunks)) : 1;
+    if (!pipe) {
+        CK(cudaEventRecord(c->ev0, s));
+        const cudaError_t e = launch(a, grid, s);
+        if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel launch failed: %s", cudaGetErrorString(e));
+        return onchip_finish(c, grid, threads, smem);
+    }
+    while (c->pipe_ev.size() < (size_t)2 * K) {
+        cudaEvent_t ev = nullptr;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->pipe_ev.push_back(ev);
+    }
+    cudaStream_t s_in = c->side_streams[0], s_out = c->side_streams[1], s_k[2] = {s, c->side_streams[2]};
+    const size_t words = (size_t)a.words;
+    CK(cudaEventRecord(c->ev0, s));
+    CK(cudaEventRecord(c->ev_fork, s));              // table uploads / counter resets on s come first everywhere
+    CK(cudaStreamWaitEvent(s_in, c->ev_fork, 0));
+    CK(cudaStreamWaitEvent(s_k[1], c->ev_fork, 0));
+    for (int k = 0; k < K; ++k) {
+        const int64_t f0 = n_frames * k / K, f1 = n_frames * (k + 1) / K, cnt = f1 - f0;
+        if (cnt == 0) continue;
+        uint32_t *d_al = const_cast<uint32_t *>(a.alice_bits) + f0 * words, *d_bo = const_cast<uint32_t *>(a.bob_bits) + f0 * words;
+        CK(cudaMemcpyAsync(d_al, pipe->h_alice + f0 * words, (size_t)cnt * words * 4, cudaMemcpyHostToDevice, s_in));
+        CK(cudaMemcpyAsync(d_bo, pipe->h_bob + f0 * words, (size_t)cnt * words * 4, cudaMemcpyHostToDevice, s_in));
+        CK(cudaEventRecord(c->pipe_ev[2 * k], s_in));
+        cudaStream_t st = s_k[k & 1];
+        CK(cudaStreamWaitEvent(st, c->pipe_ev[2 * k], 0));
+        OnchipArgs ak = a;
+        ak.n_frames = cnt;
+        ak.alice_bits = d_al;
+        ak.bob_bits = d_bo;
+        if (!a.qber_is_scalar && a.qber) ak.qber = a.qber + f0;
+        if (a.out_bits) ak.out_bits = a.out_bits + f0 * words;
+        if (a.out_iters) ak.out_iters = a.out_iters + f0;
+        if (a.out_flags) ak.out_flags = a.out_flags + f0;
+        ak.next_frame = c->counters.p + 2 + k;
+        ak.frames_per_combo = n_frames;               // a pipelined batch is a single combination: f / frames_per_combo == 0
+        const cudaError_t e = launch(ak, (int)std::min<int64_t>(cnt, grid), st);
+        if (e != cudaSuccess) {
+            cudaDeviceSynchronize();
+            return fail(QKDLDPC_ERR_CUDA, "on-chip kernel launch failed: %s", cudaGetErrorString(e));
+        }
+        c->kernel_launches += 1;
+        CK(cudaEventRecord(c->pipe_ev[2 * k + 1], st));
+        CK(cudaStreamWaitEvent(s_out, c->pipe_ev[2 * k + 1], 0));
+        if (pipe->h_out_bits && a.out_bits)
+            CK(cudaMemcpyAsync(pipe->h_out_bits + f0 * words, ak.out_bits, (size_t)cnt * words * 4, cudaMemcpyDeviceToHost, s_out));
+        if (pipe->h_out_iters && a.out_iters)
+            CK(cudaMemcpyAsync(pipe->h_out_iters + f0, ak.out_iters, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, s_out));
+        if (pipe->h_out_flags && a.out_flags) CK(cudaMemcpyAsync(pipe->h_out_flags + f0, ak.out_flags, (size_t)cnt, cudaMemcpyDeviceToHost, s_out));
+    }
+    // join: the main stream waits for the other compute stream and for the last copy-out
+    CK(cudaEventRecord(c->ev_join[0], s_k[1]));
+    CK(cudaStreamWaitEvent(s, c->ev_join[0], 0));
+    CK(cudaEventRecord(c->ev_join[1], s_out));
+    CK(cudaStreamWaitEvent(s, c->ev_join[1], 0));
+    c->kernel_launches -= 1;   // onchip_finish counts one
+    return onchip_finish(c, grid, threads, smem);
+}
+
 // One launch over n_combos x frames_per_combo frames. `combos` / `masks` are HOST tables ([n_combos], [n_combos][2][words]);
 // d_tally holds n_combos tally vectors.
 int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int64_t frames_per_combo, const OnchipCombo *combos,
                      const uint32_t *masks, const uint32_t *d_alice, const uint32_t *d_bob, const double *d_qber, int qber_is_scalar,
-                     uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally) {
+                     uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally, const HostPipe *pipe) {
     const int n = c->n, m = c->m, words = (n + 31) / 32;
     const int64_t n_frames = (int64_t)n_combos * frames_per_combo;
     const int tl = (int)qkdldpc_tally_len(P->max_iterations);
     cudaStream_t s = c->stream;
     CK(c->oc_cls.reserve((size_t)n_combos * 2 * words));
     CK(c->oc_combos.reserve((size_t)n_combos * sizeof(OnchipCombo)));
-    CK(c->counters.reserve(2));
+    CK(c->counters.reserve(2 + kMaxPipeChunks));   // [0] frame queue of a single launch, [2 + k] queue of pipeline chunk k
     CK(cudaMemcpyAsync(c->oc_cls.p, masks, (size_t)n_combos * 2 * words * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(c->oc_combos.p, combos, (size_t)n_combos * sizeof(OnchipCombo), cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));   // the caller's host tables may die after this call returns early on an error below
-    CK(cudaMemsetAsync(c->counters.p, 0, 2 * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(c->counters.p, 0, (2 + kMaxPipeChunks) * sizeof(unsigned long long), s));
     if (d_tally) CK(cudaMemsetAsync(d_tally, 0, (size_t)n_combos * tl * sizeof(uint64_t), s));
 
     OnchipArgs a{};
@@ -193,10 +262,8 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         }
         a.cn_moff = c->sp_cn_moff.p; a.sv_items = c->sp_sv_items.p; a.sv_chunk = c->sp_sv_chunk.p; a.msg_words = c->sp_msg_words;
         a.sv_group_item0 = c->sp_sv_group_item0.p; a.n_groups_sv = c->sp_groups_sv;
-        CK(cudaEventRecord(c->ev0, s));
-        e = onchip_spa_launch(P->algorithm, a, grid, threads, smem, s);
-        if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip sum-product kernel launch failed: %s", cudaGetErrorString(e));
-        return onchip_finish(c, grid, threads, smem);
+        auto launch_spa = [&](const OnchipArgs &args, int g, cudaStream_t st) { return onchip_spa_launch(P->algorithm, args, g, threads, smem, st); };
+        return onchip_launch_all(c, a, grid, threads, smem, n_frames, pipe, launch_spa);
     }
     const bool wide = c->oc_max_dc > 32;   // rows of 33..64 edges: two records per row, separate kernel instantiation
     const OnchipKernel kern = kernel_of(P->algorithm, wide, f64);
@@ -224,17 +291,17 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     a.vn_ginfo = c->oc_vn_ginfo.p;
     a.vn_bit = c->oc_vn_bit.p;
 
-    CK(cudaEventRecord(c->ev0, s));
-    kern<<<(unsigned)grid, threads, smem, s>>>(a);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel launch failed: %s", cudaGetErrorString(e));
-    return onchip_finish(c, grid, threads, smem);
+    auto launch_ms = [&](const OnchipArgs &args, int g, cudaStream_t st) {
+        kern<<<(unsigned)g, threads, smem, st>>>(args);
+        return cudaGetLastError();
+    };
+    return onchip_launch_all(c, a, grid, threads, smem, n_frames, pipe, launch_ms);
 }
 
 // The single-combination call of qkdldpc_decode_batch_device.
 int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const uint32_t *d_alice, const uint32_t *d_bob,
                const double *d_qber, int qber_is_scalar, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short,
-               uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally) {
+               uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally, const HostPipe *pipe) {
     const int words = (c->n + 31) / 32;
     std::vector<uint32_t> masks((size_t)2 * words, 0u);
     const int rc = onchip_pack_masks(c->n, punct, n_punct, shortd, n_short, masks.data());
@@ -245,7 +312,7 @@ int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const
     cb.secondary = P->secondary;
     cb.has_cls = (n_punct > 0 || n_short > 0) ? 1 : 0;
     return run_onchip_multi(c, P, 1, n_frames, &cb, masks.data(), d_alice, d_bob, d_qber, qber_is_scalar, d_out_bits, d_out_iters,
-                            d_out_flags, d_tally);
+                            d_out_flags, d_tally, pipe);
 }
 
 }  // namespace qkhost

@@ -254,10 +254,12 @@ class LdpcCode:
         inf["accurate_qber"] = acc.value
         return BatchResult(iters, flags, out_bits, tally, self.n, inf["last_batch_ms"], inf)
 
-    def run_trials_multi(self, trial_seeds, combinations, cfg: Optional[DecoderConfig] = None):
-        """Several combinations of a sweep in one call (``qkdldpc_run_trials_multi``). ``combinations``: list of dicts with
-        keys QBER, primary, secondary, punctured_bits, shortened_bits, seed_offset. Returns (iterations [C][T],
-        flags [C][T], tallies [C][tally_len], accurate_qber [C])."""
+    def run_trials_multi(self, trial_seeds, combinations, cfg: Optional[DecoderConfig] = None, want_keys: bool = False):
+        """Several combinations of a sweep in one call (``qkdldpc_run_trials_multi_keys``). ``combinations``: list of dicts with
+        keys QBER, primary, secondary, punctured_bits, shortened_bits, seed_offset and, optionally, bits_to_remove
+        (``H_matrix_params.bits_to_remove``: ``remove_bits`` then runs on the device as the last step of every trial).
+        Returns (iterations [C][T], flags [C][T], tallies [C][tally_len], accurate_qber [C]) and, with ``want_keys``, two
+        lists of packed final keys per combination (Alice's, Bob's; None where a combination has no removal list)."""
         cfg = cfg or DecoderConfig()
         L = _cabi.lib()
         seeds = np.ascontiguousarray(trial_seeds, np.uint64)
@@ -265,20 +267,31 @@ class LdpcCode:
         p = cfg.to_params((0.0, 0.0))
         table = (_cabi.Combination * max(Cn, 1))()
         keep = []
+        keys_a, keys_b = [None] * Cn, [None] * Cn
+        ptr_a, ptr_b = (C.c_void_p * max(Cn, 1))(), (C.c_void_p * max(Cn, 1))()
         for k, cb in enumerate(combinations):
             pa, pp, np_ = self._poslist(cb.get("punctured_bits", ()))
             sa, sp, ns_ = self._poslist(cb.get("shortened_bits", ()))
-            keep += [pa, sa]
+            ra, rp, nr_ = self._poslist(cb.get("bits_to_remove", ()))
+            keep += [pa, sa, ra]
             table[k] = _cabi.Combination(float(cb["QBER"]), float(cb.get("primary", 0.0)), float(cb.get("secondary", 0.0)), pp, np_, sp,
-                                         ns_, int(cb.get("seed_offset", 0)))
+                                         ns_, int(cb.get("seed_offset", 0)), rp, nr_, 0)
+            if want_keys and nr_ > 0:
+                wo = (self.n - nr_ + 31) // 32
+                keys_a[k], keys_b[k] = np.zeros((T, wo), np.uint32), np.zeros((T, wo), np.uint32)
+                ptr_a[k], ptr_b[k] = keys_a[k].ctypes.data, keys_b[k].ctypes.data
         tl = int(L.qkdldpc_tally_len(p.max_iterations))
         iters = np.zeros((Cn, T), np.int32)
         flags = np.zeros((Cn, T), np.uint8)
         tallies = np.zeros((Cn, tl), np.uint64)
         acc = np.zeros(Cn, np.float64)
-        _cabi.check(L.qkdldpc_run_trials_multi(self._h, C.byref(p), Cn, C.byref(table), T, seeds.ctypes.data, iters.ctypes.data,
-                                               flags.ctypes.data, tallies.ctypes.data, acc.ctypes.data), "qkdldpc_run_trials_multi")
+        _cabi.check(L.qkdldpc_run_trials_multi_keys(self._h, C.byref(p), Cn, C.byref(table), T, seeds.ctypes.data, iters.ctypes.data,
+                                                    flags.ctypes.data, tallies.ctypes.data, acc.ctypes.data,
+                                                    C.cast(ptr_a, C.c_void_p) if want_keys else None,
+                                                    C.cast(ptr_b, C.c_void_p) if want_keys else None), "qkdldpc_run_trials_multi_keys")
         del keep
+        if want_keys:
+            return iters, flags, tallies, acc, keys_a, keys_b
         return iters, flags, tallies, acc
 
     def generate_trial_inputs_device(self, trial_seeds, qber: float, d_alice: int, d_bob: int, seed_offset: int = 0,

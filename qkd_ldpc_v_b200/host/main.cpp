@@ -94,9 +94,9 @@ void write_sidecar(const fs::path &csv, const std::vector<sim_result> &results, 
         const auto &r = results[i];
         char buf[512];
         std::snprintf(buf, sizeof buf,
-                      "  {\"sim_number\": %zu, \"matrix\": \"%s\", \"config_QBER\": %.6g, \"batch_ms\": %.3f, \"decoded_gbit_s\": %.6g, "
-                      "\"iterations_executed\": %llu}%s\n",
-                      r.sim_number, r.matrix_filename.c_str(), r.config_QBER, r.gpu_ms, r.gpu_gbit_s,
+                      "  {\"sim_number\": %zu, \"matrix\": \"%s\", \"config_QBER\": %.6g, \"batch_ms\": %.6f, \"decoded_gbit_s\": %.6g, "
+                      "\"out_key_length\": %zu, \"iterations_executed\": %llu}%s\n",
+                      r.sim_number, r.matrix_filename.c_str(), r.config_QBER, r.gpu_ms, r.gpu_gbit_s, r.out_key_length,
                       static_cast<unsigned long long>(r.iterations_executed), i + 1 < results.size() ? "," : "");
         out << buf;
     }

@@ -265,6 +265,25 @@ namespace {
 struct range_outcome {
     double accurate_qber = 0., ms = 0.;
 };
+
+// One entry of the qkdldpc_run_trials_multi table: the combination's parameters, its position lists and -- when the
+// protocol removes bits after the decoder -- H_matrix_params.bits_to_remove.
+void fill_combination(const config_data &cfg, const sim_combination &comb, size_t curr_sim, qkdldpc_combination &e) {
+    const auto &mp = comb.matrix_params;
+    const bool ra = cfg.ENABLE_CODE_RATE_ADAPTATION;
+    e.qber = comb.config_QBER;
+    e.primary = comb.scaling_factors.primary;
+    e.secondary = comb.scaling_factors.secondary;
+    e.punct_pos = ra ? mp.punctured_bits.data() : nullptr;
+    e.n_punct = ra ? static_cast<int32_t>(mp.punctured_bits.size()) : 0;
+    e.short_pos = ra ? mp.shortened_bits.data() : nullptr;
+    e.n_short = ra ? static_cast<int32_t>(mp.shortened_bits.size()) : 0;
+    e.seed_offset = static_cast<uint64_t>(curr_sim);
+    const bool removal = (ra || cfg.ENABLE_PRIVACY_MAINTENANCE) && !mp.bits_to_remove.empty();
+    e.remove_pos = removal ? mp.bits_to_remove.data() : nullptr;
+    e.n_remove = removal ? static_cast<int32_t>(mp.bits_to_remove.size()) : 0;
+    e.reserved = 0;
+}
 range_outcome decode_trial_range(const config_data &cfg, const decoder_api &api, qkdldpc_code *code, const qkdldpc_params &P,
                                  const H_matrix &matrix, const sim_combination &comb, const std::vector<uint64_t> &seeds, size_t curr_sim,
                                  size_t lo, size_t hi, size_t chunk, size_t gen_threads, bool host_keygen, std::vector<uint64_t> &tally) {
@@ -275,14 +294,25 @@ range_outcome decode_trial_range(const config_data &cfg, const decoder_api &api,
         const auto &mp = comb.matrix_params;
         const bool ra = cfg.ENABLE_CODE_RATE_ADAPTATION;
         std::vector<uint64_t> t(tally.size());
+        // remove_bits is the last step of QKD_LDPC (privacy maintenance) and of QKD_LDPC_RATE_ADAPT (always)
+        // (qkd_ldpc_algorithm.cpp:1089-1092, 1218-1220): the combination entry carries the list and the library builds the
+        // final keys on the device inside the timed call, as the reference's chrono region does (simulation.cpp:559-568)
+        const bool removal = (ra || cfg.ENABLE_PRIVACY_MAINTENANCE) && !mp.bits_to_remove.empty() && api.run_trials_multi != nullptr;
         for (size_t pos = lo; pos < hi; pos += chunk) {
             const size_t cnt = std::min(chunk, hi - pos);
             double acc = 0.;
             const auto t0 = std::chrono::steady_clock::now();
-            const int rc = api.run_trials(code, &P, static_cast<int64_t>(cnt), seeds.data() + pos, static_cast<uint64_t>(curr_sim), comb.config_QBER,
-                                          ra ? mp.punctured_bits.data() : nullptr, ra ? static_cast<int32_t>(mp.punctured_bits.size()) : 0,
-                                          ra ? mp.shortened_bits.data() : nullptr, ra ? static_cast<int32_t>(mp.shortened_bits.size()) : 0,
-                                          nullptr, nullptr, nullptr, t.data(), &acc);
+            int rc;
+            if (removal) {
+                qkdldpc_combination cb{};
+                fill_combination(cfg, comb, curr_sim, cb);
+                rc = api.run_trials_multi(code, &P, 1, &cb, static_cast<int64_t>(cnt), seeds.data() + pos, nullptr, nullptr, t.data(), &acc);
+            } else {
+                rc = api.run_trials(code, &P, static_cast<int64_t>(cnt), seeds.data() + pos, static_cast<uint64_t>(curr_sim), comb.config_QBER,
+                                    ra ? mp.punctured_bits.data() : nullptr, ra ? static_cast<int32_t>(mp.punctured_bits.size()) : 0,
+                                    ra ? mp.shortened_bits.data() : nullptr, ra ? static_cast<int32_t>(mp.shortened_bits.size()) : 0,
+                                    nullptr, nullptr, nullptr, t.data(), &acc);
+            }
             out.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             if (rc != 0) {
                 const std::string msg = api.last_error();
@@ -413,19 +443,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
                                 continue;
                             }
                             std::vector<qkdldpc_combination> table(cnt);
-                            for (size_t k = 0; k < cnt; ++k) {
-                                const sim_combination &comb = in.combinations[c0 + k];
-                                const auto &mp = comb.matrix_params;
-                                const bool ra = cfg.ENABLE_CODE_RATE_ADAPTATION;
-                                table[k].qber = comb.config_QBER;
-                                table[k].primary = comb.scaling_factors.primary;
-                                table[k].secondary = comb.scaling_factors.secondary;
-                                table[k].punct_pos = ra ? mp.punctured_bits.data() : nullptr;
-                                table[k].n_punct = ra ? static_cast<int32_t>(mp.punctured_bits.size()) : 0;
-                                table[k].short_pos = ra ? mp.shortened_bits.data() : nullptr;
-                                table[k].n_short = ra ? static_cast<int32_t>(mp.shortened_bits.size()) : 0;
-                                table[k].seed_offset = static_cast<uint64_t>(first_sim + c0 + k);
-                            }
+                            for (size_t k = 0; k < cnt; ++k) fill_combination(cfg, in.combinations[c0 + k], first_sim + c0 + k, table[k]);
                             std::vector<uint64_t> tl(cnt * tally_len);
                             std::vector<double> acc(cnt);
                             const auto t0 = std::chrono::steady_clock::now();
@@ -504,6 +522,7 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
             const double out_key_length = (cfg.ENABLE_CODE_RATE_ADAPTATION || cfg.ENABLE_PRIVACY_MAINTENANCE)
                                               ? static_cast<double>(matrix.n() - comb.matrix_params.bits_to_remove.size())
                                               : static_cast<double>(matrix.n());
+            r.out_key_length = static_cast<size_t>(out_key_length);
             r.gpu_gbit_s = r.gpu_ms > 0 ? out_key_length * static_cast<double>(trials) / (r.gpu_ms * 1e-3) / 1e9 : 0.;
             if (cfg.ENABLE_THROUGHPUT_MEASUREMENT && r.gpu_ms > 0) {
                 double us_per_frame = r.gpu_ms * 1e3 / static_cast<double>(trials);

@@ -49,6 +49,7 @@ struct sim_result {
     double gpu_ms{};
     double gpu_gbit_s{};
     uint64_t iterations_executed{};
+    size_t out_key_length{};   // bits of the final key: n, or n - bits_to_remove (privacy maintenance / rate adaptation)
 };
 
 // Range / map lookups (simulation.cpp:182-368): first entry with code_rate >= R of an ascending list (quirk Q14).

@@ -159,6 +159,47 @@ def test_run_trials_multi_equals_one_call_per_combination(q, alg, name):
     assert 0 < (fl & 1).sum() < fl.size
 
 
+@pytest.mark.parametrize("alg,name", [(5, "I80"), (0, "I80"), (2, "K1_5")])
+def test_run_trials_multi_final_keys(q, alg, name):
+    """remove_bits as the last step of the batched run_trial (qkd_ldpc_algorithm.cpp:1089-1092, 1218-1220): combinations
+    that carry H_matrix_params.bits_to_remove get Alice's (extended) key and bob_solution without those positions, built on
+    the device inside the call. Checked against the per-combination call + numpy deletion; on-chip launch (AOMSA, NMSA)
+    and the one-combination-after-the-other fallback (SPA on the irregular n = 10240 code)."""
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays(name)
+    n = arr["n"]
+    rng = np.random.default_rng(10 + alg)
+    seeds = hostlib.trial_seeds(777, 37)
+    combos = []
+    for k in range(5):
+        pos = rng.permutation(n)
+        n_p, n_s = (0, 0) if k == 0 else (int(n * 0.015 * k), int(n * 0.01 * k))
+        p_, s_ = np.sort(pos[:n_p]).astype(np.int32), np.sort(pos[n_p:n_p + n_s]).astype(np.int32)
+        # k = 0: privacy maintenance only (some positions); k = 3: no removal list at all; else punctured + shortened + extra
+        rm = np.sort(np.concatenate([p_, s_, pos[n_p + n_s:n_p + n_s + 100 * (k % 2 == 0)]])).astype(np.int32) if k != 3 else np.zeros(0, np.int32)
+        combos.append(dict(QBER=0.012 + 0.002 * k, primary=0.7, secondary=0.9, seed_offset=50 + k, punctured_bits=p_, shortened_bits=s_,
+                           bits_to_remove=rm))
+    cfg = q.DecoderConfig(decoding_algorithm=alg, max_iterations=40)
+    h = handle(q, name)
+    it, fl, tl, acc, ka, kb = h.run_trials_multi(seeds, combos, cfg, want_keys=True)
+    it0, fl0, tl0, acc0 = h.run_trials_multi(seeds, [{k_: v for k_, v in cb.items() if k_ != "bits_to_remove"} for cb in combos], cfg)
+    assert (it == it0).all() and (fl == fl0).all() and (tl == tl0).all() and (acc == acc0).all()
+    for k, cb in enumerate(combos):
+        if cb["bits_to_remove"].size == 0:
+            assert ka[k] is None and kb[k] is None
+            continue
+        r = h.run_trials(seeds, cb["QBER"], (cb["primary"], cb["secondary"]), cfg, seed_offset=cb["seed_offset"],
+                         punctured_bits=cb["punctured_bits"], shortened_bits=cb["shortened_bits"])
+        assert (r.iterations_num == it[k]).all()
+        a, _, _ = (hostlib.gen_keys_rate_adapt(seeds + np.uint64(cb["seed_offset"]), n, cb["QBER"], cb["punctured_bits"], cb["shortened_bits"])
+                   if cb["punctured_bits"].size or cb["shortened_bits"].size else hostlib.gen_keys(seeds + np.uint64(cb["seed_offset"]), n, cb["QBER"]))
+        keep = np.setdiff1d(np.arange(n), cb["bits_to_remove"])
+        want_a = q.pack_bits(q.unpack_bits(a, n)[:, keep])
+        want_b = q.pack_bits(r.bits()[:, keep])
+        assert (ka[k] == want_a).all() and (kb[k] == want_b).all(), k
+        assert (h.remove_bits(r.bob_solution, cb["bits_to_remove"]) == kb[k]).all()
+
+
 @pytest.mark.parametrize("alg,fac", [(2, (0.75, 0.0)), (0, (0.0, 0.0))])
 def test_bench_synthetic_entry_point(q, alg, fac):
     """qkdldpc_bench_synthetic: device-generated synthetic keys, decode, tally + seconds. The tally must

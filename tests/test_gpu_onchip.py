@@ -262,3 +262,29 @@ def test_tail_compaction_with_capped_grid(q):
     r0 = handle(q, "K1_5", decoder_path=1, tail_compaction=-1).QKD_LDPC_batch(a, b, acc, (0.75, 0), cfg)
     r1 = handle(q, "K1_5", decoder_path=1, compaction_max_ctas=3, steps_per_poll=2).QKD_LDPC_batch(a, b, acc, (0.75, 0), cfg)
     same(r0, r1)
+
+
+@pytest.mark.parametrize("alg,prec", [(2, 32), (5, 64), (0, 32)])
+def test_pipelined_host_batches(q, alg, prec):
+    """qkdldpc_decode_batch cuts a host batch into pieces (copy-in of piece k+1 / copy-out of piece k-1 overlap the decoding
+    of piece k; each piece is its own launch with its own frame queue, tallies are shared): per-frame results and tallies
+    must not depend on the number of pieces -- ragged piece sizes, one QBER per frame, no decoded words requested."""
+    frames = 5003
+    a, b, acc = keys("K1_5", 4242, frames, 0.021)
+    qb = np.full(frames, acc)
+    qb[::5] *= 1.3
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=prec, max_iterations=50)
+    fac = FACT.get(alg, (0.0, 0.0))
+    r1 = handle(q, "K1_5", copy_chunks=1).QKD_LDPC_batch(a, b, qb, fac, cfg)
+    for chunks in (0, 3, 16):
+        rk = handle(q, "K1_5", copy_chunks=chunks).QKD_LDPC_batch(a, b, qb, fac, cfg)
+        assert rk.info["last_path"] == 2
+        same(r1, rk)
+        rn = handle(q, "K1_5", copy_chunks=chunks).QKD_LDPC_batch(a, b, qb, fac, cfg, want_bits=False)
+        assert (rn.iterations_num == r1.iterations_num).all() and (rn.flags == r1.flags).all() and (rn.tally == r1.tally).all()
+    rs = handle(q, "K1_5", decoder_path=1).QKD_LDPC_batch(a, b, qb, fac, cfg)      # streaming: copy in, decode, copy out
+    same(r1, rs)
+    p = np.arange(0, 40, dtype=np.int32)                                            # rate adaptation through the pipeline
+    r2 = handle(q, "K1_5", copy_chunks=5).QKD_LDPC_batch(a, b, acc, fac, cfg, punctured_bits=p)
+    r3 = handle(q, "K1_5", decoder_path=1).QKD_LDPC_batch(a, b, acc, fac, cfg, punctured_bits=p)
+    same(r2, r3)

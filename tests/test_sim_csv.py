@@ -156,6 +156,64 @@ def test_csv_trials_sharded_over_two_handles(built, tmp_path):
     assert host_lines == ref_lines
 
 
+def _adaptive_t_config():
+    """configs/ADAPTIVE T.json, the reference's one live config, restated: AOMSA, rate adaptation with
+    untainted puncturing from the per-(rate, QBER) map, privacy maintenance, throughput measurement with RTT 0.4 ms, 10 trials
+    per combination, 1 thread, seed 5555, the three irregular n = 10240 codes of matrices_2."""
+    amap = [(0.905, 0.48, 0.88), (0.855, 0.82, 1.22), (0.805, 0.7, 0.99), (0.755, 0.8, 1.05), (0.705, 0.91, 1.11), (0.655, 0.74, 0.94),
+            (0.605, 0.59, 0.8), (0.555, 0.61, 0.8), (0.505, 0.72, 0.85)]
+    qmap = {0.805: [(0.0076, 0.1, 1.85), (0.0116, 0.09, 1.5), (0.0156, 0.06, 1.39), (0.0196, 0.03, 1.28), (0.0236, 0.01, 1.21),
+                    (0.0276, 0.11, 1.2), (0.0316, 0.22, 1.22)],
+            0.655: [(0.0368, 0.12, 1.22), (0.0408, 0.1, 1.2), (0.0448, 0.06, 1.18), (0.0488, 0.06, 1.17), (0.0528, 0.01, 1.16),
+                    (0.0568, 0.06, 1.16), (0.0608, 0.11, 1.17), (0.0648, 0.16, 1.17), (0.0688, 0.23, 1.19)],
+            0.505: [(0.0734, 0.12, 1.18), (0.0774, 0.09, 1.17), (0.0814, 0.08, 1.16), (0.0854, 0.04, 1.15), (0.0894, 0.01, 1.14),
+                    (0.0934, 0.03, 1.14), (0.0974, 0.06, 1.14), (0.1014, 0.1, 1.15), (0.1054, 0.13, 1.16), (0.1094, 0.13, 1.15)]}
+    cra = dict(enable_untainted_puncturing=True, use_adaptation_parameters_ranges=False,
+               code_rate_adaptation_parameters_ranges=[
+                   dict(code_rate=0.805, delta=dict(begin=0.01, end=0.25, step=0.01), efficiency=dict(begin=1.2, end=1.6, step=0.01)),
+                   dict(code_rate=0.655, delta=dict(begin=0.05, end=0.2, step=0.05), efficiency=dict(begin=1.13, end=1.28, step=0.01)),
+                   dict(code_rate=0.505, delta=dict(begin=0.05, end=0.2, step=0.05), efficiency=dict(begin=1.12, end=1.28, step=0.01))],
+               code_rate_QBER_adaptation_parameters_maps=[dict(code_rate=r, QBER=qb, delta=d, efficiency=e)
+                                                          for r, rows in qmap.items() for qb, d, e in rows])
+    return dict(BASE, threads_number=1, trials_number=10, simulation_seed=5555, enable_privacy_maintenance=True,
+                enable_throughput_measurement=True, throughput_measurement_parameters=dict(consider_RTT=True, RTT=0.4),
+                decoding_algorithm=5, matrix_format=3, enable_code_rate_adaptation=True, code_rate_adaptation_parameters=cra,
+                adaptive_min_sum_offset_parameters=dict(
+                    use_beta_range=False, beta_range=dict(begin=0.01, end=1.0, step=0.01),
+                    code_rate_beta_maps=[dict(code_rate=r, beta=b) for r, b, _ in amap], use_sigma_range=False,
+                    sigma_range=dict(begin=0.01, end=1.0, step=0.01), code_rate_sigma_maps=[dict(code_rate=r, sigma=sg) for r, _, sg in amap]),
+                code_rate_QBER_ranges=[dict(code_rate=0.805, QBER=dict(begin=0.0096, end=0.0196, step=0.002)),
+                                       dict(code_rate=0.655, QBER=dict(begin=0.0338, end=0.0738, step=0.001)),
+                                       dict(code_rate=0.505, QBER=dict(begin=0.0714, end=0.1114, step=0.001))])
+
+
+@pytest.mark.parametrize("extra", [[], ["--trials", "10", "--concurrent", "1"]], ids=["sweep", "one_combination_per_call"])
+def test_csv_adaptive_t_privacy_maintenance_and_throughput(built, tmp_path, extra):
+    """configs/ADAPTIVE T.json (privacy maintenance + throughput columns + RTT): every column but the four THROUGHPUT_* ones
+    must equal the reference executable's under the DEFAULT precision policy (AOMSA -> float64 state on chip); the
+    throughput columns are the RTT model on the batch time: out_key_length / (batch_time / trials + RTT)
+    (simulation.cpp:626-681), with out_key_length = n - |bits_to_remove| and remove_bits executed on the device inside
+    the timed call."""
+    cfg = _adaptive_t_config()
+    _setup(tmp_path, cfg, ["I80", "I65", "I50"])
+    rname, ref_lines = _run_reference(tmp_path)
+    oname, our_lines = _run_ours(tmp_path, 0, extra)
+    assert _strip_duration(rname) == _strip_duration(oname) and ",RTT=0.400ms," in oname and "priv_maint=ON" in oname
+    hdr = ref_lines[0].split(";")
+    assert our_lines[0] == ref_lines[0] and len(our_lines) == len(ref_lines) == 1 + 7 + 9 + 10
+    thr = [hdr.index(k) for k in ("THROUGHPUT_MEAN", "THROUGHPUT_STD", "THROUGHPUT_MIN", "THROUGHPUT_MAX")]
+    side = json.loads((tmp_path / "results_gpu" / oname.replace(".csv", ".gpu.json")).read_text())["combinations"]
+    n = util.code_arrays("I80")["n"]
+    for a, b, sc in zip(our_lines[1:], ref_lines[1:], side):
+        fa, fb = a.split(";"), b.split(";")
+        assert [x for k, x in enumerate(fa) if k not in thr] == [x for k, x in enumerate(fb) if k not in thr]
+        assert 0 < sc["out_key_length"] < n     # bits were removed
+        want = sc["out_key_length"] * 1e6 / (sc["batch_ms"] * 1e3 / 10 + 0.4 * 1000.)
+        mean, std, lo, hi = (int(fa[k]) for k in thr)
+        assert abs(mean - want) <= 1.0 + 1e-6 * want and lo == hi == mean and std == 0
+        assert mean <= sc["out_key_length"] / 0.4e-3     # the RTT bounds the rate
+
+
 def test_example_program(built):
     """example/qkdldpc_example.cpp = the reference's example (N = 6, Johnson ex. 2.5) through the C ABI: iteration counts
     traced from the unmodified reference: SPA 1, SPA-lin 1, NMSA 1, OMSA 2, ANMSA 3, AOMSA 2."""
