@@ -242,6 +242,26 @@ QKDLDPC_API int qkdldpc_run_trials_multi_keys(qkdldpc_code *code, const qkdldpc_
 QKDLDPC_API int qkdldpc_remove_bits(qkdldpc_code *code, int64_t n_frames, const uint32_t *keys, const int32_t *bits_to_remove,
                         int32_t n_remove, uint32_t *out_keys);
 
+/* ---- Multi-GPU: frames are independent, so a batch is sharded by frame (contiguous trial ranges per device, no
+ * per-iteration traffic) and the ONLY collective is the sum of the tally vectors, the vector process_trials_results
+ * consumes (simulation.cpp:580-624). The handle owns the NCCL communicator. NCCL is bound at run time (libnccl.so.2);
+ * without it these calls return QKDLDPC_ERR_STATE and everything else keeps working.
+ *   one process per GPU (torchrun / MPI): rank 0 calls qkdldpc_comm_get_unique_id, the caller broadcasts the 128 bytes,
+ *       every rank calls qkdldpc_comm_init_rank on its handle;
+ *   one process, several devices (qkdldpc_sim --gpus N): qkdldpc_comm_init_all on one handle per device; the all-reduce
+ *       is then called from one host thread per device at the same time.
+ * Every rank of the communicator must make the same all-reduce calls with the same count. */
+#define QKDLDPC_COMM_ID_BYTES 128
+QKDLDPC_API int qkdldpc_comm_nccl_version(void); /* e.g. 22809; 0 when NCCL cannot be loaded */
+QKDLDPC_API int qkdldpc_comm_get_unique_id(uint8_t *id_out /* QKDLDPC_COMM_ID_BYTES */);
+QKDLDPC_API int qkdldpc_comm_init_rank(qkdldpc_code *code, const uint8_t *id, int32_t n_ranks, int32_t rank);
+QKDLDPC_API int qkdldpc_comm_init_all(qkdldpc_code *const *codes, int32_t n_codes);
+QKDLDPC_API int qkdldpc_comm_size(const qkdldpc_code *code); /* ranks of the handle's communicator, 0 without one */
+/* Sum over all ranks, in place. HOST vector (copied to the device, reduced over NVLink, copied back; returns when done): */
+QKDLDPC_API int qkdldpc_tally_allreduce(qkdldpc_code *code, uint64_t *tally, int64_t count);
+/* DEVICE vector, enqueued on the handle's stream right behind the decode that filled it (no host synchronisation): */
+QKDLDPC_API int qkdldpc_tally_allreduce_device(qkdldpc_code *code, uint64_t *d_tally, int64_t count);
+
 /* Introspection used by benchmarks and tests. */
 typedef struct qkdldpc_info {
     int32_t n, m;

@@ -63,6 +63,13 @@ SYMBOLS = {
     "qkdldpc_run_trials_multi": (C.c_int, [_VP, C.POINTER(Params), C.c_int32, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP]),
     "qkdldpc_run_trials_multi_keys": (C.c_int, [_VP, C.POINTER(Params), C.c_int32, _VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "qkdldpc_remove_bits": (C.c_int, [_VP, C.c_int64, _VP, _VP, C.c_int32, _VP]),
+    "qkdldpc_comm_nccl_version": (C.c_int, []),
+    "qkdldpc_comm_get_unique_id": (C.c_int, [_VP]),
+    "qkdldpc_comm_init_rank": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32]),
+    "qkdldpc_comm_init_all": (C.c_int, [_VP, C.c_int32]),
+    "qkdldpc_comm_size": (C.c_int, [_VP]),
+    "qkdldpc_tally_allreduce": (C.c_int, [_VP, _VP, C.c_int64]),
+    "qkdldpc_tally_allreduce_device": (C.c_int, [_VP, _VP, C.c_int64]),
     "qkdldpc_code_info": (C.c_int, [_VP, C.POINTER(Info)]),
     "qkdldpc_code_set_profiling": (C.c_int, [_VP, C.c_int32]),
 }

@@ -21,6 +21,7 @@ int run_onchip(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const
                const double *d_qber, int qber_is_scalar, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short,
                uint32_t *d_out_bits, int32_t *d_out_iters, uint8_t *d_out_flags, unsigned long long *d_tally, const HostPipe *pipe);
 bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P);
+void comm_release(qkdldpc_code *c);
 int onchip_pack_masks(int n, const int32_t *punct, int n_punct, const int32_t *shortd, int n_short, uint32_t *dst);
 int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int64_t frames_per_combo, const qk::OnchipCombo *combos,
                      const uint32_t *masks, const uint32_t *d_alice, const uint32_t *d_bob, const double *d_qber, int qber_is_scalar,
@@ -197,6 +198,8 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    comm_release(c);
+    c->comm_buf.release();
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     c->row_ptr.release(); c->col_idx.release(); c->col_ptr.release(); c->csc_edge.release(); c->csc_row.release();
     c->row_order.release(); c->col_order.release(); c->vn_ell_edge.release(); c->vn_ell_row.release();

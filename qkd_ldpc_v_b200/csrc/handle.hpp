@@ -144,6 +144,9 @@ struct qkdldpc_code {
     int sp_groups_sv = 0;
     DevBuf<uint4> sp_sv_items;
     std::vector<int> sp_group_item0;  // first item of every variable-phase group (+ total): chunk boundaries lie on these
+    void *comm = nullptr;             // ncclComm_t of the tally all-reduce (comm.cu); owned by the handle
+    int comm_ranks = 0;
+    DevBuf<unsigned long long> comm_buf;
     int last_path = 0;                // 1 streaming, 2 on-chip (of the last batch)
     int last_precision = 0;           // 32 / 64: message precision of the last batch after the policy
     // pool (device, raw bytes reinterpreted per precision)

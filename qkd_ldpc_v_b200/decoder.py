@@ -161,6 +161,38 @@ class LdpcCode:
         a = np.ascontiguousarray(x if x is not None else [], np.int32)
         return a, (a.ctypes.data if a.size else None), int(a.size)
 
+    # -- multi-GPU: the tally all-reduce (the handle owns the NCCL communicator) ------------------------------
+    @staticmethod
+    def comm_unique_id() -> np.ndarray:
+        """128 bytes from ``ncclGetUniqueId`` (rank 0 calls this, the caller broadcasts them)."""
+        ident = np.zeros(128, np.uint8)
+        _cabi.check(_cabi.lib().qkdldpc_comm_get_unique_id(ident.ctypes.data), "qkdldpc_comm_get_unique_id")
+        return ident
+
+    def comm_init_rank(self, unique_id, n_ranks: int, rank: int):
+        ident = np.ascontiguousarray(unique_id, np.uint8)
+        assert ident.size == 128
+        _cabi.check(_cabi.lib().qkdldpc_comm_init_rank(self._h, ident.ctypes.data, int(n_ranks), int(rank)), "qkdldpc_comm_init_rank")
+
+    @staticmethod
+    def comm_init_all(codes):
+        """One process, several devices: one communicator over ``codes`` (one handle per distinct device)."""
+        arr = (C.c_void_p * len(codes))(*[c._h for c in codes])
+        _cabi.check(_cabi.lib().qkdldpc_comm_init_all(C.cast(arr, C.c_void_p), len(codes)), "qkdldpc_comm_init_all")
+
+    def comm_size(self) -> int:
+        return int(_cabi.lib().qkdldpc_comm_size(self._h))
+
+    def tally_allreduce(self, tally: np.ndarray) -> np.ndarray:
+        """Sum of a HOST tally vector over all ranks, in place (``qkdldpc_tally_allreduce``)."""
+        t = np.ascontiguousarray(tally, np.uint64)
+        _cabi.check(_cabi.lib().qkdldpc_tally_allreduce(self._h, t.ctypes.data, t.size), "qkdldpc_tally_allreduce")
+        return t
+
+    def tally_allreduce_device(self, d_tally: int, count: int):
+        """Same on a DEVICE vector, enqueued on the handle's stream behind the decode that filled it."""
+        _cabi.check(_cabi.lib().qkdldpc_tally_allreduce_device(self._h, C.c_void_p(d_tally), int(count)), "qkdldpc_tally_allreduce_device")
+
     # -- the hot path ---------------------------------------------------------------------------------------
     def QKD_LDPC_batch(self, alice_bit_array, bob_bit_array, QBER, scaling_factors=(0.0, 0.0),
                        cfg: Optional[DecoderConfig] = None, punctured_bits: Sequence[int] = (),

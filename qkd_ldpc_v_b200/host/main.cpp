@@ -169,6 +169,8 @@ int main(int argc, char *argv[]) {
         api.last_error = &qkdldpc_last_error;
         api.run_trials = &qkdldpc_run_trials;
         api.run_trials_multi = &qkdldpc_run_trials_multi;
+        api.comm_init_all = &qkdldpc_comm_init_all;
+        api.tally_allreduce = &qkdldpc_tally_allreduce;
 
         std::vector<fs::path> config_paths;
         if (!config_file.empty()) config_paths.push_back(config_file);

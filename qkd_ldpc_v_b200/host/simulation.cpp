@@ -411,6 +411,22 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
             }
         }
 
+        // Trials of one combination sharded over several DISTINCT devices: the per-device tallies are summed by ONE
+        // ncclAllReduce per combination over NVLink (the handles own the communicator, include/qkdldpc.h); the same device
+        // listed twice, or a missing NCCL library, falls back to adding the vectors on the host (same integers).
+        bool nccl_reduce = false;
+        if (!sweep_mode && n_dev > 1 && api.comm_init_all && api.tally_allreduce) {
+            std::vector<int> seen;
+            bool distinct = true;
+            for (size_t d = 0; d < n_dev; ++d) {
+                distinct = distinct && std::find(seen.begin(), seen.end(), dev.devices[d]) == seen.end();
+                seen.push_back(dev.devices[d]);
+            }
+            if (distinct) {
+                nccl_reduce = api.comm_init_all(codes.data(), static_cast<int32_t>(n_dev)) == 0;
+                if (!nccl_reduce && dev.verbose) std::fprintf(stderr, "note: tallies are summed on the host (%s)\n", api.last_error());
+            }
+        }
         std::vector<std::vector<uint64_t>> totals(n_comb, std::vector<uint64_t>(tally_len, 0));
         std::vector<double> acc_qber(n_comb, 0.), comb_ms(n_comb, 0.);
         std::vector<std::string> errors(lanes);
@@ -481,11 +497,20 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
                         } catch (const std::exception &e) {
                             errors[d] = e.what();
                         }
+                        // K5: every device thread enters the collective (also after an error: the others would wait for ever)
+                        if (nccl_reduce && api.tally_allreduce(codes[d], part[d].data(), static_cast<int64_t>(tally_len)) != 0 && errors[d].empty())
+                            errors[d] = std::string("qkdldpc_tally_allreduce: ") + api.last_error();
                     });
                 for (auto &w : workers) w.join();
-                // the multi-GPU "all-reduce" of this in-process driver: integer sums of the per-device tallies
+                if (nccl_reduce) {
+                    totals[ci] = part[0];   // every rank holds the sum
+                    for (size_t d = 1; d < n_dev; ++d)
+                        if (part[d] != part[0] && errors[d].empty()) errors[d] = "tally all-reduce: ranks disagree";
+                } else {
+                    for (size_t d = 0; d < n_dev; ++d)   // integer sums of the per-device tallies on the host
+                        for (size_t k = 0; k < tally_len; ++k) totals[ci][k] += part[d][k];
+                }
                 for (size_t d = 0; d < n_dev; ++d) {
-                    for (size_t k = 0; k < tally_len; ++k) totals[ci][k] += part[d][k];
                     comb_ms[ci] = std::max(comb_ms[ci], outc[d].ms);
                 }
                 acc_qber[ci] = outc[0].accurate_qber;

@@ -86,6 +86,8 @@ struct decoder_api {
     decltype(&qkdldpc_last_error) last_error = nullptr;
     decltype(&qkdldpc_run_trials) run_trials = nullptr;   // batched run_trial with inputs generated on the device
     decltype(&qkdldpc_run_trials_multi) run_trials_multi = nullptr;   // ... for several combinations in one call
+    decltype(&qkdldpc_comm_init_all) comm_init_all = nullptr;         // multi-GPU: the handles' NCCL communicator ...
+    decltype(&qkdldpc_tally_allreduce) tally_allreduce = nullptr;     // ... and the tally all-reduce (K5)
 };
 
 std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const std::vector<sim_input> &sim_in,
