@@ -12,6 +12,8 @@
 
 #include <cuda_runtime.h>
 
+#include "onchip_layout.hpp"
+
 namespace qkhost {
 
 inline std::string &last_error() {
@@ -105,6 +107,7 @@ struct OnchipTables {
     std::vector<uint4> vT;
     std::vector<int> sp_cn_moff, sp_group_item0;
     std::vector<uint4> sp_items;
+    Oc2Tables oc2;                       // float32 min-sum kernel: storage order = processing order (onchip_layout.hpp)
 };
 }  // namespace qkhost
 
@@ -137,6 +140,17 @@ struct qkdldpc_code {
     std::vector<uint16_t> oc_vn_bit_host;
     int oc_sched_warps = 0;   // oc_cls: [2][words] punctured / shortened bit masks of the current batch
     int oc_threads = 0;               // CTA size of the last on-chip launch
+    // float32 min-sum kernel: tables of onchip_layout.hpp
+    bool oc2_eligible = false;
+    int oc2_groups_cn = 0, oc2_groups_vn = 0, oc2_rec_slots = 0, oc2_max_dc = 0, oc2_sched_warps = 0;
+    DevBuf<int4> oc2_cn_g, oc2_vn_g;
+    DevBuf<uint2> oc2_cnT;
+    DevBuf<uint4> oc2_vT;
+    DevBuf<uint16_t> oc2_slot_bit, oc2_bit_slot;
+    DevBuf<uint32_t> oc2_cls;         // [n_combos][2][words] punctured / shortened masks of the current batch, slot order
+    std::vector<Oc2Group> oc2_vn_g_host;   // canonical order; the device copy is dealt to the warps of the launch
+    std::vector<uint16_t> oc2_bit_slot_host;
+    long long oc2_model[4] = {0, 0, 0, 0};   // bank model: check gather, its minimum, variable gather, its minimum (wavefronts / iteration)
     // on-chip sum-product path (onchip_spa.cuh): one message word per edge; check phase shares oc_cn_* with min-sum
     bool sp_eligible = false;
     int sp_msg_words = 0, sp_chunk_warps = 0;

@@ -20,14 +20,15 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
             return false;
         return onchip_spa_smem_bytes(c->n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv) <= (size_t)dev_smem;
     }
-    if (!c->oc_eligible) return false;
+    const bool f64 = P->message_precision == 64;
+    if (f64 ? !c->oc_eligible : !c->oc2_eligible) return false;
     // same precondition as the FAST streaming kernels (minsum_factors_ok, handle.hpp): no message can become NaN / inf,
     // and the factors are finite and non-negative (the magnitude clamp min(c, thr) covers only the positive side)
     if (!minsum_factors_ok(P)) return false;
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return false;
-    if (P->message_precision == 64) return onchip64_smem_bytes(c->n, c->oc_rec_slots, c->oc_groups_cn) <= (size_t)dev_smem;
-    return onchip_smem_bytes(c->n, c->oc_rec_slots, c->oc_groups_cn) <= (size_t)dev_smem;
+    if (f64) return onchip64_smem_bytes(c->n, c->oc_rec_slots, c->oc_groups_cn) <= (size_t)dev_smem;
+    return onchip_staging_fits(c->n, c->oc2_rec_slots) && onchip_smem_bytes(c->n, c->oc2_rec_slots, c->oc2_groups_cn) <= (size_t)dev_smem;
 }
 
 // threads == 0: pick the CTA size that puts the most warps on an SM (shared memory decides how many CTAs fit; ties go
@@ -234,7 +235,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(max_threads, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
     const size_t smem = spa   ? onchip_spa_smem_bytes(n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv)
                         : f64 ? onchip64_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn)
-                              : onchip_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn);
+                              : onchip_smem_bytes(n, c->oc2_rec_slots, c->oc2_groups_cn);
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 
@@ -269,27 +270,65 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     const OnchipKernel kern = kernel_of(P->algorithm, wide, f64);
     e = pick_geometry(kern, max_threads, m, sms, smem, n_frames, &threads, &grid);
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel geometry failed: %s", cudaGetErrorString(e));
-    if (c->oc_sched_warps != threads / 32) {   // the variable-phase schedule depends on the number of warps per CTA
-        const std::vector<int> sched = vn_schedule(c->oc_vn_degree, threads / 32);
-        std::vector<int2> ginfo(sched.size(), make_int2(0, 0));
-        std::vector<uint16_t> bits(sched.size() * 32, (uint16_t)n);
-        for (size_t i = 0; i < sched.size(); ++i)
-            if (sched[i] >= 0) {
-                ginfo[i] = c->oc_vn_ginfo_host[sched[i]];
-                std::copy(c->oc_vn_bit_host.begin() + (size_t)sched[i] * 32, c->oc_vn_bit_host.begin() + (size_t)sched[i] * 32 + 32,
-                          bits.begin() + i * 32);
+    if (f64) {
+        if (c->oc_sched_warps != threads / 32) {   // the variable-phase schedule depends on the number of warps per CTA
+            const std::vector<int> sched = vn_schedule(c->oc_vn_degree, threads / 32);
+            std::vector<int2> ginfo(sched.size(), make_int2(0, 0));
+            std::vector<uint16_t> bits(sched.size() * 32, (uint16_t)n);
+            for (size_t i = 0; i < sched.size(); ++i)
+                if (sched[i] >= 0) {
+                    ginfo[i] = c->oc_vn_ginfo_host[sched[i]];
+                    std::copy(c->oc_vn_bit_host.begin() + (size_t)sched[i] * 32, c->oc_vn_bit_host.begin() + (size_t)sched[i] * 32 + 32,
+                              bits.begin() + i * 32);
+                }
+            CK(c->oc_vn_ginfo.reserve(ginfo.size()));
+            CK(c->oc_vn_bit.reserve(bits.size()));
+            CK(cudaMemcpyAsync(c->oc_vn_ginfo.p, ginfo.data(), ginfo.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(c->oc_vn_bit.p, bits.data(), bits.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+            c->oc_sched_warps = threads / 32;
+            c->oc_groups_vn = (int)sched.size();
+        }
+        a.n_groups_vn = c->oc_groups_vn;
+        a.vn_ginfo = c->oc_vn_ginfo.p;
+        a.vn_bit = c->oc_vn_bit.p;
+    } else {
+        // float32: the tables of onchip_layout.hpp; the canonical variable-phase groups are dealt to the warps of this CTA size
+        if (c->oc2_sched_warps != threads / 32) {
+            std::vector<int> degree;
+            for (const Oc2Group &g : c->oc2_vn_g_host) degree.push_back(g.deg);
+            const std::vector<int> sched = vn_schedule(degree, threads / 32);
+            std::vector<Oc2Group> dealt(sched.size(), Oc2Group{0, 0, 0, 0});
+            for (size_t i = 0; i < sched.size(); ++i)
+                if (sched[i] >= 0) dealt[i] = c->oc2_vn_g_host[sched[i]];
+            CK(c->oc2_vn_g.reserve(dealt.size()));
+            CK(cudaMemcpyAsync(c->oc2_vn_g.p, dealt.data(), dealt.size() * sizeof(Oc2Group), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+            c->oc2_sched_warps = threads / 32;
+            c->oc2_groups_vn = (int)dealt.size();
+        }
+        // punctured / shortened masks of every combination into slot order
+        std::vector<uint32_t> masks2((size_t)n_combos * 2 * words, 0u);
+        for (int cb = 0; cb < n_combos; ++cb) {
+            if (!combos[cb].has_cls) continue;
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t *src = masks + ((size_t)cb * 2 + h) * words;
+                uint32_t *dst = masks2.data() + ((size_t)cb * 2 + h) * words;
+                for (int w = 0; w < words; ++w)
+                    for (uint32_t bitsw = src[w]; bitsw; bitsw &= bitsw - 1) {
+                        const int sl = c->oc2_bit_slot_host[(size_t)w * 32 + __builtin_ctz(bitsw)];
+                        dst[sl >> 5] |= 1u << (sl & 31);
+                    }
             }
-        CK(c->oc_vn_ginfo.reserve(ginfo.size()));
-        CK(c->oc_vn_bit.reserve(bits.size()));
-        CK(cudaMemcpyAsync(c->oc_vn_ginfo.p, ginfo.data(), ginfo.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(c->oc_vn_bit.p, bits.data(), bits.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+        }
+        CK(c->oc2_cls.reserve(masks2.size()));
+        CK(cudaMemcpyAsync(c->oc2_cls.p, masks2.data(), masks2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
-        c->oc_sched_warps = threads / 32;
-        c->oc_groups_vn = (int)sched.size();
+        a.rec_slots = c->oc2_rec_slots;
+        a.n_groups_cn2 = c->oc2_groups_cn; a.n_groups_vn2 = c->oc2_groups_vn;
+        a.cn_g2 = c->oc2_cn_g.p; a.cnT2 = c->oc2_cnT.p; a.vn_g2 = c->oc2_vn_g.p; a.vT2 = c->oc2_vT.p;
+        a.slot_bit = c->oc2_slot_bit.p; a.bit_slot = c->oc2_bit_slot.p; a.cls_masks2 = c->oc2_cls.p;
     }
-    a.n_groups_vn = c->oc_groups_vn;
-    a.vn_ginfo = c->oc_vn_ginfo.p;
-    a.vn_bit = c->oc_vn_bit.p;
 
     auto launch_ms = [&](const OnchipArgs &args, int g, cudaStream_t st) {
         kern<<<(unsigned)g, threads, smem, st>>>(args);

@@ -1,5 +1,5 @@
-// On-chip min-sum decoder: one frame per CTA, the whole belief-propagation state of the frame lives in shared memory
-// for all iterations; HBM is touched only for the packed key bits going in and the packed decision coming out.
+// On-chip min-sum decoder (float32 state): one frame per CTA, the whole belief-propagation state of the frame lives in
+// shared memory for all iterations; HBM is touched only for the packed key bits going in and the packed decision coming out.
 //
 // Why this is possible. For the min-sum family a check node's dc outgoing messages take only two magnitudes
 // (qkd_ldpc_algorithm.cpp:400-408): factor*min1 for every edge except the one holding the minimum, which gets
@@ -9,7 +9,7 @@
 // total L and the row's previous record when the check node needs it. State per frame:
 //     L[n]   float   total LLR after the last variable-node phase (llr before the first iteration)
 //     rec[m] uint4   {bits(c1), bits(c2), sign bit per edge of the row, position of the first minimum}
-// = 4n + 16m bytes (72 KB for n=10240, m=2048 instead of 242 KB of float messages), so two frames fit one SM.
+// = 4n + 16m bytes (72 KB for n=10240, m=2048 instead of 242 KB of float messages), so three frames fit one SM.
 // Every float operation of the reference is performed on the same operands in the same order (the sum over a
 // bit's checks runs in ascending check order starting from the LLR, :414-422), so the results are bit-identical
 // to the streaming float32 kernels (step_kernels.cuh) and to the f32 oracle.
@@ -19,12 +19,20 @@
 //       The parity of the current hard decision z = (L <= 0) falls out of the same gather, which gives the syndrome
 //       test of the previous iteration (:424-445) and the adaptive variants' per-row factor (:745-757) for free.
 //   VN  thread per bit: L = llr + sum over the bit's checks of the message rebuilt from the row record.
-// Graph indices are stored per 32-node group in ELL form ([k][lane], coalesced) and shared by all CTAs through L1/L2;
-// rows and bits are sorted by degree and a group never mixes degrees, so the inner loops carry no validity tests.
+// Storage order = processing order (onchip_layout.hpp): the totals L are stored group by group as the variable phase
+// produces them and the records group by group as the check phase produces them, so both phases write coalesced and
+// conflict-free without an index; Bob's bits (the LLR signs) and the punctured / shortened masks are permuted into the
+// same slot order once per frame / per combination. Which nodes share a warp, the lane of every node and the order in
+// which a check node walks its edges (free: min1 / min2 / sign parity do not depend on it) are chosen on the host so that
+// the 4-byte gathers of the check phase hit 32 different banks (1.2 wavefronts per 32 edges in the bank model) and the
+// 16-byte record gathers of the variable phase collide as little as the graph allows. Graph indices come per 32-node
+// group in ELL form ([block of 4 edges][lane], one 8- / 16-byte load per lane and block) through L1/L2 and carry the
+// shared-memory byte offset itself, so a gather costs no address arithmetic.
 //
 // Eligibility (host): float32 messages, min-sum family with the FAST precondition of run_batch.cuh (no NaN possible),
-// every check degree <= 64 (rows of 33..64 edges own two records), fewer than 65533 records, state fits the 227 KB of
-// shared memory. SPA / SPA-lin-approx have their own on-chip kernel (onchip_spa.cuh); float64 and n = 100k codes stream.
+// every check degree <= 64 (rows of 33..64 edges own two records), n < 16384 (16-bit byte offsets), state fits the 227 KB
+// of shared memory. SPA / SPA-lin-approx have their own on-chip kernel (onchip_spa.cuh), float64 state onchip_minsum64.cuh
+// (both on the older natural-order tables of onchip_tables.cu); n = 100k codes stream.
 #pragma once
 #include "common.cuh"
 
@@ -81,13 +89,29 @@ struct OnchipArgs {
     int max_iter;
     float thr;                  // +inf when the clamp is disabled
     double thr64;               // the same for the float64 kernel (onchip_minsum64.cuh)
+    // float32 min-sum kernel: tables of onchip_layout.hpp (storage order = processing order)
+    int n_groups_cn2, n_groups_vn2;
+    const int4 *cn_g2;          // [groups] {offset into cnT2, degree, first record slot, rows in the group}
+    const uint2 *cnT2;          // [off + kb*32 + lane] 4 x uint16: shared-memory BYTE offset of the totals of edges 4kb..4kb+3
+    const int4 *vn_g2;          // [schedule entries] {offset into vT2, degree (0 = empty entry), first total slot, bits in the group}
+    const uint4 *vT2;           // [off + kb*32 + lane] 4 x uint32: (16 * record slot) << 5 | sh
+    const uint16_t *slot_bit;   // [n] bit whose total lives in slot s
+    const uint16_t *bit_slot;   // [n] inverse
+    const uint32_t *cls_masks2; // [n_combos][2][words] punctured / shortened masks in SLOT order
 };
 
-// Shared-memory layout: rec[rec_slots+2] uint4 | L[n+1] float (padded to 16 B) | bob[words] | alice[words] | syn[groups_cn] | misc
+// Shared-memory layout: L[n+1] float (padded to 16 B) | rec[rec_slots+1] uint4 | bob bits in slot order [words] | syn[groups_cn] |
+// frame id, FrameCtx. While a frame is set up the record array doubles as staging space for the key words (3 * words).
 __host__ __device__ inline size_t onchip_l_slots(int n) { return ((size_t)n + 1 + 3) / 4 * 4; }
-__host__ __device__ inline size_t onchip_smem_bytes(int n, int rec_slots, int groups_cn) {
+__host__ __device__ inline size_t onchip_misc_offset(int n, int rec_slots, int groups_cn) {
     const size_t words = (size_t)(n + 31) / 32;
-    return ((size_t)rec_slots + 2) * 16 + onchip_l_slots(n) * 4 + (2 * words + (size_t)groups_cn) * 4 + 96;   // + frame id, FrameCtx
+    return (onchip_l_slots(n) * 4 + ((size_t)rec_slots + 1) * 16 + (words + (size_t)groups_cn) * 4 + 7) / 8 * 8;
+}
+__host__ __device__ inline size_t onchip_smem_bytes(int n, int rec_slots, int groups_cn) {
+    return onchip_misc_offset(n, rec_slots, groups_cn) + 8 + 48;   // + frame id, FrameCtx
+}
+__host__ __device__ inline bool onchip_staging_fits(int n, int rec_slots) {
+    return ((size_t)rec_slots + 1) * 16 >= 3 * ((size_t)(n + 31) / 32) * 4;
 }
 
 // The sum-product kernel (onchip_spa.cuh): msg[msg_words] float instead of the records, the rest alike.
@@ -110,46 +134,51 @@ struct FrameCtx {
     u64 *tally;
 };
 
-// One edge of a check node: gather L of the bit, rebuild the bit-to-check message with the OLD record, update the
-// running min1 / min2 / argmin / sign state.  `rel` = old argmin - index of the first edge of the current block.
-#define QK_CN_EDGE(J, COL)                                                                                              \
+// One edge of a check node: gather L of the bit (OFF = byte offset of the total in shared memory), rebuild the bit-to-check
+// message with the OLD record, update the running min1 / min2 / sign state. `rel` = old argmin - index of the first edge of
+// the current block. Everything that only needs a sign bit is taken from a float subtraction (FMA pipe) instead of an
+// integer one (ALU pipe, the busier of the two): for x neither NaN nor -0, the sign bit of (0 - x) is (x > 0).
+//   * The magnitude clamp |clamp(x)| == min(|x|, thr) (:447-461) is applied to min1 / min2 after the loop instead of to
+//     every edge: min over clamped values == clamped min, and the first minimum only changes among edges that all sit at
+//     the clamp, where min2 == min1 and the position is irrelevant.
+#define QK_CN_EDGE(J, OFF)                                                                                              \
     {                                                                                                                   \
-        const float Lv = L[(COL)];                                                                                      \
+        const float Lv = *reinterpret_cast<const float *>(smem + (OFF));                                                \
         const uint32_t mag = (rel == (J)) ? ro.y : ro.x;                                                                \
-        /* clamp(L - c2b) (:447-461); first iteration: zero record and thr_b = +inf leave the unclamped LLR (:336-350) */ \
-        const float braw = Lv - __uint_as_float(mag ^ (zs & 0x80000000u));                                              \
+        const float c2b = __uint_as_float(mag ^ (zs & 0x80000000u));                                                    \
         zs <<= 1;                                                                                                       \
-        /* for x neither NaN nor -0: (x <= 0) == sign bit of (bits(x) - 1); L and b are never -0 */                     \
-        zacc ^= __float_as_uint(Lv) - 1u;                 /* parity of the hard decision L <= 0 (:414-422) */            \
-        pacc ^= __float_as_uint(braw);                    /* parity of m < 0 (:383); the clamp keeps the sign */         \
-        own = __funnelshift_l(__float_as_uint(braw) - 1u, own, 1);   /* (m > 0) ? +1 : -1 (:402): zero is negative (Q4) */ \
-        const float ab = fminf(fabsf(braw), thr_b);       /* |clamp(x)| == min(|x|, thr) */                              \
-        arg = (ab < m1) ? (kb + (J)) : arg;               /* first minimum */                                            \
-        m2 = fminf(m2, fmaxf(ab, m1));                    /* == the if / else-if chain (:386-396) */                     \
-        m1 = fminf(m1, ab);                                                                                             \
+        const float braw = Lv - c2b;        /* L - c2b (:447-461); first iteration: zero record leaves the LLR (:336-350) */ \
+        const float nb = c2b - Lv;          /* the same magnitude; a zero stays +0, so its sign bit is (m > 0) */        \
+        zpos ^= __float_as_uint(0.f - Lv);                /* parity of L > 0: the hard decision is z = !(L > 0) (:414-422) */ \
+        pacc ^= __float_as_uint(braw);                    /* parity of m < 0 (:383): zero is positive here (Q4) */       \
+        own = __funnelshift_l(__float_as_uint(nb), own, 1);              /* (m > 0) ? +1 : -1 (:402): zero is negative (Q4) */ \
+        lt = __funnelshift_l(__float_as_uint(fabsf(nb) - m1), lt, 1);    /* |m| < min1: a new first minimum */            \
+        m2 = fminf(m2, fmaxf(fabsf(nb), m1));             /* == the if / else-if chain (:386-396) */                     \
+        m1 = fminf(m1, fabsf(nb));                                                                                      \
     }
 
-// A row of 33..64 edges owns two consecutive records (edges 0..31 and 32..dc-1) with the same c1 / c2; the record that
-// does not hold the first minimum carries kNoArg in w, which no table entry matches.
+// A row of 33..64 edges owns two records (edges 0..31 and 32..dc-1) with the same c1 / c2; the record that does not hold
+// the first minimum carries kNoArg in w, which no table entry matches.
 constexpr uint32_t kNoArg = 0x100u;
 
 template <int ALG, bool WIDE>
-__device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const FrameCtx *ctx, const float *L, uint4 *rec,
+__device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const FrameCtx *ctx, const unsigned char *smem, uint4 *rec,
                                                 const uint32_t *synw, float thr_b, int warp, int lane, int nwarps) {
     bool unsat = false;
-    for (int g = warp; g < a.n_groups_cn; g += nwarps) {
-        const int2 gi = __ldg(a.cn_ginfo + g);
+    for (int g = warp; g < a.n_groups_cn2; g += nwarps) {
+        const int4 gi = __ldg(a.cn_g2 + g);
         const int dc_row = gi.y;                                  // degree of the group's rows (warp-uniform)
         const bool two = WIDE && dc_row > 32;                     // two records per row
         const int dc = two ? 32 : dc_row;                         // edges covered by the first record
-        const uint32_t row = __ldg(a.cn_row + g * 32 + lane);     // first record slot of the lane's row
-        const uint4 ro = rec[row];
-        const uint2 *cp = a.cnT + gi.x + lane;
+        const bool valid = lane < gi.w;
+        const int slot = valid ? gi.z + lane : a.rec_slots;       // padding lanes work on the scratch record
+        const uint4 ro = rec[slot];
+        const uint2 *cp = a.cnT2 + gi.x + lane;
         float m1 = FLT_MAX, m2 = FLT_MAX;
         uint32_t zs = ro.z << (32 - dc);          // sign of the old message on the current edge in bit 31
         const int arg_old = (int)ro.w - (32 - dc);
-        uint32_t own = 0, pacc = 0, zacc = 0;
-        int arg = 0, kb = 0;
+        uint32_t own = 0, pacc = 0, zpos = 0, lt = 0;
+        int kb = 0;
 #pragma unroll 2
         for (; kb + 4 <= dc; kb += 4) {
             const uint2 cw = __ldg(cp + (kb >> 2) * 32);
@@ -166,14 +195,19 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
             if (left > 1) QK_CN_EDGE(1, cw.x >> 16)
             if (left > 2) QK_CN_EDGE(2, cw.y & 0xFFFFu)
         }
+        // the last "new minimum" event is the first minimum: edge k sits in bit dc-1-k of lt (none: every |m| is FLT_MAX)
+        int arg = lt ? dc - __ffs((int)lt) : 0;
         uint32_t own_first = own;
+        int slot2 = 0;
         if constexpr (WIDE) {
             if (two) {                            // edges 32..dc_row-1: the row's second record (warp-uniform branch)
                 const int dc2 = dc_row - 32;
-                const uint4 ro2 = rec[row + 1];
+                slot2 = valid ? slot + gi.w : a.rec_slots;
+                const uint4 ro2 = rec[slot2];
                 zs = ro2.z << (32 - dc2);
                 const int arg_old2 = (int)ro2.w - (32 - dc2);   // kNoArg gives a value no edge index reaches
                 own = 0;
+                lt = 0;
                 for (; kb + 4 <= dc_row; kb += 4) {
                     const uint2 cw = __ldg(cp + (kb >> 2) * 32);
                     const int rel = arg_old2 - (kb - 32);
@@ -191,11 +225,14 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
                     if (left > 1) QK_CN_EDGE(1, cw.x >> 16)
                     if (left > 2) QK_CN_EDGE(2, cw.y & 0xFFFFu)
                 }
+                if (lt) arg = 32 + dc2 - __ffs((int)lt);
             }
         }
+        m1 = fminf(m1, thr_b);                                    // threshold_matrix(bit_to_check), magnitudes (:447-461)
+        m2 = fminf(m2, thr_b);
         const uint32_t syn = (synw[g] >> lane) & 1u;
-        const bool viol = (((zacc >> 31) ^ syn) & 1u) != 0;    // check not satisfied by the current hard decision
-        unsat |= viol && row < (uint32_t)a.rec_slots;
+        const bool viol = (((zpos >> 31) ^ (uint32_t)dc_row ^ syn) & 1u) != 0;   // parity of (L <= 0) = parity of dc + parity of (L > 0)
+        unsat |= viol && valid;
         const float factor = (ALG >= 4 && viol) ? ctx->secondary : ctx->primary;   // (:749-757, :939-947)
         float c1, c2;
         if constexpr (ALG == 2 || ALG == 4) {
@@ -212,14 +249,14 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
         uint4 rn;
         rn.x = __float_as_uint(c1);
         rn.y = __float_as_uint(c2);
-        rn.z = own_first ^ (0u - rowneg);
+        rn.z = own_first ^ (rowneg - 1u);                      // bit = message negative: !(m > 0) xor row sign
         rn.w = (!two || arg < 32) ? (uint32_t)(arg + 32 - dc) : kNoArg;
-        rec[row] = rn;
+        rec[slot] = rn;
         if constexpr (WIDE) {
             if (two) {
-                rn.z = own ^ (0u - rowneg);
+                rn.z = own ^ (rowneg - 1u);
                 rn.w = (arg >= 32) ? (uint32_t)(arg - 32 + 32 - (dc_row - 32)) : kNoArg;
-                rec[row + 1] = rn;
+                rec[slot2] = rn;
             }
         }
     }
@@ -227,37 +264,43 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
 }
 #undef QK_CN_EDGE
 
-__device__ __forceinline__ float onchip_llr(const FrameCtx *ctx, const uint32_t *bobw, uint32_t bit, float lp) {
-    const uint32_t w = bit >> 5, s = bit & 31u;
-    // qkd_ldpc_algorithm.cpp:1043-1049; `0 - lp` instead of `-lp`: never -0 (QBER 0.5 gives lp = 0), which the
-    // bit tricks of the check phase rely on -- the decision (L <= 0) is the reference's either way
-    float v = ((bobw[w] >> s) & 1u) ? 0.f - lp : lp;
+// a-priori LLR of the bit with key bit `bob` (qkd_ldpc_algorithm.cpp:1043-1049); `0 - lp` instead of `-lp`: never -0 (QBER 0.5
+// gives lp = 0), which the sign tricks of the check phase rely on -- the decision (L <= 0) is the reference's either way.
+// `pos` indexes the punctured / shortened masks (natural order for the sum-product kernel, slot order for min-sum).
+__device__ __forceinline__ float onchip_llr_of(const FrameCtx *ctx, uint32_t bob, uint32_t pos, float lp) {
+    float v = bob ? 0.f - lp : lp;
     if (ctx->has_cls) {
+        const uint32_t w = pos >> 5, s = pos & 31u;
         if ((__ldg(ctx->cls_punct + w) >> s) & 1u) v = 1e-4f;  // punctured: ALMOST_ZERO (:1155)
         else if ((__ldg(ctx->cls_short + w) >> s) & 1u) v = FLT_MAX;   // shortened: largest finite value (:1164)
     }
     return v;
 }
+__device__ __forceinline__ float onchip_llr(const FrameCtx *ctx, const uint32_t *bobw, uint32_t bit, float lp) {
+    return onchip_llr_of(ctx, (bobw[bit >> 5] >> (bit & 31u)) & 1u, bit, lp);
+}
 
-// The check-to-bit message addressed by table entry `ent` = row << 9 | sh, added to the running sum.
+// The check-to-bit message addressed by table entry `ent` = (16 * record slot) << 5 | sh, added to the running sum.
 #define QK_VN_EDGE(ENT)                                                                                                 \
     {                                                                                                                   \
         const uint4 r = *reinterpret_cast<const uint4 *>(recb + ((ENT) >> 5));                                          \
-        const uint32_t mag = (((ENT) ^ r.w) & 0x1FFu) ? r.x : r.y;   /* r.w == kNoArg never matches */                                                         \
+        const uint32_t mag = (((ENT) ^ r.w) & 0x1FFu) ? r.x : r.y;   /* r.w == kNoArg never matches */                   \
         acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.z, (ENT)) & 0x80000000u));   /* r.z << sh */           \
     }
 
-__device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *L, const uint4 *rec, const uint32_t *bobw,
+__device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *L, const uint4 *rec, const uint32_t *bobs,
                                                 float lp, int warp, int lane, int nwarps) {
     const unsigned char *recb = reinterpret_cast<const unsigned char *>(rec);
     // groups come in SCHEDULE order: entry g is handled by warp g % nwarps, and the host dealt the groups to the warps
     // longest-first so that all warps of the CTA finish the phase together (inst_onchip.cu)
-    for (int g = warp; g < a.n_groups_vn; g += nwarps) {
-        const int2 gi = __ldg(a.vn_ginfo + g);
+    for (int g = warp; g < a.n_groups_vn2; g += nwarps) {
+        const int4 gi = __ldg(a.vn_g2 + g);
         const int dv = gi.y;
-        const uint32_t bit = __ldg(a.vn_bit + g * 32 + lane);
-        float acc = onchip_llr(ctx, bobw, bit < (uint32_t)a.n ? bit : 0u, lp);
-        const uint4 *ep = a.vT + gi.x + lane;
+        if (dv == 0) continue;                    // empty entry of the schedule
+        const bool valid = lane < gi.w;
+        const uint32_t s = (uint32_t)gi.z + (valid ? (uint32_t)lane : 0u);   // slot of the lane's total (padding lanes: the group's first)
+        float acc = onchip_llr_of(ctx, (bobs[s >> 5] >> (s & 31u)) & 1u, s, lp);
+        const uint4 *ep = a.vT2 + gi.x + lane;
         int kb = 0;
         // ascending check order, starting from the LLR (std::accumulate, :414-417)
 #pragma unroll 2
@@ -275,7 +318,7 @@ __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const Frame
             if (left > 1) QK_VN_EDGE(ew.y)
             if (left > 2) QK_VN_EDGE(ew.z)
         }
-        L[bit] = acc;                             // padding lanes write the scratch slot L[n]
+        L[valid ? s : (uint32_t)a.n] = acc;       // consecutive slots: coalesced; padding lanes write the scratch slot L[n]
     }
 }
 #undef QK_VN_EDGE
@@ -283,14 +326,14 @@ __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const Frame
 template <int ALG, bool WIDE>
 __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4 *rec = reinterpret_cast<uint4 *>(smem_raw);
-    float *L = reinterpret_cast<float *>(rec + a.rec_slots + 2);
-    uint32_t *bobw = reinterpret_cast<uint32_t *>(L + onchip_l_slots(a.n));
-    uint32_t *alw = bobw + a.words;
-    uint32_t *synw = alw + a.words;
-    uint32_t *tail = synw + a.n_groups_cn;
-    long long *s_frame = reinterpret_cast<long long *>(tail + ((2 * a.words + a.n_groups_cn) & 1));
+    float *L = reinterpret_cast<float *>(smem_raw);
+    uint4 *rec = reinterpret_cast<uint4 *>(smem_raw + onchip_l_slots(a.n) * 4);
+    uint32_t *bobs = reinterpret_cast<uint32_t *>(rec + a.rec_slots + 1);
+    uint32_t *synw = bobs + a.words;
+    long long *s_frame = reinterpret_cast<long long *>(smem_raw + onchip_misc_offset(a.n, a.rec_slots, a.n_groups_cn2));
     FrameCtx *ctx = reinterpret_cast<FrameCtx *>(s_frame + 1);
+    // frame set-up only: the key words as they come from HBM and Alice's bits in slot order, inside the record array
+    uint32_t *st_bob = reinterpret_cast<uint32_t *>(rec), *st_alice = st_bob + a.words, *alice_s = st_alice + a.words;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     constexpr bool kAdaptive = (ALG >= 4);
@@ -309,7 +352,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
                 ctx->primary = (float)cb.primary;
                 ctx->secondary = (float)cb.secondary;
                 ctx->has_cls = cb.has_cls;
-                ctx->cls_punct = a.cls_masks + combo * 2 * a.words;
+                ctx->cls_punct = a.cls_masks2 + combo * 2 * a.words;   // slot order
                 ctx->cls_short = ctx->cls_punct + a.words;
                 ctx->tally = a.tally ? a.tally + combo * a.tally_len : nullptr;
             }
@@ -319,31 +362,44 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
         if (f >= a.n_frames) break;
         const float lp = ctx->lp;
         for (int w = tid; w < a.words; w += blockDim.x) {
-            bobw[w] = a.bob_bits[f * a.words + w];
-            alw[w] = a.alice_bits[f * a.words + w];
+            st_bob[w] = a.bob_bits[f * a.words + w];
+            st_alice[w] = a.alice_bits[f * a.words + w];
         }
         __syncthreads();
-        // L = a-priori LLR; Alice's syndrome (calculate_syndrome, array_and_matrix_operations.cpp:936-950); records = 0
-        for (int i = tid; i <= a.n; i += blockDim.x) L[i] = (i < a.n) ? onchip_llr(ctx, bobw, (uint32_t)i, lp) : 1.f;
-        for (int g = warp; g < a.n_groups_cn; g += nwarps) {
-            const int2 gi = __ldg(a.cn_ginfo + g);
-            const uint32_t row = __ldg(a.cn_row + g * 32 + lane);
-            const uint2 *cp = a.cnT + gi.x + lane;
-            uint32_t s = 0;
+        // key bits into slot order; L = a-priori LLR (qkd_ldpc_algorithm.cpp:1043-1049)
+        for (int s0 = warp * 32; s0 < a.n; s0 += nwarps * 32) {
+            const int s = s0 + lane;
+            const bool v = s < a.n;
+            const uint32_t bit = v ? (uint32_t)__ldg(a.slot_bit + s) : 0u;
+            const uint32_t bb = (st_bob[bit >> 5] >> (bit & 31u)) & 1u, ab = (st_alice[bit >> 5] >> (bit & 31u)) & 1u;
+            const uint32_t wb = __ballot_sync(0xffffffffu, v && bb), wa = __ballot_sync(0xffffffffu, v && ab);
+            if (lane == 0) {
+                bobs[s0 >> 5] = wb;
+                alice_s[s0 >> 5] = wa;
+            }
+            if (v) L[s] = onchip_llr_of(ctx, bb, (uint32_t)s, lp);
+        }
+        if (tid == 0) L[a.n] = 1.f;
+        __syncthreads();
+        // Alice's syndrome (calculate_syndrome, array_and_matrix_operations.cpp:936-950) over the check-phase table
+        for (int g = warp; g < a.n_groups_cn2; g += nwarps) {
+            const int4 gi = __ldg(a.cn_g2 + g);
+            const uint2 *cp = a.cnT2 + gi.x + lane;
+            uint32_t sy = 0;
             for (int kb = 0; kb < gi.y; kb += 4) {
                 const uint2 cw = __ldg(cp + (kb >> 2) * 32);
                 const int left = gi.y - kb;
-                const uint32_t c0 = cw.x & 0xFFFFu, c1 = cw.x >> 16, c2 = cw.y & 0xFFFFu, c3 = cw.y >> 16;
-                s ^= alw[c0 >> 5] >> (c0 & 31u);
-                if (left > 1) s ^= alw[c1 >> 5] >> (c1 & 31u);
-                if (left > 2) s ^= alw[c2 >> 5] >> (c2 & 31u);
-                if (left > 3) s ^= alw[c3 >> 5] >> (c3 & 31u);
+                const uint32_t c0 = (cw.x & 0xFFFFu) >> 2, c1 = cw.x >> 18, c2 = (cw.y & 0xFFFFu) >> 2, c3 = cw.y >> 18;   // slots
+                sy ^= alice_s[c0 >> 5] >> (c0 & 31u);
+                if (left > 1) sy ^= alice_s[c1 >> 5] >> (c1 & 31u);
+                if (left > 2) sy ^= alice_s[c2 >> 5] >> (c2 & 31u);
+                if (left > 3) sy ^= alice_s[c3 >> 5] >> (c3 & 31u);
             }
-            const uint32_t sw = __ballot_sync(0xffffffffu, (s & 1u) != 0 && row < (uint32_t)a.rec_slots);
+            const uint32_t sw = __ballot_sync(0xffffffffu, (sy & 1u) != 0 && lane < gi.w);
             if (lane == 0) synw[g] = sw;
-            rec[row] = make_uint4(0u, 0u, 0u, 0u);
-            if (WIDE && gi.y > 32) rec[row + 1] = make_uint4(0u, 0u, 0u, 0u);
         }
+        __syncthreads();
+        for (int i = tid; i <= a.rec_slots; i += blockDim.x) rec[i] = make_uint4(0u, 0u, 0u, 0u);   // over the staging words
         __syncthreads();
 
         int iters = a.max_iter, run = a.max_iter;
@@ -351,7 +407,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
         for (int it = 1;; ++it) {
             // the check-node pass of iteration `it`; at it = max_iter + 1 it only serves as the syndrome test of the
             // last hard decision (non-adaptive variants, :424-445)
-            const bool unsat = onchip_cn_phase<ALG, WIDE>(a, ctx, L, rec, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
+            const bool unsat = onchip_cn_phase<ALG, WIDE>(a, ctx, smem_raw, rec, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
             const bool any_unsat = __syncthreads_or(unsat) != 0;
             if (!kAdaptive) {
                 if (it > 1 && !any_unsat) { success = true; iters = run = it - 1; break; }   // z of iteration it-1 (:439-445)
@@ -359,19 +415,20 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
             } else {
                 if (!any_unsat) { success = true; iters = it; run = it - 1; break; }         // exit test before the VN step (:770-776)
             }
-            onchip_vn_phase(a, ctx, L, rec, bobw, lp, warp, lane, nwarps);
+            onchip_vn_phase(a, ctx, L, rec, bobs, lp, warp, lane, nwarps);
             __syncthreads();
             if (kAdaptive && it == a.max_iter) break;          // the decision of the last iteration is never tested (Q10)
         }
 
-        // bob_solution = last hard decision (L <= 0), packed; keys compare (arrays_equal, :1087)
+        // bob_solution = last hard decision (L <= 0), packed in natural bit order; keys compare (arrays_equal, :1087)
         uint32_t diff = 0;
         for (int w = warp; w < a.words; w += nwarps) {
             const int i = w * 32 + lane;
-            const uint32_t word = __ballot_sync(0xffffffffu, i < a.n && L[i < a.n ? i : 0] <= 0.f);
+            const uint32_t s = i < a.n ? (uint32_t)__ldg(a.bit_slot + i) : 0u;
+            const uint32_t word = __ballot_sync(0xffffffffu, i < a.n && L[s] <= 0.f);
             if (lane == 0) {
                 if (a.out_bits) a.out_bits[f * a.words + w] = word;
-                diff |= word ^ alw[w];
+                diff |= word ^ a.alice_bits[f * a.words + w];
             }
         }
         const bool keys_differ = __syncthreads_or(diff != 0) != 0;

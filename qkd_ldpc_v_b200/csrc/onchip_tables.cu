@@ -270,6 +270,10 @@ int build_onchip_tables(int n, int m, long long nnz, const std::vector<int> &rp,
         }
         if (edges_sv != (size_t)nnz) return fail(QKDLDPC_ERR_STATE, "sum-product tables cover %zu of %lld edges", edges_sv, (long long)nnz);
     }
+    // float32 min-sum kernel: its own layout (storage order = processing order, conflict-aware lanes and edge order)
+    build_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), 1, T.oc2);
+    if (const char *err = check_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), T.oc2))
+        return fail(QKDLDPC_ERR_STATE, "on-chip min-sum layout: %s", err);
     return QKDLDPC_OK;
 }
 
