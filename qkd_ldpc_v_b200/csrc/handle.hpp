@@ -142,7 +142,8 @@ struct qkdldpc_code {
     int oc_threads = 0;               // CTA size of the last on-chip launch
     // float32 min-sum kernel: tables of onchip_layout.hpp
     bool oc2_eligible = false;
-    int oc2_groups_cn = 0, oc2_groups_vn = 0, oc2_rec_slots = 0, oc2_max_dc = 0, oc2_sched_warps = 0;
+    int oc2_groups_cn = 0, oc2_l_slots = 0, oc2_rec_slots = 0, oc2_max_dc = 0, oc2_sched_warps = 0;
+    DevBuf<int> oc2_vn_start;
     DevBuf<int4> oc2_cn_g, oc2_vn_g;
     DevBuf<uint2> oc2_cnT;
     DevBuf<uint4> oc2_vT;

@@ -28,7 +28,8 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return false;
     if (f64) return onchip64_smem_bytes(c->n, c->oc_rec_slots, c->oc_groups_cn) <= (size_t)dev_smem;
-    return onchip_staging_fits(c->n, c->oc2_rec_slots) && onchip_smem_bytes(c->n, c->oc2_rec_slots, c->oc2_groups_cn) <= (size_t)dev_smem;
+    return onchip_staging_fits(c->n, c->oc2_l_slots, c->oc2_rec_slots) &&
+           onchip_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn) <= (size_t)dev_smem;
 }
 
 // threads == 0: pick the CTA size that puts the most warps on an SM (shared memory decides how many CTAs fit; ties go
@@ -235,7 +236,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(max_threads, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
     const size_t smem = spa   ? onchip_spa_smem_bytes(n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv)
                         : f64 ? onchip64_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn)
-                              : onchip_smem_bytes(n, c->oc2_rec_slots, c->oc2_groups_cn);
+                              : onchip_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn);
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 
@@ -295,25 +296,32 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     } else {
         // float32: the tables of onchip_layout.hpp; the canonical variable-phase groups are dealt to the warps of this CTA size
         if (c->oc2_sched_warps != threads / 32) {
+            const int nw = threads / 32;
             std::vector<int> degree;
             for (const Oc2Group &g : c->oc2_vn_g_host) degree.push_back(g.deg);
-            const std::vector<int> sched = vn_schedule(degree, threads / 32);
-            std::vector<Oc2Group> dealt(sched.size(), Oc2Group{0, 0, 0, 0});
-            for (size_t i = 0; i < sched.size(); ++i)
-                if (sched[i] >= 0) dealt[i] = c->oc2_vn_g_host[sched[i]];
+            const std::vector<int> sched = vn_schedule(degree, nw);   // entry i belongs to warp i % nw; -1 = none
+            std::vector<Oc2Group> dealt;
+            std::vector<int> start(nw + 1, 0);
+            for (int w = 0; w < nw; ++w) {
+                for (size_t i = (size_t)w; i < sched.size(); i += (size_t)nw)
+                    if (sched[i] >= 0) dealt.push_back(c->oc2_vn_g_host[sched[i]]);
+                start[w + 1] = (int)dealt.size();
+            }
             CK(c->oc2_vn_g.reserve(dealt.size()));
+            CK(c->oc2_vn_start.reserve(start.size()));
             CK(cudaMemcpyAsync(c->oc2_vn_g.p, dealt.data(), dealt.size() * sizeof(Oc2Group), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(c->oc2_vn_start.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
-            c->oc2_sched_warps = threads / 32;
-            c->oc2_groups_vn = (int)dealt.size();
+            c->oc2_sched_warps = nw;
         }
         // punctured / shortened masks of every combination into slot order
-        std::vector<uint32_t> masks2((size_t)n_combos * 2 * words, 0u);
+        const int swords = c->oc2_l_slots / 32;
+        std::vector<uint32_t> masks2((size_t)n_combos * 2 * swords, 0u);
         for (int cb = 0; cb < n_combos; ++cb) {
             if (!combos[cb].has_cls) continue;
             for (int h = 0; h < 2; ++h) {
                 const uint32_t *src = masks + ((size_t)cb * 2 + h) * words;
-                uint32_t *dst = masks2.data() + ((size_t)cb * 2 + h) * words;
+                uint32_t *dst = masks2.data() + ((size_t)cb * 2 + h) * swords;
                 for (int w = 0; w < words; ++w)
                     for (uint32_t bitsw = src[w]; bitsw; bitsw &= bitsw - 1) {
                         const int sl = c->oc2_bit_slot_host[(size_t)w * 32 + __builtin_ctz(bitsw)];
@@ -325,8 +333,8 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         CK(cudaMemcpyAsync(c->oc2_cls.p, masks2.data(), masks2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
         a.rec_slots = c->oc2_rec_slots;
-        a.n_groups_cn2 = c->oc2_groups_cn; a.n_groups_vn2 = c->oc2_groups_vn;
-        a.cn_g2 = c->oc2_cn_g.p; a.cnT2 = c->oc2_cnT.p; a.vn_g2 = c->oc2_vn_g.p; a.vT2 = c->oc2_vT.p;
+        a.n_groups_cn2 = c->oc2_groups_cn; a.l_slots = c->oc2_l_slots;
+        a.cn_g2 = c->oc2_cn_g.p; a.cnT2 = c->oc2_cnT.p; a.vn_g2 = c->oc2_vn_g.p; a.vn_start = c->oc2_vn_start.p; a.vT2 = c->oc2_vT.p;
         a.slot_bit = c->oc2_slot_bit.p; a.bit_slot = c->oc2_bit_slot.p; a.cls_masks2 = c->oc2_cls.p;
     }
 

@@ -34,10 +34,11 @@ struct Oc2Group { int off, deg, base, cnt; };   // int4 on the device: table off
 struct Oc2Tables {
     bool ok = false;
     int n = 0, m = 0, max_dc = 0;
-    int l_slots = 0;       // totals in use (== n); slot l_slots is scratch (padding lanes)
-    int rec_slots = 0;     // records in use (m + rows wider than 32 edges); slot rec_slots is scratch
+    int l_slots = 0;       // slots of the totals: 32 per variable-phase group (the last group of a degree class is padded)
+    int rec_slots = 0;     // records in use (m + rows wider than 32 edges); slot rec_slots is scratch for the check phase's
+                           // padding lanes, slot rec_slots + 1 stays all-zero (the +0.0f message of padding table entries)
     std::vector<int> bit_slot;        // [n] slot of a bit's total
-    std::vector<uint16_t> slot_bit;   // [n] inverse
+    std::vector<uint16_t> slot_bit;   // [l_slots] inverse; 0xFFFF = padding slot
     std::vector<int> row_slot;        // [m] record of edges at positions 0..31
     std::vector<int> row_slot2;       // [m] record of positions 32..dc-1, or -1
     std::vector<int> edge_pos;        // [nnz] position of CSR edge e in its row's processing order
@@ -145,9 +146,8 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
     int wide_rows = 0;
     for (int j = 0; j < m; ++j) wide_rows += (rp[j + 1] - rp[j]) > 32;
     // byte offsets of the totals are 16-bit table entries; record addresses (<< 5) must fit 32 bits with room to spare
-    T.ok = T.max_dc <= 64 && (long long)(n + 1) * 4 <= 65535 && (long long)m + wide_rows + 1 < (1 << 20);
+    T.ok = T.max_dc <= 64 && (long long)m + wide_rows + 2 < (1 << 20);
     if (!T.ok) return;
-    T.l_slots = n;
     T.rec_slots = m + wide_rows;
 
     // ---- stage 1: degree classes (widest first), natural order inside
@@ -205,8 +205,13 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
             for (size_t i = g0; i < std::min(cls.size(), g0 + 32); ++i) row_group[cls[i]] = n_cn_groups;
             ++n_cn_groups;
         }
-    std::vector<int> class_base(bcls.size() + 1, 0);
-    for (size_t c = 0; c < bcls.size(); ++c) class_base[c + 1] = class_base[c] + (int)bcls[c].size();
+    std::vector<int> class_base(bcls.size() + 1, 0);   // every class starts on a multiple of 32: slot & 31 == lane == bank
+    for (size_t c = 0; c < bcls.size(); ++c) class_base[c + 1] = class_base[c] + (int)((bcls[c].size() + 31) / 32 * 32);
+    T.l_slots = class_base.back();
+    if ((long long)T.l_slots * 4 > 65535) {   // byte offsets of the totals are 16-bit table entries
+        T.ok = false;
+        return;
+    }
     T.bit_slot.assign(n, 0);
     auto refresh_bit_slots = [&]() {
         for (size_t c = 0; c < bcls.size(); ++c)
@@ -287,7 +292,7 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
         }
         refresh_bit_slots();
     }
-    T.slot_bit.assign(n, 0);
+    T.slot_bit.assign(T.l_slots, (uint16_t)0xFFFF);
     for (int b = 0; b < n; ++b) T.slot_bit[T.bit_slot[b]] = (uint16_t)b;
 
     // ---- stage 4: edge order of every check group. Step k: maximum bipartite matching rows -> banks over the edges not
@@ -406,7 +411,7 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                 for (int l = 0; l < 32; ++l) {
                     uint32_t e[4];
                     for (int j = 0; j < 4; ++j) {
-                        e[j] = ((uint32_t)T.rec_slots * 16u) << 5;   // padding: the scratch record (all zero: adds +0.0f)
+                        e[j] = ((uint32_t)(T.rec_slots + 1) * 16u) << 5;   // padding: the all-zero record (adds +0.0f)
                         const int k = kb * 4 + j;
                         if (l < cnt && k < dv) {
                             const int p = col_ptr[v[g0 + l]] + k, r = csc_row[p], pos = T.edge_pos[csc_edge[p]], dcr = rp[r + 1] - rp[r];
@@ -436,13 +441,15 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
 inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, const int *col_idx, const int *col_ptr, const int *csc_edge,
                                     const int *csc_row, const Oc2Tables &T) {
     if (!T.ok) return nullptr;
-    if ((int)T.bit_slot.size() != n || (int)T.slot_bit.size() != n || (int)T.row_slot.size() != m) return "table sizes";
-    std::vector<char> seen_slot(n, 0), seen_rec(T.rec_slots, 0);
+    if ((int)T.bit_slot.size() != n || (int)T.slot_bit.size() != T.l_slots || (int)T.row_slot.size() != m || n >= 0xFFFF) return "table sizes";
+    std::vector<char> seen_slot(T.l_slots, 0), seen_rec(T.rec_slots, 0);
     for (int b = 0; b < n; ++b) {
         const int s = T.bit_slot[b];
-        if (s < 0 || s >= n || seen_slot[s] || T.slot_bit[s] != b) return "bit -> slot is not a permutation";
+        if (s < 0 || s >= T.l_slots || seen_slot[s] || T.slot_bit[s] != b) return "bit -> slot is not injective";
         seen_slot[s] = 1;
     }
+    for (int s = 0; s < T.l_slots; ++s)
+        if (!seen_slot[s] && T.slot_bit[s] != 0xFFFF) return "padding slot not marked";
     for (int j = 0; j < m; ++j) {
         const int dc = rp[j + 1] - rp[j];
         if ((dc > 32) != (T.row_slot2[j] >= 0)) return "second record of a row";
@@ -482,19 +489,19 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
             for (int l = 0; l < 32; ++l) {
                 const Oc2U2 w = T.cnT[(size_t)g.off + (size_t)kb * 32 + l];
                 for (uint32_t off : {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16})
-                    if ((off & 3u) || off / 4 > (uint32_t)n) return "check table: offset out of range";
+                    if ((off & 3u) || off / 4 >= (uint32_t)T.l_slots || T.slot_bit[off / 4] == 0xFFFF) return "check table: offset out of range";
             }
     }
     int next_slot = 0;
     for (const Oc2Group &g : T.vn_g) {
         const int blocks = (g.deg + 3) / 4;
         if (g.deg < 1 || g.cnt < 1 || g.cnt > 32 || g.base != next_slot || g.off < 0 || (size_t)g.off + (size_t)blocks * 32 > T.vT.size()) return "variable group header";
-        next_slot += g.cnt;
+        next_slot += 32;
         for (int l = 0; l < 32; ++l)
             for (int k = 0; k < blocks * 4; ++k) {
                 const uint32_t ent = (&T.vT[(size_t)g.off + (size_t)(k / 4) * 32 + l].x)[k % 4];
                 const int slot = (int)(ent >> 9), sh = (int)(ent & 511u);
-                if ((ent >> 5 & 15u) || slot > T.rec_slots || sh > 31) return "variable table: bad entry";
+                if ((ent >> 5 & 15u) || slot > T.rec_slots + 1 || sh > 31) return "variable table: bad entry";
                 if (l < g.cnt && k < g.deg) {
                     const int b = T.slot_bit[g.base + l];
                     if (col_ptr[b + 1] - col_ptr[b] != g.deg) return "variable group: bit of another degree";
@@ -502,12 +509,12 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
                     const int in_rec = (dcr <= 32) ? dcr : (pos < 32 ? 32 : dcr - 32);
                     if (slot != (pos < 32 ? T.row_slot[r] : T.row_slot2[r]) || sh != 32 - in_rec + pos % 32) return "variable table: wrong record or shift";
                     ++edges_vn;
-                } else if (slot != T.rec_slots) {
-                    return "variable table: padding entry does not point at the scratch record";
+                } else if (slot != T.rec_slots + 1) {
+                    return "variable table: padding entry does not point at the all-zero record";
                 }
             }
     }
-    if (next_slot != n) return "variable groups do not cover the totals";
+    if (next_slot != T.l_slots) return "variable groups do not cover the totals";
     if (edges_cn != nnz || edges_vn != nnz) return "tables do not cover every edge once";
     return nullptr;
 }

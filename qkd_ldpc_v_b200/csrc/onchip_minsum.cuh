@@ -90,28 +90,29 @@ struct OnchipArgs {
     float thr;                  // +inf when the clamp is disabled
     double thr64;               // the same for the float64 kernel (onchip_minsum64.cuh)
     // float32 min-sum kernel: tables of onchip_layout.hpp (storage order = processing order)
-    int n_groups_cn2, n_groups_vn2;
+    int n_groups_cn2, l_slots;  // l_slots: 32 per variable-phase group
     const int4 *cn_g2;          // [groups] {offset into cnT2, degree, first record slot, rows in the group}
     const uint2 *cnT2;          // [off + kb*32 + lane] 4 x uint16: shared-memory BYTE offset of the totals of edges 4kb..4kb+3
-    const int4 *vn_g2;          // [schedule entries] {offset into vT2, degree (0 = empty entry), first total slot, bits in the group}
-    const uint4 *vT2;           // [off + kb*32 + lane] 4 x uint32: (16 * record slot) << 5 | sh
-    const uint16_t *slot_bit;   // [n] bit whose total lives in slot s
+    const int4 *vn_g2;          // [groups, dealt to the warps] {offset into vT2, degree, first total slot (multiple of 32), bits in the group}
+    const int *vn_start;        // [warps per CTA + 1] warp w handles vn_g2[vn_start[w] .. vn_start[w+1])
+    const uint4 *vT2;           // [off + kb*32 + lane] 4 x uint32: (16 * record slot) << 5 | sh; entries past the degree: the all-zero record
+    const uint16_t *slot_bit;   // [l_slots] bit whose total lives in slot s; 0xFFFF = padding slot
     const uint16_t *bit_slot;   // [n] inverse
-    const uint32_t *cls_masks2; // [n_combos][2][words] punctured / shortened masks in SLOT order
+    const uint32_t *cls_masks2; // [n_combos][2][l_slots/32] punctured / shortened masks in SLOT order
 };
 
-// Shared-memory layout: L[n+1] float (padded to 16 B) | rec[rec_slots+1] uint4 | bob bits in slot order [words] | syn[groups_cn] |
-// frame id, FrameCtx. While a frame is set up the record array doubles as staging space for the key words (3 * words).
-__host__ __device__ inline size_t onchip_l_slots(int n) { return ((size_t)n + 1 + 3) / 4 * 4; }
-__host__ __device__ inline size_t onchip_misc_offset(int n, int rec_slots, int groups_cn) {
-    const size_t words = (size_t)(n + 31) / 32;
-    return (onchip_l_slots(n) * 4 + ((size_t)rec_slots + 1) * 16 + (words + (size_t)groups_cn) * 4 + 7) / 8 * 8;
+// Shared-memory layout: L[l_slots] float | rec[rec_slots+2] uint4 | bob bits in slot order [l_slots/32] | syn[groups_cn] |
+// frame id, FrameCtx. While a frame is set up the record array doubles as staging space for the key words
+// (2 * words as they come from HBM + l_slots/32 of Alice's bits in slot order).
+__host__ __device__ inline size_t onchip_l_slots(int n) { return ((size_t)n + 1 + 3) / 4 * 4; }   // sum-product kernel
+__host__ __device__ inline size_t onchip_misc_offset(int l_slots, int rec_slots, int groups_cn) {
+    return ((size_t)l_slots * 4 + ((size_t)rec_slots + 2) * 16 + ((size_t)l_slots / 32 + (size_t)groups_cn) * 4 + 7) / 8 * 8;
 }
-__host__ __device__ inline size_t onchip_smem_bytes(int n, int rec_slots, int groups_cn) {
-    return onchip_misc_offset(n, rec_slots, groups_cn) + 8 + 48;   // + frame id, FrameCtx
+__host__ __device__ inline size_t onchip_smem_bytes(int l_slots, int rec_slots, int groups_cn) {
+    return onchip_misc_offset(l_slots, rec_slots, groups_cn) + 8 + 48;   // + frame id, FrameCtx
 }
-__host__ __device__ inline bool onchip_staging_fits(int n, int rec_slots) {
-    return ((size_t)rec_slots + 1) * 16 >= 3 * ((size_t)(n + 31) / 32) * 4;
+__host__ __device__ inline bool onchip_staging_fits(int n, int l_slots, int rec_slots) {
+    return ((size_t)rec_slots + 2) * 16 >= (2 * ((size_t)(n + 31) / 32) + (size_t)l_slots / 32) * 4;
 }
 
 // The sum-product kernel (onchip_spa.cuh): msg[msg_words] float instead of the records, the rest alike.
@@ -288,37 +289,59 @@ __device__ __forceinline__ float onchip_llr(const FrameCtx *ctx, const uint32_t 
         acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.z, (ENT)) & 0x80000000u));   /* r.z << sh */           \
     }
 
+// A group of 32 bits of degree DV <= 8, straight line: all index blocks first, then exactly DV messages.
+template <int DV>
+__device__ __forceinline__ float onchip_vn_fixed(const uint4 *ep, const unsigned char *recb, float acc) {
+    uint4 ew[(DV + 3) / 4];
+#pragma unroll
+    for (int b = 0; b < (DV + 3) / 4; ++b) ew[b] = __ldg(ep + b * 32);
+#pragma unroll
+    for (int k = 0; k < DV; ++k) {
+        const uint32_t ent = (k % 4 == 0) ? ew[k / 4].x : (k % 4 == 1) ? ew[k / 4].y : (k % 4 == 2) ? ew[k / 4].z : ew[k / 4].w;
+        QK_VN_EDGE(ent)
+    }
+    return acc;
+}
+
 __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *L, const uint4 *rec, const uint32_t *bobs,
-                                                float lp, int warp, int lane, int nwarps) {
+                                                float lp, int warp, int lane) {
     const unsigned char *recb = reinterpret_cast<const unsigned char *>(rec);
-    // groups come in SCHEDULE order: entry g is handled by warp g % nwarps, and the host dealt the groups to the warps
-    // longest-first so that all warps of the CTA finish the phase together (inst_onchip.cu)
-    for (int g = warp; g < a.n_groups_vn2; g += nwarps) {
+    const float nlp = 0.f - lp;
+    const int has_cls = ctx->has_cls;
+    // the host dealt the groups to the warps longest-first so that all warps of the CTA finish the phase together
+    // (inst_onchip.cu); warp w owns a contiguous run of the dealt list
+    const int g_end = __ldg(a.vn_start + warp + 1);
+    for (int g = __ldg(a.vn_start + warp); g < g_end; ++g) {
         const int4 gi = __ldg(a.vn_g2 + g);
         const int dv = gi.y;
-        if (dv == 0) continue;                    // empty entry of the schedule
-        const bool valid = lane < gi.w;
-        const uint32_t s = (uint32_t)gi.z + (valid ? (uint32_t)lane : 0u);   // slot of the lane's total (padding lanes: the group's first)
-        float acc = onchip_llr_of(ctx, (bobs[s >> 5] >> (s & 31u)) & 1u, s, lp);
+        const uint32_t s = (uint32_t)gi.z + (uint32_t)lane;       // the group's 32 slots start on a multiple of 32
+        // a-priori LLR (qkd_ldpc_algorithm.cpp:1043-1049, onchip_llr_of); padding lanes see Bob bit 0
+        float acc = ((bobs[gi.z >> 5] >> lane) & 1u) ? nlp : lp;
+        if (has_cls) acc = onchip_llr_of(ctx, (bobs[gi.z >> 5] >> lane) & 1u, s, lp);
         const uint4 *ep = a.vT2 + gi.x + lane;
-        int kb = 0;
         // ascending check order, starting from the LLR (std::accumulate, :414-417)
+        switch (dv) {
+            case 1: acc = onchip_vn_fixed<1>(ep, recb, acc); break;
+            case 2: acc = onchip_vn_fixed<2>(ep, recb, acc); break;
+            case 3: acc = onchip_vn_fixed<3>(ep, recb, acc); break;
+            case 4: acc = onchip_vn_fixed<4>(ep, recb, acc); break;
+            case 5: acc = onchip_vn_fixed<5>(ep, recb, acc); break;
+            case 6: acc = onchip_vn_fixed<6>(ep, recb, acc); break;
+            case 7: acc = onchip_vn_fixed<7>(ep, recb, acc); break;
+            case 8: acc = onchip_vn_fixed<8>(ep, recb, acc); break;
+            default:
+                // whole blocks of 4: the entries past the degree address the all-zero record, and x + (+0.0f) == x for
+                // every x that is not -0 (a sum that starts from an LLR that is never -0 cannot become -0)
 #pragma unroll 2
-        for (; kb + 4 <= dv; kb += 4) {
-            const uint4 ew = __ldg(ep + (kb >> 2) * 32);
-            QK_VN_EDGE(ew.x)
-            QK_VN_EDGE(ew.y)
-            QK_VN_EDGE(ew.z)
-            QK_VN_EDGE(ew.w)
+                for (int kb = 0; kb < dv; kb += 4) {
+                    const uint4 ew = __ldg(ep + (kb >> 2) * 32);
+                    QK_VN_EDGE(ew.x)
+                    QK_VN_EDGE(ew.y)
+                    QK_VN_EDGE(ew.z)
+                    QK_VN_EDGE(ew.w)
+                }
         }
-        if (kb < dv) {                            // warp-uniform tail of 1..3 checks
-            const uint4 ew = __ldg(ep + (kb >> 2) * 32);
-            const int left = dv - kb;
-            QK_VN_EDGE(ew.x)
-            if (left > 1) QK_VN_EDGE(ew.y)
-            if (left > 2) QK_VN_EDGE(ew.z)
-        }
-        L[valid ? s : (uint32_t)a.n] = acc;       // consecutive slots: coalesced; padding lanes write the scratch slot L[n]
+        L[s] = acc;                               // consecutive slots: coalesced; padding lanes own padding slots
     }
 }
 #undef QK_VN_EDGE
@@ -327,13 +350,13 @@ template <int ALG, bool WIDE>
 __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *L = reinterpret_cast<float *>(smem_raw);
-    uint4 *rec = reinterpret_cast<uint4 *>(smem_raw + onchip_l_slots(a.n) * 4);
-    uint32_t *bobs = reinterpret_cast<uint32_t *>(rec + a.rec_slots + 1);
-    uint32_t *synw = bobs + a.words;
-    long long *s_frame = reinterpret_cast<long long *>(smem_raw + onchip_misc_offset(a.n, a.rec_slots, a.n_groups_cn2));
+    uint4 *rec = reinterpret_cast<uint4 *>(smem_raw + (size_t)a.l_slots * 4);
+    uint32_t *bobs = reinterpret_cast<uint32_t *>(rec + a.rec_slots + 2);
+    uint32_t *synw = bobs + a.l_slots / 32;
+    long long *s_frame = reinterpret_cast<long long *>(smem_raw + onchip_misc_offset(a.l_slots, a.rec_slots, a.n_groups_cn2));
     FrameCtx *ctx = reinterpret_cast<FrameCtx *>(s_frame + 1);
     // frame set-up only: the key words as they come from HBM and Alice's bits in slot order, inside the record array
-    uint32_t *st_bob = reinterpret_cast<uint32_t *>(rec), *st_alice = st_bob + a.words, *alice_s = st_alice + a.words;
+    uint32_t *st_bob = reinterpret_cast<uint32_t *>(rec), *st_alice = st_bob + a.words, *alice_s = st_alice + a.words;   // [l_slots/32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     constexpr bool kAdaptive = (ALG >= 4);
@@ -352,8 +375,8 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
                 ctx->primary = (float)cb.primary;
                 ctx->secondary = (float)cb.secondary;
                 ctx->has_cls = cb.has_cls;
-                ctx->cls_punct = a.cls_masks2 + combo * 2 * a.words;   // slot order
-                ctx->cls_short = ctx->cls_punct + a.words;
+                ctx->cls_punct = a.cls_masks2 + combo * 2 * (a.l_slots / 32);   // slot order
+                ctx->cls_short = ctx->cls_punct + a.l_slots / 32;
                 ctx->tally = a.tally ? a.tally + combo * a.tally_len : nullptr;
             }
         }
@@ -367,19 +390,19 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
         }
         __syncthreads();
         // key bits into slot order; L = a-priori LLR (qkd_ldpc_algorithm.cpp:1043-1049)
-        for (int s0 = warp * 32; s0 < a.n; s0 += nwarps * 32) {
+        for (int s0 = warp * 32; s0 < a.l_slots; s0 += nwarps * 32) {
             const int s = s0 + lane;
-            const bool v = s < a.n;
-            const uint32_t bit = v ? (uint32_t)__ldg(a.slot_bit + s) : 0u;
+            const uint32_t sb = (uint32_t)__ldg(a.slot_bit + s);
+            const bool v = sb != 0xFFFFu;             // else a padding slot: never gathered, holds a harmless finite value
+            const uint32_t bit = v ? sb : 0u;
             const uint32_t bb = (st_bob[bit >> 5] >> (bit & 31u)) & 1u, ab = (st_alice[bit >> 5] >> (bit & 31u)) & 1u;
             const uint32_t wb = __ballot_sync(0xffffffffu, v && bb), wa = __ballot_sync(0xffffffffu, v && ab);
             if (lane == 0) {
                 bobs[s0 >> 5] = wb;
                 alice_s[s0 >> 5] = wa;
             }
-            if (v) L[s] = onchip_llr_of(ctx, bb, (uint32_t)s, lp);
+            L[s] = v ? onchip_llr_of(ctx, bb, (uint32_t)s, lp) : 1.f;
         }
-        if (tid == 0) L[a.n] = 1.f;
         __syncthreads();
         // Alice's syndrome (calculate_syndrome, array_and_matrix_operations.cpp:936-950) over the check-phase table
         for (int g = warp; g < a.n_groups_cn2; g += nwarps) {
@@ -399,7 +422,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
             if (lane == 0) synw[g] = sw;
         }
         __syncthreads();
-        for (int i = tid; i <= a.rec_slots; i += blockDim.x) rec[i] = make_uint4(0u, 0u, 0u, 0u);   // over the staging words
+        for (int i = tid; i < a.rec_slots + 2; i += blockDim.x) rec[i] = make_uint4(0u, 0u, 0u, 0u);   // over the staging words
         __syncthreads();
 
         int iters = a.max_iter, run = a.max_iter;
@@ -415,7 +438,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
             } else {
                 if (!any_unsat) { success = true; iters = it; run = it - 1; break; }         // exit test before the VN step (:770-776)
             }
-            onchip_vn_phase(a, ctx, L, rec, bobs, lp, warp, lane, nwarps);
+            onchip_vn_phase(a, ctx, L, rec, bobs, lp, warp, lane);
             __syncthreads();
             if (kAdaptive && it == a.max_iter) break;          // the decision of the last iteration is never tested (Q10)
         }
