@@ -353,12 +353,22 @@ def measure(ctx, args, wl, F, steps, warmup, sampler=None, want_e2e=True):
         kname = ("onchip_minsum_kernel" if prec == 32 else "onchip_minsum64_kernel") if alg >= 2 else "onchip_spa_kernel"
         ent = db.get(kname, {})
         tr = ent.get("dram_bytes_per_frame")
+        # phase split of the float32 min-sum kernel: a SECOND, untimed pass in which every CTA clocks its check / variable phases
+        phases = None
+        if kname == "onchip_minsum_kernel":
+            code.set_profiling(True)
+            step()
+            pi = code.info()
+            code.set_profiling(False)
+            if pi["last_cn_ms"] > 0:
+                phases = {"check_ms": pi["last_cn_ms"], "variable_ms": pi["last_vn_ms"], "batch_ms": pi["last_batch_ms"],
+                          "how": "share of the CTAs' SM clocks spent in each phase x the batch time (second, untimed pass)"}
         roofline = {
             "bound": "hbm", "kernel": f"{kname}<ALG={alg}>", "achieved": ach_k, "peak": peak, "unit": "GB/s",
             "frac": ach_k / peak, "traffic": (tr * F if tr is not None else None), "peak_source": peak_src,
             "bytes_per_launch": k_bytes, "ms_per_launch": k_ms, "launches_per_step": 1,
             "whole_step_frac": (k_bytes / (elapsed_ms / steps * 1e-3) / 1e9) / peak,
-            "onchip": ent.get("onchip"),
+            "onchip": ent.get("onchip"), "phases": phases,
             "note": "algorithmic bytes = (16*E + 4*N) per frame-iteration in float32, twice that in float64 (SURVEY.md 8d); this "
                     "kernel keeps them on chip "
                     + (("(4N + 16M bytes of shared memory per frame)" if prec == 32 else "(8N + 24M bytes of shared memory per frame)")

@@ -219,7 +219,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->oc_cn_ginfo.release(); c->oc_vn_ginfo.release(); c->oc_cnT.release(); c->oc_cn_row.release(); c->oc_vn_bit.release(); c->oc_vT.release();
     c->oc_cls.release();
     c->oc2_cn_g.release(); c->oc2_vn_g.release(); c->oc2_cnT.release(); c->oc2_vT.release(); c->oc2_slot_bit.release();
-    c->oc2_bit_slot.release(); c->oc2_cls.release(); c->oc2_vn_start.release();
+    c->oc2_bit_slot.release(); c->oc2_cls.release(); c->oc2_vn_start.release(); c->oc2_phase_clk.release();
     c->sp_cn_moff.release(); c->sp_sv_items.release(); c->sp_sv_chunk.release(); c->sp_sv_group_item0.release();
     c->msg.release(); c->bobmask.release(); c->zmask.release(); c->synd.release(); c->par.release();
     c->tile_active.release(); c->tile_new.release(); c->slot_llr.release(); c->slot_frame.release();

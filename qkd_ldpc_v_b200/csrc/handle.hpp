@@ -144,6 +144,7 @@ struct qkdldpc_code {
     bool oc2_eligible = false;
     int oc2_groups_cn = 0, oc2_l_slots = 0, oc2_rec_slots = 0, oc2_max_dc = 0, oc2_sched_warps = 0;
     DevBuf<int> oc2_vn_start;
+    DevBuf<unsigned long long> oc2_phase_clk;   // profiling: clocks per phase of the last float32 on-chip min-sum launch
     DevBuf<int4> oc2_cn_g, oc2_vn_g;
     DevBuf<uint2> oc2_cnT;
     DevBuf<uint4> oc2_vT;

@@ -121,6 +121,14 @@ static int onchip_finish(qkdldpc_code *c, int grid, int threads, size_t smem) {
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->last_batch_ms = ms;
     c->last_cn_ms = c->last_vn_ms = c->last_sched_ms = 0;
+    if (c->profiling && c->oc2_phase_clk.p) {   // share of the CTAs' clocks spent in the two phases, scaled to the batch time
+        unsigned long long clk[4] = {0, 0, 0, 0};
+        CK(cudaMemcpy(clk, c->oc2_phase_clk.p, sizeof clk, cudaMemcpyDeviceToHost));
+        if (clk[2] > 0) {
+            c->last_cn_ms = ms * (double)clk[0] / (double)clk[2];
+            c->last_vn_ms = ms * (double)clk[1] / (double)clk[2];
+        }
+    }
     c->last_path = 2;
     c->frames_per_tile = 1;
     c->oc_threads = threads;
@@ -336,6 +344,11 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         a.n_groups_cn2 = c->oc2_groups_cn; a.l_slots = c->oc2_l_slots;
         a.cn_g2 = c->oc2_cn_g.p; a.cnT2 = c->oc2_cnT.p; a.vn_g2 = c->oc2_vn_g.p; a.vn_start = c->oc2_vn_start.p; a.vT2 = c->oc2_vT.p;
         a.slot_bit = c->oc2_slot_bit.p; a.bit_slot = c->oc2_bit_slot.p; a.cls_masks2 = c->oc2_cls.p;
+        if (c->profiling) {
+            CK(c->oc2_phase_clk.reserve(4));
+            CK(cudaMemsetAsync(c->oc2_phase_clk.p, 0, 4 * sizeof(unsigned long long), s));
+            a.phase_clk = c->oc2_phase_clk.p;
+        }
     }
 
     auto launch_ms = [&](const OnchipArgs &args, int g, cudaStream_t st) {

@@ -99,6 +99,7 @@ struct OnchipArgs {
     const uint16_t *slot_bit;   // [l_slots] bit whose total lives in slot s; 0xFFFF = padding slot
     const uint16_t *bit_slot;   // [n] inverse
     const uint32_t *cls_masks2; // [n_combos][2][l_slots/32] punctured / shortened masks in SLOT order
+    u64 *phase_clk;             // profiling: [0] check phases, [1] variable phases, [2] whole kernel, SM clocks summed over the CTAs
 };
 
 // Shared-memory layout: L[l_slots] float | rec[rec_slots+2] uint4 | bob bits in slot order [l_slots/32] | syn[groups_cn] |
@@ -109,7 +110,7 @@ __host__ __device__ inline size_t onchip_misc_offset(int l_slots, int rec_slots,
     return ((size_t)l_slots * 4 + ((size_t)rec_slots + 2) * 16 + ((size_t)l_slots / 32 + (size_t)groups_cn) * 4 + 7) / 8 * 8;
 }
 __host__ __device__ inline size_t onchip_smem_bytes(int l_slots, int rec_slots, int groups_cn) {
-    return onchip_misc_offset(l_slots, rec_slots, groups_cn) + 8 + 48;   // + frame id, FrameCtx
+    return onchip_misc_offset(l_slots, rec_slots, groups_cn) + 8 + 48 + 24;   // + frame id, FrameCtx, phase clocks
 }
 __host__ __device__ inline bool onchip_staging_fits(int n, int l_slots, int rec_slots) {
     return ((size_t)rec_slots + 2) * 16 >= (2 * ((size_t)(n + 31) / 32) + (size_t)l_slots / 32) * 4;
@@ -355,6 +356,11 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
     uint32_t *synw = bobs + a.l_slots / 32;
     long long *s_frame = reinterpret_cast<long long *>(smem_raw + onchip_misc_offset(a.l_slots, a.rec_slots, a.n_groups_cn2));
     FrameCtx *ctx = reinterpret_cast<FrameCtx *>(s_frame + 1);
+    long long *s_clk = reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(ctx) + 48);   // profiling: [0] check, [1] variable, [2] start
+    if (a.phase_clk && threadIdx.x == 0) {
+        s_clk[0] = s_clk[1] = 0;
+        s_clk[2] = clock64();
+    }
     // frame set-up only: the key words as they come from HBM and Alice's bits in slot order, inside the record array
     uint32_t *st_bob = reinterpret_cast<uint32_t *>(rec), *st_alice = st_bob + a.words, *alice_s = st_alice + a.words;   // [l_slots/32]
 
@@ -430,16 +436,20 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
         for (int it = 1;; ++it) {
             // the check-node pass of iteration `it`; at it = max_iter + 1 it only serves as the syndrome test of the
             // last hard decision (non-adaptive variants, :424-445)
+            if (a.phase_clk && tid == 0) s_clk[0] -= clock64();
             const bool unsat = onchip_cn_phase<ALG, WIDE>(a, ctx, smem_raw, rec, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
             const bool any_unsat = __syncthreads_or(unsat) != 0;
+            if (a.phase_clk && tid == 0) s_clk[0] += clock64();
             if (!kAdaptive) {
                 if (it > 1 && !any_unsat) { success = true; iters = run = it - 1; break; }   // z of iteration it-1 (:439-445)
                 if (it > a.max_iter) break;
             } else {
                 if (!any_unsat) { success = true; iters = it; run = it - 1; break; }         // exit test before the VN step (:770-776)
             }
+            if (a.phase_clk && tid == 0) s_clk[1] -= clock64();
             onchip_vn_phase(a, ctx, L, rec, bobs, lp, warp, lane);
             __syncthreads();
+            if (a.phase_clk && tid == 0) s_clk[1] += clock64();
             if (kAdaptive && it == a.max_iter) break;          // the decision of the last iteration is never tested (Q10)
         }
 
@@ -469,6 +479,11 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
                 atomicAdd(tally + 3, (u64)run);
             }
         }
+    }
+    if (a.phase_clk && tid == 0) {
+        atomicAdd(a.phase_clk + 0, (u64)s_clk[0]);
+        atomicAdd(a.phase_clk + 1, (u64)s_clk[1]);
+        atomicAdd(a.phase_clk + 2, (u64)(clock64() - s_clk[2]));
     }
 }
 
