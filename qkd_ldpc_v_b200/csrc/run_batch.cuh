@@ -41,7 +41,10 @@ inline int launch_cn(const qkdldpc_code *c, int alg, bool fast, int tiles, cudaS
 #ifdef QK_DEFINE_CN_LAUNCH
 template <typename T, int V, int ALG, int B>
 inline int launch_cn_bucket(const qkdldpc_code *c, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a) {
-    constexpr int DCMAX = cn_bucket_max(B);
+    // float64 sum-product: the two-pass kernel for every bucket -- the row's tanh values go back to the message array
+    // between the passes instead of staying in registers (144 registers for 24 edges x 2 frames left 3 warps per scheduler
+    // to hide the latency of the double-precision polynomial chains; the two-pass kernel needs under 64)
+    constexpr int DCMAX = (sizeof(T) == 8 && ALG == 0) ? 0 : cn_bucket_max(B);
     const int cnt = c->cn_count[B];
     if (cnt == 0) return 0;
     constexpr int threads = cn_threads(sizeof(T), V, DCMAX);

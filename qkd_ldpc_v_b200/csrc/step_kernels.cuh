@@ -18,6 +18,7 @@
 // The library is compiled with -fmad=false: no FMA contraction anywhere.
 #pragma once
 #include "common.cuh"
+#include "spa_f64_math.hpp"
 
 namespace qk {
 
@@ -40,7 +41,7 @@ __device__ __forceinline__ Vec<T, V> lane_llr(const StepArgs<T> &a, int tile, in
 }
 
 // tanh / atanh flavours.
-//  ALG 0, double messages: libm-accurate double evaluation (parity mode).
+//  ALG 0, double messages: branch-free double evaluation, <= 5 ulp from glibc (spa_f64_math.hpp; parity mode).
 //  ALG 0, float messages:  float tanh (spa_tanh_half_f32, <= 3 ulp) and a fused divide + logarithm for 2 atanh (RowState::emit).
 //         An earlier version evaluated
 //         them in double on the float value (bit-equal to the f32 oracle) but spent 92 % of the SPA step in FP64
@@ -71,7 +72,7 @@ __device__ __forceinline__ T cn_tanh_half(T x) {
     const T h = x / (T)2;
     if constexpr (ALG == 0) {
         if constexpr (sizeof(T) == 4) return spa_tanh_half_f32(x);
-        else return (T)tanh((double)h);
+        else return (T)spa_tanh_half_f64((double)x);
     } else {
         const T ax = fabs(h);
         T a = (T)0.9242, b = (T)0;
@@ -90,7 +91,7 @@ template <typename T, int ALG>
 __device__ __forceinline__ T cn_two_atanh(T y) {
     if constexpr (ALG == 0) {
         if constexpr (sizeof(T) == 4) return 2.f * atanhf(y);
-        else return (T)2 * (T)atanh((double)y);
+        else return (T)spa_two_atanh_f64((double)y);
     } else {
         const T ay = fabs(y);
         T a = (T)1.196, b = (T)0.0323;
@@ -300,18 +301,25 @@ cn_kernel(const StepArgs<T> a, const int first, const int count) {
                     st_msg<T, V>(base + (size_t)k * FT, o);
                 }
         } else {
+            // float64 sum-product: tanh is the expensive half of the row, so it is stored in place by the first pass and
+            // read back by the second (one more write of the row; the kernel is far from the HBM roofline). Everything
+            // else recomputes it (float32 tanh and the piecewise-linear table cost less than the extra traffic).
+            constexpr bool kKeepT = (ALG == 0 && sizeof(T) == 8);
+#pragma unroll 2
             for (int k = 0; k < dc; ++k) {
                 Vec<T, V> x = ld_msg<T, V>(base + (size_t)k * FT);
 #pragma unroll
-                for (int v = 0; v < V; ++v) st[v].absorb(x.v[v]);
+                for (int v = 0; v < V; ++v) x.v[v] = st[v].absorb(x.v[v]);
+                if constexpr (kKeepT) st_msg<T, V>(base + (size_t)k * FT, x);
             }
+#pragma unroll 2
             for (int k = 0; k < dc; ++k) {
                 Vec<T, V> x = ld_msg<T, V>(base + (size_t)k * FT);
                 Vec<T, V> o;
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     T kept = x.v[v];
-                    if constexpr (ALG <= 1) kept = cn_tanh_half<T, ALG>(kept);
+                    if constexpr (ALG <= 1 && !kKeepT) kept = cn_tanh_half<T, ALG>(kept);
                     T c = st[v].emit(kept, syn[v], factor[v]);
                     o.v[v] = clamp_msg(c, a.thr);
                 }

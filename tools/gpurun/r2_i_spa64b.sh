@@ -1,0 +1,8 @@
+# round 2, call I: float64 sum-product check node as a two-pass kernel (tanh stored in place, 40 registers) -- parity, throughput
+python -m pytest tests/test_gpu_points.py tests/test_gpu_large.py tests/test_gpu_parity.py -m gpu -x -q -s 2>&1 | grep -E "precision|alg=0|passed|failed|Error|error" | head -20
+python bench.py --workload A82_spa_q0162 --precision 64 --frames 8192 --no-cpu-baseline --no-secondary > gpurun_out/r2i_A82_spa_f64.json 2> gpurun_out/r2i_A82_spa_f64.err
+python -c "
+import json; d=json.load(open('gpurun_out/r2i_A82_spa_f64.json')); print('A82 SPA f64 value %.3f e2e %.3f it %.2f'%(d['value'], d['e2e']['value'], d['config']['mean_iterations_executed']), d['roofline']['both_kernels'])"
+python bench.py --workload L100k_spa_q084 --frames 1024 --no-cpu-baseline --no-secondary > gpurun_out/r2i_L100k_spa.json 2> gpurun_out/r2i_L100k_spa.err
+python -c "
+import json; d=json.load(open('gpurun_out/r2i_L100k_spa.json')); print('L100k SPA f64 value %.3f e2e %.3f it %.2f'%(d['value'], d['e2e']['value'], d['config']['mean_iterations_executed']), d['roofline']['both_kernels'])"
