@@ -158,6 +158,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         (oc_ok && ((e = up(c->oc_cn_ginfo, T.cn_ginfo)) || (e = up(c->oc_cnT, T.cnT)) || (e = up(c->oc_cn_row, T.cn_row)) || (e = up(c->oc_vn_ginfo, T.vn_ginfo)) ||
                    (e = up(c->oc_vn_bit, T.vn_bit)) || (e = up(c->oc_vT, T.vT)))) ||
         (T.oc2.ok && ((e = up(c->oc2_cn_g, T.oc2.cn_g)) || (e = up(c->oc2_cnT, T.oc2.cnT)) || (e = up(c->oc2_vT, T.oc2.vT)) ||
+                      (T.oc2.vt16_ok && (e = up(c->oc2_vT16, T.oc2.vT16))) ||
                       (e = up(c->oc2_slot_bit, T.oc2.slot_bit)) || (e = up(c->oc2_bit_slot, bit_slot16)))) ||
         (sp_ok && ((e = up(c->sp_cn_moff, T.sp_cn_moff)) || (e = up(c->sp_sv_items, T.sp_items)) || (e = up(c->sp_sv_group_item0, T.sp_group_item0)))) ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
@@ -218,7 +219,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->row_order.release(); c->col_order.release(); c->vn_ell_edge.release(); c->vn_ell_row.release();
     c->oc_cn_ginfo.release(); c->oc_vn_ginfo.release(); c->oc_cnT.release(); c->oc_cn_row.release(); c->oc_vn_bit.release(); c->oc_vT.release();
     c->oc_cls.release();
-    c->oc2_cn_g.release(); c->oc2_vn_g.release(); c->oc2_cnT.release(); c->oc2_vT.release(); c->oc2_slot_bit.release();
+    c->oc2_cn_g.release(); c->oc2_vn_g.release(); c->oc2_cnT.release(); c->oc2_vT.release(); c->oc2_vT16.release(); c->oc2_slot_bit.release();
     c->oc2_bit_slot.release(); c->oc2_cls.release(); c->oc2_vn_start.release(); c->oc2_phase_clk.release();
     c->sp_cn_moff.release(); c->sp_sv_items.release(); c->sp_sv_chunk.release(); c->sp_sv_group_item0.release();
     c->msg.release(); c->bobmask.release(); c->zmask.release(); c->synd.release(); c->par.release();

@@ -146,8 +146,8 @@ struct qkdldpc_code {
     DevBuf<int> oc2_vn_start;
     DevBuf<unsigned long long> oc2_phase_clk;   // profiling: clocks per phase of the last float32 on-chip min-sum launch
     DevBuf<int4> oc2_cn_g, oc2_vn_g;
-    DevBuf<uint2> oc2_cnT;
-    DevBuf<uint4> oc2_vT;
+    DevBuf<uint4> oc2_cnT, oc2_vT;
+    DevBuf<uint2> oc2_vT16;           // 16-bit variable-phase entries, only for codes with at most 2048 records
     DevBuf<uint16_t> oc2_slot_bit, oc2_bit_slot;
     DevBuf<uint32_t> oc2_cls;         // [n_combos][2][words] punctured / shortened masks of the current batch, slot order
     std::vector<Oc2Group> oc2_vn_g_host;   // canonical order; the device copy is dealt to the warps of the launch

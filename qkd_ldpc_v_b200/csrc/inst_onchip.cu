@@ -38,15 +38,16 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
 typedef void (*OnchipKernel)(const OnchipArgs);
 
 template <int ALG, bool WIDE>
-static OnchipKernel kernel_of(bool f64) {
-    return f64 ? (OnchipKernel)onchip_minsum64_kernel<ALG, WIDE> : (OnchipKernel)onchip_minsum_kernel<ALG, WIDE>;
+static OnchipKernel kernel_of(bool f64, bool vt16) {
+    if (f64) return (OnchipKernel)onchip_minsum64_kernel<ALG, WIDE>;
+    return vt16 ? (OnchipKernel)onchip_minsum_kernel<ALG, WIDE, true> : (OnchipKernel)onchip_minsum_kernel<ALG, WIDE, false>;
 }
-static OnchipKernel kernel_of(int alg, bool wide, bool f64) {
+static OnchipKernel kernel_of(int alg, bool wide, bool f64, bool vt16) {
     switch (alg) {
-        case 2: return wide ? kernel_of<2, true>(f64) : kernel_of<2, false>(f64);
-        case 3: return wide ? kernel_of<3, true>(f64) : kernel_of<3, false>(f64);
-        case 4: return wide ? kernel_of<4, true>(f64) : kernel_of<4, false>(f64);
-        default: return wide ? kernel_of<5, true>(f64) : kernel_of<5, false>(f64);
+        case 2: return wide ? kernel_of<2, true>(f64, vt16) : kernel_of<2, false>(f64, vt16);
+        case 3: return wide ? kernel_of<3, true>(f64, vt16) : kernel_of<3, false>(f64, vt16);
+        case 4: return wide ? kernel_of<4, true>(f64, vt16) : kernel_of<4, false>(f64, vt16);
+        default: return wide ? kernel_of<5, true>(f64, vt16) : kernel_of<5, false>(f64, vt16);
     }
 }
 
@@ -276,7 +277,8 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         return onchip_launch_all(c, a, grid, threads, smem, n_frames, pipe, launch_spa);
     }
     const bool wide = c->oc_max_dc > 32;   // rows of 33..64 edges: two records per row, separate kernel instantiation
-    const OnchipKernel kern = kernel_of(P->algorithm, wide, f64);
+    const bool vt16 = !f64 && c->oc2_vT16.p != nullptr;   // 16-bit variable-phase entries (codes with at most 2048 records)
+    const OnchipKernel kern = kernel_of(P->algorithm, wide, f64, vt16);
     e = pick_geometry(kern, max_threads, m, sms, smem, n_frames, &threads, &grid);
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel geometry failed: %s", cudaGetErrorString(e));
     if (f64) {
@@ -343,6 +345,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         a.rec_slots = c->oc2_rec_slots;
         a.n_groups_cn2 = c->oc2_groups_cn; a.l_slots = c->oc2_l_slots;
         a.cn_g2 = c->oc2_cn_g.p; a.cnT2 = c->oc2_cnT.p; a.vn_g2 = c->oc2_vn_g.p; a.vn_start = c->oc2_vn_start.p; a.vT2 = c->oc2_vT.p;
+        a.vT16 = vt16 ? c->oc2_vT16.p : nullptr;
         a.slot_bit = c->oc2_slot_bit.p; a.bit_slot = c->oc2_bit_slot.p; a.cls_masks2 = c->oc2_cls.p;
         if (c->profiling) {
             CK(c->oc2_phase_clk.reserve(4));

@@ -43,8 +43,12 @@ struct Oc2Tables {
     std::vector<int> row_slot2;       // [m] record of positions 32..dc-1, or -1
     std::vector<int> edge_pos;        // [nnz] position of CSR edge e in its row's processing order
     std::vector<Oc2Group> cn_g, vn_g; // vn_g in canonical (slot) order; the launcher deals it to the warps
-    std::vector<Oc2U2> cnT;           // [off + kb*32 + lane] 4 x u16: BYTE offset (slot*4) of the totals of edges 4kb..4kb+3
+    std::vector<Oc2U4> cnT;           // [off + kb*32 + lane] 4 x u32: BYTE offset (slot*4) of the totals of edges 4kb..4kb+3 -- 32-bit
+                                      // entries although 16 would do: the check phase is bound by the ALU pipe, not by loads, and
+                                      // an entry that IS the address costs no unpacking
     std::vector<Oc2U4> vT;            // [off + kb*32 + lane] 4 x u32: (16 * record slot) << 5 | sh, sh = 32 - edges in the record + position
+    bool vt16_ok = false;             // at most 2048 records: the same table in 16-bit entries sh << 11 | record slot -- the
+    std::vector<Oc2U2> vT16;          // variable phase is bound by the LSU pipe, so it unpacks rather than loads twice the bytes
     // bank model, wavefronts per decoder iteration
     long long cn_gather = 0, cn_gather_min = 0, vn_gather = 0, vn_gather_min = 0;
 };
@@ -208,7 +212,7 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
     std::vector<int> class_base(bcls.size() + 1, 0);   // every class starts on a multiple of 32: slot & 31 == lane == bank
     for (size_t c = 0; c < bcls.size(); ++c) class_base[c + 1] = class_base[c] + (int)((bcls[c].size() + 31) / 32 * 32);
     T.l_slots = class_base.back();
-    if ((long long)T.l_slots * 4 > 65535) {   // byte offsets of the totals are 16-bit table entries
+    if (T.l_slots > 65535) {   // slot <-> bit maps are 16-bit
         T.ok = false;
         return;
     }
@@ -394,13 +398,14 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                     uint32_t c[4] = {0, 0, 0, 0};   // padding: the total in slot 0 (a broadcast)
                     if (l < cnt)
                         for (int j = 0; j < 4 && kb * 4 + j < dc; ++j) c[j] = (uint32_t)T.bit_slot[col_idx[sched[(size_t)l * dc + kb * 4 + j]]] * 4u;
-                    T.cnT.push_back(Oc2U2{c[0] | (c[1] << 16), c[2] | (c[3] << 16)});
+                    T.cnT.push_back(Oc2U4{c[0], c[1], c[2], c[3]});
                 }
         }
     }
 
     // ---- variable-phase tables (canonical order: class by class, 32 consecutive slots per group) and their model cost
     T.vn_gather = T.vn_gather_min = 0;
+    T.vt16_ok = T.rec_slots <= 2048;
     for (size_t c = 0; c < bcls.size(); ++c) {
         const auto &v = bcls[c];
         const int dv = col_ptr[v[0] + 1] - col_ptr[v[0]], blocks = (dv + 3) / 4;
@@ -421,6 +426,11 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                         }
                     }
                     T.vT.push_back(Oc2U4{e[0], e[1], e[2], e[3]});
+                    if (T.vt16_ok) {   // entries past the degree and padding lanes: record 0 (the kernel reads exactly `deg` entries)
+                        uint32_t h[4];
+                        for (int j = 0; j < 4; ++j) h[j] = (l < cnt && kb * 4 + j < dv) ? ((e[j] & 31u) << 11) | (e[j] >> 9) : 0u;
+                        T.vT16.push_back(Oc2U2{h[0] | (h[1] << 16), h[2] | (h[3] << 16)});
+                    }
                 }
             for (int k = 0; k < dv; ++k)
                 for (int q = 0; q < 4; ++q) {
@@ -479,16 +489,15 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
             std::vector<int> by_pos(g.deg, -1);
             for (int e = rp[j]; e < rp[j + 1]; ++e) by_pos[T.edge_pos[e]] = e;
             for (int k = 0; k < g.deg; ++k) {
-                const Oc2U2 w = T.cnT[(size_t)g.off + (size_t)(k / 4) * 32 + l];
-                const uint32_t off = (k % 4 == 0) ? (w.x & 0xFFFFu) : (k % 4 == 1) ? (w.x >> 16) : (k % 4 == 2) ? (w.y & 0xFFFFu) : (w.y >> 16);
+                const uint32_t off = (&T.cnT[(size_t)g.off + (size_t)(k / 4) * 32 + l].x)[k % 4];
                 if (off != (uint32_t)T.bit_slot[col_idx[by_pos[k]]] * 4u) return "check table: wrong total for an edge";
                 ++edges_cn;
             }
         }
         for (int kb = 0; kb < blocks; ++kb)
             for (int l = 0; l < 32; ++l) {
-                const Oc2U2 w = T.cnT[(size_t)g.off + (size_t)kb * 32 + l];
-                for (uint32_t off : {w.x & 0xFFFFu, w.x >> 16, w.y & 0xFFFFu, w.y >> 16})
+                const Oc2U4 w = T.cnT[(size_t)g.off + (size_t)kb * 32 + l];
+                for (uint32_t off : {w.x, w.y, w.z, w.w})
                     if ((off & 3u) || off / 4 >= (uint32_t)T.l_slots || T.slot_bit[off / 4] == 0xFFFF) return "check table: offset out of range";
             }
     }
@@ -508,6 +517,11 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
                     const int p = col_ptr[b] + k, r = csc_row[p], pos = T.edge_pos[csc_edge[p]], dcr = rp[r + 1] - rp[r];
                     const int in_rec = (dcr <= 32) ? dcr : (pos < 32 ? 32 : dcr - 32);
                     if (slot != (pos < 32 ? T.row_slot[r] : T.row_slot2[r]) || sh != 32 - in_rec + pos % 32) return "variable table: wrong record or shift";
+                    if (T.vt16_ok) {
+                        const Oc2U2 w16 = T.vT16[(size_t)g.off + (size_t)(k / 4) * 32 + l];
+                        const uint32_t h = (k % 4 == 0) ? (w16.x & 0xFFFFu) : (k % 4 == 1) ? (w16.x >> 16) : (k % 4 == 2) ? (w16.y & 0xFFFFu) : (w16.y >> 16);
+                        if ((int)(h & 0x7FFu) != slot || (int)(h >> 11) != sh) return "16-bit variable table disagrees with the 32-bit one";
+                    }
                     ++edges_vn;
                 } else if (slot != T.rec_slots + 1) {
                     return "variable table: padding entry does not point at the all-zero record";
@@ -515,6 +529,7 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
             }
     }
     if (next_slot != T.l_slots) return "variable groups do not cover the totals";
+    if (T.vt16_ok && (T.vT16.size() != T.vT.size() || T.rec_slots > 2048)) return "16-bit variable table size";
     if (edges_cn != nnz || edges_vn != nnz) return "tables do not cover every edge once";
     return nullptr;
 }

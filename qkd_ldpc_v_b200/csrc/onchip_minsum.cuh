@@ -30,7 +30,7 @@
 // shared-memory byte offset itself, so a gather costs no address arithmetic.
 //
 // Eligibility (host): float32 messages, min-sum family with the FAST precondition of run_batch.cuh (no NaN possible),
-// every check degree <= 64 (rows of 33..64 edges own two records), n < 16384 (16-bit byte offsets), state fits the 227 KB
+// every check degree <= 64 (rows of 33..64 edges own two records), n < 65535, state fits the 227 KB
 // of shared memory. SPA / SPA-lin-approx have their own on-chip kernel (onchip_spa.cuh), float64 state onchip_minsum64.cuh
 // (both on the older natural-order tables of onchip_tables.cu); n = 100k codes stream.
 #pragma once
@@ -92,10 +92,11 @@ struct OnchipArgs {
     // float32 min-sum kernel: tables of onchip_layout.hpp (storage order = processing order)
     int n_groups_cn2, l_slots;  // l_slots: 32 per variable-phase group
     const int4 *cn_g2;          // [groups] {offset into cnT2, degree, first record slot, rows in the group}
-    const uint2 *cnT2;          // [off + kb*32 + lane] 4 x uint16: shared-memory BYTE offset of the totals of edges 4kb..4kb+3
+    const uint4 *cnT2;          // [off + kb*32 + lane] 4 x uint32: shared-memory BYTE offset of the totals of edges 4kb..4kb+3
     const int4 *vn_g2;          // [groups, dealt to the warps] {offset into vT2, degree, first total slot (multiple of 32), bits in the group}
     const int *vn_start;        // [warps per CTA + 1] warp w handles vn_g2[vn_start[w] .. vn_start[w+1])
     const uint4 *vT2;           // [off + kb*32 + lane] 4 x uint32: (16 * record slot) << 5 | sh; entries past the degree: the all-zero record
+    const uint2 *vT16;          // the same in 4 x uint16 sh << 11 | record slot (codes with at most 2048 records; else null)
     const uint16_t *slot_bit;   // [l_slots] bit whose total lives in slot s; 0xFFFF = padding slot
     const uint16_t *bit_slot;   // [n] inverse
     const uint32_t *cls_masks2; // [n_combos][2][l_slots/32] punctured / shortened masks in SLOT order
@@ -175,7 +176,7 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
         const bool valid = lane < gi.w;
         const int slot = valid ? gi.z + lane : a.rec_slots;       // padding lanes work on the scratch record
         const uint4 ro = rec[slot];
-        const uint2 *cp = a.cnT2 + gi.x + lane;
+        const uint4 *cp = a.cnT2 + gi.x + lane;
         float m1 = FLT_MAX, m2 = FLT_MAX;
         uint32_t zs = ro.z << (32 - dc);          // sign of the old message on the current edge in bit 31
         const int arg_old = (int)ro.w - (32 - dc);
@@ -183,19 +184,19 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
         int kb = 0;
 #pragma unroll 2
         for (; kb + 4 <= dc; kb += 4) {
-            const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+            const uint4 cw = __ldg(cp + (kb >> 2) * 32);
             const int rel = arg_old - kb;
-            QK_CN_EDGE(0, cw.x & 0xFFFFu)
-            QK_CN_EDGE(1, cw.x >> 16)
-            QK_CN_EDGE(2, cw.y & 0xFFFFu)
-            QK_CN_EDGE(3, cw.y >> 16)
+            QK_CN_EDGE(0, cw.x)
+            QK_CN_EDGE(1, cw.y)
+            QK_CN_EDGE(2, cw.z)
+            QK_CN_EDGE(3, cw.w)
         }
         if (kb < dc) {                            // warp-uniform tail of 1..3 edges
-            const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+            const uint4 cw = __ldg(cp + (kb >> 2) * 32);
             const int rel = arg_old - kb, left = dc - kb;
-            QK_CN_EDGE(0, cw.x & 0xFFFFu)
-            if (left > 1) QK_CN_EDGE(1, cw.x >> 16)
-            if (left > 2) QK_CN_EDGE(2, cw.y & 0xFFFFu)
+            QK_CN_EDGE(0, cw.x)
+            if (left > 1) QK_CN_EDGE(1, cw.y)
+            if (left > 2) QK_CN_EDGE(2, cw.z)
         }
         // the last "new minimum" event is the first minimum: edge k sits in bit dc-1-k of lt (none: every |m| is FLT_MAX)
         int arg = lt ? dc - __ffs((int)lt) : 0;
@@ -211,21 +212,21 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
                 own = 0;
                 lt = 0;
                 for (; kb + 4 <= dc_row; kb += 4) {
-                    const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+                    const uint4 cw = __ldg(cp + (kb >> 2) * 32);
                     const int rel = arg_old2 - (kb - 32);
                     const uint4 &ro = ro2;
-                    QK_CN_EDGE(0, cw.x & 0xFFFFu)
-                    QK_CN_EDGE(1, cw.x >> 16)
-                    QK_CN_EDGE(2, cw.y & 0xFFFFu)
-                    QK_CN_EDGE(3, cw.y >> 16)
+                    QK_CN_EDGE(0, cw.x)
+                    QK_CN_EDGE(1, cw.y)
+                    QK_CN_EDGE(2, cw.z)
+                    QK_CN_EDGE(3, cw.w)
                 }
                 if (kb < dc_row) {
-                    const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+                    const uint4 cw = __ldg(cp + (kb >> 2) * 32);
                     const int rel = arg_old2 - (kb - 32), left = dc_row - kb;
                     const uint4 &ro = ro2;
-                    QK_CN_EDGE(0, cw.x & 0xFFFFu)
-                    if (left > 1) QK_CN_EDGE(1, cw.x >> 16)
-                    if (left > 2) QK_CN_EDGE(2, cw.y & 0xFFFFu)
+                    QK_CN_EDGE(0, cw.x)
+                    if (left > 1) QK_CN_EDGE(1, cw.y)
+                    if (left > 2) QK_CN_EDGE(2, cw.z)
                 }
                 if (lt) arg = 32 + dc2 - __ffs((int)lt);
             }
@@ -290,23 +291,63 @@ __device__ __forceinline__ float onchip_llr(const FrameCtx *ctx, const uint32_t 
         acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.z, (ENT)) & 0x80000000u));   /* r.z << sh */           \
     }
 
-// A group of 32 bits of degree DV <= 8, straight line: all index blocks first, then exactly DV messages.
-template <int DV>
-__device__ __forceinline__ float onchip_vn_fixed(const uint4 *ep, const unsigned char *recb, float acc) {
-    uint4 ew[(DV + 3) / 4];
-#pragma unroll
-    for (int b = 0; b < (DV + 3) / 4; ++b) ew[b] = __ldg(ep + b * 32);
-#pragma unroll
-    for (int k = 0; k < DV; ++k) {
-        const uint32_t ent = (k % 4 == 0) ? ew[k / 4].x : (k % 4 == 1) ? ew[k / 4].y : (k % 4 == 2) ? ew[k / 4].z : ew[k / 4].w;
-        QK_VN_EDGE(ent)
+// The same for the 16-bit table entry E = sh << 11 | record slot (upper half of the register clear).
+#define QK_VN_EDGE16(E)                                                                                                 \
+    {                                                                                                                   \
+        const uint4 r = *reinterpret_cast<const uint4 *>(recb + (((E) & 0x7FFu) << 4));                                 \
+        const uint32_t sh = (E) >> 11;                                                                                  \
+        const uint32_t mag = (sh == r.w) ? r.y : r.x;                /* r.w == kNoArg never matches */                   \
+        acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.z, sh) & 0x80000000u));                                \
     }
+
+// Index blocks of 4 entries: 16 bytes (VT16 = false) or 8 bytes per lane.
+template <bool VT16>
+struct VnBlock;
+template <>
+struct VnBlock<false> {
+    uint4 w;
+    __device__ __forceinline__ void load(const void *tab, int idx) { w = __ldg(reinterpret_cast<const uint4 *>(tab) + idx); }
+    template <int J>
+    __device__ __forceinline__ float add(const unsigned char *recb, float acc) const {
+        const uint32_t ent = (J == 0) ? w.x : (J == 1) ? w.y : (J == 2) ? w.z : w.w;
+        QK_VN_EDGE(ent)
+        return acc;
+    }
+};
+template <>
+struct VnBlock<true> {
+    uint2 w;
+    __device__ __forceinline__ void load(const void *tab, int idx) { w = __ldg(reinterpret_cast<const uint2 *>(tab) + idx); }
+    template <int J>
+    __device__ __forceinline__ float add(const unsigned char *recb, float acc) const {
+        const uint32_t ent = (J == 0) ? (w.x & 0xFFFFu) : (J == 1) ? (w.x >> 16) : (J == 2) ? (w.y & 0xFFFFu) : (w.y >> 16);
+        QK_VN_EDGE16(ent)
+        return acc;
+    }
+};
+
+// A group of 32 bits of degree DV <= 8, straight line: all index blocks first, then exactly DV messages.
+template <int DV, bool VT16>
+__device__ __forceinline__ float onchip_vn_fixed(const void *tab, int idx, const unsigned char *recb, float acc) {
+    VnBlock<VT16> b0, b1;
+    b0.load(tab, idx);
+    if constexpr (DV > 4) b1.load(tab, idx + 32);
+    acc = b0.template add<0>(recb, acc);
+    if constexpr (DV > 1) acc = b0.template add<1>(recb, acc);
+    if constexpr (DV > 2) acc = b0.template add<2>(recb, acc);
+    if constexpr (DV > 3) acc = b0.template add<3>(recb, acc);
+    if constexpr (DV > 4) acc = b1.template add<0>(recb, acc);
+    if constexpr (DV > 5) acc = b1.template add<1>(recb, acc);
+    if constexpr (DV > 6) acc = b1.template add<2>(recb, acc);
+    if constexpr (DV > 7) acc = b1.template add<3>(recb, acc);
     return acc;
 }
 
+template <bool VT16>
 __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *L, const uint4 *rec, const uint32_t *bobs,
                                                 float lp, int warp, int lane) {
     const unsigned char *recb = reinterpret_cast<const unsigned char *>(rec);
+    const void *tab = VT16 ? static_cast<const void *>(a.vT16) : static_cast<const void *>(a.vT2);
     const float nlp = 0.f - lp;
     const int has_cls = ctx->has_cls;
     // the host dealt the groups to the warps longest-first so that all warps of the CTA finish the phase together
@@ -319,35 +360,45 @@ __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const Frame
         // a-priori LLR (qkd_ldpc_algorithm.cpp:1043-1049, onchip_llr_of); padding lanes see Bob bit 0
         float acc = ((bobs[gi.z >> 5] >> lane) & 1u) ? nlp : lp;
         if (has_cls) acc = onchip_llr_of(ctx, (bobs[gi.z >> 5] >> lane) & 1u, s, lp);
-        const uint4 *ep = a.vT2 + gi.x + lane;
+        const int idx = gi.x + lane;
         // ascending check order, starting from the LLR (std::accumulate, :414-417)
         switch (dv) {
-            case 1: acc = onchip_vn_fixed<1>(ep, recb, acc); break;
-            case 2: acc = onchip_vn_fixed<2>(ep, recb, acc); break;
-            case 3: acc = onchip_vn_fixed<3>(ep, recb, acc); break;
-            case 4: acc = onchip_vn_fixed<4>(ep, recb, acc); break;
-            case 5: acc = onchip_vn_fixed<5>(ep, recb, acc); break;
-            case 6: acc = onchip_vn_fixed<6>(ep, recb, acc); break;
-            case 7: acc = onchip_vn_fixed<7>(ep, recb, acc); break;
-            case 8: acc = onchip_vn_fixed<8>(ep, recb, acc); break;
-            default:
-                // whole blocks of 4: the entries past the degree address the all-zero record, and x + (+0.0f) == x for
-                // every x that is not -0 (a sum that starts from an LLR that is never -0 cannot become -0)
+            case 1: acc = onchip_vn_fixed<1, VT16>(tab, idx, recb, acc); break;
+            case 2: acc = onchip_vn_fixed<2, VT16>(tab, idx, recb, acc); break;
+            case 3: acc = onchip_vn_fixed<3, VT16>(tab, idx, recb, acc); break;
+            case 4: acc = onchip_vn_fixed<4, VT16>(tab, idx, recb, acc); break;
+            case 5: acc = onchip_vn_fixed<5, VT16>(tab, idx, recb, acc); break;
+            case 6: acc = onchip_vn_fixed<6, VT16>(tab, idx, recb, acc); break;
+            case 7: acc = onchip_vn_fixed<7, VT16>(tab, idx, recb, acc); break;
+            case 8: acc = onchip_vn_fixed<8, VT16>(tab, idx, recb, acc); break;
+            default: {
+                int kb = 0;
 #pragma unroll 2
-                for (int kb = 0; kb < dv; kb += 4) {
-                    const uint4 ew = __ldg(ep + (kb >> 2) * 32);
-                    QK_VN_EDGE(ew.x)
-                    QK_VN_EDGE(ew.y)
-                    QK_VN_EDGE(ew.z)
-                    QK_VN_EDGE(ew.w)
+                for (; kb + 4 <= dv; kb += 4) {
+                    VnBlock<VT16> b;
+                    b.load(tab, idx + (kb >> 2) * 32);
+                    acc = b.template add<0>(recb, acc);
+                    acc = b.template add<1>(recb, acc);
+                    acc = b.template add<2>(recb, acc);
+                    acc = b.template add<3>(recb, acc);
                 }
+                if (kb < dv) {                    // warp-uniform tail of 1..3 checks
+                    VnBlock<VT16> b;
+                    b.load(tab, idx + (kb >> 2) * 32);
+                    const int left = dv - kb;
+                    acc = b.template add<0>(recb, acc);
+                    if (left > 1) acc = b.template add<1>(recb, acc);
+                    if (left > 2) acc = b.template add<2>(recb, acc);
+                }
+            }
         }
         L[s] = acc;                               // consecutive slots: coalesced; padding lanes own padding slots
     }
 }
 #undef QK_VN_EDGE
+#undef QK_VN_EDGE16
 
-template <int ALG, bool WIDE>
+template <int ALG, bool WIDE, bool VT16>
 __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *L = reinterpret_cast<float *>(smem_raw);
@@ -413,12 +464,12 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
         // Alice's syndrome (calculate_syndrome, array_and_matrix_operations.cpp:936-950) over the check-phase table
         for (int g = warp; g < a.n_groups_cn2; g += nwarps) {
             const int4 gi = __ldg(a.cn_g2 + g);
-            const uint2 *cp = a.cnT2 + gi.x + lane;
+            const uint4 *cp = a.cnT2 + gi.x + lane;
             uint32_t sy = 0;
             for (int kb = 0; kb < gi.y; kb += 4) {
-                const uint2 cw = __ldg(cp + (kb >> 2) * 32);
+                const uint4 cw = __ldg(cp + (kb >> 2) * 32);
                 const int left = gi.y - kb;
-                const uint32_t c0 = (cw.x & 0xFFFFu) >> 2, c1 = cw.x >> 18, c2 = (cw.y & 0xFFFFu) >> 2, c3 = cw.y >> 18;   // slots
+                const uint32_t c0 = cw.x >> 2, c1 = cw.y >> 2, c2 = cw.z >> 2, c3 = cw.w >> 2;   // slots
                 sy ^= alice_s[c0 >> 5] >> (c0 & 31u);
                 if (left > 1) sy ^= alice_s[c1 >> 5] >> (c1 & 31u);
                 if (left > 2) sy ^= alice_s[c2 >> 5] >> (c2 & 31u);
@@ -447,7 +498,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
                 if (!any_unsat) { success = true; iters = it; run = it - 1; break; }         // exit test before the VN step (:770-776)
             }
             if (a.phase_clk && tid == 0) s_clk[1] -= clock64();
-            onchip_vn_phase(a, ctx, L, rec, bobs, lp, warp, lane);
+            onchip_vn_phase<VT16>(a, ctx, L, rec, bobs, lp, warp, lane);
             __syncthreads();
             if (a.phase_clk && tid == 0) s_clk[1] += clock64();
             if (kAdaptive && it == a.max_iter) break;          // the decision of the last iteration is never tested (Q10)
