@@ -197,7 +197,7 @@ def main():
     tmp = tempfile.mkdtemp(prefix="cfgpar_")
     setup(tmp, spec, args.ref_trials, legacy=True, coarse=True)
     report["runs"]["reference_cpu"] = {"seconds": t_ref, "threads": spec["cfg"]["threads_number"], "trials": args.ref_trials}
-    for prec in (32, 64):
+    for prec in (0, 32, 64):   # 0 = the library's precision policy (what a user gets without --precision)
         out = os.path.join(tmp, f"results_gpu{prec}")
         t0 = time.perf_counter()
         subprocess.run([SIM_BIN, "--root", tmp, "--results-dir", out, "--precision", str(prec), "--gpus", str(args.gpus), "--quiet"],
@@ -212,7 +212,7 @@ def main():
             rows.append({"matrix": name[0], "qber": num(r[6]), "fer_ref": num(r[14]), "fer_gpu": num(o[14]), "fer_ci95": [lo, hi],
                          "fer_inside_ci": lo - 1e-12 <= num(o[14]) <= hi + 1e-12, "iter_mean_ref": num(r[8]), "iter_mean_gpu": num(o[8]),
                          "row_identical": o == r})
-        report["runs"][f"qkdldpc_sim_fp{prec}"] = {"seconds": dt, "trials": args.ref_trials, "gpus": args.gpus, "rows": rows,
+        report["runs"][f"qkdldpc_sim_fp{prec}" if prec else "qkdldpc_sim_default"] = {"seconds": dt, "trials": args.ref_trials, "gpus": args.gpus, "rows": rows,
                                                   "csv_identical": all(x["row_identical"] for x in rows)}
     if args.full:
         tmp2 = tempfile.mkdtemp(prefix="cfgfull_")
