@@ -402,13 +402,25 @@ std::vector<sim_result> QKD_LDPC_batch_simulation(const config_data &cfg, const 
         auto destroy_all = [&] { for (auto *c : codes) if (c) api.code_destroy(c); };
         qkdldpc_options opt{};
         opt.pool_bytes = dev.pool_bytes;
-        for (size_t l = 0; l < lanes; ++l) {
-            const int device = dev.devices.empty() ? 0 : dev.devices[l % n_dev];
-            if (api.code_create(&codes[l], g.n, g.m, static_cast<int64_t>(g.col_idx.size()), g.row_ptr.data(), g.col_idx.data(), device, &opt) != 0) {
-                const std::string msg = api.last_error();
-                destroy_all();
-                throw std::runtime_error("qkdldpc_code_create failed for " + name + ": " + msg);
-            }
+        {
+            // one handle per lane, created concurrently: a handle costs a CUDA context on first use of its device and ~0.2 s
+            // of host-side table building, which would otherwise add up over 8 devices (qkdldpc_last_error is thread-local)
+            std::vector<std::string> create_err(lanes);
+            std::vector<std::thread> creators;
+            for (size_t l = 0; l < lanes; ++l)
+                creators.emplace_back([&, l] {
+                    const int device = dev.devices.empty() ? 0 : dev.devices[l % n_dev];
+                    if (api.code_create(&codes[l], g.n, g.m, static_cast<int64_t>(g.col_idx.size()), g.row_ptr.data(), g.col_idx.data(), device, &opt) != 0) {
+                        create_err[l] = api.last_error();
+                        if (create_err[l].empty()) create_err[l] = "unknown error";
+                    }
+                });
+            for (auto &t : creators) t.join();
+            for (size_t l = 0; l < lanes; ++l)
+                if (!create_err[l].empty()) {
+                    destroy_all();
+                    throw std::runtime_error("qkdldpc_code_create failed for " + name + ": " + create_err[l]);
+                }
         }
 
         // Trials of one combination sharded over several DISTINCT devices: the per-device tallies are summed by ONE
