@@ -280,6 +280,13 @@ typedef struct qkdldpc_info {
     int32_t reserved;
 } qkdldpc_info;
 QKDLDPC_API int qkdldpc_code_info(const qkdldpc_code *code, qkdldpc_info *info);
+/* Host only (no device needed): builds the storage layout of the float32 on-chip min-sum kernel for a graph, checks every
+ * table entry against the graph and returns the shared-memory bank model of the result, in wavefronts per decoder iteration:
+ * out[0] = 1 when the code is eligible (else the rest is 0), out[1] / out[2] = the check phase's 4-byte gathers and their
+ * conflict-free minimum, out[3] / out[4] = the variable phase's 16-byte record gathers and their minimum, out[5] = 1 when the
+ * 16-bit variable-phase table applies (at most 2048 records). QKDLDPC_ERR_STATE when a table fails its self-check. */
+QKDLDPC_API int qkdldpc_onchip_layout_model(int32_t n, int32_t m, int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx,
+                                            int64_t *out /* [6] */);
 /* When enabled, every kernel of the step loop is bracketed by CUDA events (slow; for bench roofline numbers). */
 QKDLDPC_API int qkdldpc_code_set_profiling(qkdldpc_code *code, int32_t enabled);
 

@@ -72,6 +72,7 @@ SYMBOLS = {
     "qkdldpc_tally_allreduce_device": (C.c_int, [_VP, _VP, C.c_int64]),
     "qkdldpc_code_info": (C.c_int, [_VP, C.POINTER(Info)]),
     "qkdldpc_code_set_profiling": (C.c_int, [_VP, C.c_int32]),
+    "qkdldpc_onchip_layout_model": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _VP, _VP, _VP]),
 }
 
 

@@ -278,3 +278,32 @@ int build_onchip_tables(int n, int m, long long nnz, const std::vector<int> &rp,
 }
 
 }  // namespace qkhost
+
+extern "C" int qkdldpc_onchip_layout_model(int32_t n, int32_t m, int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx, int64_t *out) {
+    if (!row_ptr || !col_idx || !out || n < 1 || m < 1 || nnz < 1 || row_ptr[0] != 0 || row_ptr[m] != nnz)
+        return fail(QKDLDPC_ERR_INVALID, "bad graph");
+    std::vector<int> col_ptr(n + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) {
+        if (col_idx[e] < 0 || col_idx[e] >= n) return fail(QKDLDPC_ERR_INVALID, "column index out of range");
+        col_ptr[col_idx[e] + 1]++;
+    }
+    for (int i = 0; i < n; ++i) col_ptr[i + 1] += col_ptr[i];
+    std::vector<int> csc_edge(nnz), csc_row(nnz), cur(col_ptr.begin(), col_ptr.end() - 1);
+    for (int j = 0; j < m; ++j)
+        for (int e = row_ptr[j]; e < row_ptr[j + 1]; ++e) {
+            const int p = cur[col_idx[e]]++;
+            csc_edge[p] = e;
+            csc_row[p] = j;
+        }
+    qkhost::Oc2Tables T;
+    qkhost::build_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), 1, T);
+    if (const char *err = qkhost::check_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), T))
+        return fail(QKDLDPC_ERR_STATE, "on-chip min-sum layout: %s", err);
+    out[0] = T.ok;
+    out[1] = T.ok ? T.cn_gather : 0;
+    out[2] = T.ok ? T.cn_gather_min : 0;
+    out[3] = T.ok ? T.vn_gather : 0;
+    out[4] = T.ok ? T.vn_gather_min : 0;
+    out[5] = T.ok && T.vt16_ok;
+    return QKDLDPC_OK;
+}
