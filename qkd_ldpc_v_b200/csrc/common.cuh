@@ -105,7 +105,6 @@ struct StepArgs {
     // decoder parameters
     T primary, secondary, thr;
     int enable_thr;
-    int vn_prefetch;        // narrow variable-node kernels: L2 prefetch of the messages of the item this many items ahead (0 = off)
 };
 
 }  // namespace qk

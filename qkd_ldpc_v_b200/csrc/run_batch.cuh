@@ -2,7 +2,6 @@
 // Instantiated once per (message type, frames per lane) in inst_*.cu so the units compile in parallel; the
 // check-node kernels of each algorithm pair live in their own units (launch_cn_alg<T, V, ALG>).
 #pragma once
-#include <cstdlib>
 #include "handle.hpp"
 #include "common.cuh"
 #include "sched_kernels.cuh"
@@ -227,10 +226,6 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     a.e_stride = (int64_t)c->nnz * FT;
     a.primary = (T)P->primary; a.secondary = (T)P->secondary; a.enable_thr = P->enable_threshold != 0;
     a.thr = a.enable_thr ? (T)P->threshold : (T)INFINITY;   // the kernels clamp unconditionally; +inf is a no-op
-    {
-        const char *pf = getenv("QKDLDPC_VN_PREFETCH");
-        a.vn_prefetch = pf ? atoi(pf) : 0;
-    }
 
     BatchArgs<T> b{};
     b.n_frames = n_frames; b.words = words; b.swords = swords;

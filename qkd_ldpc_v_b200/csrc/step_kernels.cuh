@@ -527,25 +527,6 @@ vn_kernel_ell(const StepArgs<T> a, const int first, const int count, const int e
     const int lane = threadIdx.x & 31;
     const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (idx >= count) return;
-    // The messages of the item `vn_prefetch` items ahead (same tile, or the next one past the end of the bucket) are pulled
-    // into L2 now: the warp that owns that item finds its 3-4 chunks of 512 bytes there instead of in DRAM, so the bytes in
-    // flight to HBM no longer depend on how many loads the resident warps hold in registers.
-    if (a.vn_prefetch > 0) {
-        int j = idx + a.vn_prefetch, t2 = tile;
-        if (j >= count) { j -= count; ++t2; }
-        if (t2 < (int)gridDim.y && j < count) {
-            const int4 *pe = reinterpret_cast<const int4 *>(a.vn_ell_edge + ell_base + (size_t)j * DVMAX);
-            const T *fb = a.msg + (size_t)t2 * a.e_stride + lane * V;
-#pragma unroll
-            for (int q = 0; q < DVMAX / 4; ++q) {
-                const int4 x = __ldg(pe + q);
-                if (x.x >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(fb + (size_t)x.x * FT));
-                if (x.y >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(fb + (size_t)x.y * FT));
-                if (x.z >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(fb + (size_t)x.z * FT));
-                if (x.w >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(fb + (size_t)x.w * FT));
-            }
-        }
-    }
     // first wave of loads: nothing here depends on another load
     uint32_t act[V], newm[V];
 #pragma unroll
