@@ -34,13 +34,16 @@ struct Oc2Group { int off, deg, base, cnt; };   // int4 on the device: table off
 struct Oc2Tables {
     bool ok = false;
     int n = 0, m = 0, max_dc = 0;
-    int l_slots = 0;       // slots of the totals: 32 per variable-phase group (the last group of a degree class is padded)
+    int l_slots = 0;       // slots of the totals: 32 per variable-phase group (the last group of a degree class is padded);
+                           // slot l_slots itself holds +inf (padding edges of mixed-degree check groups)
     int rec_slots = 0;     // records in use (m + rows wider than 32 edges); slot rec_slots is scratch for the check phase's
                            // padding lanes, slot rec_slots + 1 stays all-zero (the +0.0f message of padding table entries)
     std::vector<int> bit_slot;        // [n] slot of a bit's total
     std::vector<uint16_t> slot_bit;   // [l_slots] inverse; 0xFFFF = padding slot
     std::vector<int> row_slot;        // [m] record of edges at positions 0..31
     std::vector<int> row_slot2;       // [m] record of positions 32..dc-1, or -1
+    std::vector<int> row_gdeg;        // [m] degree of the check group the row sits in (>= its own: the leftovers of several
+                                      // degree classes share groups; the missing edges gather the +inf total in slot l_slots)
     std::vector<int> edge_pos;        // [nnz] position of CSR edge e in its row's processing order
     std::vector<Oc2Group> cn_g, vn_g; // vn_g in canonical (slot) order; the launcher deals it to the warps
     std::vector<Oc2U4> cnT;           // [off + kb*32 + lane] 4 x u32: BYTE offset (slot*4) of the totals of edges 4kb..4kb+3 -- 32-bit
@@ -168,24 +171,46 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
     };
     std::vector<std::vector<int>> rcls = classes_of(m, rp), bcls = classes_of(n, col_ptr);
 
-    // rows: position idx of class c -> group idx / 32, lane idx % 32; record slots are handed out group by group
-    T.row_slot.assign(m, 0);
-    T.row_slot2.assign(m, -1);
-    auto assign_row_slots = [&]() {
-        int next = 0;
+    // Check groups: 32 rows of ONE degree, in class order. The leftover rows of the classes (fewer than 32 each) are merged,
+    // widest first, into groups of mixed degree -- a row then walks `group degree` edges, the missing ones gathering a total
+    // that is +inf (min1 / min2, the sign parity and the first-minimum position ignore it; it counts as a positive total on
+    // both sides of the syndrome parity) -- as long as no row is padded by more than 3 edges. I80: 67 -> 64 groups, which
+    // 16 warps finish in 4 rounds instead of 5. Rows wider than 32 edges (two records) keep pure groups.
+    struct CnGroup { int deg; std::vector<int> rows; };
+    std::vector<CnGroup> cgroups;
+    {
+        std::vector<int> left;
         for (const auto &cls : rcls) {
-            const bool wide = rp[cls[0] + 1] - rp[cls[0]] > 32;
-            for (size_t g0 = 0; g0 < cls.size(); g0 += 32) {
-                const int cnt = (int)std::min<size_t>(32, cls.size() - g0);
-                for (int l = 0; l < cnt; ++l) {
-                    T.row_slot[cls[g0 + l]] = next + l;
-                    if (wide) T.row_slot2[cls[g0 + l]] = next + cnt + l;
-                }
-                next += wide ? 2 * cnt : cnt;
+            const int dc = rp[cls[0] + 1] - rp[cls[0]];
+            size_t g0 = 0;
+            for (; g0 + 32 <= cls.size(); g0 += 32) cgroups.push_back(CnGroup{dc, std::vector<int>(cls.begin() + g0, cls.begin() + g0 + 32)});
+            if (g0 < cls.size()) {
+                if (dc > 32) cgroups.push_back(CnGroup{dc, std::vector<int>(cls.begin() + g0, cls.end())});
+                else left.insert(left.end(), cls.begin() + g0, cls.end());   // classes come widest first
             }
         }
-    };
-    assign_row_slots();
+        for (size_t i = 0; i < left.size();) {
+            CnGroup g{rp[left[i] + 1] - rp[left[i]], {}};
+            while (i < left.size() && g.rows.size() < 32 && rp[left[i] + 1] - rp[left[i]] >= g.deg - 3) g.rows.push_back(left[i++]);
+            cgroups.push_back(std::move(g));
+        }
+    }
+    // record slots are handed out group by group: slot = first slot of the group + lane
+    T.row_slot.assign(m, 0);
+    T.row_slot2.assign(m, -1);
+    T.row_gdeg.assign(m, 0);
+    {
+        int next = 0;
+        for (const CnGroup &g : cgroups) {
+            const int cnt = (int)g.rows.size();
+            for (int l = 0; l < cnt; ++l) {
+                T.row_slot[g.rows[l]] = next + l;
+                if (g.deg > 32) T.row_slot2[g.rows[l]] = next + cnt + l;
+                T.row_gdeg[g.rows[l]] = g.deg;
+            }
+            next += g.deg > 32 ? 2 * cnt : cnt;
+        }
+    }
 
     // ---- stage 2: variable phase. Octets = 8 consecutive positions of a bit class; cell (octet, k) gathers 8 records.
     // greedy start
@@ -203,12 +228,9 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
     // ---- stage 3: slots of the totals = class order; lanes inside an octet / octets inside a class are permuted to level,
     // for every check group, the number of its edges per bank. Check groups: 32 consecutive positions of a row class.
     std::vector<int> row_group(m);
-    int n_cn_groups = 0;
-    for (const auto &cls : rcls)
-        for (size_t g0 = 0; g0 < cls.size(); g0 += 32) {
-            for (size_t i = g0; i < std::min(cls.size(), g0 + 32); ++i) row_group[cls[i]] = n_cn_groups;
-            ++n_cn_groups;
-        }
+    const int n_cn_groups = (int)cgroups.size();
+    for (int g = 0; g < n_cn_groups; ++g)
+        for (int r : cgroups[g].rows) row_group[r] = g;
     std::vector<int> class_base(bcls.size() + 1, 0);   // every class starts on a multiple of 32: slot & 31 == lane == bank
     for (size_t c = 0; c < bcls.size(); ++c) class_base[c + 1] = class_base[c] + (int)((bcls[c].size() + 31) / 32 * 32);
     T.l_slots = class_base.back();
@@ -304,22 +326,22 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
     // a row left unmatched takes the edge whose bank is least used in this step.
     T.edge_pos.assign(nnz, -1);
     T.cn_gather = T.cn_gather_min = 0;
-    for (const auto &cls : rcls) {
-        const int dc = rp[cls[0] + 1] - rp[cls[0]], blocks = (dc + 3) / 4;
-        for (size_t g0 = 0; g0 < cls.size(); g0 += 32) {
-            const int cnt = (int)std::min<size_t>(32, cls.size() - g0);
-            const int base = T.row_slot[cls[g0]];
+    {
+        for (const CnGroup &cg : cgroups) {
+            const int dc = cg.deg, blocks = (dc + 3) / 4;
+            const int cnt = (int)cg.rows.size();
+            const int base = T.row_slot[cg.rows[0]];
             Oc2Group gi{(int)T.cnT.size(), dc, base, cnt};
             T.cn_g.push_back(gi);
             // remaining edges per row, bank of each
             std::vector<std::vector<int>> rem(cnt);
             int bank_left[32] = {0};
             for (int l = 0; l < cnt; ++l)
-                for (int e = rp[cls[g0 + l]]; e < rp[cls[g0 + l] + 1]; ++e) {
+                for (int e = rp[cg.rows[l]]; e < rp[cg.rows[l] + 1]; ++e) {
                     rem[l].push_back(e);
                     bank_left[T.bit_slot[col_idx[e]] & 31]++;
                 }
-            std::vector<int> sched((size_t)cnt * dc, -1);   // [l*dc + k] = CSR edge
+            std::vector<int> sched((size_t)cnt * dc, -1);   // [l*dc + k] = CSR edge, -1 = past the row's own degree
             for (int k = 0; k < dc; ++k) {
                 int row_edge[32], bank_row[32];
                 std::fill(row_edge, row_edge + 32, -1);
@@ -372,7 +394,7 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                 for (int l = 0; l < cnt; ++l)
                     if (row_edge[l] >= 0) used[T.bit_slot[col_idx[row_edge[l]]] & 31]++;
                 for (int l = 0; l < cnt; ++l) {
-                    if (row_edge[l] >= 0) continue;
+                    if (row_edge[l] >= 0 || rem[l].empty()) continue;   // a row of a lower degree has run out of edges
                     int best = -1, best_use = 1 << 30;
                     for (int e : rem[l]) {
                         const int u = used[T.bit_slot[col_idx[e]] & 31];
@@ -381,15 +403,16 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                     row_edge[l] = best;
                     used[T.bit_slot[col_idx[best]] & 31]++;
                 }
+                int slots[32];
                 for (int l = 0; l < cnt; ++l) {
                     const int e = row_edge[l];
                     sched[(size_t)l * dc + k] = e;
+                    slots[l] = e >= 0 ? T.bit_slot[col_idx[e]] : T.l_slots;   // the +inf total: one address, a broadcast
+                    if (e < 0) continue;
                     T.edge_pos[e] = k;
                     rem[l].erase(std::find(rem[l].begin(), rem[l].end(), e));
                     bank_left[T.bit_slot[col_idx[e]] & 31]--;
                 }
-                int slots[32];
-                for (int l = 0; l < cnt; ++l) slots[l] = T.bit_slot[col_idx[row_edge[l]]];
                 T.cn_gather += warp_cost(slots, cnt);
                 T.cn_gather_min += 1;
             }
@@ -397,7 +420,10 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                 for (int l = 0; l < 32; ++l) {
                     uint32_t c[4] = {0, 0, 0, 0};   // padding: the total in slot 0 (a broadcast)
                     if (l < cnt)
-                        for (int j = 0; j < 4 && kb * 4 + j < dc; ++j) c[j] = (uint32_t)T.bit_slot[col_idx[sched[(size_t)l * dc + kb * 4 + j]]] * 4u;
+                        for (int j = 0; j < 4 && kb * 4 + j < dc; ++j) {
+                            const int e = sched[(size_t)l * dc + kb * 4 + j];
+                            c[j] = (uint32_t)(e >= 0 ? T.bit_slot[col_idx[e]] : T.l_slots) * 4u;
+                        }
                     T.cnT.push_back(Oc2U4{c[0], c[1], c[2], c[3]});
                 }
         }
@@ -419,7 +445,7 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                         e[j] = ((uint32_t)(T.rec_slots + 1) * 16u) << 5;   // padding: the all-zero record (adds +0.0f)
                         const int k = kb * 4 + j;
                         if (l < cnt && k < dv) {
-                            const int p = col_ptr[v[g0 + l]] + k, r = csc_row[p], pos = T.edge_pos[csc_edge[p]], dcr = rp[r + 1] - rp[r];
+                            const int p = col_ptr[v[g0 + l]] + k, r = csc_row[p], pos = T.edge_pos[csc_edge[p]], dcr = T.row_gdeg[r];
                             const int half = pos / 32, in_rec = (dcr <= 32) ? dcr : (half == 0 ? 32 : dcr - 32);
                             const int slot = half == 0 ? T.row_slot[r] : T.row_slot2[r];
                             e[j] = (((uint32_t)slot * 16u) << 5) | (uint32_t)(32 - in_rec + pos % 32);
@@ -468,10 +494,11 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
             if (s < 0 || s >= T.rec_slots || seen_rec[s]) return "row -> record slot is not injective";
             seen_rec[s] = 1;
         }
+        if ((int)T.row_gdeg.size() != m || T.row_gdeg[j] < dc) return "group degree of a row";
         std::vector<char> pos_seen(dc, 0);
         for (int e = rp[j]; e < rp[j + 1]; ++e) {
             const int p = T.edge_pos[e];
-            if (p < 0 || p >= dc || pos_seen[p]) return "edge order of a row is not a permutation";
+            if (p < 0 || p >= dc || pos_seen[p]) return "edge order of a row is not a permutation";   // own edges come first
             pos_seen[p] = 1;
         }
     }
@@ -484,12 +511,18 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
         if (g.deg < 1 || g.deg > 64 || g.cnt < 1 || g.cnt > 32 || g.off < 0 || (size_t)g.off + (size_t)blocks * 32 > T.cnT.size()) return "check group header";
         for (int l = 0; l < g.cnt; ++l) {
             const int j = g.base + l < T.rec_slots ? row_of_slot[g.base + l] : -1;
-            if (j < 0 || rp[j + 1] - rp[j] != g.deg) return "check group: record slot without a row of the group's degree";
+            if (j < 0 || T.row_gdeg[j] != g.deg || rp[j + 1] - rp[j] > g.deg || rp[j + 1] - rp[j] < g.deg - 3 ||
+                (g.deg > 32 && rp[j + 1] - rp[j] != g.deg))
+                return "check group: record slot without a row of (nearly) the group's degree";
             if (g.deg > 32 && T.row_slot2[j] != g.base + g.cnt + l) return "check group: second record not at base + cnt + lane";
             std::vector<int> by_pos(g.deg, -1);
             for (int e = rp[j]; e < rp[j + 1]; ++e) by_pos[T.edge_pos[e]] = e;
             for (int k = 0; k < g.deg; ++k) {
                 const uint32_t off = (&T.cnT[(size_t)g.off + (size_t)(k / 4) * 32 + l].x)[k % 4];
+                if (by_pos[k] < 0) {   // past the row's own degree: the +inf total
+                    if (k < rp[j + 1] - rp[j] || off != (uint32_t)T.l_slots * 4u) return "check table: padding edge of a mixed group";
+                    continue;
+                }
                 if (off != (uint32_t)T.bit_slot[col_idx[by_pos[k]]] * 4u) return "check table: wrong total for an edge";
                 ++edges_cn;
             }
@@ -498,7 +531,8 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
             for (int l = 0; l < 32; ++l) {
                 const Oc2U4 w = T.cnT[(size_t)g.off + (size_t)kb * 32 + l];
                 for (uint32_t off : {w.x, w.y, w.z, w.w})
-                    if ((off & 3u) || off / 4 >= (uint32_t)T.l_slots || T.slot_bit[off / 4] == 0xFFFF) return "check table: offset out of range";
+                    if ((off & 3u) || off / 4 > (uint32_t)T.l_slots || (off / 4 < (uint32_t)T.l_slots && T.slot_bit[off / 4] == 0xFFFF))
+                        return "check table: offset out of range";
             }
     }
     int next_slot = 0;
@@ -514,7 +548,7 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
                 if (l < g.cnt && k < g.deg) {
                     const int b = T.slot_bit[g.base + l];
                     if (col_ptr[b + 1] - col_ptr[b] != g.deg) return "variable group: bit of another degree";
-                    const int p = col_ptr[b] + k, r = csc_row[p], pos = T.edge_pos[csc_edge[p]], dcr = rp[r + 1] - rp[r];
+                    const int p = col_ptr[b] + k, r = csc_row[p], pos = T.edge_pos[csc_edge[p]], dcr = T.row_gdeg[r];
                     const int in_rec = (dcr <= 32) ? dcr : (pos < 32 ? 32 : dcr - 32);
                     if (slot != (pos < 32 ? T.row_slot[r] : T.row_slot2[r]) || sh != 32 - in_rec + pos % 32) return "variable table: wrong record or shift";
                     if (T.vt16_ok) {

@@ -103,18 +103,20 @@ struct OnchipArgs {
     u64 *phase_clk;             // profiling: [0] check phases, [1] variable phases, [2] whole kernel, SM clocks summed over the CTAs
 };
 
-// Shared-memory layout: L[l_slots] float | rec[rec_slots+2] uint4 | bob bits in slot order [l_slots/32] | syn[groups_cn] |
-// frame id, FrameCtx. While a frame is set up the record array doubles as staging space for the key words
-// (2 * words as they come from HBM + l_slots/32 of Alice's bits in slot order).
+// Shared-memory layout: L[l_slots + 4] float (slot l_slots holds +inf: the total that padding edges of mixed-degree check groups
+// gather) | rec[rec_slots+2] uint4 | bob bits in slot order [l_slots/32] | syn[groups_cn] | frame id, FrameCtx. While a frame is set
+// up the record array doubles as staging space for the key words (2 * words as they come from HBM + l_slots/32 + 1 of
+// Alice's bits in slot order, the last word zero for the +inf slot).
 __host__ __device__ inline size_t onchip_l_slots(int n) { return ((size_t)n + 1 + 3) / 4 * 4; }   // sum-product kernel
+__host__ __device__ inline size_t onchip_l_bytes(int l_slots) { return ((size_t)l_slots + 4) * 4; }
 __host__ __device__ inline size_t onchip_misc_offset(int l_slots, int rec_slots, int groups_cn) {
-    return ((size_t)l_slots * 4 + ((size_t)rec_slots + 2) * 16 + ((size_t)l_slots / 32 + (size_t)groups_cn) * 4 + 7) / 8 * 8;
+    return (onchip_l_bytes(l_slots) + ((size_t)rec_slots + 2) * 16 + ((size_t)l_slots / 32 + (size_t)groups_cn) * 4 + 7) / 8 * 8;
 }
 __host__ __device__ inline size_t onchip_smem_bytes(int l_slots, int rec_slots, int groups_cn) {
     return onchip_misc_offset(l_slots, rec_slots, groups_cn) + 8 + 48 + 24;   // + frame id, FrameCtx, phase clocks
 }
 __host__ __device__ inline bool onchip_staging_fits(int n, int l_slots, int rec_slots) {
-    return ((size_t)rec_slots + 2) * 16 >= (2 * ((size_t)(n + 31) / 32) + (size_t)l_slots / 32) * 4;
+    return ((size_t)rec_slots + 2) * 16 >= (2 * ((size_t)(n + 31) / 32) + (size_t)l_slots / 32 + 1) * 4;
 }
 
 // The sum-product kernel (onchip_spa.cuh): msg[msg_words] float instead of the records, the rest alike.
@@ -402,7 +404,7 @@ template <int ALG, bool WIDE, bool VT16>
 __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *L = reinterpret_cast<float *>(smem_raw);
-    uint4 *rec = reinterpret_cast<uint4 *>(smem_raw + (size_t)a.l_slots * 4);
+    uint4 *rec = reinterpret_cast<uint4 *>(smem_raw + onchip_l_bytes(a.l_slots));
     uint32_t *bobs = reinterpret_cast<uint32_t *>(rec + a.rec_slots + 2);
     uint32_t *synw = bobs + a.l_slots / 32;
     long long *s_frame = reinterpret_cast<long long *>(smem_raw + onchip_misc_offset(a.l_slots, a.rec_slots, a.n_groups_cn2));
@@ -459,6 +461,10 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
                 alice_s[s0 >> 5] = wa;
             }
             L[s] = v ? onchip_llr_of(ctx, bb, (uint32_t)s, lp) : 1.f;
+        }
+        if (tid == 0) {
+            L[a.l_slots] = inf;                   // gathered by the padding edges of mixed-degree check groups, never written
+            alice_s[a.l_slots >> 5] = 0u;         // ... and no bit of Alice's key for the syndrome
         }
         __syncthreads();
         // Alice's syndrome (calculate_syndrome, array_and_matrix_operations.cpp:936-950) over the check-phase table
