@@ -193,6 +193,7 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     c->oc2_l_slots = T.oc2.l_slots;
     c->oc2_max_dc = T.oc2.max_dc;
     c->oc2_vn_g_host = T.oc2.vn_g;
+    c->oc2_vn_gcost = T.oc2.vn_gcost;
     c->oc2_bit_slot_host = bit_slot16;
     c->oc2_model[0] = T.oc2.cn_gather; c->oc2_model[1] = T.oc2.cn_gather_min;
     c->oc2_model[2] = T.oc2.vn_gather; c->oc2_model[3] = T.oc2.vn_gather_min;

@@ -151,6 +151,7 @@ struct qkdldpc_code {
     DevBuf<uint16_t> oc2_slot_bit, oc2_bit_slot;
     DevBuf<uint32_t> oc2_cls;         // [n_combos][2][words] punctured / shortened masks of the current batch, slot order
     std::vector<Oc2Group> oc2_vn_g_host;   // canonical order; the device copy is dealt to the warps of the launch
+    std::vector<int> oc2_vn_gcost;         // bank-model cost per group: the weight of that deal
     std::vector<uint16_t> oc2_bit_slot_host;
     long long oc2_model[4] = {0, 0, 0, 0};   // bank model: check gather, its minimum, variable gather, its minimum (wavefronts / iteration)
     // on-chip sum-product path (onchip_spa.cuh): one message word per edge; check phase shares oc_cn_* with min-sum

@@ -79,16 +79,17 @@ static cudaError_t pick_geometry(OnchipKernel kern, int max_threads, int m, int 
 // Variable-phase schedule for `nwarps` warps per CTA: warp w handles entries w, w + nwarps, ... of the returned list.
 // Groups differ in cost (degree 2 ... 73), so they are dealt longest-processing-time-first to the least loaded warp
 // (round-robin over the degree-sorted list leaves the busiest warp ~10 % above the mean on the irregular codes).
-static std::vector<int> vn_schedule(const std::vector<int> &group_degree, int nwarps) {
+static std::vector<int> vn_schedule(const std::vector<int> &group_degree, int nwarps, const std::vector<int> *cost = nullptr) {
     std::vector<std::vector<int>> per_warp(nwarps);
     std::vector<long long> load(nwarps, 0);
     std::vector<int> order(group_degree.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return group_degree[x] > group_degree[y]; });
+    auto weight = [&](int g) { return cost ? (*cost)[g] : group_degree[g] + 3; };   // degree + per-group overhead (header, LLR, store)
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return weight(x) > weight(y); });
     for (int g : order) {
         const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
         per_warp[w].push_back(g);
-        load[w] += group_degree[g] + 3;   // + per-group overhead (header, LLR, store)
+        load[w] += weight(g);
     }
     size_t rounds = 0;
     for (auto &v : per_warp) rounds = std::max(rounds, v.size());
@@ -309,7 +310,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
             const int nw = threads / 32;
             std::vector<int> degree;
             for (const Oc2Group &g : c->oc2_vn_g_host) degree.push_back(g.deg);
-            const std::vector<int> sched = vn_schedule(degree, nw);   // entry i belongs to warp i % nw; -1 = none
+            const std::vector<int> sched = vn_schedule(degree, nw, &c->oc2_vn_gcost);   // entry i belongs to warp i % nw; -1 = none
             std::vector<Oc2Group> dealt;
             std::vector<int> start(nw + 1, 0);
             for (int w = 0; w < nw; ++w) {

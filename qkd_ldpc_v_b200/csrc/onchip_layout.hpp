@@ -46,6 +46,8 @@ struct Oc2Tables {
                                       // degree classes share groups; the missing edges gather the +inf total in slot l_slots)
     std::vector<int> edge_pos;        // [nnz] position of CSR edge e in its row's processing order
     std::vector<Oc2Group> cn_g, vn_g; // vn_g in canonical (slot) order; the launcher deals it to the warps
+    std::vector<int> vn_gcost;        // [vn_g] shared-memory + index wavefronts of the group in the bank model: the weight the
+                                      // launcher balances the warps of a CTA with (the variable phase is bound by the LSU pipe)
     std::vector<Oc2U4> cnT;           // [off + kb*32 + lane] 4 x u32: BYTE offset (slot*4) of the totals of edges 4kb..4kb+3 -- 32-bit
                                       // entries although 16 would do: the check phase is bound by the ALU pipe, not by loads, and
                                       // an entry that IS the address costs no unpacking
@@ -458,6 +460,7 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                         T.vT16.push_back(Oc2U2{h[0] | (h[1] << 16), h[2] | (h[3] << 16)});
                     }
                 }
+            int gcost = 4 + 2 * blocks;   // header, Bob's bits, the store of the totals; index blocks
             for (int k = 0; k < dv; ++k)
                 for (int q = 0; q < 4; ++q) {
                     int slots[8], c8 = 0;
@@ -465,9 +468,12 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                         const uint32_t ent = (&T.vT[(size_t)T.vn_g.back().off + (size_t)(k / 4) * 32 + l].x)[k % 4];
                         slots[c8++] = (int)(ent >> 9);
                     }
-                    T.vn_gather += octet_cost(slots, c8);
+                    const int oc = octet_cost(slots, c8);
+                    T.vn_gather += oc;
                     T.vn_gather_min += 1;
+                    gcost += oc;
                 }
+            T.vn_gcost.push_back(gcost);
         }
     }
 }
