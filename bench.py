@@ -353,9 +353,9 @@ def measure(ctx, args, wl, F, steps, warmup, sampler=None, want_e2e=True):
         kname = ("onchip_minsum_kernel" if prec == 32 else "onchip_minsum64_kernel") if alg >= 2 else "onchip_spa_kernel"
         ent = db.get(kname, {})
         tr = ent.get("dram_bytes_per_frame")
-        # phase split of the float32 min-sum kernel: a SECOND, untimed pass in which every CTA clocks its check / variable phases
+        # phase split of the min-sum kernels: a SECOND, untimed pass in which every CTA clocks its check / variable phases
         phases = None
-        if kname == "onchip_minsum_kernel":
+        if kname in ("onchip_minsum_kernel", "onchip_minsum64_kernel"):
             code.set_profiling(True)
             step()
             pi = code.info()

@@ -101,13 +101,12 @@ struct OnchipTables {
     bool oc_ok = false, sp_ok = false;   // min-sum / sum-product kernel can address this graph
     int max_dc = 0, rec_slots = 0, sp_msg_words = 0;
     std::vector<int> slot0;              // first record slot of every row (+ total)
-    std::vector<int2> cn_ginfo, vn_ginfo;
-    std::vector<uint16_t> cn_row, vn_bit;
+    std::vector<int2> cn_ginfo;          // check-phase groups in natural order: the sum-product kernel's (onchip_spa.cuh)
+    std::vector<uint16_t> cn_row;
     std::vector<uint2> cnT;
-    std::vector<uint4> vT;
     std::vector<int> sp_cn_moff, sp_group_item0;
     std::vector<uint4> sp_items;
-    Oc2Tables oc2;                       // float32 min-sum kernel: storage order = processing order (onchip_layout.hpp)
+    Oc2Tables oc2;                       // min-sum kernels (float32 / float64 state): storage order = processing order (onchip_layout.hpp)
 };
 }  // namespace qkhost
 
@@ -123,30 +122,22 @@ struct qkdldpc_code {
     DevBuf<int> row_ptr, col_idx, col_ptr, csc_edge, csc_row, row_order, col_order;
     DevBuf<int> vn_ell_edge, vn_ell_row;   // ELL records of the two narrow VN buckets (step_kernels.cuh: vn_kernel_ell)
     int cn_first[5] = {0}, cn_count[5] = {0}, vn_first[5] = {0}, vn_count[5] = {0};   // degree buckets in row/col_order
-    // on-chip min-sum path (onchip_minsum.cuh): ELL index arrays per 32-node group; eligible == the graph fits
-    bool oc_eligible = false;
-    int oc_groups_cn = 0, oc_groups_vn = 0, oc_max_dc = 0, oc_rec_slots = 0;
-    size_t oc_smem = 0;
-    DevBuf<int2> oc_cn_ginfo, oc_vn_ginfo;
-    DevBuf<uint16_t> oc_cn_row, oc_vn_bit;
+    // on-chip paths: check-phase groups in natural order (ELL index arrays per 32-row group) for the sum-product kernel
+    int oc_groups_cn = 0, oc_max_dc = 0, oc_rec_slots = 0;
+    DevBuf<int2> oc_cn_ginfo;
+    DevBuf<uint16_t> oc_cn_row;
     DevBuf<uint2> oc_cnT;
-    DevBuf<uint4> oc_vT;
-    DevBuf<uint32_t> oc_cls;
+    DevBuf<uint32_t> oc_cls;          // [n_combos][2][words] punctured / shortened bit masks of the current batch, natural order
     DevBuf<unsigned char> oc_combos;  // OnchipCombo table of the current launch
-    // variable-phase groups as built by code_create; the device copies (oc_vn_ginfo / oc_vn_bit) are re-laid out in
-    // schedule order for the number of warps per CTA of the launch (inst_onchip.cu)
-    std::vector<int> oc_vn_degree;
-    std::vector<int2> oc_vn_ginfo_host;
-    std::vector<uint16_t> oc_vn_bit_host;
-    int oc_sched_warps = 0;   // oc_cls: [2][words] punctured / shortened bit masks of the current batch
     int oc_threads = 0;               // CTA size of the last on-chip launch
-    // float32 min-sum kernel: tables of onchip_layout.hpp
+    // min-sum kernels (float32 and float64 state): tables of onchip_layout.hpp; eligible == the kernels can address the graph
     bool oc2_eligible = false;
-    int oc2_groups_cn = 0, oc2_l_slots = 0, oc2_rec_slots = 0, oc2_max_dc = 0, oc2_sched_warps = 0;
-    DevBuf<int> oc2_vn_start;
-    DevBuf<unsigned long long> oc2_phase_clk;   // profiling: clocks per phase of the last float32 on-chip min-sum launch
-    DevBuf<int4> oc2_cn_g, oc2_vn_g;
-    DevBuf<uint4> oc2_cnT, oc2_vT;
+    int oc2_groups_cn = 0, oc2_l_slots = 0, oc2_rec_slots = 0, oc2_max_dc = 0;
+    int oc2_sched_warps = 0, oc2_sched_warps64 = 0;   // warps per CTA the variable-phase groups are currently dealt for
+    DevBuf<int> oc2_vn_start, oc2_vn_start64;
+    DevBuf<unsigned long long> oc2_phase_clk;   // profiling: clocks per phase of the last on-chip min-sum launch
+    DevBuf<int4> oc2_cn_g, oc2_vn_g, oc2_vn_g64;
+    DevBuf<uint4> oc2_cnT, oc2_cnT64, oc2_vT;   // cnT64: byte offsets of 8-byte totals (float64 kernel)
     DevBuf<uint2> oc2_vT16;           // 16-bit variable-phase entries, only for codes with at most 2048 records
     DevBuf<uint16_t> oc2_slot_bit, oc2_bit_slot;
     DevBuf<uint32_t> oc2_cls;         // [n_combos][2][words] punctured / shortened masks of the current batch, slot order

@@ -1,4 +1,4 @@
-// On-chip min-sum path: host-side launcher (one persistent kernel per batch) and the four kernel instantiations.
+// On-chip min-sum path: host-side launcher (one persistent kernel per batch) and the kernel instantiations (float32 / float64 state).
 #include "handle.hpp"
 #include "onchip_minsum.cuh"
 #include "onchip_minsum64.cuh"
@@ -21,15 +21,15 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
         return onchip_spa_smem_bytes(c->n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv) <= (size_t)dev_smem;
     }
     const bool f64 = P->message_precision == 64;
-    if (f64 ? !c->oc_eligible : !c->oc2_eligible) return false;
+    if (!c->oc2_eligible) return false;
     // same precondition as the FAST streaming kernels (minsum_factors_ok, handle.hpp): no message can become NaN / inf,
     // and the factors are finite and non-negative (the magnitude clamp min(c, thr) covers only the positive side)
     if (!minsum_factors_ok(P)) return false;
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return false;
-    if (f64) return onchip64_smem_bytes(c->n, c->oc_rec_slots, c->oc_groups_cn) <= (size_t)dev_smem;
     return onchip_staging_fits(c->n, c->oc2_l_slots, c->oc2_rec_slots) &&
-           onchip_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn) <= (size_t)dev_smem;
+           (f64 ? onchip64_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn)
+                : onchip_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn)) <= (size_t)dev_smem;
 }
 
 // threads == 0: pick the CTA size that puts the most warps on an SM (shared memory decides how many CTAs fit; ties go
@@ -229,9 +229,8 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
 
     OnchipArgs a{};
     a.n = n; a.m = m; a.words = words; a.rec_slots = c->oc_rec_slots;
-    a.n_groups_cn = c->oc_groups_cn; a.n_groups_vn = c->oc_groups_vn;
+    a.n_groups_cn = c->oc_groups_cn;
     a.cn_ginfo = c->oc_cn_ginfo.p; a.cn_row = c->oc_cn_row.p; a.cnT = c->oc_cnT.p;
-    a.vn_ginfo = c->oc_vn_ginfo.p; a.vn_bit = c->oc_vn_bit.p; a.vT = c->oc_vT.p;
     a.combos = reinterpret_cast<const OnchipCombo *>(c->oc_combos.p); a.frames_per_combo = frames_per_combo;
     a.cls_masks = c->oc_cls.p; a.tally_len = tl;
     a.n_frames = n_frames; a.alice_bits = d_alice; a.bob_bits = d_bob; a.qber = d_qber; a.qber_is_scalar = qber_is_scalar;
@@ -245,7 +244,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     const int max_threads = (spa || f64) ? 1024 : 768;
     int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(max_threads, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
     const size_t smem = spa   ? onchip_spa_smem_bytes(n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv)
-                        : f64 ? onchip64_smem_bytes(n, c->oc_rec_slots, c->oc_groups_cn)
+                        : f64 ? onchip64_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn)
                               : onchip_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn);
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
@@ -282,31 +281,13 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     const OnchipKernel kern = kernel_of(P->algorithm, wide, f64, vt16);
     e = pick_geometry(kern, max_threads, m, sms, smem, n_frames, &threads, &grid);
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel geometry failed: %s", cudaGetErrorString(e));
-    if (f64) {
-        if (c->oc_sched_warps != threads / 32) {   // the variable-phase schedule depends on the number of warps per CTA
-            const std::vector<int> sched = vn_schedule(c->oc_vn_degree, threads / 32);
-            std::vector<int2> ginfo(sched.size(), make_int2(0, 0));
-            std::vector<uint16_t> bits(sched.size() * 32, (uint16_t)n);
-            for (size_t i = 0; i < sched.size(); ++i)
-                if (sched[i] >= 0) {
-                    ginfo[i] = c->oc_vn_ginfo_host[sched[i]];
-                    std::copy(c->oc_vn_bit_host.begin() + (size_t)sched[i] * 32, c->oc_vn_bit_host.begin() + (size_t)sched[i] * 32 + 32,
-                              bits.begin() + i * 32);
-                }
-            CK(c->oc_vn_ginfo.reserve(ginfo.size()));
-            CK(c->oc_vn_bit.reserve(bits.size()));
-            CK(cudaMemcpyAsync(c->oc_vn_ginfo.p, ginfo.data(), ginfo.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(c->oc_vn_bit.p, bits.data(), bits.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
-            CK(cudaStreamSynchronize(s));
-            c->oc_sched_warps = threads / 32;
-            c->oc_groups_vn = (int)sched.size();
-        }
-        a.n_groups_vn = c->oc_groups_vn;
-        a.vn_ginfo = c->oc_vn_ginfo.p;
-        a.vn_bit = c->oc_vn_bit.p;
-    } else {
-        // float32: the tables of onchip_layout.hpp; the canonical variable-phase groups are dealt to the warps of this CTA size
-        if (c->oc2_sched_warps != threads / 32) {
+    {
+        // the tables of onchip_layout.hpp; the canonical variable-phase groups are dealt to the warps of this CTA size
+        // (float32 and float64 launches keep their own deal: 16 and 32 warps per CTA on the n = 10k codes)
+        int &sched_warps = f64 ? c->oc2_sched_warps64 : c->oc2_sched_warps;
+        DevBuf<int4> &vn_g = f64 ? c->oc2_vn_g64 : c->oc2_vn_g;
+        DevBuf<int> &vn_start = f64 ? c->oc2_vn_start64 : c->oc2_vn_start;
+        if (sched_warps != threads / 32) {
             const int nw = threads / 32;
             std::vector<int> degree;
             for (const Oc2Group &g : c->oc2_vn_g_host) degree.push_back(g.deg);
@@ -318,12 +299,12 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
                     if (sched[i] >= 0) dealt.push_back(c->oc2_vn_g_host[sched[i]]);
                 start[w + 1] = (int)dealt.size();
             }
-            CK(c->oc2_vn_g.reserve(dealt.size()));
-            CK(c->oc2_vn_start.reserve(start.size()));
-            CK(cudaMemcpyAsync(c->oc2_vn_g.p, dealt.data(), dealt.size() * sizeof(Oc2Group), cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(c->oc2_vn_start.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            CK(vn_g.reserve(dealt.size()));
+            CK(vn_start.reserve(start.size()));
+            CK(cudaMemcpyAsync(vn_g.p, dealt.data(), dealt.size() * sizeof(Oc2Group), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(vn_start.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
-            c->oc2_sched_warps = nw;
+            sched_warps = nw;
         }
         // punctured / shortened masks of every combination into slot order
         const int swords = c->oc2_l_slots / 32;
@@ -345,7 +326,8 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         CK(cudaStreamSynchronize(s));
         a.rec_slots = c->oc2_rec_slots;
         a.n_groups_cn2 = c->oc2_groups_cn; a.l_slots = c->oc2_l_slots;
-        a.cn_g2 = c->oc2_cn_g.p; a.cnT2 = c->oc2_cnT.p; a.vn_g2 = c->oc2_vn_g.p; a.vn_start = c->oc2_vn_start.p; a.vT2 = c->oc2_vT.p;
+        // float64: the same check-phase table with byte offsets of 8-byte totals
+        a.cn_g2 = c->oc2_cn_g.p; a.cnT2 = f64 ? c->oc2_cnT64.p : c->oc2_cnT.p; a.vn_g2 = vn_g.p; a.vn_start = vn_start.p; a.vT2 = c->oc2_vT.p;
         a.vT16 = vt16 ? c->oc2_vT16.p : nullptr;
         a.slot_bit = c->oc2_slot_bit.p; a.bit_slot = c->oc2_bit_slot.p; a.cls_masks2 = c->oc2_cls.p;
         if (c->profiling) {

@@ -31,8 +31,8 @@
 //
 // Eligibility (host): float32 messages, min-sum family with the FAST precondition of run_batch.cuh (no NaN possible),
 // every check degree <= 64 (rows of 33..64 edges own two records), n < 65535, state fits the 227 KB
-// of shared memory. SPA / SPA-lin-approx have their own on-chip kernel (onchip_spa.cuh), float64 state onchip_minsum64.cuh
-// (both on the older natural-order tables of onchip_tables.cu); n = 100k codes stream.
+// of shared memory. SPA / SPA-lin-approx have their own on-chip kernel (onchip_spa.cuh, natural-order tables of
+// onchip_tables.cu); float64 state: onchip_minsum64.cuh on the same tables as this kernel; n = 100k codes stream.
 #pragma once
 #include "common.cuh"
 
@@ -50,18 +50,12 @@ struct OnchipCombo {
 struct OnchipArgs {
     int n, m, words;
     int rec_slots;              // record slots in use (m + number of rows wider than 32 edges); + 2 scratch slots
-    int n_groups_cn, n_groups_vn;
-    // Index tables: one entry per (group, block of 4 edges, lane), so a lane fetches the indices of 4 edges with ONE
-    // 8- or 16-byte load. A group holds 32 rows (bits) of ONE degree; which nodes share a group is chosen on the host
-    // so that the lanes' shared-memory gathers fall into different banks (conflict-aware grouping, onchip_tables.cu).
+    int n_groups_cn;
+    // Check-phase index table in natural order (sum-product kernel): one entry per (group, block of 4 edges, lane), so a lane
+    // fetches the indices of 4 edges with ONE 8-byte load. A group holds 32 rows of ONE degree.
     const int2 *cn_ginfo;       // [groups] {offset into cnT (in uint2), degree of the group's rows}
-    const uint16_t *cn_row;     // [groups*32] row handled by (group, lane); padding lanes hold m (a scratch record slot)
+    const uint16_t *cn_row;     // [groups*32] row handled by (group, lane); padding lanes hold m
     const uint2 *cnT;           // [off + kb*32 + lane] 4 x uint16: bit index of edges 4kb..4kb+3 of that row (padding: 0)
-    const int2 *vn_ginfo;       // [groups] {offset into vT (in uint4), degree of the group's bits}, in schedule order
-                                //          (degree 0 = an empty slot of the schedule)
-    const uint16_t *vn_bit;     // [groups*32] bit handled by (group, lane); padding lanes hold n (a scratch L slot)
-    const uint4 *vT;            // [off + kb*32 + lane] 4 x uint32: row << 9 | sh of checks 4kb..4kb+3 of that bit,
-                                //                      sh = 32 - dc(row) + position in the row (padding: scratch row m)
     // Sum-product kernel only (onchip_spa.cuh): one float per edge in shared memory, word cn_moff[group] + k * 32 + lane
     // for edge k of the row handled by (group, lane); the variable phase has its own groups and addresses the words directly.
     const int *cn_moff;         // [groups_cn] first message word of the group
@@ -89,10 +83,11 @@ struct OnchipArgs {
     int max_iter;
     float thr;                  // +inf when the clamp is disabled
     double thr64;               // the same for the float64 kernel (onchip_minsum64.cuh)
-    // float32 min-sum kernel: tables of onchip_layout.hpp (storage order = processing order)
+    // min-sum kernels (float32 and float64 state): tables of onchip_layout.hpp (storage order = processing order)
     int n_groups_cn2, l_slots;  // l_slots: 32 per variable-phase group
     const int4 *cn_g2;          // [groups] {offset into cnT2, degree, first record slot, rows in the group}
     const uint4 *cnT2;          // [off + kb*32 + lane] 4 x uint32: shared-memory BYTE offset of the totals of edges 4kb..4kb+3
+                                //                      (4 bytes per total for the float32 kernel, 8 for the float64 one)
     const int4 *vn_g2;          // [groups, dealt to the warps] {offset into vT2, degree, first total slot (multiple of 32), bits in the group}
     const int *vn_start;        // [warps per CTA + 1] warp w handles vn_g2[vn_start[w] .. vn_start[w+1])
     const uint4 *vT2;           // [off + kb*32 + lane] 4 x uint32: (16 * record slot) << 5 | sh; entries past the degree: the all-zero record
@@ -153,7 +148,7 @@ struct FrameCtx {
         const float c2b = __uint_as_float(mag ^ (zs & 0x80000000u));                                                    \
         zs <<= 1;                                                                                                       \
         const float braw = Lv - c2b;        /* L - c2b (:447-461); first iteration: zero record leaves the LLR (:336-350) */ \
-        const float nb = c2b - Lv;          /* the same magnitude; a zero stays +0, so its sign bit is (m > 0) */        \
+        const float nb = 0.f - braw;        /* m is never -0 (L never is), so the sign bit of 0 - m is exactly (m > 0) */ \
         zpos ^= __float_as_uint(0.f - Lv);                /* parity of L > 0: the hard decision is z = !(L > 0) (:414-422) */ \
         pacc ^= __float_as_uint(braw);                    /* parity of m < 0 (:383): zero is positive here (Q4) */       \
         own = __funnelshift_l(__float_as_uint(nb), own, 1);              /* (m > 0) ? +1 : -1 (:402): zero is negative (Q4) */ \

@@ -15,10 +15,9 @@ int build_onchip_tables(int n, int m, long long nnz, const std::vector<int> &rp,
     const int *row_ptr = rp.data();
     int &max_dc = T.max_dc;
     std::vector<int> &slot0 = T.slot0;
-    std::vector<int2> &oc_cn_ginfo = T.cn_ginfo, &oc_vn_ginfo = T.vn_ginfo;
-    std::vector<uint16_t> &oc_cn_row = T.cn_row, &oc_vn_bit = T.vn_bit;
+    std::vector<int2> &oc_cn_ginfo = T.cn_ginfo;
+    std::vector<uint16_t> &oc_cn_row = T.cn_row;
     std::vector<uint2> &oc_cnT = T.cnT;
-    std::vector<uint4> &oc_vT = T.vT;
     std::vector<int> &sp_cn_moff = T.sp_cn_moff, &sp_group_item0 = T.sp_group_item0;
     std::vector<uint4> &sp_items = T.sp_items;
     int &sp_msg_words = T.sp_msg_words;
@@ -118,36 +117,6 @@ int build_onchip_tables(int n, int m, long long nnz, const std::vector<int> &rp,
                     }
             }
         }
-        // variable phase: octets (one quarter-warp each), four octets per group
-        for (const auto &cls : degree_classes(n, col_ptr)) {
-            std::vector<std::vector<int>> octets;
-            pack(cls, col_ptr, csc_row.data(), 8, 8, octets, slot0.data());
-            const int dv = col_ptr[cls[0] + 1] - col_ptr[cls[0]], blocks = (dv + 3) / 4;
-            for (size_t o = 0; o < octets.size(); o += 4) {
-                int lane_bit[32];
-                for (int l = 0; l < 32; ++l) {
-                    const size_t oi = o + (size_t)l / 8;
-                    lane_bit[l] = (oi < octets.size() && (size_t)(l % 8) < octets[oi].size()) ? octets[oi][l % 8] : -1;
-                }
-                oc_vn_ginfo.push_back(make_int2((int)oc_vT.size(), dv));
-                for (int l = 0; l < 32; ++l) oc_vn_bit.push_back(lane_bit[l] >= 0 ? (uint16_t)lane_bit[l] : (uint16_t)n);
-                for (int kb = 0; kb < blocks; ++kb)
-                    for (int l = 0; l < 32; ++l) {
-                        uint32_t e[4];
-                        for (int j = 0; j < 4; ++j) {
-                            e[j] = (uint32_t)rec_slots << 9;   // padding: the scratch record
-                            const int k = kb * 4 + j;
-                            if (lane_bit[l] >= 0 && k < dv) {
-                                const int p = col_ptr[lane_bit[l]] + k, r = csc_row[p];
-                                const int pos = csc_edge[p] - rp[r], dcr = rp[r + 1] - rp[r];
-                                const int half = pos / 32, dch = (dcr <= 32) ? dcr : (half == 0 ? 32 : dcr - 32);
-                                e[j] = ((uint32_t)(slot0[r] + half) << 9) | (uint32_t)(32 - dch + pos % 32);
-                            }
-                        }
-                        oc_vT.push_back(make_uint4(e[0], e[1], e[2], e[3]));
-                    }
-            }
-        }
         // sum-product variable phase: groups of 32 bits of one degree; a 4-byte gather of the lanes' k-th messages is
         // conflict-free when the 32 rows sit in 32 different lanes of their check groups (bank = word mod 32 = lane)
         // shared-memory words: L[l_slots] first, then the messages, then the always-zero padding word
@@ -186,7 +155,7 @@ int build_onchip_tables(int n, int m, long long nnz, const std::vector<int> &rp,
     if (oc_ok) {
         // Self-check of the tables the on-chip kernel indexes shared memory with (the kernel itself does no bounds tests):
         // every bit index < n, every record slot <= m (m = scratch), every shift in [0, 31], every edge present once.
-        size_t edges_cn = 0, edges_vn = 0;
+        size_t edges_cn = 0;
         for (size_t g = 0; g < oc_cn_ginfo.size(); ++g) {
             const int dc = oc_cn_ginfo[g].y, blocks = (dc + 3) / 4;
             if (dc < 1 || dc > 64 || (size_t)oc_cn_ginfo[g].x + (size_t)blocks * 32 > oc_cnT.size())
@@ -206,28 +175,7 @@ int build_onchip_tables(int n, int m, long long nnz, const std::vector<int> &rp,
                 }
             }
         }
-        for (size_t g = 0; g < oc_vn_ginfo.size(); ++g) {
-            const int dv = oc_vn_ginfo[g].y, blocks = (dv + 3) / 4;
-            if (dv < 1 || (size_t)oc_vn_ginfo[g].x + (size_t)blocks * 32 > oc_vT.size())
-                return fail(QKDLDPC_ERR_STATE, "on-chip variable table: bad group header %zu", g);
-            for (int l = 0; l < 32; ++l) {
-                const int bit = oc_vn_bit[g * 32 + l];
-                if (bit > n) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: bit %d out of range", bit);
-                for (int k = 0; k < blocks * 4; ++k) {
-                    const uint4 w = oc_vT[oc_vn_ginfo[g].x + (k / 4) * 32 + l];
-                    const uint32_t e = (k % 4 == 0) ? w.x : (k % 4 == 1) ? w.y : (k % 4 == 2) ? w.z : w.w;
-                    const int r = (int)(e >> 9), sh = (int)(e & 511u);
-                    if (r > rec_slots || sh > 31) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: bad entry for bit %d", bit);
-                    if (bit < n && k < dv) {
-                        const int p = col_ptr[bit] + k, row = csc_row[p], pos = csc_edge[p] - rp[row];
-                        if (r != slot0[row] + pos / 32) return fail(QKDLDPC_ERR_STATE, "on-chip variable table: wrong check for bit %d", bit);
-                        ++edges_vn;
-                    }
-                }
-            }
-        }
-        if (edges_cn != (size_t)nnz || edges_vn != (size_t)nnz)
-            return fail(QKDLDPC_ERR_STATE, "on-chip tables cover %zu / %zu of %lld edges", edges_cn, edges_vn, (long long)nnz);
+        if (edges_cn != (size_t)nnz) return fail(QKDLDPC_ERR_STATE, "on-chip check table covers %zu of %lld edges", edges_cn, (long long)nnz);
     }
     if (sp_ok) {
         // the sum-product tables: every message word <= msg_words (the zero word), every edge owns exactly one word and
