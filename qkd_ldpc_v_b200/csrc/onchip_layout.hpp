@@ -476,11 +476,6 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
             T.vn_gcost.push_back(gcost);
         }
     }
-    // one padding block behind each table: the kernels request every index block one trip ahead (the float64 kernel's
-    // software-pipelined loads), so the block after the last group's last one is read -- and never used
-    T.cnT.insert(T.cnT.end(), 32, Oc2U4{0, 0, 0, 0});
-    T.vT.insert(T.vT.end(), 32, Oc2U4{0, 0, 0, 0});
-    if (T.vt16_ok) T.vT16.insert(T.vT16.end(), 32, Oc2U2{0, 0});
 }
 
 // Everything the kernel indexes shared memory with, checked against the graph (the kernel does no bounds tests). Returns

@@ -74,18 +74,8 @@ template <int ALG, bool WIDE>
 __device__ __forceinline__ bool onchip64_cn_phase(const OnchipArgs &a, const FrameCtx64 *ctx, const unsigned char *smem, uint4 *rec,
                                                   double *c2a, const uint32_t *synw, double thr_b, int warp, int lane, int nwarps) {
     bool unsat = false;
-    // Index loads come through L2 (the tables are read once per iteration and do not fit L1) and one CTA has only 32
-    // warps to hide that latency with, so they are software-pipelined: every index block is requested one trip of the edge
-    // loop ahead (the block after a group's last one is the next group's first / the table's padding block), the next
-    // group's header and first block while the current group is processed.
-    int g = warp;
-    if (g >= a.n_groups_cn2) return false;
-    int4 gi = __ldg(a.cn_g2 + g);
-    uint4 cw = __ldg(a.cnT2 + gi.x + lane);
-    for (;;) {
-        const int gn = g + nwarps;
-        const bool more = gn < a.n_groups_cn2;
-        const int4 gin = __ldg(a.cn_g2 + (more ? gn : g));
+    for (int g = warp; g < a.n_groups_cn2; g += nwarps) {
+        const int4 gi = __ldg(a.cn_g2 + g);
         const int dc_row = gi.y;                                  // degree of the group's rows (warp-uniform)
         const bool two = WIDE && dc_row > 32;                     // two records per row
         const int dc = two ? 32 : dc_row;                         // edges covered by the first record
@@ -94,7 +84,7 @@ __device__ __forceinline__ bool onchip64_cn_phase(const OnchipArgs &a, const Fra
         const uint4 ro = rec[slot];
         const double c2o = c2a[slot];
         uint32_t c1l = ro.x, c1h = ro.y, c2l = (uint32_t)__double2loint(c2o), c2h = hi32(c2o);
-        const uint4 *cp = a.cnT2 + gi.x + lane + 32;              // the block after the current one
+        const uint4 *cp = a.cnT2 + gi.x + lane;
         double m1 = DBL_MAX, m2 = DBL_MAX;                        // (:378-379)
         uint32_t zs = ro.z << (32 - dc);          // sign of the old message on the current edge in bit 31
         const int arg_old = (int)ro.w - (32 - dc);
@@ -102,15 +92,15 @@ __device__ __forceinline__ bool onchip64_cn_phase(const OnchipArgs &a, const Fra
         int kb = 0;
 #pragma unroll 2
         for (; kb + 4 <= dc; kb += 4) {
-            const uint4 cwx = __ldg(cp + (kb >> 2) * 32);
+            const uint4 cw = __ldg(cp + (kb >> 2) * 32);
             const int rel = arg_old - kb;
             QK_CN_EDGE64(0, cw.x)
             QK_CN_EDGE64(1, cw.y)
             QK_CN_EDGE64(2, cw.z)
             QK_CN_EDGE64(3, cw.w)
-            cw = cwx;
         }
         if (kb < dc) {                            // warp-uniform tail of 1..3 edges
+            const uint4 cw = __ldg(cp + (kb >> 2) * 32);
             const int rel = arg_old - kb, left = dc - kb;
             QK_CN_EDGE64(0, cw.x)
             if (left > 1) QK_CN_EDGE64(1, cw.y)
@@ -132,15 +122,15 @@ __device__ __forceinline__ bool onchip64_cn_phase(const OnchipArgs &a, const Fra
                 own = 0;
                 lt = 0;
                 for (; kb + 4 <= dc_row; kb += 4) {
-                    const uint4 cwx = __ldg(cp + (kb >> 2) * 32);
+                    const uint4 cw = __ldg(cp + (kb >> 2) * 32);
                     const int rel = arg_old2 - (kb - 32);
                     QK_CN_EDGE64(0, cw.x)
                     QK_CN_EDGE64(1, cw.y)
                     QK_CN_EDGE64(2, cw.z)
                     QK_CN_EDGE64(3, cw.w)
-                    cw = cwx;
                 }
                 if (kb < dc_row) {
+                    const uint4 cw = __ldg(cp + (kb >> 2) * 32);
                     const int rel = arg_old2 - (kb - 32), left = dc_row - kb;
                     QK_CN_EDGE64(0, cw.x)
                     if (left > 1) QK_CN_EDGE64(1, cw.y)
@@ -149,7 +139,6 @@ __device__ __forceinline__ bool onchip64_cn_phase(const OnchipArgs &a, const Fra
                 if (lt) arg = 32 + dc2 - __ffs((int)lt);
             }
         }
-        cw = __ldg(a.cnT2 + gin.x + lane);        // first block of the next group: in flight during the epilogue
         m1 = fmin(m1, thr_b);                                     // threshold_matrix(bit_to_check), magnitudes (:447-461)
         m2 = fmin(m2, thr_b);
         const uint32_t syn = (synw[g] >> lane) & 1u;
@@ -183,9 +172,6 @@ __device__ __forceinline__ bool onchip64_cn_phase(const OnchipArgs &a, const Fra
                 c2a[slot2] = c2;
             }
         }
-        if (!more) break;
-        g = gn;
-        gi = gin;
     }
     return unsat;
 }
@@ -213,51 +199,42 @@ __device__ __forceinline__ double onchip64_llr_of(const FrameCtx64 *ctx, uint32_
         acc = acc + __hiloint2double((int)(mg.y ^ (__funnelshift_l(0u, r.z, (ENT)) & 0x80000000u)), (int)mg.x);         \
     }
 
+// (Measured and not kept, B200, profiles/r02_u_onchip64.md: straight-line code per degree <= 8 with the 16-bit table of the
+// float32 kernel, -1 .. -3 %; index blocks requested one trip ahead and the next group's header / first block during the
+// current group, +1.7 % on the irregular code, -6 % on the dv = 4 codes.)
 __device__ __forceinline__ void onchip64_vn_phase(const OnchipArgs &a, const FrameCtx64 *ctx, double *L, const uint4 *rec, const double *c2a,
                                                   const uint32_t *bobs, double lp, int warp, int lane) {
     const unsigned char *recb = reinterpret_cast<const unsigned char *>(rec);
     const unsigned char *c2b = reinterpret_cast<const unsigned char *>(c2a);
     const double nlp = 0. - lp;
     const int has_cls = ctx->has_cls;
-    // the host dealt the groups to the warps longest-first (inst_onchip.cu); warp w owns a contiguous run of the dealt list.
-    // Index loads are software-pipelined like the check phase's: the header of the group after next and the first index
-    // block of the next group are requested before the current group is processed.
+    // the host dealt the groups to the warps longest-first (inst_onchip.cu); warp w owns a contiguous run of the dealt list
     const int g_end = __ldg(a.vn_start + warp + 1);
-    int g = __ldg(a.vn_start + warp);
-    if (g >= g_end) return;
-    int4 gi = __ldg(a.vn_g2 + g);
-    int4 gin = __ldg(a.vn_g2 + min(g + 1, g_end - 1));
-    uint4 ew = __ldg(a.vT2 + gi.x + lane);
-    for (;; ++g) {
-        const uint4 ewn = __ldg(a.vT2 + gin.x + lane);
-        const int4 ginn = __ldg(a.vn_g2 + min(g + 2, g_end - 1));
+    for (int g = __ldg(a.vn_start + warp); g < g_end; ++g) {
+        const int4 gi = __ldg(a.vn_g2 + g);
         const int dv = gi.y;
         const uint32_t s = (uint32_t)gi.z + (uint32_t)lane;       // the group's 32 slots start on a multiple of 32
         double acc = ((bobs[gi.z >> 5] >> lane) & 1u) ? nlp : lp; // a-priori LLR; padding lanes see Bob bit 0
         if (has_cls) acc = onchip64_llr_of(ctx, (bobs[gi.z >> 5] >> lane) & 1u, s, lp);
-        const uint4 *ep = a.vT2 + gi.x + lane + 32;               // the block after the current one
+        const uint4 *ep = a.vT2 + gi.x + lane;
         int kb = 0;
         // ascending check order, starting from the LLR (std::accumulate, :414-417)
 #pragma unroll 2
         for (; kb + 4 <= dv; kb += 4) {
-            const uint4 ewx = __ldg(ep + (kb >> 2) * 32);
+            const uint4 ew = __ldg(ep + (kb >> 2) * 32);
             QK_VN_EDGE64(ew.x)
             QK_VN_EDGE64(ew.y)
             QK_VN_EDGE64(ew.z)
             QK_VN_EDGE64(ew.w)
-            ew = ewx;
         }
         if (kb < dv) {                            // warp-uniform tail of 1..3 checks
+            const uint4 ew = __ldg(ep + (kb >> 2) * 32);
             const int left = dv - kb;
             QK_VN_EDGE64(ew.x)
             if (left > 1) QK_VN_EDGE64(ew.y)
             if (left > 2) QK_VN_EDGE64(ew.z)
         }
         L[s] = acc;                               // consecutive slots: coalesced; padding lanes own padding slots
-        if (g + 1 >= g_end) break;
-        gi = gin;
-        gin = ginn;
-        ew = ewn;
     }
 }
 #undef QK_VN_EDGE64
