@@ -288,19 +288,30 @@ __global__ void __launch_bounds__(1024, 1) onchip_minsum64_kernel(const OnchipAr
             st_alice[w] = a.alice_bits[f * a.words + w];
         }
         __syncthreads();
-        // key bits into slot order; L = a-priori LLR (qkd_ldpc_algorithm.cpp:1043-1049)
-        for (int s0 = warp * 32; s0 < a.l_slots; s0 += nwarps * 32) {
-            const int s = s0 + lane;
-            const uint32_t sb = (uint32_t)__ldg(a.slot_bit + s);
-            const bool v = sb != 0xFFFFu;             // else a padding slot: never gathered, holds a harmless finite value
-            const uint32_t bit = v ? sb : 0u;
-            const uint32_t bb = (st_bob[bit >> 5] >> (bit & 31u)) & 1u, ab = (st_alice[bit >> 5] >> (bit & 31u)) & 1u;
-            const uint32_t wb = __ballot_sync(0xffffffffu, v && bb), wa = __ballot_sync(0xffffffffu, v && ab);
-            if (lane == 0) {
-                bobs[s0 >> 5] = wb;
-                alice_s[s0 >> 5] = wa;
+        // key bits into slot order; L = a-priori LLR (qkd_ldpc_algorithm.cpp:1043-1049). Four words per trip, their slot -> bit
+        // entries (L2) requested together: frame set-up is a chain of latencies, not of work
+        for (int s0 = warp * 32; s0 < a.l_slots; s0 += nwarps * 128) {
+            uint32_t sbs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int s = s0 + u * nwarps * 32 + lane;
+                sbs[u] = s < a.l_slots ? (uint32_t)__ldg(a.slot_bit + s) : 0xFFFFu;
             }
-            L[s] = v ? onchip64_llr_of(ctx, bb, (uint32_t)s, lp) : 1.;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int sw = s0 + u * nwarps * 32, s = sw + lane;
+                if (sw >= a.l_slots) break;           // warp-uniform
+                const uint32_t sb = sbs[u];
+                const bool v = sb != 0xFFFFu;             // else a padding slot: never gathered, holds a harmless finite value
+                const uint32_t bit = v ? sb : 0u;
+                const uint32_t bb = (st_bob[bit >> 5] >> (bit & 31u)) & 1u, ab = (st_alice[bit >> 5] >> (bit & 31u)) & 1u;
+                const uint32_t wb = __ballot_sync(0xffffffffu, v && bb), wa = __ballot_sync(0xffffffffu, v && ab);
+                if (lane == 0) {
+                    bobs[sw >> 5] = wb;
+                    alice_s[sw >> 5] = wa;
+                }
+                L[s] = v ? onchip64_llr_of(ctx, bb, (uint32_t)s, lp) : 1.;
+            }
         }
         if (tid == 0) {
             L[a.l_slots] = inf;                   // gathered by the padding edges of mixed-degree check groups, never written
@@ -312,14 +323,21 @@ __global__ void __launch_bounds__(1024, 1) onchip_minsum64_kernel(const OnchipAr
             const int4 gi = __ldg(a.cn_g2 + g);
             const uint4 *cp = a.cnT2 + gi.x + lane;
             uint32_t sy = 0;
-            for (int kb = 0; kb < gi.y; kb += 4) {
-                const uint4 cw = __ldg(cp + (kb >> 2) * 32);
-                const int left = gi.y - kb;
-                const uint32_t c0 = cw.x >> 3, c1 = cw.y >> 3, c2 = cw.z >> 3, c3 = cw.w >> 3;   // slots
-                sy ^= alice_s[c0 >> 5] >> (c0 & 31u);
-                if (left > 1) sy ^= alice_s[c1 >> 5] >> (c1 & 31u);
-                if (left > 2) sy ^= alice_s[c2 >> 5] >> (c2 & 31u);
-                if (left > 3) sy ^= alice_s[c3 >> 5] >> (c3 & 31u);
+            const int last_block = (gi.y - 1) >> 2;
+            for (int kb = 0; kb < gi.y; kb += 16) {       // four index blocks (L2) in flight
+                uint4 cws[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) cws[u] = __ldg(cp + min((kb >> 2) + u, last_block) * 32);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int left = gi.y - kb - 4 * u;
+                    if (left <= 0) break;                 // warp-uniform
+                    const uint32_t c0 = cws[u].x >> 3, c1 = cws[u].y >> 3, c2 = cws[u].z >> 3, c3 = cws[u].w >> 3;   // slots
+                    sy ^= alice_s[c0 >> 5] >> (c0 & 31u);
+                    if (left > 1) sy ^= alice_s[c1 >> 5] >> (c1 & 31u);
+                    if (left > 2) sy ^= alice_s[c2 >> 5] >> (c2 & 31u);
+                    if (left > 3) sy ^= alice_s[c3 >> 5] >> (c3 & 31u);
+                }
             }
             const uint32_t sw = __ballot_sync(0xffffffffu, (sy & 1u) != 0 && lane < gi.w);
             if (lane == 0) synw[g] = sw;
@@ -354,14 +372,29 @@ __global__ void __launch_bounds__(1024, 1) onchip_minsum64_kernel(const OnchipAr
         }
 
         // bob_solution = last hard decision (L <= 0), packed in natural bit order; keys compare (arrays_equal, :1087)
+        // (lane r of a warp fetches Alice's word of the warp's round r up front; bit -> slot entries four rounds at a time)
         uint32_t diff = 0;
-        for (int w = warp; w < a.words; w += nwarps) {
-            const int i = w * 32 + lane;
-            const uint32_t s = i < a.n ? (uint32_t)__ldg(a.bit_slot + i) : 0u;
-            const uint32_t word = __ballot_sync(0xffffffffu, i < a.n && L[s] <= 0.);
-            if (lane == 0) {
-                if (a.out_bits) a.out_bits[f * a.words + w] = word;
-                diff |= word ^ a.alice_bits[f * a.words + w];
+        for (int w0 = warp; w0 < a.words; w0 += nwarps * 32) {
+            const int wl = w0 + lane * nwarps;
+            const uint32_t aw = wl < a.words ? a.alice_bits[f * a.words + wl] : 0u;
+            for (int r0 = 0; r0 < 32 && w0 + r0 * nwarps < a.words; r0 += 4) {
+                uint32_t sl[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = (w0 + (r0 + u) * nwarps) * 32 + lane;
+                    sl[u] = i < a.n ? (uint32_t)__ldg(a.bit_slot + i) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int w = w0 + (r0 + u) * nwarps, i = w * 32 + lane;
+                    if (w >= a.words) break;          // warp-uniform
+                    const uint32_t word = __ballot_sync(0xffffffffu, i < a.n && L[sl[u]] <= 0.);
+                    const uint32_t al = __shfl_sync(0xffffffffu, aw, r0 + u);
+                    if (lane == 0) {
+                        if (a.out_bits) a.out_bits[f * a.words + w] = word;
+                        diff |= word ^ al;
+                    }
+                }
             }
         }
         const bool keys_differ = __syncthreads_or(diff != 0) != 0;
