@@ -71,6 +71,8 @@ def parse():
     p.add_argument("--path", type=int, default=0, choices=[0, 1, 2],
                    help="decoder path: 0 auto (on-chip kernels when eligible), 1 streaming (messages in HBM), 2 on-chip")
     p.add_argument("--onchip-threads", type=int, default=0)
+    p.add_argument("--record-bytes", type=int, default=0, choices=[0, 8, 16],
+                   help="float32 on-chip min-sum: record format (0 auto: 8-byte records when every row has at most 51 edges)")
     p.add_argument("--copy-chunks", type=int, default=0, help="pieces a host batch is cut into for copy / compute overlap (0 auto, 1 none)")
     p.add_argument("--no-compaction", action="store_true", help="streaming path: do not compact the tail of a draining batch")
     p.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU-baseline sample (0 = auto)")
@@ -271,7 +273,8 @@ def measure(ctx, args, wl, F, steps, warmup, sampler=None, want_e2e=True):
     words = (n + 31) // 32
     code = q.LdpcCode(n, m, arr["row_ptr"], arr["col_idx"], device=local_rank, pool_slots=args.pool_slots,
                       frames_per_lane_f32=args.frames_per_lane, decoder_path=args.path, onchip_threads=args.onchip_threads,
-                      tail_compaction=-1 if args.no_compaction else 0, copy_chunks=args.copy_chunks)
+                      tail_compaction=-1 if args.no_compaction else 0, copy_chunks=args.copy_chunks,
+                      onchip_record_bytes=args.record_bytes)
     code.set_stream(stream.cuda_stream)
     if world > 1:
         # the handle owns the NCCL communicator of the tally all-reduce (include/qkdldpc.h): rank 0 draws the unique id,
@@ -445,6 +448,7 @@ def measure(ctx, args, wl, F, steps, warmup, sampler=None, want_e2e=True):
         "decoder_path": (("on-chip min-sum" if alg >= 2 else "on-chip sum-product") + " (frame state in shared memory)")
                         if onchip else "streaming (messages in HBM)",
         "onchip_threads": inf.get("onchip_threads") if onchip else None,
+        "onchip_record_bytes": (inf.get("onchip_record_bytes") or None) if onchip and alg >= 2 and prec == 32 else None,
         "frames_per_tile": inf["frames_per_tile"], "pool_tiles": inf["pool_tiles"], "pool_bytes": inf["pool_bytes"],
         "l2_policy": ("inputs larger than L2: %.0f MB of packed keys in + decisions out per step, read once; decoder "
                       "state is in shared memory" % (3 * F * words * 4 / 1e6)) if onchip else
@@ -522,7 +526,8 @@ def main():
             "config": {"workload": head["workload"], "workload_id": args.workload, "frames_per_step_per_gpu": F,
                        "max_iterations": MAX_ITER, "threshold": THRESHOLD, "accurate_qber": head["accurate_qber"],
                        "frames_per_tile": head["frames_per_tile"], "pool_tiles": head["pool_tiles"], "pool_bytes": head["pool_bytes"],
-                       "decoder_path": head["decoder_path"], "onchip_threads": head["onchip_threads"], "l2_policy": head["l2_policy"],
+                       "decoder_path": head["decoder_path"], "onchip_threads": head["onchip_threads"],
+                       "onchip_record_bytes": head["onchip_record_bytes"], "l2_policy": head["l2_policy"],
                        "mean_iterations_executed": head["mean_iterations_executed"], "fer": head["fer"],
                        "parallelism": f"frames sharded over {world} GPU(s), tally all-reduce only (ncclAllReduce of {head['tally_len']} x u64 inside the library)"},
             "roofline": head["roofline"], "cpu_baseline": cpu_baseline, "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],

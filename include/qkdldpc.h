@@ -101,7 +101,11 @@ typedef struct qkdldpc_options {
     int32_t copy_chunks;    /* qkdldpc_decode_batch (host buffers): number of chunks the batch is cut into so that the
                                host-to-device copy of chunk k+1 and the device-to-host copy of chunk k-1 overlap the
                                decoding of chunk k; 0 = auto, 1 = no overlap (copy, decode, copy back)                  */
-    int32_t reserved[4];
+    int32_t onchip_record_bytes; /* float32 on-chip min-sum kernel: 16 = one 16-byte record per row {c1, c2, signs, argmin}
+                               (rows of 33..64 edges: two), 8 = 8-byte records {c1, signs | argmin} + a c2 array (rows of
+                               28..51 edges: two; wider rows: the 16-byte format), 0 = auto: 8 when every row has at most
+                               27 edges; results are identical                                                           */
+    int32_t reserved[3];
 } qkdldpc_options;
 
 QKDLDPC_API int qkdldpc_version(void);
@@ -277,16 +281,17 @@ typedef struct qkdldpc_info {
     int32_t last_path;         /* decoder path of the last batch: 1 streaming, 2 on-chip */
     int32_t onchip_threads;    /* CTA size of the last on-chip launch */
     int32_t last_precision;    /* message precision the last batch ran in (32 / 64), after the precision policy */
-    int32_t reserved;
+    int32_t onchip_record_bytes; /* record format of the last float32 on-chip min-sum launch (16 / 8; 0 = none yet) */
 } qkdldpc_info;
 QKDLDPC_API int qkdldpc_code_info(const qkdldpc_code *code, qkdldpc_info *info);
-/* Host only (no device needed): builds the storage layout of the float32 on-chip min-sum kernel for a graph, checks every
- * table entry against the graph and returns the shared-memory bank model of the result, in wavefronts per decoder iteration:
+/* Host only (no device needed): builds the storage layouts of the on-chip min-sum kernels for a graph, checks every table
+ * entry against the graph and returns the shared-memory bank model of the result, in wavefronts per decoder iteration:
  * out[0] = 1 when the code is eligible (else the rest is 0), out[1] / out[2] = the check phase's 4-byte gathers and their
- * conflict-free minimum, out[3] / out[4] = the variable phase's 16-byte record gathers and their minimum, out[5] = 1 when the
- * 16-bit variable-phase table applies (at most 2048 records). QKDLDPC_ERR_STATE when a table fails its self-check. */
+ * conflict-free minimum, out[3] / out[4] = the variable phase's record gathers and their minimum (one wavefront per 128
+ * bytes), out[5] = 1 when the 16-bit variable-phase table applies (at most 2048 records) -- for the 16-byte record format;
+ * out[6..11] the same for the float32 kernel's 8-byte records. QKDLDPC_ERR_STATE when a table fails its self-check. */
 QKDLDPC_API int qkdldpc_onchip_layout_model(int32_t n, int32_t m, int64_t nnz, const int32_t *row_ptr, const int32_t *col_idx,
-                                            int64_t *out /* [6] */);
+                                            int64_t *out /* [12] */);
 /* When enabled, every kernel of the step loop is bracketed by CUDA events (slow; for bench roofline numbers). */
 QKDLDPC_API int qkdldpc_code_set_profiling(qkdldpc_code *code, int32_t enabled);
 

@@ -19,7 +19,7 @@ class Options(C.Structure):
     _fields_ = [("pool_bytes", C.c_int64), ("pool_slots", C.c_int32), ("steps_per_poll", C.c_int32),
                 ("frames_per_lane_f32", C.c_int32), ("use_graph", C.c_int32), ("decoder_path", C.c_int32),
                 ("onchip_threads", C.c_int32), ("tail_compaction", C.c_int32), ("compaction_max_ctas", C.c_int32),
-                ("copy_chunks", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("copy_chunks", C.c_int32), ("onchip_record_bytes", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Combination(C.Structure):
@@ -33,7 +33,8 @@ class Info(C.Structure):
                 ("frames_per_tile", C.c_int32), ("pool_tiles", C.c_int32), ("pool_bytes", C.c_int64),
                 ("kernel_launches", C.c_int64), ("decoder_steps", C.c_int64), ("last_batch_ms", C.c_double),
                 ("last_cn_ms", C.c_double), ("last_vn_ms", C.c_double), ("last_sched_ms", C.c_double),
-                ("last_path", C.c_int32), ("onchip_threads", C.c_int32), ("last_precision", C.c_int32), ("reserved", C.c_int32)]
+                ("last_path", C.c_int32), ("onchip_threads", C.c_int32), ("last_precision", C.c_int32),
+                ("onchip_record_bytes", C.c_int32)]
 
 
 # every symbol include/qkdldpc.h declares: name -> (restype, argtypes)

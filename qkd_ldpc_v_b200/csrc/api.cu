@@ -149,18 +149,12 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
         return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
     };
     std::vector<int> ci(col_idx, col_idx + nnz);
-    std::vector<uint16_t> bit_slot16(T.oc2.bit_slot.begin(), T.oc2.bit_slot.end());
-    std::vector<Oc2U4> cnT64(T.oc2.cnT);   // float64 kernel: the same offsets for 8-byte totals
-    for (Oc2U4 &w : cnT64) { w.x *= 2; w.y *= 2; w.z *= 2; w.w *= 2; }
-    static_assert(sizeof(Oc2Group) == sizeof(int4) && sizeof(Oc2U2) == sizeof(uint2) && sizeof(Oc2U4) == sizeof(uint4), "table layouts");
     cudaError_t e = cudaSuccess;
     if ((e = up(c->row_ptr, rp)) || (e = up(c->col_idx, ci)) || (e = up(c->col_ptr, col_ptr)) ||
         (e = up(c->csc_edge, csc_edge)) || (e = up(c->csc_row, csc_row)) || (e = up(c->row_order, row_order)) ||
         (e = up(c->col_order, col_order)) || (e = up(c->vn_ell_edge, vn_ell_edge)) || (e = up(c->vn_ell_row, vn_ell_row)) ||
         (oc_ok && ((e = up(c->oc_cn_ginfo, T.cn_ginfo)) || (e = up(c->oc_cnT, T.cnT)) || (e = up(c->oc_cn_row, T.cn_row)))) ||
-        (T.oc2.ok && ((e = up(c->oc2_cn_g, T.oc2.cn_g)) || (e = up(c->oc2_cnT, T.oc2.cnT)) || (e = up(c->oc2_cnT64, cnT64)) || (e = up(c->oc2_vT, T.oc2.vT)) ||
-                      (T.oc2.vt16_ok && (e = up(c->oc2_vT16, T.oc2.vT16))) ||
-                      (e = up(c->oc2_slot_bit, T.oc2.slot_bit)) || (e = up(c->oc2_bit_slot, bit_slot16)))) ||
+        (e = c->oc2.upload(T.oc2, true)) || (e = c->oc2r8.upload(T.oc2r8, false)) ||
         (sp_ok && ((e = up(c->sp_cn_moff, T.sp_cn_moff)) || (e = up(c->sp_sv_items, T.sp_items)) || (e = up(c->sp_sv_group_item0, T.sp_group_item0)))) ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) ||
         (e = cudaMallocHost(&c->h_done, 2 * sizeof(unsigned long long))) || (e = cudaEventCreate(&c->ev0)) ||
@@ -183,16 +177,6 @@ int qkdldpc_code_create(qkdldpc_code **out, int32_t n, int32_t m, int64_t nnz, c
     c->oc_max_dc = T.max_dc;
     c->oc_rec_slots = T.rec_slots;
     c->oc_groups_cn = (int)T.cn_ginfo.size();
-    c->oc2_eligible = T.oc2.ok;
-    c->oc2_groups_cn = (int)T.oc2.cn_g.size();
-    c->oc2_rec_slots = T.oc2.rec_slots;
-    c->oc2_l_slots = T.oc2.l_slots;
-    c->oc2_max_dc = T.oc2.max_dc;
-    c->oc2_vn_g_host = T.oc2.vn_g;
-    c->oc2_vn_gcost = T.oc2.vn_gcost;
-    c->oc2_bit_slot_host = bit_slot16;
-    c->oc2_model[0] = T.oc2.cn_gather; c->oc2_model[1] = T.oc2.cn_gather_min;
-    c->oc2_model[2] = T.oc2.vn_gather; c->oc2_model[3] = T.oc2.vn_gather_min;
     c->sp_eligible = sp_ok;
     c->sp_group_item0 = T.sp_group_item0;
     c->sp_groups_sv = sp_ok ? (int)T.sp_group_item0.size() - 1 : 0;
@@ -216,9 +200,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     c->row_order.release(); c->col_order.release(); c->vn_ell_edge.release(); c->vn_ell_row.release();
     c->oc_cn_ginfo.release(); c->oc_cnT.release(); c->oc_cn_row.release();
     c->oc_cls.release();
-    c->oc2_cn_g.release(); c->oc2_vn_g.release(); c->oc2_vn_g64.release(); c->oc2_cnT.release(); c->oc2_cnT64.release(); c->oc2_vT.release();
-    c->oc2_vT16.release(); c->oc2_slot_bit.release(); c->oc2_bit_slot.release(); c->oc2_cls.release(); c->oc2_vn_start.release();
-    c->oc2_vn_start64.release(); c->oc2_phase_clk.release();
+    c->oc2.release(); c->oc2r8.release(); c->oc2_cls.release(); c->oc2_phase_clk.release();
     c->sp_cn_moff.release(); c->sp_sv_items.release(); c->sp_sv_chunk.release(); c->sp_sv_group_item0.release();
     c->msg.release(); c->bobmask.release(); c->zmask.release(); c->synd.release(); c->par.release();
     c->tile_active.release(); c->tile_new.release(); c->slot_llr.release(); c->slot_frame.release();
@@ -785,7 +767,7 @@ int qkdldpc_code_info(const qkdldpc_code *c, qkdldpc_info *info) {
     info->last_path = c->last_path;
     info->onchip_threads = c->oc_threads;
     info->last_precision = c->last_precision;
-    info->reserved = 0;
+    info->onchip_record_bytes = c->last_rec_bytes;
     info->last_cn_ms = c->last_cn_ms; info->last_vn_ms = c->last_vn_ms; info->last_sched_ms = c->last_sched_ms;
     return QKDLDPC_OK;
 }

@@ -107,6 +107,60 @@ struct OnchipTables {
     std::vector<int> sp_cn_moff, sp_group_item0;
     std::vector<uint4> sp_items;
     Oc2Tables oc2;                       // min-sum kernels (float32 / float64 state): storage order = processing order (onchip_layout.hpp)
+    Oc2Tables oc2r8;                     // the same for the float32 kernel's 8-byte records (Oc2Params::rec8)
+};
+
+// Device copy of one Oc2Tables (+ what the launcher needs of it on the host).
+struct Oc2Device {
+    bool eligible = false;               // the kernels can address the graph with this layout
+    Oc2Params prm;
+    int groups_cn = 0, l_slots = 0, rec_slots = 0, max_dc = 0;
+    DevBuf<int4> cn_g;
+    DevBuf<uint4> cnT, cnT64, vT;        // cnT64: byte offsets of 8-byte totals (float64 kernel; 16-byte records only)
+    DevBuf<uint2> vT16;                  // 16-bit variable-phase entries, only for codes with at most 2048 records
+    DevBuf<uint16_t> slot_bit, bit_slot;
+    // the variable-phase groups dealt to the warps of a CTA: [0] float32 launches, [1] float64 launches (different CTA sizes)
+    int sched_warps[2] = {0, 0};
+    DevBuf<int4> vn_g[2];
+    DevBuf<int> vn_start[2];
+    std::vector<Oc2Group> vn_g_host;     // canonical order
+    std::vector<int> vn_gcost;           // bank-model cost per group: the weight of that deal
+    std::vector<uint16_t> bit_slot_host;
+    long long model[4] = {0, 0, 0, 0};   // bank model: check gather, its minimum, variable gather, its minimum (wavefronts / iteration)
+    cudaError_t upload(const Oc2Tables &T, bool with_f64) {
+        eligible = false;
+        prm = T.prm;
+        if (!T.ok) return cudaSuccess;
+        auto up = [](auto &buf, const auto &vec) -> cudaError_t {
+            cudaError_t e = buf.reserve(vec.size());
+            if (e != cudaSuccess) return e;
+            return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
+        };
+        static_assert(sizeof(Oc2Group) == sizeof(int4) && sizeof(Oc2U2) == sizeof(uint2) && sizeof(Oc2U4) == sizeof(uint4), "table layouts");
+        bit_slot_host.assign(T.bit_slot.begin(), T.bit_slot.end());
+        cudaError_t e;
+        if ((e = up(cn_g, T.cn_g)) || (e = up(cnT, T.cnT)) || (e = up(vT, T.vT)) || (T.vt16_ok && (e = up(vT16, T.vT16))) ||
+            (e = up(slot_bit, T.slot_bit)) || (e = up(bit_slot, bit_slot_host)))
+            return e;
+        if (with_f64) {
+            std::vector<Oc2U4> t64(T.cnT);   // the same offsets for 8-byte totals
+            for (Oc2U4 &w : t64) { w.x *= 2; w.y *= 2; w.z *= 2; w.w *= 2; }
+            if ((e = up(cnT64, t64))) return e;
+        }
+        groups_cn = (int)T.cn_g.size();
+        rec_slots = T.rec_slots;
+        l_slots = T.l_slots;
+        max_dc = T.max_dc;
+        vn_g_host = T.vn_g;
+        vn_gcost = T.vn_gcost;
+        model[0] = T.cn_gather; model[1] = T.cn_gather_min; model[2] = T.vn_gather; model[3] = T.vn_gather_min;
+        eligible = true;
+        return cudaSuccess;
+    }
+    void release() {
+        cn_g.release(); cnT.release(); cnT64.release(); vT.release(); vT16.release(); slot_bit.release(); bit_slot.release();
+        for (int k = 0; k < 2; ++k) { vn_g[k].release(); vn_start[k].release(); }
+    }
 };
 }  // namespace qkhost
 
@@ -130,21 +184,11 @@ struct qkdldpc_code {
     DevBuf<uint32_t> oc_cls;          // [n_combos][2][words] punctured / shortened bit masks of the current batch, natural order
     DevBuf<unsigned char> oc_combos;  // OnchipCombo table of the current launch
     int oc_threads = 0;               // CTA size of the last on-chip launch
-    // min-sum kernels (float32 and float64 state): tables of onchip_layout.hpp; eligible == the kernels can address the graph
-    bool oc2_eligible = false;
-    int oc2_groups_cn = 0, oc2_l_slots = 0, oc2_rec_slots = 0, oc2_max_dc = 0;
-    int oc2_sched_warps = 0, oc2_sched_warps64 = 0;   // warps per CTA the variable-phase groups are currently dealt for
-    DevBuf<int> oc2_vn_start, oc2_vn_start64;
+    // min-sum kernels: tables of onchip_layout.hpp -- 16-byte records (float32 and float64 state) and 8-byte records (float32)
+    Oc2Device oc2, oc2r8;
     DevBuf<unsigned long long> oc2_phase_clk;   // profiling: clocks per phase of the last on-chip min-sum launch
-    DevBuf<int4> oc2_cn_g, oc2_vn_g, oc2_vn_g64;
-    DevBuf<uint4> oc2_cnT, oc2_cnT64, oc2_vT;   // cnT64: byte offsets of 8-byte totals (float64 kernel)
-    DevBuf<uint2> oc2_vT16;           // 16-bit variable-phase entries, only for codes with at most 2048 records
-    DevBuf<uint16_t> oc2_slot_bit, oc2_bit_slot;
-    DevBuf<uint32_t> oc2_cls;         // [n_combos][2][words] punctured / shortened masks of the current batch, slot order
-    std::vector<Oc2Group> oc2_vn_g_host;   // canonical order; the device copy is dealt to the warps of the launch
-    std::vector<int> oc2_vn_gcost;         // bank-model cost per group: the weight of that deal
-    std::vector<uint16_t> oc2_bit_slot_host;
-    long long oc2_model[4] = {0, 0, 0, 0};   // bank model: check gather, its minimum, variable gather, its minimum (wavefronts / iteration)
+    DevBuf<uint32_t> oc2_cls;         // [n_combos][2][l_slots/32] punctured / shortened masks of the current batch, slot order
+    int last_rec_bytes = 0;           // 16 / 8: record format of the last float32 on-chip min-sum launch
     // on-chip sum-product path (onchip_spa.cuh): one message word per edge; check phase shares oc_cn_* with min-sum
     bool sp_eligible = false;
     int sp_msg_words = 0, sp_chunk_warps = 0;

@@ -21,15 +21,29 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
         return onchip_spa_smem_bytes(c->n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv) <= (size_t)dev_smem;
     }
     const bool f64 = P->message_precision == 64;
-    if (!c->oc2_eligible) return false;
+    if (!c->oc2.eligible) return false;
     // same precondition as the FAST streaming kernels (minsum_factors_ok, handle.hpp): no message can become NaN / inf,
     // and the factors are finite and non-negative (the magnitude clamp min(c, thr) covers only the positive side)
     if (!minsum_factors_ok(P)) return false;
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return false;
-    return onchip_staging_fits(c->n, c->oc2_l_slots, c->oc2_rec_slots) &&
-           (f64 ? onchip64_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn)
-                : onchip_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn)) <= (size_t)dev_smem;
+    const Oc2Device &d = c->oc2;
+    return onchip_staging_fits(c->n, d.l_slots, d.rec_slots) &&
+           (f64 ? onchip64_smem_bytes(d.l_slots, d.rec_slots, d.groups_cn) : onchip_smem_bytes(d.l_slots, d.rec_slots, d.groups_cn)) <= (size_t)dev_smem;
+}
+
+// float32 launches: 8-byte records when every row fits ONE of them (at most 27 edges: the alist n = 10k codes of
+// config 10k NMSA.json) -- three 512-thread CTAs per SM instead of two of 768 and half the record bytes per gather: A79 NMSA @
+// 2 % 9.23 -> 9.56 Gbit/s. With two records per row (28..51 edges) the format loses: on the irregular R = 0.8 code every row
+// splits, the check phase grows by a quarter and the 32-bit index entries eat half of what the variable phase saves (1.042 ->
+// 0.968 Gbit/s, profiles/r02_z_rec8.md), so that case runs only on request (qkdldpc_options.onchip_record_bytes = 8).
+static bool use_rec8(const qkdldpc_code *c) {
+    int dev_smem = 0;
+    if (c->opt.onchip_record_bytes == 16 || !c->oc2r8.eligible || (c->opt.onchip_record_bytes != 8 && c->oc2r8.max_dc > c->oc2r8.prm.rec_cap) ||
+        cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess)
+        return false;
+    const Oc2Device &d = c->oc2r8;
+    return onchip_staging_fits(c->n, d.l_slots, d.rec_slots, 12) && onchip_smem_bytes(d.l_slots, d.rec_slots, d.groups_cn, 12) <= (size_t)dev_smem;
 }
 
 // threads == 0: pick the CTA size that puts the most warps on an SM (shared memory decides how many CTAs fit; ties go
@@ -38,16 +52,17 @@ bool onchip_usable(const qkdldpc_code *c, const qkdldpc_params *P) {
 typedef void (*OnchipKernel)(const OnchipArgs);
 
 template <int ALG, bool WIDE>
-static OnchipKernel kernel_of(bool f64, bool vt16) {
+static OnchipKernel kernel_of(bool f64, bool vt16, bool rec8) {
     if (f64) return (OnchipKernel)onchip_minsum64_kernel<ALG, WIDE>;
-    return vt16 ? (OnchipKernel)onchip_minsum_kernel<ALG, WIDE, true> : (OnchipKernel)onchip_minsum_kernel<ALG, WIDE, false>;
+    if (rec8) return vt16 ? (OnchipKernel)onchip_minsum_kernel<ALG, WIDE, true, true> : (OnchipKernel)onchip_minsum_kernel<ALG, WIDE, false, true>;
+    return vt16 ? (OnchipKernel)onchip_minsum_kernel<ALG, WIDE, true, false> : (OnchipKernel)onchip_minsum_kernel<ALG, WIDE, false, false>;
 }
-static OnchipKernel kernel_of(int alg, bool wide, bool f64, bool vt16) {
+static OnchipKernel kernel_of(int alg, bool wide, bool f64, bool vt16, bool rec8) {
     switch (alg) {
-        case 2: return wide ? kernel_of<2, true>(f64, vt16) : kernel_of<2, false>(f64, vt16);
-        case 3: return wide ? kernel_of<3, true>(f64, vt16) : kernel_of<3, false>(f64, vt16);
-        case 4: return wide ? kernel_of<4, true>(f64, vt16) : kernel_of<4, false>(f64, vt16);
-        default: return wide ? kernel_of<5, true>(f64, vt16) : kernel_of<5, false>(f64, vt16);
+        case 2: return wide ? kernel_of<2, true>(f64, vt16, rec8) : kernel_of<2, false>(f64, vt16, rec8);
+        case 3: return wide ? kernel_of<3, true>(f64, vt16, rec8) : kernel_of<3, false>(f64, vt16, rec8);
+        case 4: return wide ? kernel_of<4, true>(f64, vt16, rec8) : kernel_of<4, false>(f64, vt16, rec8);
+        default: return wide ? kernel_of<5, true>(f64, vt16, rec8) : kernel_of<5, false>(f64, vt16, rec8);
     }
 }
 
@@ -241,11 +256,13 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
     a.thr64 = P->enable_threshold ? P->threshold : (double)INFINITY;
 
     const bool spa = P->algorithm < 2, f64 = P->message_precision == 64;
+    const bool rec8 = !spa && !f64 && use_rec8(c);
+    Oc2Device &d = rec8 ? c->oc2r8 : c->oc2;      // layout of this launch (min-sum kernels)
     const int max_threads = (spa || f64) ? 1024 : 768;
     int threads = c->opt.onchip_threads > 0 ? std::max(32, std::min(max_threads, c->opt.onchip_threads / 32 * 32)) : 0;   // 0 = auto
     const size_t smem = spa   ? onchip_spa_smem_bytes(n, c->sp_msg_words, c->oc_groups_cn, c->sp_groups_sv)
-                        : f64 ? onchip64_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn)
-                              : onchip_smem_bytes(c->oc2_l_slots, c->oc2_rec_slots, c->oc2_groups_cn);
+                        : f64 ? onchip64_smem_bytes(d.l_slots, d.rec_slots, d.groups_cn)
+                              : onchip_smem_bytes(d.l_slots, d.rec_slots, d.groups_cn, rec8 ? 12 : 16);
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 
@@ -276,27 +293,27 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         auto launch_spa = [&](const OnchipArgs &args, int g, cudaStream_t st) { return onchip_spa_launch(P->algorithm, args, g, threads, smem, st); };
         return onchip_launch_all(c, a, grid, threads, smem, n_frames, pipe, launch_spa);
     }
-    const bool wide = c->oc_max_dc > 32;   // rows of 33..64 edges: two records per row, separate kernel instantiation
-    const bool vt16 = !f64 && c->oc2_vT16.p != nullptr;   // 16-bit variable-phase entries (codes with at most 2048 records)
-    const OnchipKernel kern = kernel_of(P->algorithm, wide, f64, vt16);
+    const bool wide = d.max_dc > d.prm.rec_cap;   // rows of two records: separate kernel instantiation
+    const bool vt16 = !f64 && d.vT16.p != nullptr;   // 16-bit variable-phase entries (codes with at most 2048 records)
+    const OnchipKernel kern = kernel_of(P->algorithm, wide, f64, vt16, rec8);
     e = pick_geometry(kern, max_threads, m, sms, smem, n_frames, &threads, &grid);
     if (e != cudaSuccess) return fail(QKDLDPC_ERR_CUDA, "on-chip kernel geometry failed: %s", cudaGetErrorString(e));
     {
         // the tables of onchip_layout.hpp; the canonical variable-phase groups are dealt to the warps of this CTA size
         // (float32 and float64 launches keep their own deal: 16 and 32 warps per CTA on the n = 10k codes)
-        int &sched_warps = f64 ? c->oc2_sched_warps64 : c->oc2_sched_warps;
-        DevBuf<int4> &vn_g = f64 ? c->oc2_vn_g64 : c->oc2_vn_g;
-        DevBuf<int> &vn_start = f64 ? c->oc2_vn_start64 : c->oc2_vn_start;
+        int &sched_warps = d.sched_warps[f64];
+        DevBuf<int4> &vn_g = d.vn_g[f64];
+        DevBuf<int> &vn_start = d.vn_start[f64];
         if (sched_warps != threads / 32) {
             const int nw = threads / 32;
             std::vector<int> degree;
-            for (const Oc2Group &g : c->oc2_vn_g_host) degree.push_back(g.deg);
-            const std::vector<int> sched = vn_schedule(degree, nw, &c->oc2_vn_gcost);   // entry i belongs to warp i % nw; -1 = none
+            for (const Oc2Group &g : d.vn_g_host) degree.push_back(g.deg);
+            const std::vector<int> sched = vn_schedule(degree, nw, &d.vn_gcost);   // entry i belongs to warp i % nw; -1 = none
             std::vector<Oc2Group> dealt;
             std::vector<int> start(nw + 1, 0);
             for (int w = 0; w < nw; ++w) {
                 for (size_t i = (size_t)w; i < sched.size(); i += (size_t)nw)
-                    if (sched[i] >= 0) dealt.push_back(c->oc2_vn_g_host[sched[i]]);
+                    if (sched[i] >= 0) dealt.push_back(d.vn_g_host[sched[i]]);
                 start[w + 1] = (int)dealt.size();
             }
             CK(vn_g.reserve(dealt.size()));
@@ -307,7 +324,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
             sched_warps = nw;
         }
         // punctured / shortened masks of every combination into slot order
-        const int swords = c->oc2_l_slots / 32;
+        const int swords = d.l_slots / 32;
         std::vector<uint32_t> masks2((size_t)n_combos * 2 * swords, 0u);
         for (int cb = 0; cb < n_combos; ++cb) {
             if (!combos[cb].has_cls) continue;
@@ -316,7 +333,7 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
                 uint32_t *dst = masks2.data() + ((size_t)cb * 2 + h) * swords;
                 for (int w = 0; w < words; ++w)
                     for (uint32_t bitsw = src[w]; bitsw; bitsw &= bitsw - 1) {
-                        const int sl = c->oc2_bit_slot_host[(size_t)w * 32 + __builtin_ctz(bitsw)];
+                        const int sl = d.bit_slot_host[(size_t)w * 32 + __builtin_ctz(bitsw)];
                         dst[sl >> 5] |= 1u << (sl & 31);
                     }
             }
@@ -324,12 +341,13 @@ int run_onchip_multi(qkdldpc_code *c, const qkdldpc_params *P, int n_combos, int
         CK(c->oc2_cls.reserve(masks2.size()));
         CK(cudaMemcpyAsync(c->oc2_cls.p, masks2.data(), masks2.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
-        a.rec_slots = c->oc2_rec_slots;
-        a.n_groups_cn2 = c->oc2_groups_cn; a.l_slots = c->oc2_l_slots;
+        a.rec_slots = d.rec_slots;
+        a.n_groups_cn2 = d.groups_cn; a.l_slots = d.l_slots;
         // float64: the same check-phase table with byte offsets of 8-byte totals
-        a.cn_g2 = c->oc2_cn_g.p; a.cnT2 = f64 ? c->oc2_cnT64.p : c->oc2_cnT.p; a.vn_g2 = vn_g.p; a.vn_start = vn_start.p; a.vT2 = c->oc2_vT.p;
-        a.vT16 = vt16 ? c->oc2_vT16.p : nullptr;
-        a.slot_bit = c->oc2_slot_bit.p; a.bit_slot = c->oc2_bit_slot.p; a.cls_masks2 = c->oc2_cls.p;
+        a.cn_g2 = d.cn_g.p; a.cnT2 = f64 ? d.cnT64.p : d.cnT.p; a.vn_g2 = vn_g.p; a.vn_start = vn_start.p; a.vT2 = d.vT.p;
+        a.vT16 = vt16 ? d.vT16.p : nullptr;
+        a.slot_bit = d.slot_bit.p; a.bit_slot = d.bit_slot.p; a.cls_masks2 = c->oc2_cls.p;
+        if (!f64) c->last_rec_bytes = rec8 ? 8 : 16;
         if (c->profiling) {
             CK(c->oc2_phase_clk.reserve(4));
             CK(cudaMemsetAsync(c->oc2_phase_clk.p, 0, 4 * sizeof(unsigned long long), s));

@@ -31,8 +31,21 @@ struct Oc2U2 { uint32_t x, y; };
 struct Oc2U4 { uint32_t x, y, z, w; };
 struct Oc2Group { int off, deg, base, cnt; };   // int4 on the device: table offset, degree, first slot, nodes in the group
 
+// Record format the tables are built for. REC16 (float32 and float64 kernels): one 16-byte record per row of up to 32 edges
+// (gathered per quarter-warp: 8 lanes on 8 bank groups), rows of 33..64 edges own two (32 + the rest). REC8 (float32 kernel
+// only): 8-byte records {c1, signs << 5 | position code} gathered per half-warp (16 lanes on 16 bank pairs) -- half the
+// variable phase's shared-memory traffic --, which leaves 27 sign bits: rows of 28..51 edges own two records (24 + the rest).
+struct Oc2Params {
+    int rec_cap = 32;     // edges one record can describe
+    int split = 32;       // edges in the first record of a two-record row (a multiple of 4: index blocks do not straddle)
+    int vn_w = 8;         // lanes served together by one record gather = bank classes of the record slots
+    int rec_bytes = 16;
+    static Oc2Params rec8() { return Oc2Params{27, 24, 16, 8}; }
+};
+
 struct Oc2Tables {
     bool ok = false;
+    Oc2Params prm;
     int n = 0, m = 0, max_dc = 0;
     int l_slots = 0;       // slots of the totals: 32 per variable-phase group (the last group of a degree class is padded);
                            // slot l_slots itself holds +inf (padding edges of mixed-degree check groups)
@@ -51,7 +64,7 @@ struct Oc2Tables {
     std::vector<Oc2U4> cnT;           // [off + kb*32 + lane] 4 x u32: BYTE offset (slot*4) of the totals of edges 4kb..4kb+3 -- 32-bit
                                       // entries although 16 would do: the check phase is bound by the ALU pipe, not by loads, and
                                       // an entry that IS the address costs no unpacking
-    std::vector<Oc2U4> vT;            // [off + kb*32 + lane] 4 x u32: (16 * record slot) << 5 | sh, sh = 32 - edges in the record + position
+    std::vector<Oc2U4> vT;            // [off + kb*32 + lane] 4 x u32: (rec_bytes * record slot) << 5 | sh, sh = rec_cap - edges in the record + position
     bool vt16_ok = false;             // at most 2048 records: the same table in 16-bit entries sh << 11 | record slot -- the
     std::vector<Oc2U2> vT16;          // variable phase is bound by the LSU pipe, so it unpacks rather than loads twice the bytes
     // bank model, wavefronts per decoder iteration
@@ -70,14 +83,15 @@ struct Rng {   // xorshift64*: layout search only, no relation to the trial gene
     uint32_t below(uint32_t k) { return (uint32_t)(((uint64_t)next() * k) >> 32); }
 };
 
-// wavefronts of one quarter-warp 16-byte gather: per bank group (slot mod 8) the number of DISTINCT slots, maximum over groups
-inline int octet_cost(const int *slots, int cnt) {
+// wavefronts of one record gather by `cnt` = vn_w lanes (a quarter-warp of 16-byte records, a half-warp of 8-byte ones): per
+// bank class (slot mod w) the number of DISTINCT slots, maximum over the classes
+inline int octet_cost(const int *slots, int cnt, int w = 8) {
     int best = 0;
     for (int i = 0; i < cnt; ++i) {
         if (slots[i] < 0) continue;
         int c = 0;
         for (int j = 0; j < cnt; ++j) {
-            if (slots[j] < 0 || (slots[j] & 7) != (slots[i] & 7)) continue;
+            if (slots[j] < 0 || (slots[j] & (w - 1)) != (slots[i] & (w - 1))) continue;
             bool dup = false;
             for (int t = 0; t < j; ++t) dup |= slots[t] == slots[j];
             c += !dup;
@@ -146,16 +160,18 @@ inline void pack(const std::vector<int> &members, const int *ptr, const int *nbr
 
 // effort: 0 = greedy stages only (no bank levelling, no matching), 1 = default, larger = more levelling sweeps
 inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const int *col_idx, const int *col_ptr, const int *csc_edge,
-                             const int *csc_row, int effort, Oc2Tables &T) {
+                             const int *csc_row, int effort, Oc2Tables &T, const Oc2Params prm = Oc2Params()) {
     using namespace oc2;
     T = Oc2Tables();
+    T.prm = prm;
     T.n = n;
     T.m = m;
+    const int W = prm.vn_w, CAP = prm.rec_cap, SPLIT = prm.split;
     for (int j = 0; j < m; ++j) T.max_dc = std::max(T.max_dc, rp[j + 1] - rp[j]);
     int wide_rows = 0;
-    for (int j = 0; j < m; ++j) wide_rows += (rp[j + 1] - rp[j]) > 32;
+    for (int j = 0; j < m; ++j) wide_rows += (rp[j + 1] - rp[j]) > CAP;
     // byte offsets of the totals are 16-bit table entries; record addresses (<< 5) must fit 32 bits with room to spare
-    T.ok = T.max_dc <= 64 && (long long)m + wide_rows + 2 < (1 << 20);
+    T.ok = T.max_dc <= SPLIT + CAP && (long long)m + wide_rows + 2 < (1 << 20);
     if (!T.ok) return;
     T.rec_slots = m + wide_rows;
 
@@ -177,7 +193,7 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
     // widest first, into groups of mixed degree -- a row then walks `group degree` edges, the missing ones gathering a total
     // that is +inf (min1 / min2, the sign parity and the first-minimum position ignore it; it counts as a positive total on
     // both sides of the syndrome parity) -- as long as no row is padded by more than 3 edges. I80: 67 -> 64 groups, which
-    // 16 warps finish in 4 rounds instead of 5. Rows wider than 32 edges (two records) keep pure groups.
+    // 16 warps finish in 4 rounds instead of 5. Rows of two records keep pure groups.
     struct CnGroup { int deg; std::vector<int> rows; };
     std::vector<CnGroup> cgroups;
     {
@@ -187,13 +203,13 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
             size_t g0 = 0;
             for (; g0 + 32 <= cls.size(); g0 += 32) cgroups.push_back(CnGroup{dc, std::vector<int>(cls.begin() + g0, cls.begin() + g0 + 32)});
             if (g0 < cls.size()) {
-                if (dc > 32) cgroups.push_back(CnGroup{dc, std::vector<int>(cls.begin() + g0, cls.end())});
+                if (dc > CAP) cgroups.push_back(CnGroup{dc, std::vector<int>(cls.begin() + g0, cls.end())});
                 else left.insert(left.end(), cls.begin() + g0, cls.end());   // classes come widest first
             }
         }
         for (size_t i = 0; i < left.size();) {
             CnGroup g{rp[left[i] + 1] - rp[left[i]], {}};
-            while (i < left.size() && g.rows.size() < 32 && rp[left[i] + 1] - rp[left[i]] >= g.deg - 3) g.rows.push_back(left[i++]);
+            while (i < left.size() && g.rows.size() < 32 && rp[left[i] + 1] - rp[left[i]] >= g.deg - 3) g.rows.push_back(left[i++]);   // g.deg <= CAP
             cgroups.push_back(std::move(g));
         }
     }
@@ -207,19 +223,21 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
             const int cnt = (int)g.rows.size();
             for (int l = 0; l < cnt; ++l) {
                 T.row_slot[g.rows[l]] = next + l;
-                if (g.deg > 32) T.row_slot2[g.rows[l]] = next + cnt + l;
+                if (g.deg > CAP) T.row_slot2[g.rows[l]] = next + cnt + l;
                 T.row_gdeg[g.rows[l]] = g.deg;
             }
-            next += g.deg > 32 ? 2 * cnt : cnt;
+            next += g.deg > CAP ? 2 * cnt : cnt;
         }
     }
 
-    // ---- stage 2: variable phase. Octets = 8 consecutive positions of a bit class; cell (octet, k) gathers 8 records.
+    // ---- stage 2: variable phase. Octets = W consecutive positions of a bit class (8 for 16-byte records, 16 for 8-byte ones);
+    // cell (octet, k) gathers W records. (The second record of a two-record row sits a whole group -- 32 slots for all but
+    // the last group of a class -- behind the first, i.e. in the same bank class.)
     // greedy start
     for (auto &cls : bcls) {
-        if (cls.size() <= 8) continue;
+        if ((int)cls.size() <= W) continue;
         std::vector<int> order;
-        pack(cls, col_ptr, csc_row, T.row_slot.data(), 8, 8, order);
+        pack(cls, col_ptr, csc_row, T.row_slot.data(), W, W, order);
         cls = order;
     }
     // (A local search over octet membership and record slots -- swaps of two bits / two rows, wavefront count or pair
@@ -272,8 +290,8 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                 auto &v = bcls[c];
                 const int base = class_base[c];
                 // lanes inside an octet
-                for (size_t o = 0; o < v.size(); o += 8) {
-                    const size_t end = std::min(v.size(), o + 8);
+                for (size_t o = 0; o < v.size(); o += W) {
+                    const size_t end = std::min(v.size(), o + W);
                     for (size_t i = o; i < end; ++i)
                         for (size_t j = i + 1; j < end; ++j) {
                             const int bi = (base + (int)i) & 31, bj = (base + (int)j) & 31;
@@ -290,28 +308,28 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                             }
                         }
                 }
-                // whole octets at positions with a different quarter (bank offset differs by a multiple of 8)
-                const size_t full = v.size() / 8;
+                // whole octets at positions with a different quarter (bank offset differs by a multiple of W)
+                const size_t full = v.size() / W;
                 for (size_t a = 0; a + 1 < full; ++a)
                     for (size_t t = 0; t < 6; ++t) {
                         const size_t b2 = a + 1 + (size_t)((a * 7 + t * 13 + (size_t)sweep * 5) % (full - a - 1));
-                        if (((a ^ b2) & 3) == 0) continue;
+                        if (((a ^ b2) & (size_t)(32 / W - 1)) == 0) continue;
                         long long d = 0;
-                        for (int l = 0; l < 8; ++l) {
-                            const int ba = (base + (int)(a * 8) + l) & 31, bb = (base + (int)(b2 * 8) + l) & 31;
-                            d += delta_move(v[a * 8 + l], ba, bb);
-                            apply_move(v[a * 8 + l], ba, bb);
-                            d += delta_move(v[b2 * 8 + l], bb, ba);
-                            apply_move(v[b2 * 8 + l], bb, ba);
+                        for (int l = 0; l < W; ++l) {
+                            const int ba = (base + (int)(a * W) + l) & 31, bb = (base + (int)(b2 * W) + l) & 31;
+                            d += delta_move(v[a * W + l], ba, bb);
+                            apply_move(v[a * W + l], ba, bb);
+                            d += delta_move(v[b2 * W + l], bb, ba);
+                            apply_move(v[b2 * W + l], bb, ba);
                         }
                         if (d < 0) {
-                            for (int l = 0; l < 8; ++l) std::swap(v[a * 8 + l], v[b2 * 8 + l]);
+                            for (int l = 0; l < W; ++l) std::swap(v[a * W + l], v[b2 * W + l]);
                             gained -= d;
                         } else {
-                            for (int l = 0; l < 8; ++l) {
-                                const int ba = (base + (int)(a * 8) + l) & 31, bb = (base + (int)(b2 * 8) + l) & 31;
-                                apply_move(v[a * 8 + l], bb, ba);
-                                apply_move(v[b2 * 8 + l], ba, bb);
+                            for (int l = 0; l < W; ++l) {
+                                const int ba = (base + (int)(a * W) + l) & 31, bb = (base + (int)(b2 * W) + l) & 31;
+                                apply_move(v[a * W + l], bb, ba);
+                                apply_move(v[b2 * W + l], ba, bb);
                             }
                         }
                     }
@@ -444,31 +462,32 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
                 for (int l = 0; l < 32; ++l) {
                     uint32_t e[4];
                     for (int j = 0; j < 4; ++j) {
-                        e[j] = ((uint32_t)(T.rec_slots + 1) * 16u) << 5;   // padding: the all-zero record (adds +0.0f)
+                        e[j] = ((uint32_t)(T.rec_slots + 1) * (uint32_t)prm.rec_bytes) << 5;   // padding: the all-zero record (adds +0.0f)
                         const int k = kb * 4 + j;
                         if (l < cnt && k < dv) {
                             const int p = col_ptr[v[g0 + l]] + k, r = csc_row[p], pos = T.edge_pos[csc_edge[p]], dcr = T.row_gdeg[r];
-                            const int half = pos / 32, in_rec = (dcr <= 32) ? dcr : (half == 0 ? 32 : dcr - 32);
+                            const bool two = dcr > CAP;
+                            const int half = two && pos >= SPLIT ? 1 : 0, in_rec = !two ? dcr : (half == 0 ? SPLIT : dcr - SPLIT);
                             const int slot = half == 0 ? T.row_slot[r] : T.row_slot2[r];
-                            e[j] = (((uint32_t)slot * 16u) << 5) | (uint32_t)(32 - in_rec + pos % 32);
+                            e[j] = (((uint32_t)slot * (uint32_t)prm.rec_bytes) << 5) | (uint32_t)(CAP - in_rec + pos - half * SPLIT);
                         }
                     }
                     T.vT.push_back(Oc2U4{e[0], e[1], e[2], e[3]});
                     if (T.vt16_ok) {   // entries past the degree and padding lanes: record 0 (the kernel reads exactly `deg` entries)
                         uint32_t h[4];
-                        for (int j = 0; j < 4; ++j) h[j] = (l < cnt && kb * 4 + j < dv) ? ((e[j] & 31u) << 11) | (e[j] >> 9) : 0u;
+                        for (int j = 0; j < 4; ++j) h[j] = (l < cnt && kb * 4 + j < dv) ? ((e[j] & 31u) << 11) | ((e[j] >> 5) / (uint32_t)prm.rec_bytes) : 0u;
                         T.vT16.push_back(Oc2U2{h[0] | (h[1] << 16), h[2] | (h[3] << 16)});
                     }
                 }
             int gcost = 4 + 2 * blocks;   // header, Bob's bits, the store of the totals; index blocks
             for (int k = 0; k < dv; ++k)
-                for (int q = 0; q < 4; ++q) {
-                    int slots[8], c8 = 0;
-                    for (int l = q * 8; l < q * 8 + 8; ++l) {
+                for (int q = 0; q < 32 / W; ++q) {
+                    int slots[16], c8 = 0;
+                    for (int l = q * W; l < q * W + W; ++l) {
                         const uint32_t ent = (&T.vT[(size_t)T.vn_g.back().off + (size_t)(k / 4) * 32 + l].x)[k % 4];
-                        slots[c8++] = (int)(ent >> 9);
+                        slots[c8++] = (int)((ent >> 5) / (uint32_t)prm.rec_bytes);
                     }
-                    const int oc = octet_cost(slots, c8);
+                    const int oc = octet_cost(slots, c8, W);
                     T.vn_gather += oc;
                     T.vn_gather_min += 1;
                     gcost += oc;
@@ -483,6 +502,8 @@ inline void build_oc2_layout(int n, int m, long long nnz, const int *rp, const i
 inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, const int *col_idx, const int *col_ptr, const int *csc_edge,
                                     const int *csc_row, const Oc2Tables &T) {
     if (!T.ok) return nullptr;
+    const int CAP = T.prm.rec_cap, SPLIT = T.prm.split;
+    const uint32_t RB = (uint32_t)T.prm.rec_bytes;
     if ((int)T.bit_slot.size() != n || (int)T.slot_bit.size() != T.l_slots || (int)T.row_slot.size() != m || n >= 0xFFFF) return "table sizes";
     std::vector<char> seen_slot(T.l_slots, 0), seen_rec(T.rec_slots, 0);
     for (int b = 0; b < n; ++b) {
@@ -494,8 +515,8 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
         if (!seen_slot[s] && T.slot_bit[s] != 0xFFFF) return "padding slot not marked";
     for (int j = 0; j < m; ++j) {
         const int dc = rp[j + 1] - rp[j];
-        if ((dc > 32) != (T.row_slot2[j] >= 0)) return "second record of a row";
-        for (int h = 0; h < (dc > 32 ? 2 : 1); ++h) {
+        if ((dc > CAP) != (T.row_slot2[j] >= 0)) return "second record of a row";
+        for (int h = 0; h < (dc > CAP ? 2 : 1); ++h) {
             const int s = h ? T.row_slot2[j] : T.row_slot[j];
             if (s < 0 || s >= T.rec_slots || seen_rec[s]) return "row -> record slot is not injective";
             seen_rec[s] = 1;
@@ -514,13 +535,13 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
     long long edges_cn = 0, edges_vn = 0;
     for (const Oc2Group &g : T.cn_g) {
         const int blocks = (g.deg + 3) / 4;
-        if (g.deg < 1 || g.deg > 64 || g.cnt < 1 || g.cnt > 32 || g.off < 0 || (size_t)g.off + (size_t)blocks * 32 > T.cnT.size()) return "check group header";
+        if (g.deg < 1 || g.deg > SPLIT + CAP || g.cnt < 1 || g.cnt > 32 || g.off < 0 || (size_t)g.off + (size_t)blocks * 32 > T.cnT.size()) return "check group header";
         for (int l = 0; l < g.cnt; ++l) {
             const int j = g.base + l < T.rec_slots ? row_of_slot[g.base + l] : -1;
             if (j < 0 || T.row_gdeg[j] != g.deg || rp[j + 1] - rp[j] > g.deg || rp[j + 1] - rp[j] < g.deg - 3 ||
-                (g.deg > 32 && rp[j + 1] - rp[j] != g.deg))
+                (g.deg > CAP && rp[j + 1] - rp[j] != g.deg))
                 return "check group: record slot without a row of (nearly) the group's degree";
-            if (g.deg > 32 && T.row_slot2[j] != g.base + g.cnt + l) return "check group: second record not at base + cnt + lane";
+            if (g.deg > CAP && T.row_slot2[j] != g.base + g.cnt + l) return "check group: second record not at base + cnt + lane";
             std::vector<int> by_pos(g.deg, -1);
             for (int e = rp[j]; e < rp[j + 1]; ++e) by_pos[T.edge_pos[e]] = e;
             for (int k = 0; k < g.deg; ++k) {
@@ -549,14 +570,15 @@ inline const char *check_oc2_layout(int n, int m, long long nnz, const int *rp, 
         for (int l = 0; l < 32; ++l)
             for (int k = 0; k < blocks * 4; ++k) {
                 const uint32_t ent = (&T.vT[(size_t)g.off + (size_t)(k / 4) * 32 + l].x)[k % 4];
-                const int slot = (int)(ent >> 9), sh = (int)(ent & 511u);
-                if ((ent >> 5 & 15u) || slot > T.rec_slots + 1 || sh > 31) return "variable table: bad entry";
+                const int slot = (int)((ent >> 5) / RB), sh = (int)(ent & 31u);
+                if ((ent >> 5) % RB || slot > T.rec_slots + 1 || sh >= CAP) return "variable table: bad entry";
                 if (l < g.cnt && k < g.deg) {
                     const int b = T.slot_bit[g.base + l];
                     if (col_ptr[b + 1] - col_ptr[b] != g.deg) return "variable group: bit of another degree";
                     const int p = col_ptr[b] + k, r = csc_row[p], pos = T.edge_pos[csc_edge[p]], dcr = T.row_gdeg[r];
-                    const int in_rec = (dcr <= 32) ? dcr : (pos < 32 ? 32 : dcr - 32);
-                    if (slot != (pos < 32 ? T.row_slot[r] : T.row_slot2[r]) || sh != 32 - in_rec + pos % 32) return "variable table: wrong record or shift";
+                    const bool two = dcr > CAP, second = two && pos >= SPLIT;
+                    const int in_rec = !two ? dcr : (second ? dcr - SPLIT : SPLIT);
+                    if (slot != (second ? T.row_slot2[r] : T.row_slot[r]) || sh != CAP - in_rec + pos - (second ? SPLIT : 0)) return "variable table: wrong record or shift";
                     if (T.vt16_ok) {
                         const Oc2U2 w16 = T.vT16[(size_t)g.off + (size_t)(k / 4) * 32 + l];
                         const uint32_t h = (k % 4 == 0) ? (w16.x & 0xFFFFu) : (k % 4 == 1) ? (w16.x >> 16) : (k % 4 == 2) ? (w16.y & 0xFFFFu) : (w16.y >> 16);

@@ -99,19 +99,21 @@ struct OnchipArgs {
 };
 
 // Shared-memory layout: L[l_slots + 4] float (slot l_slots holds +inf: the total that padding edges of mixed-degree check groups
-// gather) | rec[rec_slots+2] uint4 | bob bits in slot order [l_slots/32] | syn[groups_cn] | frame id, FrameCtx. While a frame is set
+// gather) | rec[rec_slots+2] uint4 (REC8: uint2 records, then c2[rec_slots+2] float) | bob bits in slot order [l_slots/32] |
+// syn[groups_cn] | frame id, FrameCtx. While a frame is set
 // up the record array doubles as staging space for the key words (2 * words as they come from HBM + l_slots/32 + 1 of
 // Alice's bits in slot order, the last word zero for the +inf slot).
 __host__ __device__ inline size_t onchip_l_slots(int n) { return ((size_t)n + 1 + 3) / 4 * 4; }   // sum-product kernel
 __host__ __device__ inline size_t onchip_l_bytes(int l_slots) { return ((size_t)l_slots + 4) * 4; }
-__host__ __device__ inline size_t onchip_misc_offset(int l_slots, int rec_slots, int groups_cn) {
-    return (onchip_l_bytes(l_slots) + ((size_t)rec_slots + 2) * 16 + ((size_t)l_slots / 32 + (size_t)groups_cn) * 4 + 7) / 8 * 8;
+// rec_bytes: 16 (one uint4 record per slot) or 12 (REC8: an 8-byte record {c1, signs << 5 | position code} + a float c2 per slot)
+__host__ __device__ inline size_t onchip_misc_offset(int l_slots, int rec_slots, int groups_cn, int rec_bytes = 16) {
+    return (onchip_l_bytes(l_slots) + ((size_t)rec_slots + 2) * (size_t)rec_bytes + ((size_t)l_slots / 32 + (size_t)groups_cn) * 4 + 7) / 8 * 8;
 }
-__host__ __device__ inline size_t onchip_smem_bytes(int l_slots, int rec_slots, int groups_cn) {
-    return onchip_misc_offset(l_slots, rec_slots, groups_cn) + 8 + 48 + 24;   // + frame id, FrameCtx, phase clocks
+__host__ __device__ inline size_t onchip_smem_bytes(int l_slots, int rec_slots, int groups_cn, int rec_bytes = 16) {
+    return onchip_misc_offset(l_slots, rec_slots, groups_cn, rec_bytes) + 8 + 48 + 24;   // + frame id, FrameCtx, phase clocks
 }
-__host__ __device__ inline bool onchip_staging_fits(int n, int l_slots, int rec_slots) {
-    return ((size_t)rec_slots + 2) * 16 >= (2 * ((size_t)(n + 31) / 32) + (size_t)l_slots / 32 + 1) * 4;
+__host__ __device__ inline bool onchip_staging_fits(int n, int l_slots, int rec_slots, int rec_bytes = 16) {
+    return ((size_t)rec_slots + 2) * (size_t)rec_bytes >= (2 * ((size_t)(n + 31) / 32) + (size_t)l_slots / 32 + 1) * 4;
 }
 
 // The sum-product kernel (onchip_spa.cuh): msg[msg_words] float instead of the records, the rest alike.
@@ -122,9 +124,15 @@ __host__ __device__ inline size_t onchip_spa_smem_bytes(int n, int msg_words, in
 }
 constexpr size_t kOnchipSmemMax = 227 * 1024;   // opt-in shared memory per CTA on sm_100
 
-// Record of a row: x = bits(c1), y = bits(c2) (non-negative magnitudes), z = final sign of the message on edge k in bit
-// (dc-1-k), w = 32 - dc + position of the first minimum. A reader that knows sh = 32 - dc + k gets the sign with
+// Record of a row (16-byte format): x = bits(c1), y = bits(c2) (non-negative magnitudes), z = final sign of the message on
+// edge k in bit (dc-1-k), w = 32 - dc + position of the first minimum. A reader that knows sh = 32 - dc + k gets the sign with
 // (z << sh) & 0x80000000 and the magnitude with (sh == w) ? c2 : c1.
+// REC8 format (template parameter; codes whose rows have at most 51 edges): the variable phase is bound by the LSU pipe, and
+// 16 of the 32 lanes' 16 bytes are c2 / padding that only the first-minimum edge wants. An 8-byte record {bits(c1), signs <<
+// 5 | code} is gathered instead (a half-warp per wavefront), code = 27 - dc + position of the first minimum (31: not in this
+// record), sign of edge k = (word << (27 - dc + k)) & 0x80000000; c2 lives in a float array beside it, read by the check
+// phase (coalesced) and by the one variable-phase edge per row whose code matches. 27 sign bits per record: rows of 28..51
+// edges own two records (24 edges + the rest), like the rows of 33..64 edges of the 16-byte format.
 
 // Per-frame parameters (shared memory, written by thread 0 when the CTA takes a frame).
 struct FrameCtx {
@@ -144,7 +152,7 @@ struct FrameCtx {
 #define QK_CN_EDGE(J, OFF)                                                                                              \
     {                                                                                                                   \
         const float Lv = *reinterpret_cast<const float *>(smem + (OFF));                                                \
-        const uint32_t mag = (rel == (J)) ? ro.y : ro.x;                                                                \
+        const uint32_t mag = (rel == (J)) ? c2o : c1o;                                                                  \
         const float c2b = __uint_as_float(mag ^ (zs & 0x80000000u));                                                    \
         zs <<= 1;                                                                                                       \
         const float braw = Lv - c2b;        /* L - c2b (:447-461); first iteration: zero record leaves the LLR (:336-350) */ \
@@ -158,25 +166,40 @@ struct FrameCtx {
     }
 
 // A row of 33..64 edges owns two records (edges 0..31 and 32..dc-1) with the same c1 / c2; the record that does not hold
-// the first minimum carries kNoArg in w, which no table entry matches.
+// the first minimum carries kNoArg in w, which no table entry matches (REC8: code 31).
 constexpr uint32_t kNoArg = 0x100u;
 
-template <int ALG, bool WIDE>
-__device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const FrameCtx *ctx, const unsigned char *smem, uint4 *rec,
+template <int ALG, bool WIDE, bool REC8>
+__device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const FrameCtx *ctx, const unsigned char *smem, void *recv, float *c2a,
                                                 const uint32_t *synw, float thr_b, int warp, int lane, int nwarps) {
+    constexpr int kCap = REC8 ? 27 : 32, kSplit = REC8 ? 24 : 32;   // edges per record / in the first of two records
+    uint4 *rec = reinterpret_cast<uint4 *>(recv);
+    uint2 *rec8 = reinterpret_cast<uint2 *>(recv);
     bool unsat = false;
     for (int g = warp; g < a.n_groups_cn2; g += nwarps) {
         const int4 gi = __ldg(a.cn_g2 + g);
         const int dc_row = gi.y;                                  // degree of the group's rows (warp-uniform)
-        const bool two = WIDE && dc_row > 32;                     // two records per row
-        const int dc = two ? 32 : dc_row;                         // edges covered by the first record
+        const bool two = WIDE && dc_row > kCap;                   // two records per row
+        const int dc = two ? kSplit : dc_row;                     // edges covered by the first record
         const bool valid = lane < gi.w;
         const int slot = valid ? gi.z + lane : a.rec_slots;       // padding lanes work on the scratch record
-        const uint4 ro = rec[slot];
+        uint32_t c1o, c2o, zs;                    // old magnitudes; sign of the old message on the current edge in bit 31 of zs
+        int arg_old;
+        if constexpr (REC8) {
+            const uint2 ro = rec8[slot];
+            c1o = ro.x;
+            c2o = __float_as_uint(c2a[slot]);
+            zs = (ro.y & ~31u) << (kCap - dc);
+            arg_old = (int)(ro.y & 31u) - (kCap - dc);
+        } else {
+            const uint4 ro = rec[slot];
+            c1o = ro.x;
+            c2o = ro.y;
+            zs = ro.z << (32 - dc);
+            arg_old = (int)ro.w - (32 - dc);
+        }
         const uint4 *cp = a.cnT2 + gi.x + lane;
         float m1 = FLT_MAX, m2 = FLT_MAX;
-        uint32_t zs = ro.z << (32 - dc);          // sign of the old message on the current edge in bit 31
-        const int arg_old = (int)ro.w - (32 - dc);
         uint32_t own = 0, pacc = 0, zpos = 0, lt = 0;
         int kb = 0;
 #pragma unroll 2
@@ -200,18 +223,24 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
         uint32_t own_first = own;
         int slot2 = 0;
         if constexpr (WIDE) {
-            if (two) {                            // edges 32..dc_row-1: the row's second record (warp-uniform branch)
-                const int dc2 = dc_row - 32;
+            if (two) {                            // edges kSplit..dc_row-1: the row's second record (warp-uniform branch)
+                const int dc2 = dc_row - kSplit;
                 slot2 = valid ? slot + gi.w : a.rec_slots;
-                const uint4 ro2 = rec[slot2];
-                zs = ro2.z << (32 - dc2);
-                const int arg_old2 = (int)ro2.w - (32 - dc2);   // kNoArg gives a value no edge index reaches
+                int arg_old2;                     // the "not here" code gives a value no edge index reaches
+                if constexpr (REC8) {
+                    const uint32_t w2 = rec8[slot2].y;
+                    zs = (w2 & ~31u) << (kCap - dc2);
+                    arg_old2 = (int)(w2 & 31u) - (kCap - dc2);
+                } else {
+                    const uint4 ro2 = rec[slot2];
+                    zs = ro2.z << (32 - dc2);
+                    arg_old2 = (int)ro2.w - (32 - dc2);
+                }
                 own = 0;
                 lt = 0;
                 for (; kb + 4 <= dc_row; kb += 4) {
                     const uint4 cw = __ldg(cp + (kb >> 2) * 32);
-                    const int rel = arg_old2 - (kb - 32);
-                    const uint4 &ro = ro2;
+                    const int rel = arg_old2 - (kb - kSplit);
                     QK_CN_EDGE(0, cw.x)
                     QK_CN_EDGE(1, cw.y)
                     QK_CN_EDGE(2, cw.z)
@@ -219,13 +248,12 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
                 }
                 if (kb < dc_row) {
                     const uint4 cw = __ldg(cp + (kb >> 2) * 32);
-                    const int rel = arg_old2 - (kb - 32), left = dc_row - kb;
-                    const uint4 &ro = ro2;
+                    const int rel = arg_old2 - (kb - kSplit), left = dc_row - kb;
                     QK_CN_EDGE(0, cw.x)
                     if (left > 1) QK_CN_EDGE(1, cw.y)
                     if (left > 2) QK_CN_EDGE(2, cw.z)
                 }
-                if (lt) arg = 32 + dc2 - __ffs((int)lt);
+                if (lt) arg = kSplit + dc2 - __ffs((int)lt);
             }
         }
         m1 = fminf(m1, thr_b);                                    // threshold_matrix(bit_to_check), magnitudes (:447-461)
@@ -246,17 +274,30 @@ __device__ __forceinline__ bool onchip_cn_phase(const OnchipArgs &a, const Frame
         c1 = fminf(c1, a.thr);                                 // threshold_matrix(check_to_bit), magnitudes (:411-412)
         c2 = fminf(c2, a.thr);
         const uint32_t rowneg = ((pacc >> 31) ^ syn) & 1u;     // (syndrome ? -1 : 1) * (-1)^negatives (:398-399)
-        uint4 rn;
-        rn.x = __float_as_uint(c1);
-        rn.y = __float_as_uint(c2);
-        rn.z = own_first ^ (rowneg - 1u);                      // bit = message negative: !(m > 0) xor row sign
-        rn.w = (!two || arg < 32) ? (uint32_t)(arg + 32 - dc) : kNoArg;
-        rec[slot] = rn;
-        if constexpr (WIDE) {
-            if (two) {
-                rn.z = own ^ (rowneg - 1u);
-                rn.w = (arg >= 32) ? (uint32_t)(arg - 32 + 32 - (dc_row - 32)) : kNoArg;
-                rec[slot2] = rn;
+        const uint32_t flip = rowneg - 1u;                     // bit = message negative: !(m > 0) xor row sign
+        if constexpr (REC8) {
+            const bool first = !two || arg < kSplit;
+            rec8[slot] = make_uint2(__float_as_uint(c1), ((own_first ^ flip) << 5) | (first ? (uint32_t)(arg + kCap - dc) : 31u));
+            c2a[slot] = c2;
+            if constexpr (WIDE) {
+                if (two) {
+                    rec8[slot2] = make_uint2(__float_as_uint(c1), ((own ^ flip) << 5) | (first ? 31u : (uint32_t)(arg - kSplit + kCap - (dc_row - kSplit))));
+                    c2a[slot2] = c2;
+                }
+            }
+        } else {
+            uint4 rn;
+            rn.x = __float_as_uint(c1);
+            rn.y = __float_as_uint(c2);
+            rn.z = own_first ^ flip;
+            rn.w = (!two || arg < 32) ? (uint32_t)(arg + 32 - dc) : kNoArg;
+            rec[slot] = rn;
+            if constexpr (WIDE) {
+                if (two) {
+                    rn.z = own ^ flip;
+                    rn.w = (arg >= 32) ? (uint32_t)(arg - 32 + 32 - (dc_row - 32)) : kNoArg;
+                    rec[slot2] = rn;
+                }
             }
         }
     }
@@ -297,53 +338,72 @@ __device__ __forceinline__ float onchip_llr(const FrameCtx *ctx, const uint32_t 
         acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.z, sh) & 0x80000000u));                                \
     }
 
+// REC8: `ent` = (8 * record slot) << 5 | sh, record {c1, signs << 5 | code}; the edge whose sh equals the code (the row's
+// first minimum; code 31 matches none) fetches c2 from the float array beside the records (byte offset 4 * slot = ent >> 6).
+#define QK_VN_EDGE_R8(ENT)                                                                                              \
+    {                                                                                                                   \
+        const uint2 r = *reinterpret_cast<const uint2 *>(recb + ((ENT) >> 5));                                          \
+        uint32_t mag = r.x;                                                                                             \
+        if ((((ENT) ^ r.y) & 31u) == 0) mag = *reinterpret_cast<const uint32_t *>(c2b + ((ENT) >> 6));                  \
+        acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.y, (ENT)) & 0x80000000u));   /* r.y << sh */           \
+    }
+#define QK_VN_EDGE16_R8(E)                                                                                              \
+    {                                                                                                                   \
+        const uint2 r = *reinterpret_cast<const uint2 *>(recb + (((E) & 0x7FFu) << 3));                                 \
+        const uint32_t sh = (E) >> 11;                                                                                  \
+        uint32_t mag = r.x;                                                                                             \
+        if (sh == (r.y & 31u)) mag = *reinterpret_cast<const uint32_t *>(c2b + (((E) & 0x7FFu) << 2));                  \
+        acc = acc + __uint_as_float(mag ^ (__funnelshift_l(0u, r.y, sh) & 0x80000000u));                                \
+    }
+
 // Index blocks of 4 entries: 16 bytes (VT16 = false) or 8 bytes per lane.
-template <bool VT16>
+template <bool VT16, bool REC8>
 struct VnBlock;
-template <>
-struct VnBlock<false> {
+template <bool REC8>
+struct VnBlock<false, REC8> {
     uint4 w;
     __device__ __forceinline__ void load(const void *tab, int idx) { w = __ldg(reinterpret_cast<const uint4 *>(tab) + idx); }
     template <int J>
-    __device__ __forceinline__ float add(const unsigned char *recb, float acc) const {
+    __device__ __forceinline__ float add(const unsigned char *recb, const unsigned char *c2b, float acc) const {
         const uint32_t ent = (J == 0) ? w.x : (J == 1) ? w.y : (J == 2) ? w.z : w.w;
-        QK_VN_EDGE(ent)
+        if constexpr (REC8) QK_VN_EDGE_R8(ent) else QK_VN_EDGE(ent)
         return acc;
     }
 };
-template <>
-struct VnBlock<true> {
+template <bool REC8>
+struct VnBlock<true, REC8> {
     uint2 w;
     __device__ __forceinline__ void load(const void *tab, int idx) { w = __ldg(reinterpret_cast<const uint2 *>(tab) + idx); }
     template <int J>
-    __device__ __forceinline__ float add(const unsigned char *recb, float acc) const {
+    __device__ __forceinline__ float add(const unsigned char *recb, const unsigned char *c2b, float acc) const {
         const uint32_t ent = (J == 0) ? (w.x & 0xFFFFu) : (J == 1) ? (w.x >> 16) : (J == 2) ? (w.y & 0xFFFFu) : (w.y >> 16);
-        QK_VN_EDGE16(ent)
+        if constexpr (REC8) QK_VN_EDGE16_R8(ent) else QK_VN_EDGE16(ent)
         return acc;
     }
 };
 
 // A group of 32 bits of degree DV <= 8, straight line: all index blocks first, then exactly DV messages.
-template <int DV, bool VT16>
-__device__ __forceinline__ float onchip_vn_fixed(const void *tab, int idx, const unsigned char *recb, float acc) {
-    VnBlock<VT16> b0, b1;
+template <int DV, bool VT16, bool REC8>
+__device__ __forceinline__ float onchip_vn_fixed(const void *tab, int idx, const unsigned char *recb, const unsigned char *c2b, float acc) {
+    VnBlock<VT16, REC8> b0, b1;
     b0.load(tab, idx);
     if constexpr (DV > 4) b1.load(tab, idx + 32);
-    acc = b0.template add<0>(recb, acc);
-    if constexpr (DV > 1) acc = b0.template add<1>(recb, acc);
-    if constexpr (DV > 2) acc = b0.template add<2>(recb, acc);
-    if constexpr (DV > 3) acc = b0.template add<3>(recb, acc);
-    if constexpr (DV > 4) acc = b1.template add<0>(recb, acc);
-    if constexpr (DV > 5) acc = b1.template add<1>(recb, acc);
-    if constexpr (DV > 6) acc = b1.template add<2>(recb, acc);
-    if constexpr (DV > 7) acc = b1.template add<3>(recb, acc);
+    acc = b0.template add<0>(recb, c2b, acc);
+    if constexpr (DV > 1) acc = b0.template add<1>(recb, c2b, acc);
+    if constexpr (DV > 2) acc = b0.template add<2>(recb, c2b, acc);
+    if constexpr (DV > 3) acc = b0.template add<3>(recb, c2b, acc);
+    if constexpr (DV > 4) acc = b1.template add<0>(recb, c2b, acc);
+    if constexpr (DV > 5) acc = b1.template add<1>(recb, c2b, acc);
+    if constexpr (DV > 6) acc = b1.template add<2>(recb, c2b, acc);
+    if constexpr (DV > 7) acc = b1.template add<3>(recb, c2b, acc);
     return acc;
 }
 
-template <bool VT16>
-__device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *L, const uint4 *rec, const uint32_t *bobs,
-                                                float lp, int warp, int lane) {
+template <bool VT16, bool REC8>
+__device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const FrameCtx *ctx, float *L, const void *rec, const float *c2a,
+                                                const uint32_t *bobs, float lp, int warp, int lane) {
     const unsigned char *recb = reinterpret_cast<const unsigned char *>(rec);
+    const unsigned char *c2b = reinterpret_cast<const unsigned char *>(c2a);
     const void *tab = VT16 ? static_cast<const void *>(a.vT16) : static_cast<const void *>(a.vT2);
     const float nlp = 0.f - lp;
     const int has_cls = ctx->has_cls;
@@ -360,32 +420,32 @@ __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const Frame
         const int idx = gi.x + lane;
         // ascending check order, starting from the LLR (std::accumulate, :414-417)
         switch (dv) {
-            case 1: acc = onchip_vn_fixed<1, VT16>(tab, idx, recb, acc); break;
-            case 2: acc = onchip_vn_fixed<2, VT16>(tab, idx, recb, acc); break;
-            case 3: acc = onchip_vn_fixed<3, VT16>(tab, idx, recb, acc); break;
-            case 4: acc = onchip_vn_fixed<4, VT16>(tab, idx, recb, acc); break;
-            case 5: acc = onchip_vn_fixed<5, VT16>(tab, idx, recb, acc); break;
-            case 6: acc = onchip_vn_fixed<6, VT16>(tab, idx, recb, acc); break;
-            case 7: acc = onchip_vn_fixed<7, VT16>(tab, idx, recb, acc); break;
-            case 8: acc = onchip_vn_fixed<8, VT16>(tab, idx, recb, acc); break;
+            case 1: acc = onchip_vn_fixed<1, VT16, REC8>(tab, idx, recb, c2b, acc); break;
+            case 2: acc = onchip_vn_fixed<2, VT16, REC8>(tab, idx, recb, c2b, acc); break;
+            case 3: acc = onchip_vn_fixed<3, VT16, REC8>(tab, idx, recb, c2b, acc); break;
+            case 4: acc = onchip_vn_fixed<4, VT16, REC8>(tab, idx, recb, c2b, acc); break;
+            case 5: acc = onchip_vn_fixed<5, VT16, REC8>(tab, idx, recb, c2b, acc); break;
+            case 6: acc = onchip_vn_fixed<6, VT16, REC8>(tab, idx, recb, c2b, acc); break;
+            case 7: acc = onchip_vn_fixed<7, VT16, REC8>(tab, idx, recb, c2b, acc); break;
+            case 8: acc = onchip_vn_fixed<8, VT16, REC8>(tab, idx, recb, c2b, acc); break;
             default: {
                 int kb = 0;
 #pragma unroll 2
                 for (; kb + 4 <= dv; kb += 4) {
-                    VnBlock<VT16> b;
+                    VnBlock<VT16, REC8> b;
                     b.load(tab, idx + (kb >> 2) * 32);
-                    acc = b.template add<0>(recb, acc);
-                    acc = b.template add<1>(recb, acc);
-                    acc = b.template add<2>(recb, acc);
-                    acc = b.template add<3>(recb, acc);
+                    acc = b.template add<0>(recb, c2b, acc);
+                    acc = b.template add<1>(recb, c2b, acc);
+                    acc = b.template add<2>(recb, c2b, acc);
+                    acc = b.template add<3>(recb, c2b, acc);
                 }
                 if (kb < dv) {                    // warp-uniform tail of 1..3 checks
-                    VnBlock<VT16> b;
+                    VnBlock<VT16, REC8> b;
                     b.load(tab, idx + (kb >> 2) * 32);
                     const int left = dv - kb;
-                    acc = b.template add<0>(recb, acc);
-                    if (left > 1) acc = b.template add<1>(recb, acc);
-                    if (left > 2) acc = b.template add<2>(recb, acc);
+                    acc = b.template add<0>(recb, c2b, acc);
+                    if (left > 1) acc = b.template add<1>(recb, c2b, acc);
+                    if (left > 2) acc = b.template add<2>(recb, c2b, acc);
                 }
             }
         }
@@ -394,15 +454,19 @@ __device__ __forceinline__ void onchip_vn_phase(const OnchipArgs &a, const Frame
 }
 #undef QK_VN_EDGE
 #undef QK_VN_EDGE16
+#undef QK_VN_EDGE_R8
+#undef QK_VN_EDGE16_R8
 
-template <int ALG, bool WIDE, bool VT16>
+template <int ALG, bool WIDE, bool VT16, bool REC8>
 __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kRecBytes = REC8 ? 12 : 16;     // per record slot: uint4, or uint2 + a float of the c2 array behind the records
     float *L = reinterpret_cast<float *>(smem_raw);
-    uint4 *rec = reinterpret_cast<uint4 *>(smem_raw + onchip_l_bytes(a.l_slots));
-    uint32_t *bobs = reinterpret_cast<uint32_t *>(rec + a.rec_slots + 2);
+    unsigned char *rec = smem_raw + onchip_l_bytes(a.l_slots);
+    float *c2a = reinterpret_cast<float *>(rec + ((size_t)a.rec_slots + 2) * 8);   // REC8 only
+    uint32_t *bobs = reinterpret_cast<uint32_t *>(rec + ((size_t)a.rec_slots + 2) * kRecBytes);
     uint32_t *synw = bobs + a.l_slots / 32;
-    long long *s_frame = reinterpret_cast<long long *>(smem_raw + onchip_misc_offset(a.l_slots, a.rec_slots, a.n_groups_cn2));
+    long long *s_frame = reinterpret_cast<long long *>(smem_raw + onchip_misc_offset(a.l_slots, a.rec_slots, a.n_groups_cn2, kRecBytes));
     FrameCtx *ctx = reinterpret_cast<FrameCtx *>(s_frame + 1);
     long long *s_clk = reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(ctx) + 48);   // profiling: [0] check, [1] variable, [2] start
     if (a.phase_clk && threadIdx.x == 0) {
@@ -480,7 +544,11 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
             if (lane == 0) synw[g] = sw;
         }
         __syncthreads();
-        for (int i = tid; i < a.rec_slots + 2; i += blockDim.x) rec[i] = make_uint4(0u, 0u, 0u, 0u);   // over the staging words
+        if constexpr (REC8) {                                 // records + c2 array: zero over the staging words
+            for (int i = tid; i < (a.rec_slots + 2) * 3; i += blockDim.x) reinterpret_cast<uint32_t *>(rec)[i] = 0u;
+        } else {
+            for (int i = tid; i < a.rec_slots + 2; i += blockDim.x) reinterpret_cast<uint4 *>(rec)[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
 
         int iters = a.max_iter, run = a.max_iter;
@@ -489,7 +557,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
             // the check-node pass of iteration `it`; at it = max_iter + 1 it only serves as the syndrome test of the
             // last hard decision (non-adaptive variants, :424-445)
             if (a.phase_clk && tid == 0) s_clk[0] -= clock64();
-            const bool unsat = onchip_cn_phase<ALG, WIDE>(a, ctx, smem_raw, rec, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
+            const bool unsat = onchip_cn_phase<ALG, WIDE, REC8>(a, ctx, smem_raw, rec, c2a, synw, it == 1 ? inf : a.thr, warp, lane, nwarps);
             const bool any_unsat = __syncthreads_or(unsat) != 0;
             if (a.phase_clk && tid == 0) s_clk[0] += clock64();
             if (!kAdaptive) {
@@ -499,7 +567,7 @@ __global__ void __launch_bounds__(768, 2) onchip_minsum_kernel(const OnchipArgs 
                 if (!any_unsat) { success = true; iters = it; run = it - 1; break; }         // exit test before the VN step (:770-776)
             }
             if (a.phase_clk && tid == 0) s_clk[1] -= clock64();
-            onchip_vn_phase<VT16>(a, ctx, L, rec, bobs, lp, warp, lane);
+            onchip_vn_phase<VT16, REC8>(a, ctx, L, rec, c2a, bobs, lp, warp, lane);
             __syncthreads();
             if (a.phase_clk && tid == 0) s_clk[1] += clock64();
             if (kAdaptive && it == a.max_iter) break;          // the decision of the last iteration is never tested (Q10)

@@ -218,10 +218,14 @@ int build_onchip_tables(int n, int m, long long nnz, const std::vector<int> &rp,
         }
         if (edges_sv != (size_t)nnz) return fail(QKDLDPC_ERR_STATE, "sum-product tables cover %zu of %lld edges", edges_sv, (long long)nnz);
     }
-    // float32 min-sum kernel: its own layout (storage order = processing order, conflict-aware lanes and edge order)
+    // min-sum kernels: their own layout (storage order = processing order, conflict-aware lanes and edge order), once for
+    // 16-byte records (float32 / float64 state) and once for the float32 kernel's 8-byte records
     build_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), 1, T.oc2);
     if (const char *err = check_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), T.oc2))
         return fail(QKDLDPC_ERR_STATE, "on-chip min-sum layout: %s", err);
+    build_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), 1, T.oc2r8, Oc2Params::rec8());
+    if (const char *err = check_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), T.oc2r8))
+        return fail(QKDLDPC_ERR_STATE, "on-chip min-sum layout (8-byte records): %s", err);
     return QKDLDPC_OK;
 }
 
@@ -243,15 +247,19 @@ extern "C" int qkdldpc_onchip_layout_model(int32_t n, int32_t m, int64_t nnz, co
             csc_edge[p] = e;
             csc_row[p] = j;
         }
-    qkhost::Oc2Tables T;
-    qkhost::build_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), 1, T);
-    if (const char *err = qkhost::check_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), T))
-        return fail(QKDLDPC_ERR_STATE, "on-chip min-sum layout: %s", err);
-    out[0] = T.ok;
-    out[1] = T.ok ? T.cn_gather : 0;
-    out[2] = T.ok ? T.cn_gather_min : 0;
-    out[3] = T.ok ? T.vn_gather : 0;
-    out[4] = T.ok ? T.vn_gather_min : 0;
-    out[5] = T.ok && T.vt16_ok;
+    for (int r8 = 0; r8 < 2; ++r8) {   // 16-byte records, then the float32 kernel's 8-byte records
+        qkhost::Oc2Tables T;
+        qkhost::build_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), 1, T,
+                                 r8 ? qkhost::Oc2Params::rec8() : qkhost::Oc2Params());
+        if (const char *err = qkhost::check_oc2_layout(n, m, nnz, row_ptr, col_idx, col_ptr.data(), csc_edge.data(), csc_row.data(), T))
+            return fail(QKDLDPC_ERR_STATE, "on-chip min-sum layout (%d-byte records): %s", r8 ? 8 : 16, err);
+        int64_t *o = out + 6 * r8;
+        o[0] = T.ok;
+        o[1] = T.ok ? T.cn_gather : 0;
+        o[2] = T.ok ? T.cn_gather_min : 0;
+        o[3] = T.ok ? T.vn_gather : 0;
+        o[4] = T.ok ? T.vn_gather_min : 0;
+        o[5] = T.ok && T.vt16_ok;
+    }
     return QKDLDPC_OK;
 }

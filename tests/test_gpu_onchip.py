@@ -65,6 +65,25 @@ def test_onchip_equals_streaming_and_oracle(q, alg, name, qber, frames):
 
 
 @pytest.mark.parametrize("alg", [2, 3, 4, 5])
+@pytest.mark.parametrize("name,qber,frames", [("K1_5", 0.02, 300), ("A79", 0.021, 300), ("A82", 0.0161, 300), ("I80", 0.017, 300),
+                                              ("I65", 0.03, 150), ("I50", 0.07, 120), ("N6", 0.2, 33)])
+def test_record_formats_agree(q, alg, name, qber, frames):
+    """float32 on-chip min-sum: 8-byte records {c1, signs | argmin} + c2 array (the default when every row fits one record of 27
+    edges; on request rows of 28..51 edges own two) against one 16-byte record per row -- the same arithmetic, so identical
+    results."""
+    a, b, acc = keys(name, 177 + alg, frames, qber)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32)
+    r0 = handle(q, name, decoder_path=2).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    r8 = handle(q, name, decoder_path=2, onchip_record_bytes=8).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    r16 = handle(q, name, decoder_path=2, onchip_record_bytes=16).QKD_LDPC_batch(a, b, acc, FACT[alg], cfg)
+    dc_max = int(np.diff(util.code_arrays(name)["row_ptr"]).max())
+    assert r0.info["onchip_record_bytes"] == (8 if dc_max <= 27 else 16)
+    assert r8.info["onchip_record_bytes"] == (8 if dc_max <= 51 else 16) and r16.info["onchip_record_bytes"] == 16
+    same(r8, r16)
+    same(r0, r16)
+
+
+@pytest.mark.parametrize("alg", [2, 3, 4, 5])
 @pytest.mark.parametrize("max_iter", [1, 2, 3, 7])
 def test_iteration_limits(q, alg, max_iter):
     """Q9/Q10: a frame that needs exactly max_iter iterations; the adaptive variants never test the last decision."""

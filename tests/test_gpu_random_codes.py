@@ -48,6 +48,8 @@ CASES = [
     (4, 1000, 300, (2, 3, 4, 7, 12), 64, 0.01),
     (5, 1500, 1000, (3,), 0, 0.06),
     (6, 999, 333, (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 17), 33, 0.01),
+    (7, 900, 200, (2, 3, 6, 11), 51, 0.01),     # widest row the 8-byte record format takes (24 + 27 edges)
+    (8, 700, 130, (3, 4, 8), 28, 0.01),         # rows on both sides of the 27-edge record limit
 ]
 FACT = {0: (0.0, 0.0), 1: (0.0, 0.0), 2: (0.8, 0.0), 3: (0.4, 0.0), 4: (0.8, 0.6), 5: (0.3, 0.7)}
 
@@ -68,14 +70,23 @@ def test_random_graph_all_paths(built, seed, n, m, degs, wide, qber):
     acc = n_err / n
     with q.LdpcCode(n, m, row_ptr, col_idx, device=0, decoder_path=1) as stream, \
             q.LdpcCode(n, m, row_ptr, col_idx, device=0, decoder_path=2) as chip, \
-            q.LdpcCode(n, m, row_ptr, col_idx, device=0, decoder_path=2, onchip_threads=96) as chip96:
+            q.LdpcCode(n, m, row_ptr, col_idx, device=0, decoder_path=2, onchip_threads=96) as chip96, \
+            q.LdpcCode(n, m, row_ptr, col_idx, device=0, decoder_path=2, onchip_record_bytes=16) as chip16, \
+            q.LdpcCode(n, m, row_ptr, col_idx, device=0, decoder_path=2, onchip_record_bytes=8) as chip8:
         for alg in range(6):
             cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=32, max_iterations=40)
             rs = stream.QKD_LDPC_batch(alice, bob, acc, FACT[alg], cfg)
             rc = chip.QKD_LDPC_batch(alice, bob, acc, FACT[alg], cfg)
             r9 = chip96.QKD_LDPC_batch(alice, bob, acc, FACT[alg], cfg)
+            r16 = chip16.QKD_LDPC_batch(alice, bob, acc, FACT[alg], cfg)
+            r8 = chip8.QKD_LDPC_batch(alice, bob, acc, FACT[alg], cfg)
             assert rs.info["last_path"] == 1 and rc.info["last_path"] == 2
-            for r in (rc, r9):
+            if alg >= 2:   # min-sum family: 8-byte records by default when every row fits one (27 edges), on request up to 51 edges
+                dc_max = int(np.diff(row_ptr).max())
+                assert rc.info["onchip_record_bytes"] == (8 if dc_max <= 27 else 16)
+                assert r8.info["onchip_record_bytes"] == (8 if dc_max <= 51 else 16)
+                assert r16.info["onchip_record_bytes"] == 16
+            for r in (rc, r9, r16, r8):
                 assert (rs.iterations_num == r.iterations_num).all(), alg
                 assert (rs.flags == r.flags).all() and (rs.bob_solution == r.bob_solution).all(), alg
                 assert (rs.tally == r.tally).all(), alg

@@ -15,7 +15,7 @@ CODES = ("N6", "N7", "N100", "N10s1", "K1_3", "K1_4", "K1_5", "K1_hi", "A79", "A
 
 def model(name):
     a = util.code_arrays(name)
-    out = np.zeros(6, np.int64)
+    out = np.zeros(12, np.int64)
     rc = _cabi.lib().qkdldpc_onchip_layout_model(a["n"], a["m"], a["nnz"], np.ascontiguousarray(a["row_ptr"], np.int32).ctypes.data,
                                                  np.ascontiguousarray(a["col_idx"], np.int32).ctypes.data, out.ctypes.data)
     assert rc == 0, (name, rc, _cabi.lib().qkdldpc_last_error())
@@ -32,6 +32,13 @@ def test_layout_tables_are_sound(built, name):
     if eligible:
         assert out[1] >= out[2] > 0 and out[3] >= out[4] > 0
         assert bool(out[5]) == (a["m"] + int((np.diff(a["row_ptr"]) > 32).sum()) <= 2048)
+    # the float32 kernel's 8-byte records: 27 edges per record, rows of 28..51 edges own two
+    eligible8 = dc_max <= 51 and a["n"] <= 65000
+    assert bool(out[6]) == eligible8, (name, out)
+    if eligible8:
+        assert out[7] >= out[8] > 0 and out[9] >= out[10] > 0
+        assert out[10] * 2 == out[4] or not eligible   # half the wavefronts when conflict-free: 16 lanes per 128 bytes instead of 8
+        assert bool(out[11]) == (a["m"] + int((np.diff(a["row_ptr"]) > 27).sum()) <= 2048)
 
 
 @pytest.mark.parametrize("name,cn_bar,vn_bar", [("I80", 1.30, 1.75), ("A79", 1.25, 1.18), ("A82", 1.25, 1.18), ("I65", 1.35, 1.9), ("I50", 1.65, 1.9)])
@@ -43,3 +50,7 @@ def test_bank_model_bounds(built, name, cn_bar, vn_bar):
     cn, vn = out[1] / out[2], out[3] / out[4]
     print(f"\n{name}: check-phase gathers {cn:.3f} x conflict-free, variable-phase record gathers {vn:.3f} x")
     assert cn <= cn_bar and vn <= vn_bar
+    # 8-byte records: twice as many lanes per wavefront collide more often, but the absolute count must drop well below the
+    # 16-byte format's (I80: 12 665 -> 7 292 wavefronts per iteration, A79: 5 765 -> 3 619)
+    print(f"{name}: 8-byte records {out[9]} wavefronts ({out[9] / out[10]:.3f} x conflict-free) against {out[3]} with 16-byte records")
+    assert out[6] and out[7] / out[8] <= cn_bar + 0.05 and out[9] <= 0.68 * out[3]

@@ -26,26 +26,32 @@ int main(int argc, char **argv) {
             csc_edge[p] = e;
             csc_row[p] = j;
         }
-    for (int effort = 0; effort <= (argc > 2 ? atoi(argv[2]) : 1); ++effort) {
+    for (int rec8 = 0; rec8 <= 1; ++rec8) {
+        const qkhost::Oc2Params prm = rec8 ? qkhost::Oc2Params::rec8() : qkhost::Oc2Params();
+        const int effort = argc > 2 ? atoi(argv[2]) : 1;
         qkhost::Oc2Tables T;
         const auto t0 = std::chrono::steady_clock::now();
-        qkhost::build_oc2_layout(n, m, nnz, rp.data(), ci.data(), col_ptr.data(), csc_edge.data(), csc_row.data(), effort, T);
+        qkhost::build_oc2_layout(n, m, nnz, rp.data(), ci.data(), col_ptr.data(), csc_edge.data(), csc_row.data(), effort, T, prm);
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (!T.ok) { printf("not eligible\n"); return 0; }
+        if (!T.ok) { printf("%s: not eligible\n", rec8 ? "8-byte records" : "16-byte records"); continue; }
         const char *err = qkhost::check_oc2_layout(n, m, nnz, rp.data(), ci.data(), col_ptr.data(), csc_edge.data(), csc_row.data(), T);
         const double units = nnz / 32.0;
-        printf("effort %d: %.0f ms  check %s | CN gather %lld (min %lld) = %.3f per 32 edges | VN gather %lld (min %lld) = %.3f per 32 edges | groups cn %zu vn %zu\n",
-               effort, ms, err ? err : "ok", T.cn_gather, T.cn_gather_min, T.cn_gather / units, T.vn_gather, T.vn_gather_min, T.vn_gather / units,
-               T.cn_g.size(), T.vn_g.size());
+        // a record gather of vn_w lanes moves vn_w * rec_bytes = 128 bytes: one wavefront when conflict-free
+        printf("%s, effort %d: %.0f ms  check %s | CN gather %lld (min %lld) = %.3f per 32 edges | VN record gather %lld (min %lld) = %.3f wavefronts per 32 edges | "
+               "groups cn %zu vn %zu, record slots %d, l_slots %d\n",
+               rec8 ? "8-byte records" : "16-byte records", effort, ms, err ? err : "ok", T.cn_gather, T.cn_gather_min, T.cn_gather / units, T.vn_gather,
+               T.vn_gather_min, T.vn_gather / units, T.cn_g.size(), T.vn_g.size(), T.rec_slots, T.l_slots);
         // per degree class of the variable phase
         {
+            const int W = prm.vn_w;
             std::vector<long long> cost(256, 0), mn(256, 0);
             for (const auto &g : T.vn_g)
                 for (int k = 0; k < g.deg; ++k)
-                    for (int q = 0; q < 4; ++q) {
-                        int slots[8];
-                        for (int l = 0; l < 8; ++l) slots[l] = (int)((&T.vT[(size_t)g.off + (size_t)(k / 4) * 32 + q * 8 + l].x)[k % 4] >> 9);
-                        cost[g.deg] += qkhost::oc2::octet_cost(slots, 8);
+                    for (int q = 0; q < 32 / W; ++q) {
+                        int slots[16];
+                        for (int l = 0; l < W; ++l)
+                            slots[l] = (int)(((&T.vT[(size_t)g.off + (size_t)(k / 4) * 32 + q * W + l].x)[k % 4] >> 5) / (unsigned)prm.rec_bytes);
+                        cost[g.deg] += qkhost::oc2::octet_cost(slots, W, W);
                         mn[g.deg] += 1;
                     }
             for (int d = 0; d < 256; ++d)
