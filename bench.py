@@ -71,6 +71,10 @@ def parse():
     p.add_argument("--path", type=int, default=0, choices=[0, 1, 2],
                    help="decoder path: 0 auto (on-chip kernels when eligible), 1 streaming (messages in HBM), 2 on-chip")
     p.add_argument("--onchip-threads", type=int, default=0)
+    p.add_argument("--vn-items", type=int, default=0,
+                   help="streaming path, narrow variable-node buckets: items per warp (0 = auto, 1 = one item per warp)")
+    p.add_argument("--vn-ctas", type=int, default=0, choices=[0, 4, 5, 6],
+                   help="resident CTAs per SM of the dv <= 4 float32 variable-node kernel (0 = auto)")
     p.add_argument("--record-bytes", type=int, default=0, choices=[0, 8, 16],
                    help="float32 on-chip min-sum: record format (0 auto: 8-byte records when every row has at most 51 edges)")
     p.add_argument("--copy-chunks", type=int, default=0, help="pieces a host batch is cut into for copy / compute overlap (0 auto, 1 none)")
@@ -274,7 +278,7 @@ def measure(ctx, args, wl, F, steps, warmup, sampler=None, want_e2e=True):
     code = q.LdpcCode(n, m, arr["row_ptr"], arr["col_idx"], device=local_rank, pool_slots=args.pool_slots,
                       frames_per_lane_f32=args.frames_per_lane, decoder_path=args.path, onchip_threads=args.onchip_threads,
                       tail_compaction=-1 if args.no_compaction else 0, copy_chunks=args.copy_chunks,
-                      onchip_record_bytes=args.record_bytes)
+                      onchip_record_bytes=args.record_bytes, vn_items_per_warp=args.vn_items, vn_ctas_per_sm=args.vn_ctas)
     code.set_stream(stream.cuda_stream)
     if world > 1:
         # the handle owns the NCCL communicator of the tally all-reduce (include/qkdldpc.h): rank 0 draws the unique id,

@@ -105,7 +105,11 @@ typedef struct qkdldpc_options {
                                (rows of 33..64 edges: two), 8 = 8-byte records {c1, signs | argmin} + a c2 array (rows of
                                28..51 edges: two; wider rows: the 16-byte format), 0 = auto: 8 when every row has at most
                                27 edges; results are identical                                                           */
-    int32_t reserved[3];
+    int32_t vn_items_per_warp; /* streaming path, narrow variable-node buckets (dv <= 8): items one warp walks per launch,
+                               the next item's index record requested behind the current item's messages; 0 = auto,
+                               1 = one item per warp (vn_kernel_ell); results are identical                                */
+    int32_t vn_ctas_per_sm; /* resident CTAs per SM the dv <= 4 float32 variable-node kernel is compiled for: 5 or 6; 0 = auto */
+    int32_t reserved[1];
 } qkdldpc_options;
 
 QKDLDPC_API int qkdldpc_version(void);

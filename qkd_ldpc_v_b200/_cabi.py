@@ -19,7 +19,8 @@ class Options(C.Structure):
     _fields_ = [("pool_bytes", C.c_int64), ("pool_slots", C.c_int32), ("steps_per_poll", C.c_int32),
                 ("frames_per_lane_f32", C.c_int32), ("use_graph", C.c_int32), ("decoder_path", C.c_int32),
                 ("onchip_threads", C.c_int32), ("tail_compaction", C.c_int32), ("compaction_max_ctas", C.c_int32),
-                ("copy_chunks", C.c_int32), ("onchip_record_bytes", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("copy_chunks", C.c_int32), ("onchip_record_bytes", C.c_int32), ("vn_items_per_warp", C.c_int32),
+                ("vn_ctas_per_sm", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class Combination(C.Structure):

@@ -20,6 +20,15 @@ inline bool fast_minsum_ok(const qkdldpc_params *P) {
 
 inline unsigned ceil_div(int a, int b) { return (unsigned)((a + b - 1) / b); }
 
+// qkdldpc_options.vn_items_per_warp: 0 = auto
+#ifndef QK_VN_ITEMS_AUTO
+#define QK_VN_ITEMS_AUTO 1
+#endif
+inline int vn_items_per_warp(const qkdldpc_code *c) {
+    const int v = c->opt.vn_items_per_warp;
+    return v <= 0 ? QK_VN_ITEMS_AUTO : std::min(v, 64);
+}
+
 // One launch per non-empty degree bucket. Returns the number of kernels launched.
 template <typename T, int V, int ALG>
 int launch_cn_alg(const qkdldpc_code *c, bool fast, int tiles, cudaStream_t s, const StepArgs<T> &a);
@@ -76,6 +85,29 @@ inline int launch_vn_bucket(const qkdldpc_code *c, bool fast, int tiles, cudaStr
     const dim3 grid(ceil_div(cnt, threads / 32), (unsigned)tiles);
     if constexpr (DVMAX == 4 || DVMAX == 8) {   // narrow buckets: ELL records, two waves of loads (vn_kernel_ell)
         const int ell_base = (B == 0) ? 0 : c->vn_count[0] * vn_bucket_max(0);
+        const int items = vn_items_per_warp(c);
+        if (items > 1) {   // several items per warp, index records one item ahead (vn_kernel_ell_loop)
+            const dim3 lgrid(ceil_div(cnt, (threads / 32) * items), (unsigned)tiles);
+            constexpr int ctas = vn_ell_min_ctas(sizeof(T), V, DVMAX);
+            if constexpr (sizeof(T) == 4) {
+                if (fast) {
+                    if constexpr (DVMAX == 4) {
+                        if (c->opt.vn_ctas_per_sm == 5) {
+                            vn_kernel_ell_loop<T, V, DVMAX, true, 5><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items);
+                            return 1;
+                        }
+                        if (c->opt.vn_ctas_per_sm == 4) {
+                            vn_kernel_ell_loop<T, V, DVMAX, true, 4><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items);
+                            return 1;
+                        }
+                    }
+                    vn_kernel_ell_loop<T, V, DVMAX, true, ctas><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items);
+                    return 1;
+                }
+            }
+            vn_kernel_ell_loop<T, V, DVMAX, false, ctas><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items);
+            return 1;
+        }
         if constexpr (sizeof(T) == 4) {
             if (fast) {
                 vn_kernel_ell<T, V, DVMAX, true><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base);

@@ -453,10 +453,22 @@ vn_kernel(const StepArgs<T> a, const int first, const int count) {
 // that depends only on (tile, item) is fetched at once -- tile masks, slot LLR magnitudes, the bit id and the item's
 // ELL record of edge and check ids (vn_ell_edge / vn_ell_row, -1 = padding) -- and everything that needs the bit id or
 // the edge ids in a second wave (bit class, Bob's mask word unconditionally, the messages).
+template <int V>
+__device__ __forceinline__ void vn_lane_words(const uint32_t (&act)[V], const uint32_t (&newm)[V], int lane,
+                                              uint32_t &actl, uint32_t &newl) {
+    actl = 0;
+    newl = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        actl = (lane == v) ? act[v] : actl;
+        newl |= ((newm[v] >> lane) & 1u) << v;
+    }
+}
 template <typename T, int V, int DVMAX, bool FAST, bool HASNEW>
 __device__ __forceinline__ void vn_body_ell(const StepArgs<T> &a, int tile, int bit, int lane, bool lane_act,
-                                            const uint32_t (&act)[V], const uint32_t (&newm)[V], const int (&e)[DVMAX],
+                                            const uint32_t actl, const uint32_t newl, const int (&e)[DVMAX],
                                             const int (&r)[DVMAX], const Vec<T, V> &lp) {
+    // actl: the tile's active mask of word `lane` (lanes < V, else 0); newl: bit v set <=> this lane's slot v was just refilled
     constexpr int FT = kWarp * V;
     T *tbase = a.msg + (size_t)tile * a.e_stride + lane * V;
     // second wave of loads
@@ -476,7 +488,7 @@ __device__ __forceinline__ void vn_body_ell(const StepArgs<T> &a, int tile, int 
     Vec<T, V> L = llr;
     bool isnew[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) isnew[v] = HASNEW && ((newm[v] >> lane) & 1u);
+    for (int v = 0; v < V; ++v) isnew[v] = HASNEW && ((newl >> v) & 1u);
     if (lane_act) {
 #pragma unroll
         for (int k = 0; k < DVMAX; ++k)
@@ -494,9 +506,10 @@ __device__ __forceinline__ void vn_body_ell(const StepArgs<T> &a, int tile, int 
     uint32_t zw = 0;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        const uint32_t w = __ballot_sync(0xffffffffu, lane_act && (L.v[v] <= (T)0)) & act[v];
+        const uint32_t w = __ballot_sync(0xffffffffu, lane_act && (L.v[v] <= (T)0));
         if (lane == v) zw = w;
     }
+    zw &= actl;
     if (lane < V) {
         a.zmask[((size_t)tile * a.n + bit) * V + lane] = zw;
         if (zw != 0) {
@@ -555,8 +568,133 @@ vn_kernel_ell(const StepArgs<T> a, const int first, const int count, const int e
         lane_act |= (act[v] >> lane) & 1u;
     }
     if (!any_act) return;
-    if (any_new) vn_body_ell<T, V, DVMAX, FAST, true>(a, tile, bit, lane, lane_act, act, newm, e, r, lp);
-    else vn_body_ell<T, V, DVMAX, FAST, false>(a, tile, bit, lane, lane_act, act, newm, e, r, lp);
+    uint32_t actl, newl;
+    vn_lane_words<V>(act, newm, lane, actl, newl);
+    if (any_new) vn_body_ell<T, V, DVMAX, FAST, true>(a, tile, bit, lane, lane_act, actl, newl, e, r, lp);
+    else vn_body_ell<T, V, DVMAX, FAST, false>(a, tile, bit, lane, lane_act, actl, newl, e, r, lp);
+}
+
+
+// The same kernel with SEVERAL items per warp (qkdldpc_options.vn_items_per_warp): a warp of vn_kernel_ell spends about a
+// third of its life in the first wave (index loads, L2 hits) with no message bytes in flight, and every CTA pays its launch
+// for eight items only. Here a warp walks items idx, idx + W, idx + 2 W ... (W warps per CTA, so the CTA's warps stay on
+// adjacent ELL records: one 128-byte line of edge ids per eight items). Right behind an item's message loads the warp
+// PREFETCHES INTO L1 the lines it will need next -- the next item's bit id and edge record, this item's check ids -- so that
+// from the second item on the index loads are L1 hits and only the second wave (the messages) is exposed. A prefetch costs
+// no registers (holding the next record in registers did: 48 registers still spilled 170 bytes); the check ids are loaded
+// last, just before the parity RED, and the slots' LLR magnitudes come from L1 with every item instead of staying live.
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <typename T, int V, int DVMAX>
+__device__ __forceinline__ void vn_ell_record(const int *tab, int (&x)[DVMAX]) {
+    const int4 *p = reinterpret_cast<const int4 *>(tab);
+#pragma unroll
+    for (int j = 0; j < DVMAX / 4; ++j) {
+        const int4 t = __ldg(p + j);
+        x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+    }
+}
+template <typename T, int V, int DVMAX, bool FAST, bool HASNEW>
+__device__ __forceinline__ void vn_items_ell(const StepArgs<T> &a, int tile, int lane, bool lane_act,
+                                             const uint32_t actl, const uint32_t newl, const int first, const int count,
+                                             const int ell_base, int idx, const int stride, int items) {
+    constexpr int FT = kWarp * V;
+    T *tbase = a.msg + (size_t)tile * a.e_stride + lane * V;
+    const Vec<T, V> *lpp = reinterpret_cast<const Vec<T, V> *>(a.slot_llr + (size_t)tile * FT + lane * V);
+    bool isnew[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) isnew[v] = HASNEW && ((newl >> v) & 1u);
+    for (;;) {
+        // first wave: L1 hits from the warp's second item on
+        const int bit = __ldg(a.col_order + first + idx);
+        int e[DVMAX];
+        vn_ell_record<T, V, DVMAX>(a.vn_ell_edge + ell_base + (size_t)idx * DVMAX, e);
+        const int *rows = a.vn_ell_row + ell_base + (size_t)idx * DVMAX;
+        // second wave
+        const uint8_t cls = __ldg(a.bitclass + bit);
+        const Vec<uint32_t, V> bm = *reinterpret_cast<const Vec<uint32_t, V> *>(a.bobmask + ((size_t)tile * a.n + bit) * V);
+        const Vec<T, V> lp = *lpp;
+        Vec<T, V> c[DVMAX];
+#pragma unroll
+        for (int k = 0; k < DVMAX; ++k)
+            if (lane_act && e[k] >= 0) c[k] = ld_msg<T, V>(tbase + (size_t)e[k] * FT);
+        idx += stride;
+        const bool more = --items > 0 && idx < count;   // warp-uniform
+        prefetch_l1(rows);
+        if constexpr (DVMAX == 8) prefetch_l1(rows + 4);
+        if (more) {
+            prefetch_l1(a.col_order + first + idx);
+            prefetch_l1(a.vn_ell_edge + ell_base + (size_t)idx * DVMAX);
+            if constexpr (DVMAX == 8) prefetch_l1(a.vn_ell_edge + ell_base + (size_t)idx * DVMAX + 4);
+        }
+        // from here on: vn_body_ell's arithmetic, operation by operation
+        Vec<T, V> llr;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const T pay = ((bm.v[v] >> lane) & 1u) ? -lp.v[v] : lp.v[v];
+            llr.v[v] = (cls == 0) ? pay : ((cls == 1) ? (T)1e-4 : Lim<T>::max());
+        }
+        Vec<T, V> L = llr;
+        if (lane_act) {
+#pragma unroll
+            for (int k = 0; k < DVMAX; ++k)
+                if (e[k] >= 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        if constexpr (HASNEW) c[k].v[v] = isnew[v] ? (T)0 : c[k].v[v];
+                        L.v[v] = L.v[v] + c[k].v[v];
+                    }
+                }
+#pragma unroll
+            for (int k = 0; k < DVMAX; ++k)
+                if (e[k] >= 0) st_msg<T, V>(tbase + (size_t)e[k] * FT, vn_out<T, V, FAST, HASNEW>(a, L, c[k], llr, isnew));
+        }
+        uint32_t zw = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const uint32_t w = __ballot_sync(0xffffffffu, lane_act && (L.v[v] <= (T)0));
+            if (lane == v) zw = w;
+        }
+        zw &= actl;
+        if (lane < V) {
+            a.zmask[((size_t)tile * a.n + bit) * V + lane] = zw;
+            if (zw != 0) {
+                int r[DVMAX];
+                vn_ell_record<T, V, DVMAX>(rows, r);
+#pragma unroll
+                for (int k = 0; k < DVMAX; ++k)
+                    if (r[k] >= 0) atomicXor(a.par + ((size_t)tile * a.m + r[k]) * V + lane, zw);
+            }
+        }
+        if (!more) break;
+    }
+}
+template <typename T, int V, int DVMAX, bool FAST, int CTAS>
+__global__ void __launch_bounds__(vn_threads(sizeof(T), V, DVMAX), CTAS)
+vn_kernel_ell_loop(const StepArgs<T> a, const int first, const int count, const int ell_base, const int items) {
+    static_assert(DVMAX == 4 || DVMAX == 8, "ELL records exist for the two narrow buckets");
+    const int tile = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const int idx = blockIdx.x * wpc * items + (threadIdx.x >> 5);
+    if (idx >= count) return;
+    uint32_t act[V], newm[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        act[v] = a.tile_active[tile * V + v];
+        newm[v] = a.tile_new[tile * V + v];
+    }
+    bool any_act = false, any_new = false, lane_act = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        any_act |= act[v] != 0;
+        any_new |= newm[v] != 0;
+        lane_act |= (act[v] >> lane) & 1u;
+    }
+    if (!any_act) return;
+    uint32_t actl, newl;
+    vn_lane_words<V>(act, newm, lane, actl, newl);
+    if (any_new) vn_items_ell<T, V, DVMAX, FAST, true>(a, tile, lane, lane_act, actl, newl, first, count, ell_base, idx, wpc, items);
+    else vn_items_ell<T, V, DVMAX, FAST, false>(a, tile, lane, lane_act, actl, newl, first, count, ell_base, idx, wpc, items);
 }
 
 }  // namespace qk

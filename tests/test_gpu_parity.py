@@ -334,3 +334,27 @@ def test_tail_compaction_does_not_change_results(q, alg, prec, fpl, frames):
     assert (on.iterations_num == off.iterations_num).all() and (on.flags == off.flags).all()
     assert (on.bob_solution == off.bob_solution).all() and (on.tally == off.tally).all()
     assert on.info["decoder_steps"] <= off.info["decoder_steps"]
+
+
+@pytest.mark.parametrize("name,alg,prec,fpl,frames,qber", [
+    ("K1_4", 2, 32, 4, 3000, 0.038), ("K1_5", 0, 32, 2, 1500, 0.03), ("I80", 2, 32, 4, 700, 0.017),
+    ("K1_4", 5, 64, 0, 1200, 0.038), ("I80", 3, 32, 1, 300, 0.017)])
+def test_vn_items_per_warp_does_not_change_results(q, name, alg, prec, fpl, frames, qber):
+    """Streaming path, narrow variable-node buckets (dv <= 4, dv <= 8): vn_kernel_ell_loop walks several items per warp
+    with the next item's index records prefetched into L1 (qkdldpc_options.vn_items_per_warp, vn_ctas_per_sm). The
+    arithmetic per bit is vn_kernel_ell's, so every per-frame result must be identical -- on a pool smaller than the batch,
+    so that refilled slots (the HASNEW flavour) and partly active tiles are walked too, and with item counts that do not
+    divide the bucket sizes."""
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays(name)
+    seeds = hostlib.trial_seeds(2718, frames)
+    a, b, acc = hostlib.gen_keys(seeds, arr["n"], qber)
+    fac = {0: (0, 0), 2: (0.75, 0), 3: (0.3, 0), 5: (0.3, 0.9)}[alg]
+    cfg = q.DecoderConfig(decoding_algorithm=alg, message_precision=prec)
+    kw = dict(decoder_path=1, frames_per_lane_f32=fpl, pool_slots=256)
+    one = handle(q, name, vn_items_per_warp=1, **kw).QKD_LDPC_batch(a, b, acc, fac, cfg)
+    assert 0 < (one.flags & 1).sum(), "need converging frames (slots are refilled when they retire)"
+    for items, ctas in ((0, 0), (2, 0), (3, 5), (7, 4), (64, 6)):
+        r = handle(q, name, vn_items_per_warp=items, vn_ctas_per_sm=ctas, **kw).QKD_LDPC_batch(a, b, acc, fac, cfg)
+        assert (r.iterations_num == one.iterations_num).all() and (r.flags == one.flags).all(), (items, ctas)
+        assert (r.bob_solution == one.bob_solution).all() and (r.tally == one.tally).all(), (items, ctas)
