@@ -106,9 +106,11 @@ typedef struct qkdldpc_options {
                                28..51 edges: two; wider rows: the 16-byte format), 0 = auto: 8 when every row has at most
                                27 edges; results are identical                                                           */
     int32_t vn_items_per_warp; /* streaming path, narrow variable-node buckets (dv <= 8): items one warp walks per launch,
-                               the next item's index record requested behind the current item's messages; 0 = auto,
-                               1 = one item per warp (vn_kernel_ell); results are identical                                */
-    int32_t vn_ctas_per_sm; /* resident CTAs per SM the dv <= 4 float32 variable-node kernel is compiled for: 5 or 6; 0 = auto */
+                               the next item's index records prefetched into L1 behind the current item's messages;
+                               1 = one item per warp (vn_kernel_ell), 0 = auto: a walk sized to the grid for float32
+                               messages with 4 frames per lane, else 1; results are identical                            */
+    int32_t vn_ctas_per_sm; /* resident CTAs per SM the dv <= 4 float32 walking kernel is compiled for (3..6: 72 / 64 / 48 /
+                               40 registers; the dv <= 8 kernel: 2 for 3, else 3); 0 = auto (4)                          */
     int32_t reserved[1];
 } qkdldpc_options;
 

@@ -20,13 +20,29 @@ inline bool fast_minsum_ok(const qkdldpc_params *P) {
 
 inline unsigned ceil_div(int a, int b) { return (unsigned)((a + b - 1) / b); }
 
-// qkdldpc_options.vn_items_per_warp: 0 = auto
-#ifndef QK_VN_ITEMS_AUTO
-#define QK_VN_ITEMS_AUTO 1
-#endif
-inline int vn_items_per_warp(const qkdldpc_code *c) {
-    const int v = c->opt.vn_items_per_warp;
-    return v <= 0 ? QK_VN_ITEMS_AUTO : std::min(v, 64);
+// Narrow variable-node buckets: which kernel, how many items per warp, how many resident CTAs per SM (B200, profiles/
+// r02_ab_vn_loop.md). float32 with 4 frames per lane: vn_kernel_ell_loop, 4 CTAs per SM for dv <= 4 (64 registers, no
+// spills: the 5 / 6-CTA builds spill 180 - 300 bytes inside the loop and lose to vn_kernel_ell), 3 for dv <= 8; a walk as long
+// as leaves ~24 waves of CTAs in the grid (n = 102400: VN 0.71 -> 0.86 of the HBM peak at 32 - 64 items; n = 10240: best at
+// 8, a longer walk leaves too few CTAs for the tail). 2 frames per lane and float64 keep vn_kernel_ell (the loop kernel
+// needs 59 - 116 registers there and loses occupancy: A82 SPA float32 0.63 -> 0.59, float64 0.56 -> 0.54).
+struct VnLoopPlan {
+    int items;   // <= 1 with ctas == 0: vn_kernel_ell
+    int ctas;    // of the dv <= 4 kernel
+};
+inline VnLoopPlan vn_loop_plan(const qkdldpc_code *c, size_t elem_bytes, int V, int cnt, int tiles, int warps_per_cta) {
+    VnLoopPlan p{c->opt.vn_items_per_warp, c->opt.vn_ctas_per_sm};
+    if (p.items > 0) {
+        p.items = std::min(p.items, 64);
+        return p;
+    }
+    if (elem_bytes != 4 || V != 4) return VnLoopPlan{1, p.ctas};
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int ctas = p.ctas > 0 ? p.ctas : 4;
+    const long long per_wave = (long long)sms * ctas * warps_per_cta;
+    const long long it = ((long long)cnt * tiles + per_wave * 12) / (per_wave * 24);   // rounded
+    return VnLoopPlan{(int)std::max<long long>(1, std::min<long long>(it, 64)), ctas};
 }
 
 // One launch per non-empty degree bucket. Returns the number of kernels launched.
@@ -85,27 +101,33 @@ inline int launch_vn_bucket(const qkdldpc_code *c, bool fast, int tiles, cudaStr
     const dim3 grid(ceil_div(cnt, threads / 32), (unsigned)tiles);
     if constexpr (DVMAX == 4 || DVMAX == 8) {   // narrow buckets: ELL records, two waves of loads (vn_kernel_ell)
         const int ell_base = (B == 0) ? 0 : c->vn_count[0] * vn_bucket_max(0);
-        const int items = vn_items_per_warp(c);
-        if (items > 1) {   // several items per warp, index records one item ahead (vn_kernel_ell_loop)
+        const VnLoopPlan plan = vn_loop_plan(c, sizeof(T), V, cnt, tiles, threads / 32);
+        const int items = plan.items, want = plan.ctas;   // CTAs of the dv <= 4 kernel; the dv <= 8 kernel: 3, or 2 for 3
+        if (items > 1 || want > 0) {   // several items per warp, index records one item ahead in L1
             const dim3 lgrid(ceil_div(cnt, (threads / 32) * items), (unsigned)tiles);
-            constexpr int ctas = vn_ell_min_ctas(sizeof(T), V, DVMAX);
+#define QK_VN_LOOP(FA, CT) vn_kernel_ell_loop<T, V, DVMAX, FA, CT><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items)
+#define QK_VN_LOOP_CTAS(FA)                                 \
+    do {                                                    \
+        if constexpr (sizeof(T) != 4) QK_VN_LOOP(FA, 1);    \
+        else if constexpr (DVMAX == 4) {                    \
+            if (want == 6) QK_VN_LOOP(FA, 6);               \
+            else if (want == 5) QK_VN_LOOP(FA, 5);          \
+            else if (want == 3) QK_VN_LOOP(FA, 3);          \
+            else QK_VN_LOOP(FA, 4);                         \
+        } else {                                            \
+            if (want == 3) QK_VN_LOOP(FA, 2);               \
+            else QK_VN_LOOP(FA, 3);                         \
+        }                                                   \
+    } while (0)
             if constexpr (sizeof(T) == 4) {
                 if (fast) {
-                    if constexpr (DVMAX == 4) {
-                        if (c->opt.vn_ctas_per_sm == 5) {
-                            vn_kernel_ell_loop<T, V, DVMAX, true, 5><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items);
-                            return 1;
-                        }
-                        if (c->opt.vn_ctas_per_sm == 4) {
-                            vn_kernel_ell_loop<T, V, DVMAX, true, 4><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items);
-                            return 1;
-                        }
-                    }
-                    vn_kernel_ell_loop<T, V, DVMAX, true, ctas><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items);
+                    QK_VN_LOOP_CTAS(true);
                     return 1;
                 }
             }
-            vn_kernel_ell_loop<T, V, DVMAX, false, ctas><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items);
+            QK_VN_LOOP_CTAS(false);
+#undef QK_VN_LOOP_CTAS
+#undef QK_VN_LOOP
             return 1;
         }
         if constexpr (sizeof(T) == 4) {

@@ -24,13 +24,14 @@ def main():
     settings = [tuple(int(x) for x in s.split(":")) for s in sys.argv[6].split()]
     reps = int(sys.argv[7]) if len(sys.argv) > 7 else 3
     pool_slots = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+    prec = int(sys.argv[9]) if len(sys.argv) > 9 else 32
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         peak = 6534.5
     arr = util.code_arrays(name)
     n, nnz = arr["n"], arr["nnz"]
-    cfg = q.DecoderConfig(decoding_algorithm=alg, max_iterations=100, message_precision=32)
+    cfg = q.DecoderConfig(decoding_algorithm=alg, max_iterations=100, message_precision=prec)
     for items, ctas in settings:
         with q.LdpcCode(n, arr["m"], arr["row_ptr"], arr["col_idx"], device=0, decoder_path=1, vn_items_per_warp=items,
                         vn_ctas_per_sm=ctas, pool_slots=pool_slots) as code:
@@ -40,11 +41,11 @@ def main():
             tally, _ = code.bench_synthetic(frames, qber, (pri, 0.0), cfg, seed=5)
             inf = code.info()
             executed = float(tally[q.decoder.TALLY_ITERATIONS])   # sum of executed iterations over the batch
-            half = executed * 8.0 * nnz          # one kernel: 4 B read + 4 B written per edge and executed iteration
-            print("%s frames %d items %d ctas %d pool_tiles %d: %.3f Gbit/s  (%.1f ms)  mean it %.2f  cn %.2f ms (%.3f)  vn %.2f ms (%.3f)"
-                  % (name, frames, items, ctas, inf["pool_tiles"], n * frames / best / 1e9, best * 1e3, executed / frames,
+            half = executed * 8.0 * nnz * (prec // 32)          # one kernel: 4 B read + 4 B written per edge and executed iteration
+            print("%s f%d frames %d items %d ctas %d pool_tiles %d: %.3f Gbit/s  (%.1f ms)  mean it %.2f  cn %.2f ms (%.3f)  vn %.2f ms (%.3f)"
+                  % (name, prec, frames, items, ctas, inf["pool_tiles"], n * frames / best / 1e9, best * 1e3, executed / frames,
                      inf["last_cn_ms"], half / (inf["last_cn_ms"] * 1e-3) / 1e9 / peak,
-                     inf["last_vn_ms"], (half + executed * 4.0 * n) / (inf["last_vn_ms"] * 1e-3) / 1e9 / peak), flush=True)
+                     inf["last_vn_ms"], (half + executed * 4.0 * n * (prec // 32)) / (inf["last_vn_ms"] * 1e-3) / 1e9 / peak), flush=True)
 
 
 if __name__ == "__main__":
