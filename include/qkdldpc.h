@@ -111,7 +111,8 @@ typedef struct qkdldpc_options {
                                messages with 4 frames per lane, else 1; results are identical                            */
     int32_t vn_ctas_per_sm; /* resident CTAs per SM the dv <= 4 float32 walking kernel is compiled for (3..6: 72 / 64 / 48 /
                                40 registers; the dv <= 8 kernel: 2 for 3, else 3); 0 = auto (4)                          */
-    int32_t reserved[1];
+    int32_t compaction_fill_pct; /* tail compaction starts once the queue is empty and at most this percentage of the resident
+                               slots is still occupied (1..99); 0 = auto (50)                                            */
 } qkdldpc_options;
 
 QKDLDPC_API int qkdldpc_version(void);

@@ -20,7 +20,7 @@ class Options(C.Structure):
                 ("frames_per_lane_f32", C.c_int32), ("use_graph", C.c_int32), ("decoder_path", C.c_int32),
                 ("onchip_threads", C.c_int32), ("tail_compaction", C.c_int32), ("compaction_max_ctas", C.c_int32),
                 ("copy_chunks", C.c_int32), ("onchip_record_bytes", C.c_int32), ("vn_items_per_warp", C.c_int32),
-                ("vn_ctas_per_sm", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("vn_ctas_per_sm", C.c_int32), ("compaction_fill_pct", C.c_int32)]
 
 
 class Combination(C.Structure):

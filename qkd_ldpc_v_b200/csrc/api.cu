@@ -195,7 +195,7 @@ void qkdldpc_code_destroy(qkdldpc_code *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     comm_release(c);
     c->comm_buf.release();
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    c->drop_graphs();
     c->row_ptr.release(); c->col_idx.release(); c->col_ptr.release(); c->csc_edge.release(); c->csc_row.release();
     c->row_order.release(); c->col_order.release(); c->vn_ell_edge.release(); c->vn_ell_row.release();
     c->oc_cn_ginfo.release(); c->oc_cnT.release(); c->oc_cn_row.release();
@@ -233,7 +233,7 @@ int qkdldpc_code_set_stream(qkdldpc_code *c, void *cuda_stream) {
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     c->stream = static_cast<cudaStream_t>(cuda_stream);
     c->own_stream = false;
-    c->graph_key.clear();
+    c->drop_graphs();   // they were captured on the old stream
     return QKDLDPC_OK;
 }
 

@@ -231,8 +231,19 @@ struct qkdldpc_code {
     unsigned long long *h_done = nullptr;   // pinned [2]: frames handed out, frames finished
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll = nullptr;
     // captured step graph
-    cudaGraphExec_t graph_exec = nullptr;
-    std::string graph_key;
+    // captured step graphs, newest last: a batch uses one for its full pool and one per tile count the tail compaction
+    // leaves (quantised, run_batch.cuh), and the next batch of the same combination finds them again
+    struct StepGraph {
+        std::string key;
+        cudaGraphExec_t exec;
+    };
+    std::vector<StepGraph> graphs;
+    static constexpr size_t kMaxGraphs = 24;
+    void drop_graphs() {
+        for (auto &g : graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
+    }
     // stats
     int frames_per_tile = 0, pool_tiles = 0;
     int64_t pool_bytes = 0, kernel_launches = 0, decoder_steps = 0;

@@ -20,6 +20,17 @@ inline bool fast_minsum_ok(const qkdldpc_params *P) {
 
 inline unsigned ceil_div(int a, int b) { return (unsigned)((a + b - 1) / b); }
 
+// Smallest of 1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48 ... that holds `need` tiles.
+inline long long quantised_tiles(long long need) {
+    long long q = 1;
+    while (q < need) {
+        if (q < 4) ++q;
+        else if ((q & (q - 1)) == 0) q += q / 2;   // 2^k -> 3 * 2^(k-1)
+        else q = q / 3 * 4;                        // 3 * 2^(k-1) -> 2^(k+1)
+    }
+    return q;
+}
+
 // Narrow variable-node buckets: which kernel, how many items per warp, how many resident CTAs per SM (B200, profiles/
 // r02_ab_vn_loop.md). float32 with 4 frames per lane: vn_kernel_ell_loop, 4 CTAs per SM for dv <= 4 (64 registers, no
 // spills: the 5 / 6-CTA builds spill 180 - 300 bytes inside the loop and lose to vn_kernel_ell), 3 for dv <= 8; a walk as long
@@ -325,11 +336,18 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
 
     // steps between two host polls of the done counter: a frame needs at most max_iter steps, and the host
     // only has to look when a whole generation of slots may have drained
-    int spp = c->opt.steps_per_poll > 0 ? c->opt.steps_per_poll : std::max(1, std::min(P->max_iterations, 16));
+    // Auto: about 4 ms of decoding between two polls, 16 steps at most. Every step past the one that retires the last frame
+    // still launches the whole grid over empty tiles (n = 102400, 32 tiles: 1.2 ms per step, three of them = 7 % of a batch
+    // whose frames all converge within 13 iterations), and the tail compaction can only start at a poll; a poll itself is a
+    // stream synchronisation and a graph launch (tens of microseconds), so short steps keep the long interval.
+    const double step_seconds = (double)tiles * (double)per_tile * 4.0 / 5e12;   // CN + VN: every message read and written twice
+    const int auto_spp = (int)std::max(1.0, std::min(16.0, std::floor(4e-3 / step_seconds + 0.5)));
+    int spp = c->opt.steps_per_poll > 0 ? c->opt.steps_per_poll : std::max(1, std::min(P->max_iterations, auto_spp));
     // (the legacy default stream cannot be captured: plain launches there)
     const bool use_graph = c->opt.use_graph >= 0 && !c->profiling && s != nullptr;
 
     // the captured launches embed every pointer and parameter of this batch: the cache is keyed on all of them
+    cudaGraphExec_t graph_exec = nullptr;
     auto ensure_graph = [&]() -> int {
         unsigned long long h = 1469598103934665603ull;
         auto mixin = [&h](const void *p, size_t nbytes) {
@@ -343,27 +361,33 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
         mixin(&work, sizeof work);
         char key[64];
         snprintf(key, sizeof key, "%016llx", h);
-        if (c->graph_key != key) {
-            if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-            c->graph_key.clear();
-            cudaGraph_t g = nullptr;
-            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            // from here to EndCapture nothing may return early: a failure would leave the handle's stream (and the forked
-            // side streams) in capture mode and every later call on the handle would fail
-            for (int k = 0; k < spp; ++k) one_step(s, false);
-            cudaError_t ce = cudaGetLastError();   // launch errors of the captured kernels
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->h_done, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
-            const cudaError_t ee = cudaStreamEndCapture(s, &g);   // always: ends the capture even when it is invalidated
-            if (ce == cudaSuccess) ce = ee;
-            if (ce == cudaSuccess) ce = cudaGraphInstantiate(&c->graph_exec, g, 0);
-            if (g) cudaGraphDestroy(g);
-            if (ce != cudaSuccess) {
-                c->graph_exec = nullptr;
-                cudaGetLastError();
-                return fail(QKDLDPC_ERR_CUDA, "capture of the step graph failed: %s", cudaGetErrorString(ce));
+        for (size_t i = 0; i < c->graphs.size(); ++i)
+            if (c->graphs[i].key == key) {
+                graph_exec = c->graphs[i].exec;
+                return QKDLDPC_OK;
             }
-            c->graph_key = key;
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        // from here to EndCapture nothing may return early: a failure would leave the handle's stream (and the forked
+        // side streams) in capture mode and every later call on the handle would fail
+        for (int k = 0; k < spp; ++k) one_step(s, false);
+        cudaError_t ce = cudaGetLastError();   // launch errors of the captured kernels
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->h_done, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+        const cudaError_t ee = cudaStreamEndCapture(s, &g);   // always: ends the capture even when it is invalidated
+        if (ce == cudaSuccess) ce = ee;
+        cudaGraphExec_t ex = nullptr;
+        if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ex, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            return fail(QKDLDPC_ERR_CUDA, "capture of the step graph failed: %s", cudaGetErrorString(ce));
         }
+        if (c->graphs.size() >= qkdldpc_code::kMaxGraphs) {   // oldest out (a sweep over combinations keeps capturing)
+            cudaGraphExecDestroy(c->graphs.front().exec);
+            c->graphs.erase(c->graphs.begin());
+        }
+        c->graphs.push_back({key, ex});
+        graph_exec = ex;
         return QKDLDPC_OK;
     };
     if (use_graph) {
@@ -378,9 +402,10 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     const int64_t step_limit = (generations + 1) * ((int64_t)P->max_iterations + 2) + spp;
     int64_t steps = 0;
     const bool compaction = c->opt.tail_compaction >= 0;
+    const long long fill_pct = c->opt.compaction_fill_pct > 0 ? std::min(c->opt.compaction_fill_pct, 99) : 50;
     while (true) {
         if (use_graph) {
-            CK(cudaGraphLaunch(c->graph_exec, s));
+            CK(cudaGraphLaunch(graph_exec, s));
         } else {
             for (int k = 0; k < spp; ++k) one_step(s, c->profiling);
             CK(cudaMemcpyAsync(c->h_done, c->counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -399,13 +424,17 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
         if (steps > step_limit)
             return fail(QKDLDPC_ERR_STATE, "decoder did not finish: %llu of %lld frames after %lld steps", done, (long long)n_frames,
                         (long long)steps);
-        // Tail compaction: the queue is empty and at most half of the slots of >= 4 tiles are still occupied
+        // Tail compaction: the queue is empty and at most fill_pct % (default: half) of the slots of >= 4 tiles are still occupied
         const long long remaining = (long long)n_frames - (long long)done;
-        if (compaction && handed_out >= (unsigned long long)n_frames && cur_tiles >= 4 && remaining * 2 <= (long long)cur_tiles * FT) {
+        // (the tile count is rounded up to 1, 2, 3, 4, 6, 8, 12, 16, 24 ...: the step graphs of the next batch's tail are then
+        // the ones captured here, and a compaction that would not shrink the grid is skipped)
+        const long long q_tiles = quantised_tiles(std::max<long long>(1, (remaining + FT - 1) / FT));
+        if (compaction && handed_out >= (unsigned long long)n_frames && cur_tiles >= 4 && remaining * 100 <= (long long)cur_tiles * FT * fill_pct &&
+            q_tiles < cur_tiles) {
             CK(c->compact_moves.reserve((size_t)cur_tiles * FT));
             CK(c->compact_plan.reserve(2));
             auto *plan = reinterpret_cast<CompactPlan *>(c->compact_plan.p);
-            compact_plan_kernel<FT><<<1, 32, 0, s>>>(cur_tiles, c->slot_frame.p, c->compact_moves.p, plan);
+            compact_plan_kernel<FT><<<1, 1024, 0, s>>>(cur_tiles, c->slot_frame.p, c->compact_moves.p, plan);
             // both copy kernels stride over plan->n_moves, so a capped grid still moves every frame (a pool of many
             // thousand tiles of a short code can hold more than 65535 stragglers)
             const long long move_cap = c->opt.compaction_max_ctas > 0 ? c->opt.compaction_max_ctas : 65535;
@@ -416,7 +445,7 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
                                                           a.tile_active, a.tile_new);
             c->kernel_launches += 4;
             CK(cudaGetLastError());
-            cur_tiles = (int)std::max<long long>(1, (remaining + FT - 1) / FT);   // == plan->new_tiles (active == remaining)
+            cur_tiles = (int)q_tiles;   // >= plan->new_tiles (active == remaining); the tiles past it are empty
             if (use_graph) {
                 const int rc = ensure_graph();
                 if (rc) return rc;

@@ -348,23 +348,61 @@ struct CompactPlan {
     int new_tiles;
 };
 
-// One thread walks the slot table (a few thousand entries, a few times per batch).
-template <int FT>
-__global__ void compact_plan_kernel(int tiles, const long long *slot_frame, int2 *moves, CompactPlan *plan) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int slots = tiles * FT;
-    int active = 0;
-    for (int s = 0; s < slots; ++s) active += slot_frame[s] >= 0;
-    const int new_tiles = max(1, (active + FT - 1) / FT);
-    int n = 0, dst = 0;
-    const int low = new_tiles * FT;
-    for (int src = low; src < slots; ++src) {
-        if (slot_frame[src] < 0) continue;
-        while (dst < low && slot_frame[dst] >= 0) ++dst;   // next free slot of the low tiles (exists: active <= low)
-        moves[n++] = make_int2(src, dst++);
+// One CTA plans the compaction: the k-th occupied slot past the tiles that stay is moved into the k-th free slot inside
+// them (both in ascending order -- the plan a single thread walking the table would make, which is what this kernel was
+// until the polls got frequent enough for its serial loads to show: 13 000 slots took a millisecond).
+__device__ __forceinline__ int block_exclusive_scan_1024(int x, int *warp_sums, int &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
     }
-    plan->n_moves = n;
-    plan->new_tiles = new_tiles;
+    __syncthreads();   // warp_sums may still be read by the previous call
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int v = warp_sums[k];
+        base += (k < w) ? v : 0;
+        tot += v;
+    }
+    total = tot;
+    return base + incl - x;
+}
+template <int FT>
+__global__ void __launch_bounds__(1024) compact_plan_kernel(int tiles, const long long *slot_frame, int2 *moves, CompactPlan *plan) {
+    __shared__ int warp_sums[32];
+    const int slots = tiles * FT;
+    int mine = 0, active = 0;
+    for (int s = threadIdx.x; s < slots; s += 1024) mine += slot_frame[s] >= 0;
+    block_exclusive_scan_1024(mine, warp_sums, active);
+    const int new_tiles = max(1, (active + FT - 1) / FT);
+    const int low = new_tiles * FT;
+    int n_src = 0;   // sources: occupied slots of [low, slots)
+    for (int base = low; base < slots; base += 1024) {
+        const int s = base + threadIdx.x;
+        const int occ = (s < slots && slot_frame[s] >= 0) ? 1 : 0;
+        int tot;
+        const int rank = n_src + block_exclusive_scan_1024(occ, warp_sums, tot);
+        if (occ) moves[rank].x = s;
+        n_src += tot;
+    }
+    int n_dst = 0;   // destinations: free slots of [0, low), as many as there are sources (active <= low: they exist)
+    for (int base = 0; base < low && n_dst < n_src; base += 1024) {
+        const int s = base + threadIdx.x;
+        const int fr = (s < low && slot_frame[s] < 0) ? 1 : 0;
+        int tot;
+        const int rank = n_dst + block_exclusive_scan_1024(fr, warp_sums, tot);
+        if (fr && rank < n_src) moves[rank].y = s;
+        n_dst += tot;
+    }
+    if (threadIdx.x == 0) {
+        plan->n_moves = n_src;
+        plan->new_tiles = new_tiles;
+    }
 }
 
 // grid = (moves, chunks): messages of the moved frames. Slot position p of a tile <-> message lane p (common.cuh).

@@ -111,7 +111,8 @@ class LdpcCode:
     def __init__(self, n: int, m: int, row_ptr, col_idx, device: int = 0, pool_bytes: int = 0, pool_slots: int = 0,
                  steps_per_poll: int = 0, frames_per_lane_f32: int = 0, use_graph: int = 0, decoder_path: int = 0,
                  onchip_threads: int = 0, tail_compaction: int = 0, compaction_max_ctas: int = 0, copy_chunks: int = 0,
-                 onchip_record_bytes: int = 0, vn_items_per_warp: int = 0, vn_ctas_per_sm: int = 0):
+                 onchip_record_bytes: int = 0, vn_items_per_warp: int = 0, vn_ctas_per_sm: int = 0,
+                 compaction_fill_pct: int = 0):
         L = _cabi.lib()
         self.n, self.m = int(n), int(m)
         self.row_ptr = np.ascontiguousarray(row_ptr, np.int32)
@@ -122,7 +123,7 @@ class LdpcCode:
         # decoder_path: 0 auto, 1 streaming kernels (messages in HBM), 2 on-chip min-sum (frame state in shared memory)
         opt = Options(int(pool_bytes), int(pool_slots), int(steps_per_poll), int(frames_per_lane_f32), int(use_graph),
                       int(decoder_path), int(onchip_threads), int(tail_compaction), int(compaction_max_ctas), int(copy_chunks),
-                      int(onchip_record_bytes), int(vn_items_per_warp), int(vn_ctas_per_sm))
+                      int(onchip_record_bytes), int(vn_items_per_warp), int(vn_ctas_per_sm), int(compaction_fill_pct))
         h = C.c_void_p()
         _cabi.check(L.qkdldpc_code_create(C.byref(h), self.n, self.m, self.nnz, self.row_ptr.ctypes.data,
                                           self.col_idx.ctypes.data, device, C.byref(opt)), "qkdldpc_code_create")
