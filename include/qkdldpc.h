@@ -112,7 +112,7 @@ typedef struct qkdldpc_options {
     int32_t vn_ctas_per_sm; /* resident CTAs per SM the dv <= 4 float32 walking kernel is compiled for (3..6: 72 / 64 / 48 /
                                40 registers; the dv <= 8 kernel: 2 for 3, else 3); 0 = auto (4)                          */
     int32_t compaction_fill_pct; /* tail compaction starts once the queue is empty and at most this percentage of the resident
-                               slots is still occupied (1..99); 0 = auto (50)                                            */
+                               slots is still occupied (1..99); 0 = auto (75)                                            */
 } qkdldpc_options;
 
 QKDLDPC_API int qkdldpc_version(void);
@@ -289,6 +289,9 @@ typedef struct qkdldpc_info {
     int32_t onchip_threads;    /* CTA size of the last on-chip launch */
     int32_t last_precision;    /* message precision the last batch ran in (32 / 64), after the precision policy */
     int32_t onchip_record_bytes; /* record format of the last float32 on-chip min-sum launch (16 / 8; 0 = none yet) */
+    int64_t tail_compactions;  /* streaming path: tail compactions run by this handle so far */
+    int32_t last_steps_per_poll; /* streaming path: decoder steps between two host polls in the last batch */
+    int32_t last_vn_items_per_warp; /* streaming path: items per warp of the dv <= 4 variable-node kernel in the last batch (0: no such bucket) */
 } qkdldpc_info;
 QKDLDPC_API int qkdldpc_code_info(const qkdldpc_code *code, qkdldpc_info *info);
 /* Host only (no device needed): builds the storage layouts of the on-chip min-sum kernels for a graph, checks every table

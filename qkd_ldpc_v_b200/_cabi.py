@@ -35,7 +35,8 @@ class Info(C.Structure):
                 ("kernel_launches", C.c_int64), ("decoder_steps", C.c_int64), ("last_batch_ms", C.c_double),
                 ("last_cn_ms", C.c_double), ("last_vn_ms", C.c_double), ("last_sched_ms", C.c_double),
                 ("last_path", C.c_int32), ("onchip_threads", C.c_int32), ("last_precision", C.c_int32),
-                ("onchip_record_bytes", C.c_int32)]
+                ("onchip_record_bytes", C.c_int32), ("tail_compactions", C.c_int64), ("last_steps_per_poll", C.c_int32),
+                ("last_vn_items_per_warp", C.c_int32)]
 
 
 # every symbol include/qkdldpc.h declares: name -> (restype, argtypes)

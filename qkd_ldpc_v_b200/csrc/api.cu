@@ -768,6 +768,9 @@ int qkdldpc_code_info(const qkdldpc_code *c, qkdldpc_info *info) {
     info->onchip_threads = c->oc_threads;
     info->last_precision = c->last_precision;
     info->onchip_record_bytes = c->last_rec_bytes;
+    info->tail_compactions = c->tail_compactions;
+    info->last_steps_per_poll = c->last_spp;
+    info->last_vn_items_per_warp = c->last_vn_items;
     info->last_cn_ms = c->last_cn_ms; info->last_vn_ms = c->last_vn_ms; info->last_sched_ms = c->last_sched_ms;
     return QKDLDPC_OK;
 }

@@ -188,6 +188,8 @@ struct qkdldpc_code {
     Oc2Device oc2, oc2r8;
     DevBuf<unsigned long long> oc2_phase_clk;   // profiling: clocks per phase of the last on-chip min-sum launch
     DevBuf<uint32_t> oc2_cls;         // [n_combos][2][l_slots/32] punctured / shortened masks of the current batch, slot order
+    int64_t tail_compactions = 0;     // streaming path
+    int last_spp = 0, last_vn_items = 0;
     int last_rec_bytes = 0;           // 16 / 8: record format of the last float32 on-chip min-sum launch
     // on-chip sum-product path (onchip_spa.cuh): one message word per edge; check phase shares oc_cn_* with min-sum
     bool sp_eligible = false;

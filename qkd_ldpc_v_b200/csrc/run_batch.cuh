@@ -343,6 +343,8 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     const double step_seconds = (double)tiles * (double)per_tile * 4.0 / 5e12;   // CN + VN: every message read and written twice
     const int auto_spp = (int)std::max(1.0, std::min(16.0, std::floor(4e-3 / step_seconds + 0.5)));
     int spp = c->opt.steps_per_poll > 0 ? c->opt.steps_per_poll : std::max(1, std::min(P->max_iterations, auto_spp));
+    c->last_spp = spp;
+    c->last_vn_items = c->vn_count[0] > 0 ? vn_loop_plan(c, sizeof(T), V, c->vn_count[0], (int)tiles, vn_threads(sizeof(T), V, 4) / 32).items : 0;
     // (the legacy default stream cannot be captured: plain launches there)
     const bool use_graph = c->opt.use_graph >= 0 && !c->profiling && s != nullptr;
 
@@ -402,7 +404,8 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     const int64_t step_limit = (generations + 1) * ((int64_t)P->max_iterations + 2) + spp;
     int64_t steps = 0;
     const bool compaction = c->opt.tail_compaction >= 0;
-    const long long fill_pct = c->opt.compaction_fill_pct > 0 ? std::min(c->opt.compaction_fill_pct, 99) : 50;
+    const long long fill_pct = c->opt.compaction_fill_pct > 0 ? std::min(c->opt.compaction_fill_pct, 99) : 75;
+    unsigned long long prev_done = 0;
     while (true) {
         if (use_graph) {
             CK(cudaGraphLaunch(graph_exec, s));
@@ -424,13 +427,22 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
         if (steps > step_limit)
             return fail(QKDLDPC_ERR_STATE, "decoder did not finish: %llu of %lld frames after %lld steps", done, (long long)n_frames,
                         (long long)steps);
-        // Tail compaction: the queue is empty and at most fill_pct % (default: half) of the slots of >= 4 tiles are still occupied
+        // Tail compaction: the queue is empty and at most fill_pct % (default: 75) of the slots of >= 4 tiles are still occupied
         const long long remaining = (long long)n_frames - (long long)done;
         // (the tile count is rounded up to 1, 2, 3, 4, 6, 8, 12, 16, 24 ...: the step graphs of the next batch's tail are then
         // the ones captured here, and a compaction that would not shrink the grid is skipped)
         const long long q_tiles = quantised_tiles(std::max<long long>(1, (remaining + FT - 1) / FT));
+        // A move costs about 64 B of sector traffic per edge (one 4-byte word out of a 512-byte chunk and into another), a
+        // tile about 2 KB per edge and step: the moves are paid back after ~4 x occupancy steps on the smaller grid. Frames
+        // that are about to converge anyway are not worth moving (n = 102400 NMSA: every frame converges at iteration
+        // 10..13, compacting the 28 % left after iteration 11 cost 5 ms and saved 3.5), so the batch must be expected to
+        // last twice that long at the rate frames retired since the last poll; stragglers that fail retire at rate 0.
+        const double retire_rate = (double)(done - prev_done) / (double)spp;   // frames per step
+        const double occupancy = (double)remaining / ((double)cur_tiles * FT);
+        const bool lasts = (double)remaining > retire_rate * 8.0 * occupancy;
+        prev_done = done;
         if (compaction && handed_out >= (unsigned long long)n_frames && cur_tiles >= 4 && remaining * 100 <= (long long)cur_tiles * FT * fill_pct &&
-            q_tiles < cur_tiles) {
+            q_tiles < cur_tiles && lasts) {
             CK(c->compact_moves.reserve((size_t)cur_tiles * FT));
             CK(c->compact_plan.reserve(2));
             auto *plan = reinterpret_cast<CompactPlan *>(c->compact_plan.p);
@@ -444,6 +456,7 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
             compact_finish_kernel<T, V><<<1, 1024, 0, s>>>(c->compact_moves.p, plan, cur_tiles, c->slot_frame.p, c->slot_iter.p, a.slot_llr,
                                                           a.tile_active, a.tile_new);
             c->kernel_launches += 4;
+            ++c->tail_compactions;
             CK(cudaGetLastError());
             cur_tiles = (int)q_tiles;   // >= plan->new_tiles (active == remaining); the tiles past it are empty
             if (use_graph) {

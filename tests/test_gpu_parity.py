@@ -334,6 +334,8 @@ def test_tail_compaction_does_not_change_results(q, alg, prec, fpl, frames):
     assert (on.iterations_num == off.iterations_num).all() and (on.flags == off.flags).all()
     assert (on.bob_solution == off.bob_solution).all() and (on.tally == off.tally).all()
     assert on.info["decoder_steps"] <= off.info["decoder_steps"]
+    # the stragglers fail (they retire at rate 0), so the compaction must have run -- and never on the other handle
+    assert on.info["tail_compactions"] > 0 and off.info["tail_compactions"] == 0
 
 
 @pytest.mark.parametrize("name,alg,prec,fpl,frames,qber", [
@@ -358,3 +360,24 @@ def test_vn_items_per_warp_does_not_change_results(q, name, alg, prec, fpl, fram
         r = handle(q, name, vn_items_per_warp=items, vn_ctas_per_sm=ctas, **kw).QKD_LDPC_batch(a, b, acc, fac, cfg)
         assert (r.iterations_num == one.iterations_num).all() and (r.flags == one.flags).all(), (items, ctas)
         assert (r.bob_solution == one.bob_solution).all() and (r.tally == one.tally).all(), (items, ctas)
+
+
+def test_step_graphs_are_cached_per_tile_count(q):
+    """Streaming path: the step graph of the full pool and the graphs of the compacted tails are kept (handle.hpp
+    StepGraph), so a second batch of the same combination replays them; its results must equal the first batch's and
+    those of plain launches -- with a poll after every step, so that the tail shrinks through several tile counts."""
+    from qkd_ldpc_v_b200 import hostlib
+    arr = util.code_arrays("K1_4")
+    seeds = hostlib.trial_seeds(99, 4000)
+    a, b, acc = hostlib.gen_keys(seeds, arr["n"], 0.038)
+    cfg = q.DecoderConfig(decoding_algorithm=2, message_precision=32)
+    kw = dict(decoder_path=1, frames_per_lane_f32=4, steps_per_poll=1)
+    h = handle(q, "K1_4", **kw)
+    first = h.QKD_LDPC_batch(a, b, acc, (0.75, 0), cfg)
+    n_comp = first.info["tail_compactions"]
+    again = h.QKD_LDPC_batch(a, b, acc, (0.75, 0), cfg)
+    plain = handle(q, "K1_4", use_graph=-1, **kw).QKD_LDPC_batch(a, b, acc, (0.75, 0), cfg)
+    assert n_comp >= 2 and again.info["tail_compactions"] == 2 * n_comp and first.info["last_steps_per_poll"] == 1
+    for r in (again, plain):
+        assert (r.iterations_num == first.iterations_num).all() and (r.flags == first.flags).all()
+        assert (r.bob_solution == first.bob_solution).all() and (r.tally == first.tally).all()
