@@ -336,12 +336,13 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
 
     // steps between two host polls of the done counter: a frame needs at most max_iter steps, and the host
     // only has to look when a whole generation of slots may have drained
-    // Auto: about 4 ms of decoding between two polls, 16 steps at most. Every step past the one that retires the last frame
+    // Auto: about 8 ms of decoding between two polls, 16 steps at most. Every step past the one that retires the last frame
     // still launches the whole grid over empty tiles (n = 102400, 32 tiles: 1.2 ms per step, three of them = 7 % of a batch
     // whose frames all converge within 13 iterations), and the tail compaction can only start at a poll; a poll itself is a
-    // stream synchronisation and a graph launch (tens of microseconds), so short steps keep the long interval.
+    // stream synchronisation and a graph launch (tens of microseconds), so short steps keep the long interval (A79, 32 tiles,
+    // 0.5 ms per step: 7 steps per poll lost 2.7 % against 16; 102 tiles, 1.7 ms: 2..4 steps per poll gain 6 %).
     const double step_seconds = (double)tiles * (double)per_tile * 4.0 / 5e12;   // CN + VN: every message read and written twice
-    const int auto_spp = (int)std::max(1.0, std::min(16.0, std::floor(4e-3 / step_seconds + 0.5)));
+    const int auto_spp = (int)std::max(1.0, std::min(16.0, std::floor(8e-3 / step_seconds + 0.5)));
     int spp = c->opt.steps_per_poll > 0 ? c->opt.steps_per_poll : std::max(1, std::min(P->max_iterations, auto_spp));
     c->last_spp = spp;
     c->last_vn_items = c->vn_count[0] > 0 ? vn_loop_plan(c, sizeof(T), V, c->vn_count[0], (int)tiles, vn_threads(sizeof(T), V, 4) / 32).items : 0;
