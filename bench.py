@@ -454,6 +454,9 @@ def measure(ctx, args, wl, F, steps, warmup, sampler=None, want_e2e=True):
         "onchip_threads": inf.get("onchip_threads") if onchip else None,
         "onchip_record_bytes": (inf.get("onchip_record_bytes") or None) if onchip and alg >= 2 and prec == 32 else None,
         "frames_per_tile": inf["frames_per_tile"], "pool_tiles": inf["pool_tiles"], "pool_bytes": inf["pool_bytes"],
+        "streaming": None if onchip else {"steps_per_poll": inf.get("last_steps_per_poll"),
+                                          "vn_items_per_warp": inf.get("last_vn_items_per_warp"),
+                                          "tail_compactions": inf.get("tail_compactions")},
         "l2_policy": ("inputs larger than L2: %.0f MB of packed keys in + decisions out per step, read once; decoder "
                       "state is in shared memory" % (3 * F * words * 4 / 1e6)) if onchip else
                      ("inputs larger than L2 (message pool %.1f GB >> 126 MB)" % (inf["pool_bytes"] / 1e9)),
