@@ -73,7 +73,7 @@ def parse():
     p.add_argument("--onchip-threads", type=int, default=0)
     p.add_argument("--vn-items", type=int, default=0,
                    help="streaming path, narrow variable-node buckets: items per warp (0 = auto, 1 = one item per warp)")
-    p.add_argument("--vn-ctas", type=int, default=0, choices=[0, 3, 4, 5, 6],
+    p.add_argument("--vn-ctas", type=int, default=0, choices=[0, 1, 3, 4, 5, 6],
                    help="resident CTAs per SM of the dv <= 4 float32 variable-node kernel (0 = auto)")
     p.add_argument("--record-bytes", type=int, default=0, choices=[0, 8, 16],
                    help="float32 on-chip min-sum: record format (0 auto: 8-byte records when every row has at most 51 edges)")

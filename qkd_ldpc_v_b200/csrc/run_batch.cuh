@@ -35,8 +35,10 @@ inline long long quantised_tiles(long long need) {
 // r02_ab_vn_loop.md). float32 with 4 frames per lane: vn_kernel_ell_loop, 4 CTAs per SM for dv <= 4 (64 registers, no
 // spills: the 5 / 6-CTA builds spill 180 - 300 bytes inside the loop and lose to vn_kernel_ell), 3 for dv <= 8; a walk as long
 // as leaves ~24 waves of CTAs in the grid (n = 102400: VN 0.71 -> 0.86 of the HBM peak at 32 - 64 items; n = 10240: best at
-// 8, a longer walk leaves too few CTAs for the tail). 2 frames per lane and float64 keep vn_kernel_ell (the loop kernel
-// needs 59 - 116 registers there and loses occupancy: A82 SPA float32 0.63 -> 0.59, float64 0.56 -> 0.54).
+// 8, a longer walk leaves too few CTAs for the tail). float64 (2 frames per lane, the same 16 bytes per lane): 3 CTAs per
+// SM for dv <= 4 (77 registers, no spills; uncapped it takes 88 and runs 2 CTAs: A82 SPA float64 0.56 -> 0.54 against
+// 0.57 -> 0.60 at 3, n = 102400 SPA float64 0.54 -> 0.67). float32 with 2 frames per lane keeps vn_kernel_ell (half the
+// bytes per warp; the loop kernel measured 0.63 -> 0.59 at 4 CTAs and no better than vn_kernel_ell at 5 or 6).
 struct VnLoopPlan {
     int items;   // <= 1 with ctas == 0: vn_kernel_ell
     int ctas;    // of the dv <= 4 kernel
@@ -47,10 +49,11 @@ inline VnLoopPlan vn_loop_plan(const qkdldpc_code *c, size_t elem_bytes, int V, 
         p.items = std::min(p.items, 64);
         return p;
     }
-    if (elem_bytes != 4 || V != 4) return VnLoopPlan{1, p.ctas};
+    const bool f64 = elem_bytes == 8;
+    if (!f64 && V != 4) return VnLoopPlan{1, p.ctas};
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const int ctas = p.ctas > 0 ? p.ctas : 4;
+    const int ctas = p.ctas > 0 ? p.ctas : (f64 ? 3 : 4);
     const long long per_wave = (long long)sms * ctas * warps_per_cta;
     const long long it = ((long long)cnt * tiles + per_wave * 12) / (per_wave * 24);   // rounded
     return VnLoopPlan{(int)std::max<long long>(1, std::min<long long>(it, 64)), ctas};
@@ -119,7 +122,12 @@ inline int launch_vn_bucket(const qkdldpc_code *c, bool fast, int tiles, cudaStr
 #define QK_VN_LOOP(FA, CT) vn_kernel_ell_loop<T, V, DVMAX, FA, CT><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base, items)
 #define QK_VN_LOOP_CTAS(FA)                                 \
     do {                                                    \
-        if constexpr (sizeof(T) != 4) QK_VN_LOOP(FA, 1);    \
+        if constexpr (sizeof(T) != 4) {                     \
+            if constexpr (DVMAX == 4) {                     \
+                if (want == 1) QK_VN_LOOP(FA, 1);           \
+                else QK_VN_LOOP(FA, 3);                     \
+            } else QK_VN_LOOP(FA, 1);                       \
+        }                                                   \
         else if constexpr (DVMAX == 4) {                    \
             if (want == 6) QK_VN_LOOP(FA, 6);               \
             else if (want == 5) QK_VN_LOOP(FA, 5);          \
