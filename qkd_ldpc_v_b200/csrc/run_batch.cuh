@@ -360,18 +360,14 @@ int run_batch(qkdldpc_code *c, const qkdldpc_params *P, int64_t n_frames, const 
     // the captured launches embed every pointer and parameter of this batch: the cache is keyed on all of them
     cudaGraphExec_t graph_exec = nullptr;
     auto ensure_graph = [&]() -> int {
-        unsigned long long h = 1469598103934665603ull;
-        auto mixin = [&h](const void *p, size_t nbytes) {
-            const unsigned char *q = static_cast<const unsigned char *>(p);
-            for (size_t i = 0; i < nbytes; ++i) h = (h ^ q[i]) * 1099511628211ull;
-        };
+        // the key is the launch arguments themselves, byte for byte (the structs are value-initialised, padding included)
+        std::string key;
+        auto mixin = [&key](const void *p, size_t nbytes) { key.append(static_cast<const char *>(p), nbytes); };
         mixin(&a, sizeof a);
         mixin(&b, sizeof b);
         const int geo[8] = {(int)sizeof(T), V, alg, cur_tiles, spp, fast ? 1 : 0, rows_per_part, (int)move_parts};
         mixin(geo, sizeof geo);
         mixin(&work, sizeof work);
-        char key[64];
-        snprintf(key, sizeof key, "%016llx", h);
         for (size_t i = 0; i < c->graphs.size(); ++i)
             if (c->graphs[i].key == key) {
                 graph_exec = c->graphs[i].exec;
