@@ -455,19 +455,24 @@ vn_kernel(const StepArgs<T> a, const int first, const int count) {
 // the edge ids in a second wave (bit class, Bob's mask word unconditionally, the messages).
 template <int V>
 __device__ __forceinline__ void vn_lane_words(const uint32_t (&act)[V], const uint32_t (&newm)[V], int lane,
-                                              uint32_t &actl, uint32_t &newl) {
+                                              uint32_t &actl, uint32_t &newl, bool &stale) {
     actl = 0;
     newl = 0;
+    uint32_t old = 0;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         actl = (lane == v) ? act[v] : actl;
         newl |= ((newm[v] >> lane) & 1u) << v;
+        old |= (act[v] & ~newm[v]) >> lane;
     }
+    // stale: some active slot of this lane carries messages of earlier iterations. A lane whose active slots were all just
+    // refilled (every lane in the first step of a batch) writes b2c = llr without reading the pool's leftovers.
+    stale = (old & 1u) != 0;
 }
 template <typename T, int V, int DVMAX, bool FAST, bool HASNEW>
 __device__ __forceinline__ void vn_body_ell(const StepArgs<T> &a, int tile, int bit, int lane, bool lane_act,
-                                            const uint32_t actl, const uint32_t newl, const int (&e)[DVMAX],
-                                            const int (&r)[DVMAX], const Vec<T, V> &lp) {
+                                            const uint32_t actl, const uint32_t newl, const bool stale,
+                                            const int (&e)[DVMAX], const int (&r)[DVMAX], const Vec<T, V> &lp) {
     // actl: the tile's active mask of word `lane` (lanes < V, else 0); newl: bit v set <=> this lane's slot v was just refilled
     constexpr int FT = kWarp * V;
     T *tbase = a.msg + (size_t)tile * a.e_stride + lane * V;
@@ -475,9 +480,12 @@ __device__ __forceinline__ void vn_body_ell(const StepArgs<T> &a, int tile, int 
     const uint8_t cls = __ldg(a.bitclass + bit);
     const Vec<uint32_t, V> bm = *reinterpret_cast<const Vec<uint32_t, V> *>(a.bobmask + ((size_t)tile * a.n + bit) * V);
     Vec<T, V> c[DVMAX];
+    const bool ld = lane_act && (!HASNEW || stale);
 #pragma unroll
-    for (int k = 0; k < DVMAX; ++k)
-        if (lane_act && e[k] >= 0) c[k] = ld_msg<T, V>(tbase + (size_t)e[k] * FT);
+    for (int k = 0; k < DVMAX; ++k) {
+        if constexpr (HASNEW) c[k] = Vec<T, V>{};
+        if (ld && e[k] >= 0) c[k] = ld_msg<T, V>(tbase + (size_t)e[k] * FT);
+    }
     // a-priori LLR (lane_llr)
     Vec<T, V> llr;
 #pragma unroll
@@ -569,9 +577,10 @@ vn_kernel_ell(const StepArgs<T> a, const int first, const int count, const int e
     }
     if (!any_act) return;
     uint32_t actl, newl;
-    vn_lane_words<V>(act, newm, lane, actl, newl);
-    if (any_new) vn_body_ell<T, V, DVMAX, FAST, true>(a, tile, bit, lane, lane_act, actl, newl, e, r, lp);
-    else vn_body_ell<T, V, DVMAX, FAST, false>(a, tile, bit, lane, lane_act, actl, newl, e, r, lp);
+    bool stale;
+    vn_lane_words<V>(act, newm, lane, actl, newl, stale);
+    if (any_new) vn_body_ell<T, V, DVMAX, FAST, true>(a, tile, bit, lane, lane_act, actl, newl, stale, e, r, lp);
+    else vn_body_ell<T, V, DVMAX, FAST, false>(a, tile, bit, lane, lane_act, actl, newl, stale, e, r, lp);
 }
 
 
@@ -595,14 +604,15 @@ __device__ __forceinline__ void vn_ell_record(const int *tab, int (&x)[DVMAX]) {
 }
 template <typename T, int V, int DVMAX, bool FAST, bool HASNEW>
 __device__ __forceinline__ void vn_items_ell(const StepArgs<T> &a, int tile, int lane, bool lane_act,
-                                             const uint32_t actl, const uint32_t newl, const int first, const int count,
-                                             const int ell_base, int idx, const int stride, int items) {
+                                             const uint32_t actl, const uint32_t newl, const bool stale, const int first,
+                                             const int count, const int ell_base, int idx, const int stride, int items) {
     constexpr int FT = kWarp * V;
     T *tbase = a.msg + (size_t)tile * a.e_stride + lane * V;
     const Vec<T, V> *lpp = reinterpret_cast<const Vec<T, V> *>(a.slot_llr + (size_t)tile * FT + lane * V);
     bool isnew[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) isnew[v] = HASNEW && ((newl >> v) & 1u);
+    const bool ld = lane_act && (!HASNEW || stale);
     for (;;) {
         // first wave: L1 hits from the warp's second item on
         const int bit = __ldg(a.col_order + first + idx);
@@ -615,8 +625,10 @@ __device__ __forceinline__ void vn_items_ell(const StepArgs<T> &a, int tile, int
         const Vec<T, V> lp = *lpp;
         Vec<T, V> c[DVMAX];
 #pragma unroll
-        for (int k = 0; k < DVMAX; ++k)
-            if (lane_act && e[k] >= 0) c[k] = ld_msg<T, V>(tbase + (size_t)e[k] * FT);
+        for (int k = 0; k < DVMAX; ++k) {
+            if constexpr (HASNEW) c[k] = Vec<T, V>{};
+            if (ld && e[k] >= 0) c[k] = ld_msg<T, V>(tbase + (size_t)e[k] * FT);
+        }
         idx += stride;
         const bool more = --items > 0 && idx < count;   // warp-uniform
         prefetch_l1(rows);
@@ -692,9 +704,10 @@ vn_kernel_ell_loop(const StepArgs<T> a, const int first, const int count, const 
     }
     if (!any_act) return;
     uint32_t actl, newl;
-    vn_lane_words<V>(act, newm, lane, actl, newl);
-    if (any_new) vn_items_ell<T, V, DVMAX, FAST, true>(a, tile, lane, lane_act, actl, newl, first, count, ell_base, idx, wpc, items);
-    else vn_items_ell<T, V, DVMAX, FAST, false>(a, tile, lane, lane_act, actl, newl, first, count, ell_base, idx, wpc, items);
+    bool stale;
+    vn_lane_words<V>(act, newm, lane, actl, newl, stale);
+    if (any_new) vn_items_ell<T, V, DVMAX, FAST, true>(a, tile, lane, lane_act, actl, newl, stale, first, count, ell_base, idx, wpc, items);
+    else vn_items_ell<T, V, DVMAX, FAST, false>(a, tile, lane, lane_act, actl, newl, stale, first, count, ell_base, idx, wpc, items);
 }
 
 }  // namespace qk
