@@ -396,11 +396,13 @@ def measure(ctx, args, wl, F, steps, warmup, sampler=None, want_e2e=True):
         ach = {k: (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0) for k, v in kern.items()}
         launches_per_step = launches / steps
         n_cn_launches = max(1.0, (launches_per_step - 2) / 3)
-        tr = db.get({"cn": "cn_kernel", "vn": "vn_kernel"}[dom], {}).get("dram_bytes_per_frame_iter")
+        per_code = db.get(name, db) if sz == 4 and alg >= 2 else {}     # captures exist for the float32 min-sum kernels
+        tr = per_code.get({"cn": "cn_kernel", "vn": "vn_kernel"}[dom], {}).get("dram_bytes_per_frame_iter")
+        vn_name = "vn_kernel_ell_loop" if (pi.get("last_vn_items_per_warp") or 0) > 1 else "vn_kernel_ell"
         roofline = {
-            "bound": "hbm", "kernel": {"cn": f"cn_kernel<{'float' if sz == 4 else 'double'},ALG={alg}>", "vn": "vn_kernel"}[dom],
+            "bound": "hbm", "kernel": {"cn": f"cn_kernel<{'float' if sz == 4 else 'double'},ALG={alg}>", "vn": vn_name}[dom],
             "achieved": ach[dom], "peak": peak, "unit": "GB/s", "frac": ach[dom] / peak,
-            "traffic": (tr * it_rank / n_cn_launches if tr is not None and sz == 4 and name == "I80" else None),
+            "traffic": (tr * it_rank / n_cn_launches if tr is not None and name in ("I80", "L100k") else None),
             "peak_source": peak_src,
             "bytes_per_launch": kern[dom][0] / n_cn_launches, "ms_per_launch": kern[dom][1] / n_cn_launches,
             "launches_per_step": n_cn_launches,

@@ -188,6 +188,7 @@ struct qkdldpc_code {
     Oc2Device oc2, oc2r8;
     DevBuf<unsigned long long> oc2_phase_clk;   // profiling: clocks per phase of the last on-chip min-sum launch
     DevBuf<uint32_t> oc2_cls;         // [n_combos][2][l_slots/32] punctured / shortened masks of the current batch, slot order
+    mutable int sm_count = 0;         // multiprocessors of `device`, read on first use (run_batch.cuh: vn_loop_plan)
     int64_t tail_compactions = 0;     // streaming path
     int last_spp = 0, last_vn_items = 0;
     int last_rec_bytes = 0;           // 16 / 8: record format of the last float32 on-chip min-sum launch

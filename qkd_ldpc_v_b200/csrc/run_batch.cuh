@@ -51,8 +51,8 @@ inline VnLoopPlan vn_loop_plan(const qkdldpc_code *c, size_t elem_bytes, int V, 
     }
     const bool f64 = elem_bytes == 8;
     if (!f64 && V != 4) return VnLoopPlan{1, p.ctas};
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    if (c->sm_count <= 0 && cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess) c->sm_count = 148;
+    const int sms = c->sm_count;
     const int ctas = p.ctas > 0 ? p.ctas : (f64 ? 3 : 4);
     const long long per_wave = (long long)sms * ctas * warps_per_cta;
     const long long it = ((long long)cnt * tiles + per_wave * 12) / (per_wave * 24);   // rounded
