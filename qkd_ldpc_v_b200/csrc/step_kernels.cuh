@@ -593,6 +593,7 @@ vn_kernel_ell(const StepArgs<T> a, const int first, const int count, const int e
 // no registers (holding the next record in registers did: 48 registers still spilled 170 bytes); the check ids are loaded
 // last, just before the parity RED, and the slots' LLR magnitudes come from L1 with every item instead of staying live.
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <typename T, int V, int DVMAX>
 __device__ __forceinline__ void vn_ell_record(const int *tab, int (&x)[DVMAX]) {
     const int4 *p = reinterpret_cast<const int4 *>(tab);
@@ -602,7 +603,7 @@ __device__ __forceinline__ void vn_ell_record(const int *tab, int (&x)[DVMAX]) {
         x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
     }
 }
-template <typename T, int V, int DVMAX, bool FAST, bool HASNEW>
+template <typename T, int V, int DVMAX, bool FAST, bool HASNEW, int L2PF>
 __device__ __forceinline__ void vn_items_ell(const StepArgs<T> &a, int tile, int lane, bool lane_act,
                                              const uint32_t actl, const uint32_t newl, const bool stale, const int first,
                                              const int count, const int ell_base, int idx, const int stride, int items) {
@@ -633,10 +634,36 @@ __device__ __forceinline__ void vn_items_ell(const StepArgs<T> &a, int tile, int
         const bool more = --items > 0 && idx < count;   // warp-uniform
         prefetch_l1(rows);
         if constexpr (DVMAX == 8) prefetch_l1(rows + 4);
-        if (more) {
-            prefetch_l1(a.col_order + first + idx);
-            prefetch_l1(a.vn_ell_edge + ell_base + (size_t)idx * DVMAX);
-            if constexpr (DVMAX == 8) prefetch_l1(a.vn_ell_edge + ell_base + (size_t)idx * DVMAX + 4);
+        if constexpr (L2PF == 0) {
+            if (more) {
+                prefetch_l1(a.col_order + first + idx);
+                prefetch_l1(a.vn_ell_edge + ell_base + (size_t)idx * DVMAX);
+                if constexpr (DVMAX == 8) prefetch_l1(a.vn_ell_edge + ell_base + (size_t)idx * DVMAX + 4);
+            }
+        } else {
+            // L2PF = D (default 1): the edge record of the item D ahead is read now (an L1 hit: its line was prefetched one
+            // item earlier) and its message chunks are requested into L2 -- one 128-byte line per lane --, so that its loads
+            // find them a short latency away: bytes in flight without registers. The index lines are prefetched D + 1 items
+            // ahead. Measured (B200, profiles/r02_ab_vn_loop.md 5): float64 VN 0.66 -> 0.75 of the HBM peak on the n = 102400
+            // code (3 CTAs per SM leave few loads in flight), float32 0.873 -> 0.885; D = 2, 3 are 1-2 % behind D = 1.
+            const int ip = idx + (L2PF - 1) * stride;   // idx is the next item already
+            if (items >= L2PF && ip < count) {
+                int en[DVMAX];
+                vn_ell_record<T, V, DVMAX>(a.vn_ell_edge + ell_base + (size_t)ip * DVMAX, en);
+                constexpr int LPC = FT * (int)sizeof(T) / 128;   // lines per chunk
+                const int kk = lane / LPC;
+                int ek = -1;
+#pragma unroll
+                for (int k = 0; k < DVMAX; ++k) ek = (kk == k) ? en[k] : ek;
+                if (ek >= 0)
+                    prefetch_l2(reinterpret_cast<const char *>(a.msg + (size_t)tile * a.e_stride + (size_t)ek * FT) + (lane % LPC) * 128);
+                const int iq = ip + stride;
+                if (items > L2PF && iq < count) {
+                    prefetch_l1(a.col_order + first + iq);
+                    prefetch_l1(a.vn_ell_edge + ell_base + (size_t)iq * DVMAX);
+                    if constexpr (DVMAX == 8) prefetch_l1(a.vn_ell_edge + ell_base + (size_t)iq * DVMAX + 4);
+                }
+            }
         }
         // from here on: vn_body_ell's arithmetic, operation by operation
         Vec<T, V> llr;
@@ -680,7 +707,7 @@ __device__ __forceinline__ void vn_items_ell(const StepArgs<T> &a, int tile, int
         if (!more) break;
     }
 }
-template <typename T, int V, int DVMAX, bool FAST, int CTAS>
+template <typename T, int V, int DVMAX, bool FAST, int CTAS, int L2PF = 1>
 __global__ void __launch_bounds__(vn_threads(sizeof(T), V, DVMAX), CTAS)
 vn_kernel_ell_loop(const StepArgs<T> a, const int first, const int count, const int ell_base, const int items) {
     static_assert(DVMAX == 4 || DVMAX == 8, "ELL records exist for the two narrow buckets");
@@ -706,8 +733,8 @@ vn_kernel_ell_loop(const StepArgs<T> a, const int first, const int count, const 
     uint32_t actl, newl;
     bool stale;
     vn_lane_words<V>(act, newm, lane, actl, newl, stale);
-    if (any_new) vn_items_ell<T, V, DVMAX, FAST, true>(a, tile, lane, lane_act, actl, newl, stale, first, count, ell_base, idx, wpc, items);
-    else vn_items_ell<T, V, DVMAX, FAST, false>(a, tile, lane, lane_act, actl, newl, stale, first, count, ell_base, idx, wpc, items);
+    if (any_new) vn_items_ell<T, V, DVMAX, FAST, true, L2PF>(a, tile, lane, lane_act, actl, newl, stale, first, count, ell_base, idx, wpc, items);
+    else vn_items_ell<T, V, DVMAX, FAST, false, L2PF>(a, tile, lane, lane_act, actl, newl, stale, first, count, ell_base, idx, wpc, items);
 }
 
 }  // namespace qk
