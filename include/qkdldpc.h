@@ -107,11 +107,11 @@ typedef struct qkdldpc_options {
                                27 edges; results are identical                                                           */
     int32_t vn_items_per_warp; /* streaming path, narrow variable-node buckets (dv <= 8): items one warp walks per launch,
                                the next item's index records prefetched into L1 behind the current item's messages;
-                               1 = one item per warp (vn_kernel_ell), 0 = auto: a walk sized to the grid for 16 bytes of
-                               messages per lane (float32 x 4 frames, float64 x 2), else 1; results are identical       */
+                               1 = one item per warp (vn_kernel_ell), 0 = auto: a walk sized to the grid (float32 with 2
+                               or 4 frames per lane, float64), 1 for float32 with 1 frame per lane; results are identical */
     int32_t vn_ctas_per_sm; /* resident CTAs per SM the dv <= 4 walking kernel is compiled for; float32: 3..6 (72 / 64 / 48 /
                                40 registers; the dv <= 8 kernel: 2 for 3, else 3), float64: 3 (77 registers) or 1 (88);
-                               0 = auto (float32 4, float64 3)                                                           */
+                               0 = auto (float32: 4, with 2 frames per lane 5; float64: 3)                               */
     int32_t compaction_fill_pct; /* tail compaction starts once the queue is empty and at most this percentage of the resident
                                slots is still occupied (1..99); 0 = auto (75)                                            */
 } qkdldpc_options;

@@ -37,8 +37,9 @@ inline long long quantised_tiles(long long need) {
 // as leaves ~24 waves of CTAs in the grid (n = 102400: VN 0.71 -> 0.86 of the HBM peak at 32 - 64 items; n = 10240: best at
 // 8, a longer walk leaves too few CTAs for the tail). float64 (2 frames per lane, the same 16 bytes per lane): 3 CTAs per
 // SM for dv <= 4 (77 registers, no spills; uncapped it takes 88 and runs 2 CTAs: A82 SPA float64 0.56 -> 0.54 against
-// 0.57 -> 0.60 at 3, n = 102400 SPA float64 0.54 -> 0.67). float32 with 2 frames per lane keeps vn_kernel_ell (half the
-// bytes per warp; the loop kernel measured 0.63 -> 0.59 at 4 CTAs and no better than vn_kernel_ell at 5 or 6).
+// 0.57 -> 0.60 at 3, n = 102400 SPA float64 0.54 -> 0.67). float32 with 2 frames per lane (the sum-product variants: half
+// the bytes per warp): 5 CTAs per SM (48 registers, 16 bytes of spill); no gain before the kernel prefetched the next
+// item's messages into L2, with it A82 SPA float32 VN 0.755 -> 0.854 (0.820 at 4 CTAs). 1 frame per lane keeps vn_kernel_ell.
 struct VnLoopPlan {
     int items;   // <= 1 with ctas == 0: vn_kernel_ell
     int ctas;    // of the dv <= 4 kernel
@@ -50,10 +51,10 @@ inline VnLoopPlan vn_loop_plan(const qkdldpc_code *c, size_t elem_bytes, int V, 
         return p;
     }
     const bool f64 = elem_bytes == 8;
-    if (!f64 && V != 4) return VnLoopPlan{1, p.ctas};
+    if (!f64 && V != 4 && V != 2) return VnLoopPlan{1, p.ctas};
     if (c->sm_count <= 0 && cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess) c->sm_count = 148;
     const int sms = c->sm_count;
-    const int ctas = p.ctas > 0 ? p.ctas : (f64 ? 3 : 4);
+    const int ctas = p.ctas > 0 ? p.ctas : (f64 ? 3 : (V == 2 ? 5 : 4));
     const long long per_wave = (long long)sms * ctas * warps_per_cta;
     const long long it = ((long long)cnt * tiles + per_wave * 12) / (per_wave * 24);   // rounded
     return VnLoopPlan{(int)std::max<long long>(1, std::min<long long>(it, 64)), ctas};
