@@ -46,15 +46,13 @@ struct VnLoopPlan {
 };
 inline VnLoopPlan vn_loop_plan(const qkdldpc_code *c, size_t elem_bytes, int V, int cnt, int tiles, int warps_per_cta) {
     VnLoopPlan p{c->opt.vn_items_per_warp, c->opt.vn_ctas_per_sm};
-    if (p.items > 0) {
-        p.items = std::min(p.items, 64);
-        return p;
-    }
     const bool f64 = elem_bytes == 8;
+    const int ctas = p.ctas > 0 ? p.ctas : (f64 ? 3 : (V == 2 ? 5 : 4));
+    if (p.items == 1) return p;   // vn_kernel_ell, unless a CTA count was asked for too (the walking kernel with one item)
+    if (p.items > 1) return VnLoopPlan{std::min(p.items, 64), ctas};
     if (!f64 && V != 4 && V != 2) return VnLoopPlan{1, p.ctas};
     if (c->sm_count <= 0 && cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess) c->sm_count = 148;
     const int sms = c->sm_count;
-    const int ctas = p.ctas > 0 ? p.ctas : (f64 ? 3 : (V == 2 ? 5 : 4));
     const long long per_wave = (long long)sms * ctas * warps_per_cta;
     const long long it = ((long long)cnt * tiles + per_wave * 12) / (per_wave * 24);   // rounded
     return VnLoopPlan{(int)std::max<long long>(1, std::min<long long>(it, 64)), ctas};
