@@ -347,6 +347,12 @@ def test_tail_compaction_does_not_change_results(q, alg, prec, fpl, frames):
     assert on.info["decoder_steps"] <= off.info["decoder_steps"]
     # the stragglers fail (they retire at rate 0), so the compaction must have run -- and never on the other handle
     assert on.info["tail_compactions"] > 0 and off.info["tail_compactions"] == 0
+    # the occupancy at which it starts and the poll interval change when frames are moved, never what they decode to
+    for fill, spp in ((30, 1), (99, 3)):
+        r = handle(q, "K1_4", compaction_fill_pct=fill, steps_per_poll=spp, **kw).QKD_LDPC_batch(a, b, acc, fac, cfg)
+        assert (r.iterations_num == off.iterations_num).all() and (r.flags == off.flags).all(), (fill, spp)
+        assert (r.bob_solution == off.bob_solution).all() and (r.tally == off.tally).all(), (fill, spp)
+        assert r.info["tail_compactions"] > 0 and r.info["last_steps_per_poll"] == spp
 
 
 @pytest.mark.parametrize("name,alg,prec,fpl,frames,qber", [
