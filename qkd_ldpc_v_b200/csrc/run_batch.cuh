@@ -159,6 +159,22 @@ inline int launch_vn_bucket(const qkdldpc_code *c, bool fast, int tiles, cudaStr
         vn_kernel_ell<T, V, DVMAX, false><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt, ell_base);
         return 1;
     } else {
+        if constexpr (DVMAX == 16 || DVMAX == 32) {   // wide buckets: coalesced index loads, the next item's ids and messages ahead
+            VnLoopPlan plan = vn_loop_plan(c, sizeof(T), V, cnt, tiles, threads / 32);
+            // (float64: 126 / 176 registers leave 2 CTAs of 128 threads per SM, and the I80 workload measured 0.862 -> 0.787
+            // Gbit/s with every bucket walking: float64 keeps vn_kernel for the wide buckets)
+            if (c->opt.vn_items_per_warp != 1 && V > 1 && sizeof(T) == 4) {
+                const dim3 lgrid(ceil_div(cnt, (threads / 32) * plan.items), (unsigned)tiles);
+                if constexpr (sizeof(T) == 4) {
+                    if (fast) {
+                        vn_kernel_wide_loop<T, V, DVMAX, true><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, plan.items);
+                        return 1;
+                    }
+                }
+                vn_kernel_wide_loop<T, V, DVMAX, false><<<lgrid, threads, 0, s>>>(a, c->vn_first[B], cnt, plan.items);
+                return 1;
+            }
+        }
         if constexpr (sizeof(T) == 4) {
             if (fast) {
                 vn_kernel<T, V, DVMAX, true><<<grid, threads, 0, s>>>(a, c->vn_first[B], cnt);

@@ -737,4 +737,121 @@ vn_kernel_ell_loop(const StepArgs<T> a, const int first, const int count, const 
     else vn_items_ell<T, V, DVMAX, FAST, false, L2PF>(a, tile, lane, lane_act, actl, newl, stale, first, count, ell_base, idx, wpc, items);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3 for the wide buckets (8 < dv <= 32), walking: vn_kernel chases col_order -> col_ptr -> csc_edge[k] -> message for every
+// edge (one uniform index load per edge, again before the stores and before the parity RED). Here the edge and check ids of an
+// item are ONE coalesced load each (lane k holds the k-th id; the edges read them by shuffle), and while an item's messages
+// are in flight the warp fetches the NEXT item's ids the same way and asks for its message chunks in L2 (one chunk per lane),
+// as vn_kernel_ell_loop does for the narrow buckets. The arithmetic is vn_body's, operation by operation.
+template <typename T, int V, int DVMAX, bool FAST, bool HASNEW>
+__device__ __forceinline__ void vn_items_wide(const StepArgs<T> &a, int tile, int lane, bool lane_act, const uint32_t actl,
+                                              const uint32_t newl, const bool stale, const int first, const int count, int idx,
+                                              const int stride, int items) {
+    constexpr int FT = kWarp * V;
+    constexpr int LPC = FT * (int)sizeof(T) / 128;   // 128-byte lines per message chunk
+    T *tbase = a.msg + (size_t)tile * a.e_stride + lane * V;
+    const char *pbase = reinterpret_cast<const char *>(a.msg + (size_t)tile * a.e_stride);
+    const Vec<T, V> *lpp = reinterpret_cast<const Vec<T, V> *>(a.slot_llr + (size_t)tile * FT + lane * V);
+    bool isnew[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) isnew[v] = HASNEW && ((newl >> v) & 1u);
+    const bool ld = lane_act && (!HASNEW || stale);
+    int bit = __ldg(a.col_order + first + idx);
+    int c0 = __ldg(a.col_ptr + bit);
+    int dv = __ldg(a.col_ptr + bit + 1) - c0;
+    int e_l = lane < dv ? __ldg(a.csc_edge + c0 + lane) : -1;
+    int r_l = lane < dv ? __ldg(a.csc_row + c0 + lane) : -1;
+    for (;;) {
+        const uint8_t cls = __ldg(a.bitclass + bit);
+        const Vec<uint32_t, V> bm = *reinterpret_cast<const Vec<uint32_t, V> *>(a.bobmask + ((size_t)tile * a.n + bit) * V);
+        const Vec<T, V> lp = *lpp;
+        Vec<T, V> c[DVMAX];
+#pragma unroll
+        for (int k = 0; k < DVMAX; ++k) {
+            if constexpr (HASNEW) c[k] = Vec<T, V>{};
+            if (k < dv) {   // warp-uniform
+                const int ek = __shfl_sync(0xffffffffu, e_l, k);
+                if (ld) c[k] = ld_msg<T, V>(tbase + (size_t)ek * FT);
+            }
+        }
+        idx += stride;
+        const bool more = --items > 0 && idx < count;   // warp-uniform
+        int bit_n = 0, dv_n = 0, e_n = -1, r_n = -1;
+        if (more) {
+            bit_n = __ldg(a.col_order + first + idx);
+            const int c0n = __ldg(a.col_ptr + bit_n);
+            dv_n = __ldg(a.col_ptr + bit_n + 1) - c0n;
+            if (lane < dv_n) {
+                e_n = __ldg(a.csc_edge + c0n + lane);
+                r_n = __ldg(a.csc_row + c0n + lane);
+#pragma unroll
+                for (int j = 0; j < LPC; ++j) prefetch_l2(pbase + (size_t)e_n * (FT * sizeof(T)) + j * 128);
+            }
+        }
+        Vec<T, V> llr;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const T pay = ((bm.v[v] >> lane) & 1u) ? -lp.v[v] : lp.v[v];
+            llr.v[v] = (cls == 0) ? pay : ((cls == 1) ? (T)1e-4 : Lim<T>::max());
+        }
+        Vec<T, V> L = llr;
+#pragma unroll
+        for (int k = 0; k < DVMAX; ++k)
+            if (k < dv && lane_act) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    if constexpr (HASNEW) c[k].v[v] = isnew[v] ? (T)0 : c[k].v[v];
+                    L.v[v] = L.v[v] + c[k].v[v];
+                }
+            }
+#pragma unroll
+        for (int k = 0; k < DVMAX; ++k)
+            if (k < dv) {
+                const int ek = __shfl_sync(0xffffffffu, e_l, k);
+                if (lane_act) st_msg<T, V>(tbase + (size_t)ek * FT, vn_out<T, V, FAST, HASNEW>(a, L, c[k], llr, isnew));
+            }
+        uint32_t zw = 0;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const uint32_t w = __ballot_sync(0xffffffffu, lane_act && (L.v[v] <= (T)0));
+            if (lane == v) zw = w;
+        }
+        zw &= actl;
+        if (lane < V) a.zmask[((size_t)tile * a.n + bit) * V + lane] = zw;
+        for (int k = 0; k < dv; ++k) {
+            const int rk = __shfl_sync(0xffffffffu, r_l, k);
+            if (lane < V && zw != 0) atomicXor(a.par + ((size_t)tile * a.m + rk) * V + lane, zw);
+        }
+        if (!more) break;
+        bit = bit_n; dv = dv_n; e_l = e_n; r_l = r_n;
+    }
+}
+template <typename T, int V, int DVMAX, bool FAST>
+__global__ void __launch_bounds__(vn_threads(sizeof(T), V, DVMAX))
+vn_kernel_wide_loop(const StepArgs<T> a, const int first, const int count, const int items) {
+    static_assert(DVMAX == 16 || DVMAX == 32, "wide buckets whose edges fit a register array and a warp's lanes");
+    const int tile = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const int idx = blockIdx.x * wpc * items + (threadIdx.x >> 5);
+    if (idx >= count) return;
+    uint32_t act[V], newm[V];
+    bool any_act = false, any_new = false, lane_act = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        act[v] = a.tile_active[tile * V + v];
+        newm[v] = a.tile_new[tile * V + v];
+        any_act |= act[v] != 0;
+        any_new |= newm[v] != 0;
+        lane_act |= (act[v] >> lane) & 1u;
+    }
+    if (!any_act) return;
+    uint32_t actl, newl;
+    bool stale;
+    vn_lane_words<V>(act, newm, lane, actl, newl, stale);
+    if (any_new) vn_items_wide<T, V, DVMAX, FAST, true>(a, tile, lane, lane_act, actl, newl, stale, first, count, idx, wpc, items);
+    else vn_items_wide<T, V, DVMAX, FAST, false>(a, tile, lane, lane_act, actl, newl, stale, first, count, idx, wpc, items);
+}
+
 }  // namespace qk
