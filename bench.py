@@ -44,12 +44,13 @@ WORKLOADS = {
     "A82_omsa_q0154": ("A82", 3, 0.81, 0.0, 0.0154, "n=10240 m=1801 alist R=0.82, OMSA beta=0.81, QBER 1.54%"),
     "A82_anmsa_q0161": ("A82", 4, 0.80, 0.71, 0.0161, "n=10240 m=1801 alist R=0.82, ANMSA alpha=0.8 nu=0.71, QBER 1.61%"),
     "A82_aomsa_q0161": ("A82", 5, 0.68, 1.25, 0.0161, "n=10240 m=1801 alist R=0.82, AOMSA beta=0.68 sigma=1.25, QBER 1.61%"),
+    "I80_spa_q015": ("I80", 0, 0.0, 0.0, 0.015, "n=10240 m=2048 irregular R=0.8 (E=60430), SPA, QBER 1.5% (4 E + 4 n bytes do not fit an SM: streaming path)"),
     "I80_aomsa_q015": ("I80", 5, 0.70, 0.99, 0.015, "n=10240 m=2048 irregular R=0.8 (E=60430), AOMSA beta=0.70 sigma=0.99, QBER 1.5% (ADAPTIVE R.json family)"),
 }
 HEADLINE = "I80_nmsa_q030"
 # further workloads of the default run: (id, frames per GPU per step) -- sized so that each takes a few seconds
 SECONDARY = [("A79_nmsa_q020", 65536), ("I80_nmsa_q015", 65536), ("A82_spa_q0162", 32768), ("A82_spalin_q0162", 32768),
-             ("A82_aomsa_q0161", 32768), ("L100k_nmsa_q060", 4096), ("L100k_spa_q084", 1024)]
+             ("A82_aomsa_q0161", 32768), ("L100k_nmsa_q060", 4096), ("L100k_spa_q084", 1024), ("I80_spa_q015", 32768)]
 MAX_ITER, THRESHOLD = 100, 100.0
 
 
